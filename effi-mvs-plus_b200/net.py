@@ -1,0 +1,305 @@
+"""Host-side network around the hot path (stock PyTorch), checkpoint-compatible
+with upstream ``Effi_MVS_plus`` (models/Effi_MVS_plus.py:315-568).
+
+Only the *callers* of the hot path live here: the 2-D feature pyramid
+(models/module.py:346-412), the ConvGRU update block (models/update.py:10-141),
+the convex upsampling (Effi_MVS_plus.py:167-178) and the three-stage cascade that
+strings them together.  They stay stock PyTorch (BASELINE.json north_star).  All
+cost-volume work is delegated to a *hot-path table* -- by default
+``hotpath.CudaHotPath`` (hand-written sm_100a kernels behind the C-ABI); tests and
+the CPU-baseline leg of bench.py inject the oracle's table instead.
+
+Parameter names reproduce upstream's ``state_dict`` layout (including the
+duplicate registrations ``update_block_depth1`` / ``update_block.0`` etc.) so that
+``model_dtu.ckpt`` / ``model_tank.ckpt`` load with ``strict=True``.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------
+# building blocks (attribute names .conv / .bn are the checkpoint format)
+# ----------------------------------------------------------------------------
+class ConvBNReLU2d(nn.Module):
+    """conv2d(bias-free) + BatchNorm2d + ReLU  (upstream Conv2d / ConvBnReLU)."""
+
+    def __init__(self, cin, cout, k, stride=1, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
+        self.bn = nn.BatchNorm2d(cout)
+
+    def forward(self, x):
+        return F.relu(self.bn(self.conv(x)), inplace=True)
+
+
+class ConvBN3d(nn.Module):
+    """Parameter holder for one 3-D (de)conv + BN layer of the regularization nets.
+
+    The arithmetic runs inside the hot-path table (CUDA kernels with the BN folded in),
+    so this module has no forward of its own.
+    """
+
+    def __init__(self, cin, cout, transposed=False):
+        super().__init__()
+        if transposed:
+            self.conv = nn.ConvTranspose3d(cin, cout, 3, bias=False)
+        else:
+            self.conv = nn.Conv3d(cin, cout, 3, bias=False)
+        self.bn = nn.BatchNorm3d(cout)
+        self.transposed = transposed
+
+
+class RegNet3D(nn.Module):
+    """Weights of CostRegNet_2_sample_FPN3D_Fast (models/module.py:435-452)."""
+
+    def __init__(self, cin=1, base=8):
+        super().__init__()
+        self.conv0 = ConvBN3d(cin, base)
+        self.conv1 = ConvBN3d(base, base)
+        self.conv2 = ConvBN3d(base, base * 2)
+        self.conv3 = ConvBN3d(base * 2, base * 2)
+        self.conv4 = ConvBN3d(base * 2, base * 4)
+        self.conv5 = ConvBN3d(base * 4, base * 4)
+        self.conv6 = ConvBN3d(base * 4, base * 2, transposed=True)
+        self.conv7 = ConvBN3d(base * 2, base, transposed=True)
+        self.prob = nn.Conv3d(base, 1, 3, stride=1, padding=1, bias=False)
+
+
+class CrossScaleNet3D(nn.Module):
+    """Weights of cost_up_small (models/module.py:501-508)."""
+
+    def __init__(self, cin=1, base=8):
+        super().__init__()
+        self.conv0 = ConvBN3d(cin, base)
+        self.conv_cost = ConvBN3d(1, base)
+        self.conv1 = ConvBN3d(base * 2, base)
+        self.conv2 = ConvBN3d(base, 1, transposed=True)
+
+
+class FeaturePyramid(nn.Module):
+    """P_1to8_FeatureNet_Fast (models/module.py:346-412): strides 1,2,4,8; heads at 1/8, 1/4, 1/2."""
+
+    def __init__(self, chans, heads):
+        super().__init__()
+        c0, c1, c2, c3 = chans
+        self.conv0 = nn.Sequential(ConvBNReLU2d(3, c0, 3, 1, 1), ConvBNReLU2d(c0, c0, 3, 1, 1))
+        self.conv1 = nn.Sequential(ConvBNReLU2d(c0, c1, 5, 2, 2), ConvBNReLU2d(c1, c1, 3, 1, 1), ConvBNReLU2d(c1, c1, 3, 1, 1))
+        self.conv2 = nn.Sequential(ConvBNReLU2d(c1, c2, 5, 2, 2), ConvBNReLU2d(c2, c2, 3, 1, 1), ConvBNReLU2d(c2, c2, 3, 1, 1))
+        self.conv3 = nn.Sequential(ConvBNReLU2d(c2, c3, 5, 2, 2), ConvBNReLU2d(c3, c3, 3, 1, 1), ConvBNReLU2d(c3, c3, 3, 1, 1))
+        self.out1 = nn.Conv2d(c3, heads[0], 1, bias=False)
+        self.inner1 = nn.Conv2d(c2, c3, 1, bias=True)
+        self.inner2 = nn.Conv2d(c1, c3, 1, bias=True)
+        self.out2 = nn.Conv2d(c3, heads[1], 3, padding=1, bias=False)
+        self.out3 = nn.Conv2d(c3, heads[2], 3, padding=1, bias=False)
+
+    def forward(self, x):
+        l1 = self.conv1(self.conv0(x))
+        l2 = self.conv2(l1)
+        top = self.conv3(l2)
+        s1 = self.out1(top)
+        top = F.interpolate(top, scale_factor=2, mode="nearest") + self.inner1(l2)
+        s2 = self.out2(top)
+        top = F.interpolate(top, scale_factor=2, mode="nearest") + self.inner2(l1)
+        s3 = self.out3(top)
+        return [s1, s2, s3]
+
+
+class CostEncoder(nn.Module):
+    """ProjectionInput (models/update.py:69-99)."""
+
+    def __init__(self, cost_dim, hidden, context_dim):
+        super().__init__()
+        self.convc1 = nn.Conv2d(cost_dim, hidden, 1)
+        self.convc2 = nn.Conv2d(hidden, hidden, 3, padding=1)
+        self.convd1 = nn.Conv2d(1, hidden, 7, padding=3)
+        self.convd2 = nn.Conv2d(hidden, hidden, 3, padding=1)
+        self.convd = nn.Conv2d(2 * hidden, hidden - context_dim, 3, padding=1)
+        self.convc = nn.Conv2d(hidden, hidden, 1)
+
+    def forward(self, inv_depth, cost, context):
+        c = F.relu(self.convc2(F.relu(self.convc1(cost))))
+        d = F.relu(self.convd2(F.relu(self.convd1(inv_depth))))
+        m = self.convd(torch.cat([c, d], dim=1))
+        return F.relu(self.convc(torch.cat([m, context], dim=1)))
+
+
+class GRUCell2d(nn.Module):
+    """ConvGRU (models/update.py:33-49)."""
+
+    def __init__(self, hidden, inp):
+        super().__init__()
+        self.convz = nn.Conv2d(hidden + inp, hidden, 3, padding=1)
+        self.convr = nn.Conv2d(hidden + inp, hidden, 3, padding=1)
+        self.convq = nn.Conv2d(hidden + inp, hidden, 3, padding=1)
+
+    def forward(self, h, x):
+        hx = torch.cat([h, x], dim=1)
+        z = torch.sigmoid(self.convz(hx))
+        r = torch.sigmoid(self.convr(hx))
+        q = torch.tanh(self.convq(torch.cat([r * h, x], dim=1)))
+        return (1 - z) * h + z * q
+
+
+class DeltaHead(nn.Module):
+    """DepthHead (models/update.py:10-27), eval mode: tanh(conv2(relu(conv1)))."""
+
+    def __init__(self, hidden):
+        super().__init__()
+        self.conv1 = nn.Conv2d(hidden, hidden, 3, padding=1)
+        self.conv2 = nn.Conv2d(hidden, 1, 3, padding=1)
+
+    def forward(self, x):
+        return torch.tanh(self.conv2(F.relu(self.conv1(x))))
+
+
+class UpdateBlock(nn.Module):
+    """BasicUpdateBlock (models/update.py:101-141): GRU iterations that query the
+    dynamic cost volume through ``cost_fn(depth)`` (the a7 hot-path row)."""
+
+    def __init__(self, hidden, cost_dim, ratio, context_dim):
+        super().__init__()
+        self.encoder = CostEncoder(cost_dim, hidden, context_dim)
+        self.depth_gru = GRUCell2d(hidden, hidden)
+        self.depth_head = DeltaHead(hidden)
+        self.mask = nn.Sequential(nn.Conv2d(hidden, hidden * 2, 3, padding=1), nn.ReLU(inplace=True),
+                                  nn.Conv2d(hidden * 2, ratio * ratio * 9, 1))
+
+    def forward(self, net, cost_fn, inv_depth, context, iters, to_depth):
+        inv_seq = []
+        for _ in range(iters):
+            inv_depth = inv_depth.detach()
+            x = self.encoder(inv_depth, cost_fn(to_depth(inv_depth)), context)
+            net = self.depth_gru(net, x)
+            inv_depth = inv_depth + self.depth_head(net)
+            inv_seq.append(inv_depth)
+        return net, 0.25 * self.mask(net), inv_seq
+
+
+def convex_upsample(x, mask, ratio):
+    """upsample_depth (Effi_MVS_plus.py:167-178): softmax-weighted 3x3 upsampling."""
+    N, _, H, W = x.shape
+    m = torch.softmax(mask.view(N, 1, 9, ratio, ratio, H, W), dim=2)
+    nb = F.unfold(x, [3, 3], padding=1).view(N, 1, 9, 1, 1, H, W)
+    up = torch.sum(m * nb, dim=2).permute(0, 1, 4, 2, 5, 3)
+    return up.reshape(N, ratio * H, ratio * W)
+
+
+# ----------------------------------------------------------------------------
+# the cascade
+# ----------------------------------------------------------------------------
+class EffiMVSPlus(nn.Module):
+    """Three-stage Effi-MVS+ cascade; same constructor fields and forward contract as
+    upstream (``args.ndepths``, ``args.GRUiters``, ``args.CostNum``; forward(imgs
+    (B,V,3,H,W), proj_matrices {"stage1".."stage3": (B,V,2,4,4)}, depth_values (B,Dv))
+    -> {"depth": 13 maps, "photometric_confidence"})."""
+
+    RATIOS = (4, 2, 1)           # depth_interals_ratio, Effi_MVS_plus.py:316
+    HIDDEN = (48, 32, 16)        # :337
+    CONTEXT = (12, 8, 4)         # :338
+    FEAT = (32, 16, 8)           # :350
+    G = 1                        # :349
+
+    def __init__(self, args, hotpath=None):
+        super().__init__()
+        self.ndepths = [int(e) for e in str(args.ndepths).split(",")]
+        self.iters = [int(e) for e in str(args.GRUiters).split(",")]
+        self.cost_num = int(args.CostNum)
+        self.PixelwiseNet = nn.Sequential(ConvBNReLU2d(1, 16, 3, 1, 1), ConvBNReLU2d(16, 16, 3, 1, 1),
+                                          ConvBNReLU2d(16, 8, 3, 1, 1), nn.Conv2d(8, 1, 1), nn.Sigmoid())
+        self.feature = FeaturePyramid((8, 16, 32, 64), self.FEAT)
+        self.cnet_depth = FeaturePyramid((4, 8, 16, 32), (60, 40, 20))
+        blocks = [UpdateBlock(self.HIDDEN[i], self.G * self.cost_num * 2, 2, self.CONTEXT[i]) for i in range(3)]
+        self.update_block_depth1, self.update_block_depth2, self.update_block_depth3 = blocks
+        self.update_block = nn.ModuleList(blocks)
+        self.CSP_R1, self.CSP_R2 = CrossScaleNet3D(self.G), CrossScaleNet3D(self.G)
+        self.CSP_R = nn.ModuleList([self.CSP_R1, self.CSP_R2])
+        self.CSP_C1, self.CSP_C2 = CrossScaleNet3D(self.G), CrossScaleNet3D(self.G)
+        self.CSP_C = nn.ModuleList([self.CSP_C1, self.CSP_C2])
+        self.cost_regularization = RegNet3D(self.G, 8)
+        object.__setattr__(self, "_hotpath", hotpath)
+
+    # the table is not a submodule: keep it out of state_dict / .to()
+    @property
+    def hotpath(self):
+        hp = self._hotpath
+        if hp is None:
+            from .hotpath import CudaHotPath      # raises if libeffimvs.so is missing
+            hp = CudaHotPath()
+            object.__setattr__(self, "_hotpath", hp)
+        return hp
+
+    def set_hotpath(self, hp):
+        object.__setattr__(self, "_hotpath", hp)
+
+    def encode(self, imgs):
+        """FPN over all V views in one batch -> per stage a list of V (B,C,h,w) maps."""
+        B, V = imgs.shape[:2]
+        pyr = self.feature(imgs.reshape(B * V, *imgs.shape[2:]))
+        return [[p.reshape(B, V, *p.shape[1:])[:, v] for v in range(V)] for p in pyr]
+
+    def forward(self, imgs, proj_matrices, depth_values):
+        hp = self.hotpath
+        B = imgs.shape[0]
+        disp_min = depth_values[:, 0].reshape(B, 1, 1, 1)
+        disp_max = depth_values[:, -1].reshape(B, 1, 1, 1)
+        depth_far, depth_near = 1.0 / disp_min, 1.0 / disp_max
+        unit = (disp_max - disp_min) / depth_values.size(1)
+
+        lo_disp, hi_disp = 1.0 / depth_far, 1.0 / depth_near   # double reciprocal, as upstream rounds it
+
+        def to_depth(inv):                      # disp_to_depth, Effi_MVS_plus.py:138-148
+            return 1.0 / (lo_disp + (hi_disp - lo_disp) * inv).clamp(min=1e-4)
+
+        feats = self.encode(imgs)
+        ctx_pyr = self.cnet_depth(imgs[:, 0])
+
+        preds = []
+        conf = None
+        view_w = raw_vol = reg_vol = None
+        vol_near, vol_far = depth_near, depth_far        # range of the volume the GRU reads
+        for s in range(3):
+            f = feats[s]
+            cams = proj_matrices["stage{}".format(s + 1)]
+            hidden, context = torch.split(ctx_pyr[s], [self.HIDDEN[s], self.CONTEXT[s]], dim=1)
+            hidden, context = torch.tanh(hidden), torch.relu(context)
+            H, W = f[0].shape[2:]
+            if s == 0:
+                D = self.ndepths[0]
+                k = torch.arange(D, device=imgs.device, dtype=imgs.dtype).reshape(1, D)
+                inv_s = disp_min.reshape(B, 1) + k * ((disp_max - disp_min).reshape(B, 1) / (D - 1))
+                hyp = (1.0 / inv_s).reshape(B, D, 1, 1).expand(B, D, H, W).contiguous()
+                out = hp.stage1(f, cams, hyp, self.PixelwiseNet, self.cost_regularization, self.G)
+                conf = F.interpolate(out["photometric_confidence"].unsqueeze(1), [H * 4, W * 4], mode="nearest").squeeze(1)
+                view_w = out["view_weights"]
+                raw_vol = out["volume"].squeeze(1)
+                reg_vol = out["reg_volume"]
+                cur_depth = out["depth"].unsqueeze(1)
+                preds.append(out["depth"])
+            else:
+                cur_depth = preds[-1].unsqueeze(1).detach()
+                view_w = F.interpolate(view_w, scale_factor=2, mode="nearest")
+                D = self.ndepths[s]
+                loc, hyp = hp.local_volume(cur_depth, f, cams, unit * self.RATIOS[s], view_w, D, self.G)
+                hyp_low = hyp[:, :, ::2, ::2]                 # nearest x1/2 (Effi_MVS_plus.py:514)
+                loc5 = loc.reshape(B, self.G, D, H, W)
+                reg_prev = hp.volume_lookup(reg_vol, hyp_low, vol_near, vol_far)
+                raw_prev = hp.volume_lookup(raw_vol, hyp_low, vol_near, vol_far)
+                reg_vol = hp.cross_scale(self.CSP_R[s - 1], loc5, reg_prev.unsqueeze(1)).squeeze(1)
+                raw_vol = hp.cross_scale(self.CSP_C[s - 1], loc5, raw_prev.unsqueeze(1)).squeeze(1)
+                vol_far, vol_near = hyp[:, 0:1], hyp[:, -1:]
+
+            inv0 = (1.0 / cur_depth - 1.0 / depth_far) / ((1.0 / depth_near - 1.0 / depth_far) + 1e-10)
+            interval = unit * self.RATIOS[s]
+
+            def cost_fn(depth, _raw=raw_vol, _reg=reg_vol, _iv=interval, _n=vol_near, _f=vol_far):
+                return hp.dynamic_cost(depth, _raw, _reg, _iv, _n, _f, self.cost_num)
+
+            _, mask, inv_seq = self.update_block[s](hidden, cost_fn, inv0, context, self.iters[s], to_depth)
+            for inv in inv_seq:
+                preds.append(to_depth(inv).squeeze(1))
+            up = convex_upsample(inv_seq[-1], mask, 2).unsqueeze(1)
+            preds.append(to_depth(up).squeeze(1))
+        return {"depth": preds, "photometric_confidence": conf}
