@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- depth maps/s of the Effi-MVS+ cascade at the DTU evaluation shape
+(1600x1184, 1 reference + 4 source views, ndepths 48,8,8, 3 GRU iterations per stage) with the
+cost-volume hot path on hand-written sm_100a kernels.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f32|bf16]
+
+One JSON line on stdout (rank 0).  A "step" is one depth map (one pass of the whole cascade over
+one 5-view batch of synthetic images).  `value` = depth maps/s with the inputs resident in HBM;
+`e2e` = the same through the public API with pinned-host inputs copied in and the depth map read
+back every step; `roofline` = the fused warp+correlation kernel (stage 3, the largest launch)
+against the measured HBM copy peak; `cpu_baseline` / `--impl reference` = the oracle port of the
+upstream path on the host cores (upstream itself is Python and does not travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "depth_maps_per_sec_1600x1184_5view"
+UNIT = "depth maps/s"
+WORKLOAD = "configs[2]: DTU eval shape 1600x1184, 5 views, full cross-scale cascade with dynamic cost volume (ndepths 48,8,8; GRU 3,3,3)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("EFFIMVS_PRECISION", "f32"), choices=["f32", "bf16"])
+    ap.add_argument("--shape", default="dtu", choices=["dtu", "tanks", "plumbing"])
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0)
+    return ap.parse_args()
+
+
+def build_model(hotpath, device, ndepths):
+    import effimvs_b200  # noqa: F401
+    from effimvs_b200 import net
+    args = types.SimpleNamespace(ndepths=ndepths, GRUiters="3,3,3", CostNum=3)
+    torch.manual_seed(0)
+    model = net.EffiMVSPlus(args, hotpath=hotpath)
+    wfile = os.path.join(ROOT, "tests", "golden", "dtu_weights.pt")
+    data = "synthetic images/cameras (seeded); random-init weights (seed 0)"
+    if os.path.exists(wfile):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from util import load_dtu_weights
+        load_dtu_weights(model)
+        data = "synthetic images/cameras (seeded); weights = upstream model_dtu.ckpt values (tests/golden/dtu_weights.pt)"
+    return model.to(device).eval(), data
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.th.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p["bf16_tflops"], "measured (MEASURED_PEAKS.json)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(a, rank, world):
+    """Oracle port of the upstream path on the host cores (kind 'port'); rank 0 only."""
+    if rank != 0:
+        return
+    import effimvs_b200  # noqa: F401
+    from effimvs_b200 import synthetic
+    from oracle import hotpath as ohp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, data = build_model(ohp.OracleHotPath(), "cpu", synthetic.SHAPES[a.shape]["ndepths"])
+    s = synthetic.make_sample(a.shape, seed=0)
+    times = []
+    t_begin = time.perf_counter()
+    done_w = 0
+    last = 0.0
+
+    def one():
+        t0 = time.perf_counter()
+        model(s["imgs"], s["proj_matrices"], s["depth_values"])
+        return time.perf_counter() - t0
+
+    with torch.no_grad():
+        for i in range(max(a.warmup, 1)):
+            if i >= 1 and (time.perf_counter() - t_begin) + last > 0.3 * a.cpu_budget_s:
+                break
+            last = one()
+            done_w += 1
+        for i in range(a.steps):
+            if i >= 1 and (time.perf_counter() - t_begin) + last > a.cpu_budget_s:
+                break
+            last = one()
+            times.append(last)
+    done_k = len(times)
+    total = sum(times)
+    value = done_k / total
+    sample = "{} of {} requested steps, each one full {} depth map on {} host threads ({} warm-up; {:.0f} s cap)".format(
+        done_k, a.steps, a.shape, cores, done_w, a.cpu_budget_s)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done_k,
+            "warmup": done_w, "ms_per_step": 1e3 * total / done_k, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": data, "config": {"workload": WORKLOAD, "device": "cpu"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class TimedHotPath:
+    """Wraps a hot-path table and brackets every call with CUDA events on the current stream."""
+
+    def __init__(self, inner):
+        self.inner, self.records = inner, []
+
+    def _wrap(self, name):
+        fn = getattr(self.inner, name)
+
+        def call(*args, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*args, **kw)
+            e1.record()
+            self.records.append((name, args, e0, e1))
+            return out
+        return call
+
+    def __getattr__(self, name):
+        if name in ("stage1", "local_volume", "volume_lookup", "cross_scale", "dynamic_cost"):
+            return self._wrap(name)
+        return getattr(self.inner, name)
+
+
+def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
+    """Per-kernel device time of the hot-path launches at the bench shape, timed in isolation with
+    CUDA events on the launching stream, an L2 flush (256 MiB memset) before every launch."""
+    from effimvs_b200 import capi, ops
+    dev = sample["imgs"].device
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    feats = model.encode(sample["imgs"])
+    out = {}
+
+    def timed(fn):
+        ts = []
+        for _ in range(reps + 1):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts[1:]) / reps   # ms, first (cold) launch dropped
+
+    B, V = sample["imgs"].shape[:2]
+    # stage 1: per-view similarity + entropy kernel
+    f = feats[0]
+    C, H, W = f[0].shape[1:]
+    D = model.ndepths[0]
+    cams = sample["proj_matrices"]["stage1"]
+    proj = hp.relative_projection(cams)
+    planes = (1.0 / torch.linspace(1 / 935.0, 1 / 425.0, D, device=dev)).reshape(1, D).repeat(B, 1)
+    ms = timed(lambda: ops.warp_corr_views(f[0], f[1:], proj, planes, capi.HYP_PLANES, D))
+    by = 4.0 * (V * C * H * W + D + (V - 1) * D * H * W + (V - 1) * H * W)
+    out["warp_corr_views_stage1"] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6}
+    # stages 2, 3: fused warp + correlation + aggregation with in-kernel hypotheses
+    for s in (1, 2):
+        f = feats[s]
+        C, H, W = f[0].shape[1:]
+        D = model.ndepths[s]
+        cams = sample["proj_matrices"]["stage{}".format(s + 1)]
+        proj = hp.relative_projection(cams)
+        cur = torch.full((B, 1, H, W), 680.0, device=dev) + 40 * torch.rand(B, 1, H, W, device=dev)
+        iv = torch.full((B,), (1 / 425.0 - 1 / 935.0) / 384 * model.RATIOS[s], device=dev)
+        wts = torch.rand(B, V - 1, H, W, device=dev)
+        ms = timed(lambda: ops.warp_corr_agg(f[0], f[1:], proj, cur, capi.HYP_LOCAL, iv, wts, D, 1, True))
+        by = 4.0 * (V * C * H * W + H * W + (V - 1) * H * W + D * H * W + D * H * W)
+        out["warp_corr_agg_stage{}".format(s + 1)] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6}
+    # regularization nets
+    Hs, Ws = feats[0][0].shape[2:]
+    x = torch.randn(B, 1, model.ndepths[0], Hs, Ws, device=dev)
+    ms = timed(lambda: hp.cost_regularization(model.cost_regularization, x))
+    vox = model.ndepths[0] * Hs * Ws
+    fl = 2.0 * 27 * vox * (1 * 8 + 8 * 8 + 8 * 16 / 8 + 16 * 16 / 8 + 16 * 32 / 64 + 32 * 32 / 64 + 32 * 16 / 64 + 16 * 8 / 8 + 8)
+    out["costreg_fpn3d"] = {"ms": ms, "flops": fl, "tflops": fl / ms / 1e9}
+    for s in (1, 2):
+        Hs, Ws = feats[s][0].shape[2:]
+        D = model.ndepths[s]
+        x = torch.randn(B, 1, D, Hs, Ws, device=dev)
+        prev = torch.randn(B, 1, D, Hs // 2, Ws // 2, device=dev)
+        ms = timed(lambda: hp.cross_scale(model.CSP_R[s - 1], x, prev))
+        vq = D * (Hs // 2) * (Ws // 2)
+        fl = 2.0 * 27 * vq * (8 + 8 + 16 * 8 + 8)
+        out["cost_up_small_stage{}".format(s + 1)] = {"ms": ms, "flops": fl, "tflops": fl / ms / 1e9}
+    dom = out["warp_corr_agg_stage3"]
+    roof = {"kernel": "warp_corr_agg_kernel<8,1> (stage 3, 800x592, D=8, 4 source views)", "bound": "hbm",
+            "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak, "traffic": None,
+            "peak_source": peak_src, "algorithmic_bytes": dom["bytes"], "ms": dom["ms"]}
+    reg_ms = out["costreg_fpn3d"]["ms"] + 2 * out["cost_up_small_stage2"]["ms"] + 2 * out["cost_up_small_stage3"]["ms"]
+    reg_fl = out["costreg_fpn3d"]["flops"] + 2 * out["cost_up_small_stage2"]["flops"] + 2 * out["cost_up_small_stage3"]["flops"]
+    roof_reg = {"kernel": "3-D regularization (costreg_fpn3d + 4x cost_up_small)", "bound": "tensor", "achieved": reg_fl / reg_ms / 1e9,
+                "peak": tf_peak, "unit": "TFLOP/s", "frac": reg_fl / reg_ms / 1e9 / tf_peak, "flops": reg_fl, "ms": reg_ms}
+    return roof, roof_reg, out
+
+
+def run_ours(a, rank, world, local_rank):
+    import effimvs_b200  # noqa: F401
+    from effimvs_b200 import hotpath, ops, synthetic
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True      # as upstream's test script (test_dtu_dypcd.py:41)
+    hp = hotpath.CudaHotPath(a.precision, native_projection=True)
+    ndepths = synthetic.SHAPES[a.shape]["ndepths"]
+    model, data = build_model(hp, dev, ndepths)
+    s_host = synthetic.make_sample(a.shape, seed=rank)
+    pin = {"imgs": s_host["imgs"].pin_memory(), "depth_values": s_host["depth_values"].pin_memory(),
+           "proj_matrices": {k: v.pin_memory() for k, v in s_host["proj_matrices"].items() if k != "stage4"}}
+    stat = {"imgs": pin["imgs"].to(dev), "depth_values": pin["depth_values"].to(dev),
+            "proj_matrices": {k: v.to(dev) for k, v in pin["proj_matrices"].items()}}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def forward():
+        return model(stat["imgs"], stat["proj_matrices"], stat["depth_values"])
+
+    graph = None
+    with torch.no_grad():
+        ops.LAUNCHES = 0
+        out = forward()
+        launches_per_step = ops.LAUNCHES
+        for _ in range(2):
+            out = forward()
+        torch.cuda.synchronize()
+        if not a.no_graph:
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    forward()
+                torch.cuda.current_stream().wait_stream(side)
+                with torch.cuda.graph(g):
+                    out = forward()
+                graph = g
+            except Exception as e:  # noqa: BLE001  (capture is an optimisation; eager stays correct)
+                sys.stderr.write("CUDA graph capture failed, running eagerly: {}\n".format(e))
+                graph = None
+                torch.cuda.synchronize()
+
+        def step():
+            flush.zero_()
+            if graph is not None:
+                graph.replay()
+                return out
+            return forward()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def timed(fn, K, W):
+            for _ in range(W):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(K):
+                fn()
+            e1.record()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms)
+
+        with ClockSampler(local_rank) as clk:
+            ms_dev = timed(step, a.steps, max(a.warmup, 3))
+
+            # end to end through the public API: pinned host -> device every step, depth map read back
+            host_depth = torch.empty(out["depth"][-1].shape, dtype=torch.float32).pin_memory()
+            host_conf = torch.empty(out["photometric_confidence"].shape, dtype=torch.float32).pin_memory()
+
+            def e2e_step():
+                stat["imgs"].copy_(pin["imgs"], non_blocking=True)
+                stat["depth_values"].copy_(pin["depth_values"], non_blocking=True)
+                for k in stat["proj_matrices"]:
+                    stat["proj_matrices"][k].copy_(pin["proj_matrices"][k], non_blocking=True)
+                o = step()
+                host_depth.copy_(o["depth"][-1], non_blocking=True)
+                host_conf.copy_(o["photometric_confidence"], non_blocking=True)
+                torch.cuda.current_stream().synchronize()     # the caller consumes the depth map
+
+            ms_e2e = timed(e2e_step, a.steps, max(a.warmup, 3))
+        h2d = pin["imgs"].numel() * 4 + pin["depth_values"].numel() * 4 + sum(v.numel() * 4 for v in pin["proj_matrices"].values())
+        d2h = host_depth.numel() * 4 + host_conf.numel() * 4
+
+        hbm_peak, tf_peak, peak_src = peaks()
+        roof = roof_reg = kern = None
+        if rank == 0:
+            roof, roof_reg, kern = kernel_rooflines(hp, model, stat, hbm_peak, tf_peak, peak_src)
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cpu = cpu_baseline(a, ndepths)
+    if rank != 0:
+        return
+    value = world * a.steps / (ms_dev / 1e3)
+    e2e = world * a.steps / (ms_e2e / 1e3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if a.precision == "f32" else "bf16 (3-D regularization) / f32 (warp, lookup, regression)",
+            "data": data,
+            "config": {"workload": WORKLOAD, "shape": a.shape, "views": int(stat["imgs"].shape[1]), "ndepths": ndepths,
+                       "sharding": "one reference view per rank per step, no collective", "cuda_graph": graph is not None,
+                       "l2": "256 MiB memset between steps (inside the timed region)",
+                       "stock_pytorch": "FPN, ConvGRU, convex upsampling: cuDNN, TF32 allowed (torch default, as upstream)"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
+            "clocks": clk.summary(), "roofline": roof, "roofline_regularization": roof_reg, "kernels": kern}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(a, ndepths):
+    """Oracle port of the same workload on this box's host cores, bounded to a few forwards."""
+    from effimvs_b200 import synthetic
+    from oracle import hotpath as ohp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model, _ = build_model(ohp.OracleHotPath(), "cpu", ndepths)
+    s = synthetic.make_sample(a.shape, seed=0)
+    ts = []
+    with torch.no_grad():
+        for i in range(3):
+            t0 = time.perf_counter()
+            model(s["imgs"], s["proj_matrices"], s["depth_values"])
+            ts.append(time.perf_counter() - t0)
+            if sum(ts) > 45:
+                break
+    timed = ts[1:] if len(ts) > 1 else ts
+    v = len(timed) / sum(timed)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "{} full {} depth map(s) after {} warm-up, oracle port (torch CPU kernels) on {} threads".format(
+                len(timed), a.shape, len(ts) - len(timed), cores)}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(a, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""ctypes binding of libeffimvs.so (include/effimvs.h).  No torch types cross this boundary:
+only raw device pointers, sizes and a cudaStream_t.  Importing this module raises if the
+library has not been built (``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C effi-mvs-plus_b200/csrc``) -- there is no CPU or eager fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeffimvs.so")
+
+OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
+HYP_TENSOR, HYP_PLANES, HYP_LOCAL = 0, 1, 2
+RANGE_SCALAR, RANGE_PIXEL = 0, 1
+PREC_F32, PREC_BF16 = 0, 1
+MAX_SRC_VIEWS = 16
+
+
+class EffiMVSError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libeffimvs error {}: {}".format(code, msg))
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("libeffimvs.so is not built ({}); run __graft_entry__.build() -- the hot path has no "
+                      "CPU or PyTorch fallback".format(LIB_PATH))
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_pp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/effimvs.h one to one
+SIGNATURES = {
+    "effimvs_last_error": (C.c_char_p, []),
+    "effimvs_version": (_i, []),
+    "effimvs_relative_projection_f32": (_i, [_p, _i, _i, _p, _p]),
+    "effimvs_warp_corr_agg_f32": (_i, [_p, _pp, _i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "effimvs_warp_corr_views_f32": (_i, [_p, _pp, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "effimvs_weighted_agg_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "effimvs_volume_lookup_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "effimvs_dynamic_cost_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "effimvs_softmax_regress_conf_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "effimvs_conv3d_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "effimvs_costreg_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "effimvs_costreg_fpn3d": (_i, [_p, _pp, _pp, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "effimvs_cost_up_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "effimvs_cost_up_small": (_i, [_p, _p, _pp, _pp, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "effimvs_fusion_reproject_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "effimvs_fusion_filter_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _i, _p, _p, _p, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)        # AttributeError here = header and library disagree
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return lib.effimvs_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise EffiMVSError(rc, last_error())
+
+
+def ptr_array(ptrs):
+    """Host array of device pointers (``const float* const*``)."""
+    arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(p) for p in ptrs])
+    return C.cast(arr, _pp), arr     # keep `arr` alive for the duration of the call

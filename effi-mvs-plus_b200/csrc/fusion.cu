@@ -1,0 +1,268 @@
+// Geometric-consistency filter: ref -> src -> ref reprojection with a bilinear sample of the
+// source depth, the ladder of distance / depth thresholds, view votes, masked depth average and
+// back-projection to world points -- one thread per reference pixel, one pass over the v source
+// depth maps, nothing but the final mask / depth / points written back.
+//
+//   get_pixel_grids, idx_img2cam, idx_cam2world, idx_world2cam, idx_cam2img
+//                                       upstream misc/fusion.py:8-47
+//   get_reproj_dynamic                  upstream misc/fusion.py:117-154
+//   vis_filter_dynamic                  upstream misc/fusion.py:157-181
+//   vote / average / back-projection    upstream test_tank.py:473-515
+//
+// HBM-bound: per reference view it reads (1 + v) depth maps + the confidence map once and
+// writes 1 + 4 + 12 bytes per pixel.
+#include "common.cuh"
+
+namespace effimvs {
+namespace {
+
+constexpr int MAXV = EFFIMVS_MAX_SRC_VIEWS;
+
+struct Cam {       // one camera in shared memory
+    float E[16];   // world -> camera
+    float Ei[16];  // inverse(E)
+    float K[9];
+    float Ki[9];
+};
+
+__device__ bool invert_n(const double* A, double* inv, int n) {
+    double M[4][8];
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) {
+            M[r][c] = A[r * n + c];
+            M[r][c + n] = (r == c) ? 1.0 : 0.0;
+        }
+    for (int col = 0; col < n; ++col) {
+        int piv = col;
+        double best = fabs(M[col][col]);
+        for (int r = col + 1; r < n; ++r)
+            if (fabs(M[r][col]) > best) { best = fabs(M[r][col]); piv = r; }
+        if (best == 0.0) return false;
+        if (piv != col)
+            for (int c = 0; c < 2 * n; ++c) { double t = M[col][c]; M[col][c] = M[piv][c]; M[piv][c] = t; }
+        double s = 1.0 / M[col][col];
+        for (int c = 0; c < 2 * n; ++c) M[col][c] *= s;
+        for (int r = 0; r < n; ++r) {
+            if (r == col) continue;
+            double f = M[r][col];
+            for (int c = 0; c < 2 * n; ++c) M[r][c] -= f * M[col][c];
+        }
+    }
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) inv[r * n + c] = M[r][c + n];
+    return true;
+}
+
+// cam: (2,4,4) fp32.  inv: (2,4,4) holding inverse(E), inverse(K) padded, or nullptr -> invert here.
+__device__ void load_cam(Cam& c, const float* __restrict__ cam, const float* __restrict__ inv) {
+    for (int i = 0; i < 16; ++i) c.E[i] = cam[i];
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) c.K[r * 3 + k] = cam[16 + r * 4 + k];
+    if (inv) {
+        for (int i = 0; i < 16; ++i) c.Ei[i] = inv[i];
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k) c.Ki[r * 3 + k] = inv[16 + r * 4 + k];
+    } else {
+        double A[16], I[16];
+        for (int i = 0; i < 16; ++i) A[i] = c.E[i];
+        bool ok = invert_n(A, I, 4);
+        for (int i = 0; i < 16; ++i) c.Ei[i] = ok ? (float)I[i] : __int_as_float(0x7fc00000);
+        for (int i = 0; i < 9; ++i) A[i] = c.K[i];
+        ok = invert_n(A, I, 3);
+        for (int i = 0; i < 9; ++i) c.Ki[i] = ok ? (float)I[i] : __int_as_float(0x7fc00000);
+    }
+}
+
+__device__ __forceinline__ void mat3(const float* M, float x, float y, float z, float o[3]) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o[r] = fmaf(M[r * 3 + 2], z, fmaf(M[r * 3 + 1], y, __fmul_rn(M[r * 3], x)));
+}
+__device__ __forceinline__ void mat4(const float* M, const float p[4], float o[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        o[r] = fmaf(M[r * 4 + 3], p[3], fmaf(M[r * 4 + 2], p[2], fmaf(M[r * 4 + 1], p[1], __fmul_rn(M[r * 4], p[0]))));
+}
+
+// idx_img2cam + idx_cam2world (fusion.py:23-34): pixel (u,v,1), depth -> homogeneous world point
+__device__ __forceinline__ void img_to_world(const Cam& c, float u, float v, float depth, float pw[4]) {
+    float k[3];
+    mat3(c.Ki, u, v, 1.0f, k);
+    float zz = __fadd_rn(k[2], 1e-9f);
+    float pc[4] = {__fmul_rn(__fdiv_rn(k[0], zz), depth), __fmul_rn(__fdiv_rn(k[1], zz), depth),
+                   __fmul_rn(__fdiv_rn(k[2], zz), depth), 1.0f};
+    float w[4];
+    mat4(c.Ei, pc, w);
+    float ww = __fadd_rn(w[3], 1e-9f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pw[i] = __fdiv_rn(w[i], ww);
+}
+
+// idx_world2cam (fusion.py:37-40)
+__device__ __forceinline__ void world_to_cam(const Cam& c, const float pw[4], float pc[4]) {
+    float t[4];
+    mat4(c.E, pw, t);
+    float ww = __fadd_rn(t[3], 1e-9f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pc[i] = __fdiv_rn(t[i], ww);
+}
+
+// idx_cam2img (fusion.py:43-47)
+__device__ __forceinline__ void cam_to_img(const Cam& c, const float pc[4], float& u, float& v) {
+    float ww = __fadd_rn(pc[3], 1e-9f);
+    float k[3];
+    mat3(c.K, __fdiv_rn(pc[0], ww), __fdiv_rn(pc[1], ww), __fdiv_rn(pc[2], ww), k);
+    float zz = __fadd_rn(k[2], 1e-9f);
+    u = __fdiv_rn(k[0], zz);
+    v = __fdiv_rn(k[1], zz);
+}
+
+// bilinear sample, zeros padding, align_corners=True, pixel coordinates (u,v) normalised the way
+// fusion.py:134-139 + ATen do it on a CUDA device
+__device__ __forceinline__ float sample_depth(const float* __restrict__ img, int h, int w, float u, float v,
+                                              float inv_half_w, float inv_half_h) {
+    float gx = __fsub_rn(__fmul_rn(u, inv_half_w), 1.0f);
+    float gy = __fsub_rn(__fmul_rn(v, inv_half_h), 1.0f);
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(w - 1));
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(h - 1));
+    float fx = floorf(ix), fy = floorf(iy);
+    bool x0 = (fx >= 0.0f) && (fx <= (float)(w - 1));
+    bool x1 = (fx >= -1.0f) && (fx <= (float)(w - 2));
+    bool y0 = (fy >= 0.0f) && (fy <= (float)(h - 1));
+    bool y1 = (fy >= -1.0f) && (fy <= (float)(h - 2));
+    if (!((x0 || x1) && (y0 || y1))) return 0.0f;
+    int xi = (int)fx, yi = (int)fy;
+    const float* p = img + (ptrdiff_t)yi * w + xi;
+    float ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix), ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+    float dx = __fsub_rn(ix, fx), dy = __fsub_rn(iy, fy);
+    float out = 0.0f;
+    if (x0 && y0) out = __fmul_rn(__ldg(p), __fmul_rn(ex, ey));
+    if (x1 && y0) out = fmaf(__ldg(p + 1), __fmul_rn(dx, ey), out);
+    if (x0 && y1) out = fmaf(__ldg(p + w), __fmul_rn(ex, dy), out);
+    if (x1 && y1) out = fmaf(__ldg(p + w + 1), __fmul_rn(dx, dy), out);
+    return out;
+}
+
+struct Reproj { float x, y, d; };
+
+__device__ __forceinline__ Reproj reproject(const Cam& ref, const Cam& src, const float ref_world[4],
+                                            const float* __restrict__ src_depth, int h, int w,
+                                            float inv_half_w, float inv_half_h) {
+    float pc[4], u, v;
+    world_to_cam(src, ref_world, pc);
+    cam_to_img(src, pc, u, v);
+    float ds = sample_depth(src_depth, h, w, u, v, inv_half_w, inv_half_h);
+    float pw[4], back[4];
+    img_to_world(src, u, v, ds, pw);
+    world_to_cam(ref, pw, back);
+    Reproj r;
+    r.d = back[2];
+    cam_to_img(ref, back, r.x, r.y);
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
+fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ srcs_depth, const float* __restrict__ conf,
+              const float* __restrict__ ref_cam, const float* __restrict__ srcs_cam, const float* __restrict__ inv_cams,
+              int v, int h, int w, int hc, int wc, float dist_base, float rel_diff_base, int thres_view,
+              float prob_threshold, int relative, float* __restrict__ reproj_xyd, uint8_t* __restrict__ final_mask,
+              float* __restrict__ depth_avg, float* __restrict__ points, uint8_t* __restrict__ masks_out) {
+    __shared__ Cam cams[MAXV + 1];
+    const int n = blockIdx.y;
+    if (threadIdx.x <= v) {
+        const float* cam = threadIdx.x == 0 ? ref_cam + (size_t)n * 32 : srcs_cam + ((size_t)n * v + threadIdx.x - 1) * 32;
+        const float* inv = inv_cams ? inv_cams + ((size_t)n * (v + 1) + threadIdx.x) * 32 : nullptr;
+        load_cam(cams[threadIdx.x], cam, inv);
+    }
+    __syncthreads();
+    const int hw = h * w;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= hw) return;
+    const int yi = pix / w, xi = pix - yi * w;
+    const float cx = (float)xi + 0.5f, cy = (float)yi + 0.5f;
+    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(w - 1) / 2.0));
+    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(h - 1) / 2.0));
+    const float dref = __ldg(ref_depth + (size_t)n * hw + pix);
+    float ref_world[4];
+    img_to_world(cams[0], cx, cy, dref, ref_world);
+
+    const int K = v - thres_view + 1;
+    int votes[MAXV];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) votes[k] = 0;
+    float sum_d = 0.0f;
+    int n_last = 0;
+    for (int s = 0; s < v; ++s) {
+        Reproj r = reproject(cams[0], cams[s + 1], ref_world, srcs_depth + ((size_t)n * v + s) * hw, h, w, inv_half_w, inv_half_h);
+        if (reproj_xyd) {
+            float* o = reproj_xyd + (((size_t)n * v + s) * 3) * hw + pix;
+            o[0] = r.x; o[(size_t)hw] = r.y; o[(size_t)2 * hw] = r.d;
+        }
+        if (!final_mask) continue;
+        float ex = __fsub_rn(r.x, cx), ey = __fsub_rn(r.y, cy);
+        float e_xy = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+        float e_d = fabsf(__fsub_rn(dref, r.d));
+        if (relative) e_d = __fdiv_rn(e_d, dref);
+#pragma unroll
+        for (int k = 0; k < MAXV; ++k) {
+            if (k < K) {
+                float kk = (float)(thres_view + k);
+                bool m = (e_xy < __fdiv_rn(kk, dist_base)) && (e_d < __fdiv_rn(kk, rel_diff_base));
+                votes[k] += m ? 1 : 0;
+                if (masks_out) masks_out[(((size_t)n * v + s) * K + k) * hw + pix] = m ? 1 : 0;
+                if (k == K - 1 && m) { sum_d = __fadd_rn(sum_d, r.d); n_last += 1; }
+            }
+        }
+    }
+    if (!final_mask) return;
+    bool geo = false;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+        if (k < K) geo = geo || (votes[k] >= thres_view + k);
+    // nearest resize of the confidence map: src index = floor(dst * in / out)  (F.interpolate 'nearest')
+    int sy = (int)floorf((float)yi * ((float)hc / (float)h)), sx = (int)floorf((float)xi * ((float)wc / (float)w));
+    sy = sy < hc - 1 ? sy : hc - 1; sx = sx < wc - 1 ? sx : wc - 1;
+    bool prob = __ldg(conf + ((size_t)n * hc + sy) * wc + sx) > prob_threshold;
+    float avg = __fdiv_rn(__fadd_rn(sum_d, dref), (float)(n_last + 1));
+    float pw[4];
+    img_to_world(cams[0], cx, cy, avg, pw);
+    final_mask[(size_t)n * hw + pix] = (prob && geo) ? 1 : 0;
+    depth_avg[(size_t)n * hw + pix] = avg;
+    points[((size_t)n * 3 + 0) * hw + pix] = pw[0];
+    points[((size_t)n * 3 + 1) * hw + pix] = pw[1];
+    points[((size_t)n * 3 + 2) * hw + pix] = pw[2];
+}
+
+}  // namespace
+}  // namespace effimvs
+
+using namespace effimvs;
+
+extern "C" int effimvs_fusion_reproject_f32(const float* ref_depth, const float* srcs_depth, const float* ref_cam,
+                                            const float* srcs_cam, const float* inv_cams, int n, int v, int h, int w,
+                                            float* reproj_xyd, void* stream) {
+    EFFI_REQUIRE(ref_depth && srcs_depth && ref_cam && srcs_cam && reproj_xyd, EFFIMVS_EINVAL, "fusion_reproject: null pointer");
+    EFFI_REQUIRE(n > 0 && v >= 1 && v <= MAXV && h > 1 && w > 1, EFFIMVS_EINVAL, "fusion_reproject: bad sizes (v in [1,%d])", MAXV);
+    dim3 block(128), grid(ceil_div(h * w, 128), n);
+    fusion_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, nullptr, ref_cam, srcs_cam, inv_cams, v, h, w,
+                                                           1, 1, 1.0f, 1.0f, 1, 0.0f, 0, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
+    return check_launch("fusion_kernel(reproject)");
+}
+
+extern "C" int effimvs_fusion_filter_f32(const float* ref_depth, const float* srcs_depth, const float* conf,
+                                         const float* ref_cam, const float* srcs_cam, const float* inv_cams,
+                                         int n, int v, int h, int w, int hc, int wc,
+                                         float dist_base, float rel_diff_base, int thres_view, float prob_threshold,
+                                         int relative, uint8_t* final_mask, float* depth_avg, float* points,
+                                         uint8_t* masks_out, void* stream) {
+    EFFI_REQUIRE(ref_depth && srcs_depth && conf && ref_cam && srcs_cam && final_mask && depth_avg && points, EFFIMVS_EINVAL,
+                 "fusion_filter: null pointer");
+    EFFI_REQUIRE(n > 0 && v >= 1 && v <= MAXV && h > 1 && w > 1 && hc > 0 && wc > 0, EFFIMVS_EINVAL,
+                 "fusion_filter: bad sizes (v in [1,%d])", MAXV);
+    EFFI_REQUIRE(thres_view >= 1 && thres_view <= v, EFFIMVS_EINVAL, "fusion_filter: thres_view=%d outside [1,%d]", thres_view, v);
+    EFFI_REQUIRE(dist_base > 0.0f && rel_diff_base > 0.0f, EFFIMVS_EINVAL, "fusion_filter: thresholds must be positive");
+    dim3 block(128), grid(ceil_div(h * w, 128), n);
+    fusion_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, v, h, w, hc, wc,
+                                                           dist_base, rel_diff_base, thres_view, prob_threshold, relative,
+                                                           nullptr, final_mask, depth_avg, points, masks_out);
+    return check_launch("fusion_kernel(filter)");
+}

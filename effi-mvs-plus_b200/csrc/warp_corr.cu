@@ -1,0 +1,352 @@
+// Fused homography warp + group-wise correlation (+ view aggregation / softmax entropy).
+//
+// Replaces, without ever materialising the warped (B,C,D,H,W) volume:
+//   homo_warping_new                 upstream models/module.py:303-344
+//   group-wise correlation           upstream models/Effi_MVS_plus.py:39-40, 222-224
+//   weighted view aggregation        upstream models/Effi_MVS_plus.py:52-53, 67, 233-234, 244
+//   softmax entropy of a view        upstream models/Effi_MVS_plus.py:43-44
+//   local hypothesis generation      upstream models/module.py:554-570
+//
+// Thread mapping: blockDim = (32 pixels, DT depth lanes).  A warp owns 32 consecutive reference
+// pixels of one depth plane, so every bilinear tap of a channel is one (nearly) contiguous
+// 128-byte request on the NCHW source map; the C reference-feature values of the pixel live in
+// registers and are reused across source views (and depth planes in the stage-1 kernel).
+// Reductions over the channels of a group and over the views stay in registers; the stage-1
+// kernel reduces softmax statistics over D through shared memory.
+#include "common.cuh"
+
+namespace effimvs {
+namespace {
+
+constexpr int DT = 8;  // depth lanes per block
+
+struct Taps {
+    int o_nw;               // linear offset of the north-west corner (y0 * W + x0), clamped to be loadable
+    float w_nw, w_ne, w_sw, w_se;
+    bool v_nw, v_ne, v_sw, v_se;
+    bool any;
+};
+
+// Coordinates exactly as upstream computes them on a CUDA device (no FMA contraction where torch
+// issues separate kernels): ray = rot @ (x,y,1) [matmul: fma chain], p = ray * depth + trans,
+// z == 0 -> z + 1e-8, u = px / pz, normalise u * (1 / ((W-1)/2)) - 1 (torch's CUDA div-by-scalar
+// multiplies by the reciprocal), ATen un-normalise ((g + 1) / 2) * (W - 1), bilinear corner
+// weights as in ATen's grid_sampler_2d (zeros padding, align_corners=True).
+__device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float x, float y, float depth,
+                                          int H, int W, float inv_half_w, float inv_half_h) {
+    float rx = fmaf(P[2], 1.0f, fmaf(P[1], y, __fmul_rn(P[0], x)));
+    float ry = fmaf(P[5], 1.0f, fmaf(P[4], y, __fmul_rn(P[3], x)));
+    float rz = fmaf(P[8], 1.0f, fmaf(P[7], y, __fmul_rn(P[6], x)));
+    float px = __fadd_rn(__fmul_rn(rx, depth), P[9]);
+    float py = __fadd_rn(__fmul_rn(ry, depth), P[10]);
+    float pz = __fadd_rn(__fmul_rn(rz, depth), P[11]);
+    if (pz == 0.0f) pz = __fadd_rn(pz, 1e-8f);
+    float u = __fdiv_rn(px, pz);
+    float v = __fdiv_rn(py, pz);
+    float gx = __fsub_rn(__fmul_rn(u, inv_half_w), 1.0f);
+    float gy = __fsub_rn(__fmul_rn(v, inv_half_h), 1.0f);
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
+    float fx = floorf(ix), fy = floorf(iy);
+    Taps t;
+    // comparisons are false for NaN/inf -> every corner contributes zero (ATen CUDA behaviour)
+    bool x0 = (fx >= 0.0f) && (fx <= (float)(W - 1));
+    bool x1 = (fx >= -1.0f) && (fx <= (float)(W - 2));
+    bool y0 = (fy >= 0.0f) && (fy <= (float)(H - 1));
+    bool y1 = (fy >= -1.0f) && (fy <= (float)(H - 2));
+    t.v_nw = x0 && y0; t.v_ne = x1 && y0; t.v_sw = x0 && y1; t.v_se = x1 && y1;
+    t.any = t.v_nw || t.v_ne || t.v_sw || t.v_se;
+    float ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix);   // ix_se - ix
+    float ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy);   // iy_se - iy
+    float dx = __fsub_rn(ix, fx);
+    float dy = __fsub_rn(iy, fy);
+    t.w_nw = __fmul_rn(ex, ey); t.w_ne = __fmul_rn(dx, ey);
+    t.w_sw = __fmul_rn(ex, dy); t.w_se = __fmul_rn(dx, dy);
+    int xi = t.any ? (int)fx : 0;
+    int yi = t.any ? (int)fy : 0;
+    t.o_nw = yi * W + xi;
+    return t;
+}
+
+template <int C, int G>
+__device__ __forceinline__ void correlate(const float* __restrict__ src, int HW, int W, const Taps& t,
+                                          const float (&ref)[C], float (&sim)[G]) {
+    constexpr int CG = C / G;
+#pragma unroll
+    for (int g = 0; g < G; ++g) sim[g] = 0.0f;
+    if (!t.any) return;
+    const float* p = src + t.o_nw;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int cc = 0; cc < CG; ++cc) {
+            const float* q = p + (size_t)(g * CG + cc) * HW;
+            float a = t.v_nw ? __ldg(q) : 0.0f;
+            float b = t.v_ne ? __ldg(q + 1) : 0.0f;
+            float c = t.v_sw ? __ldg(q + W) : 0.0f;
+            float d = t.v_se ? __ldg(q + W + 1) : 0.0f;
+            float w = a * t.w_nw;
+            w = fmaf(b, t.w_ne, w);
+            w = fmaf(c, t.w_sw, w);
+            w = fmaf(d, t.w_se, w);
+            acc = fmaf(w, ref[g * CG + cc], acc);
+        }
+        sim[g] = acc * (1.0f / CG);
+    }
+}
+
+// inverse-depth samples around cur_depth, exactly the op sequence of models/module.py:558-570
+__device__ __forceinline__ float local_hypothesis(float cur_depth, float interval, int D, int d) {
+    float inv = __fdiv_rn(1.0f, cur_depth);
+    float half = __fmul_rn((float)(D / 2), interval);
+    float lo = fmaxf(__fsub_rn(inv, half), 1e-4f);
+    float hi = fminf(fmaxf(__fadd_rn(inv, half), 1e-4f), 1e4f);
+    float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1));
+    float s = fmaxf(__fadd_rn(lo, __fmul_rn((float)d, step)), 1e-5f);
+    return __fdiv_rn(1.0f, s);
+}
+
+__device__ __forceinline__ float fetch_hypothesis(const float* __restrict__ hyp, int mode, const float* __restrict__ interval,
+                                                  int b, int d, int D, int pix, int HW) {
+    if (mode == EFFIMVS_HYP_TENSOR) return __ldg(hyp + ((size_t)b * D + d) * HW + pix);
+    if (mode == EFFIMVS_HYP_PLANES) return __ldg(hyp + b * D + d);
+    return local_hypothesis(__ldg(hyp + (size_t)b * HW + pix), __ldg(interval + b), D, d);
+}
+
+template <int C, int G>
+__global__ void __launch_bounds__(32 * DT)
+warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
+                     const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval,
+                     const float* __restrict__ weights, int C_rt, int H, int W, int D,
+                     float* __restrict__ sim_out, float* __restrict__ hyp_out) {
+    __shared__ float sP[EFFIMVS_MAX_SRC_VIEWS * 12];
+    __shared__ const float* sSrc[EFFIMVS_MAX_SRC_VIEWS];
+    const int b = blockIdx.z;
+    const int HW = H * W;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < n_src * 12; i += 32 * DT) sP[i] = proj[(size_t)b * n_src * 12 + i];
+    if (tid < EFFIMVS_MAX_SRC_VIEWS) sSrc[tid] = srcs.p[tid];
+    __syncthreads();
+    const int pix = blockIdx.x * 32 + threadIdx.x;
+    const int d = blockIdx.y * DT + threadIdx.y;
+    if (pix >= HW || d >= D) return;
+    const int yi = pix / W, xi = pix - yi * W;
+    const float x = (float)xi, y = (float)yi;
+    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
+    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
+
+    float ref[C];
+    const float* rp = ref_fea + (size_t)b * C * HW + pix;
+#pragma unroll
+    for (int c = 0; c < C; ++c) ref[c] = __ldg(rp + (size_t)c * HW);
+
+    const float depth = fetch_hypothesis(hyp, hyp_mode, interval, b, d, D, pix, HW);
+    if (hyp_out) hyp_out[((size_t)b * D + d) * HW + pix] = depth;
+
+    float num[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) num[g] = 0.0f;
+    float den = 0.0f;
+    for (int v = 0; v < n_src; ++v) {
+        Taps t = make_taps(sP + v * 12, x, y, depth, H, W, inv_half_w, inv_half_h);
+        float sim[G];
+        correlate<C, G>(sSrc[v] + (size_t)b * C * HW, HW, W, t, ref, sim);
+        if (weights) {
+            float w = __ldg(weights + ((size_t)b * n_src + v) * HW + pix);
+#pragma unroll
+            for (int g = 0; g < G; ++g) num[g] = __fadd_rn(num[g], __fmul_rn(sim[g], w));
+            den = __fadd_rn(den, w);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) num[g] = __fadd_rn(num[g], sim[g]);
+        }
+    }
+    const float div = weights ? __fadd_rn(den, 1e-6f) : (float)n_src;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        sim_out[(((size_t)b * G + g) * D + d) * HW + pix] = __fdiv_rn(num[g], div);
+}
+
+// Stage-1 form: one source view per blockIdx.y; all D planes of 32 pixels per block so that the
+// softmax entropy over D can be reduced on chip.
+template <int C>
+__global__ void __launch_bounds__(32 * DT)
+warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
+                       const float* __restrict__ hyp, int hyp_mode, int H, int W, int D,
+                       float* __restrict__ sims_out, float* __restrict__ entropy_out) {
+    extern __shared__ float s_sim[];  // [D][32]
+    __shared__ float sP[12];
+    const int b = blockIdx.z, v = blockIdx.y;
+    const int HW = H * W;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    __shared__ const float* sSrc;
+    if (tid < 12) sP[tid] = proj[((size_t)b * n_src + v) * 12 + tid];
+    if (tid < EFFIMVS_MAX_SRC_VIEWS && tid == v) sSrc = srcs.p[tid];
+    __syncthreads();
+    const int pix = blockIdx.x * 32 + threadIdx.x;
+    const bool live = pix < HW;
+    if (live) {
+        const int yi = pix / W, xi = pix - yi * W;
+        const float x = (float)xi, y = (float)yi;
+        const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
+        const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
+        float ref[C];
+        const float* rp = ref_fea + (size_t)b * C * HW + pix;
+#pragma unroll
+        for (int c = 0; c < C; ++c) ref[c] = __ldg(rp + (size_t)c * HW);
+        const float* src = sSrc + (size_t)b * C * HW;
+        float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
+        for (int d = threadIdx.y; d < D; d += DT) {
+            const float depth = fetch_hypothesis(hyp, hyp_mode, nullptr, b, d, D, pix, HW);
+            Taps t = make_taps(sP, x, y, depth, H, W, inv_half_w, inv_half_h);
+            float sim[1];
+            correlate<C, 1>(src, HW, W, t, ref, sim);
+            out[(size_t)d * HW] = sim[0];
+            s_sim[d * 32 + threadIdx.x] = sim[0];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.y == 0 && live) {
+        float m = -INFINITY;
+        for (int d = 0; d < D; ++d) m = fmaxf(m, s_sim[d * 32 + threadIdx.x]);
+        float z = 0.0f;
+        for (int d = 0; d < D; ++d) z += expf(s_sim[d * 32 + threadIdx.x] - m);
+        float ent = 0.0f;
+        for (int d = 0; d < D; ++d) {
+            float p = __fdiv_rn(expf(s_sim[d * 32 + threadIdx.x] - m), z);
+            ent -= p * logf(p + 1e-7f);
+        }
+        entropy_out[((size_t)b * n_src + v) * HW + pix] = ent;
+    }
+}
+
+__global__ void weighted_agg_kernel(const float* __restrict__ sims, const float* __restrict__ weights,
+                                    int n_src, int D, int HW, float* __restrict__ out) {
+    const int b = blockIdx.z;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    float w[EFFIMVS_MAX_SRC_VIEWS];
+    float den = 0.0f;
+#pragma unroll
+    for (int v = 0; v < EFFIMVS_MAX_SRC_VIEWS; ++v) {
+        if (v < n_src) {
+            w[v] = __ldg(weights + ((size_t)b * n_src + v) * HW + pix);
+            den = __fadd_rn(den, w[v]);
+        }
+    }
+    den = __fadd_rn(den, 1e-6f);
+    for (int d = blockIdx.y; d < D; d += gridDim.y) {
+        float num = 0.0f;
+#pragma unroll
+        for (int v = 0; v < EFFIMVS_MAX_SRC_VIEWS; ++v)
+            if (v < n_src) num = __fadd_rn(num, __fmul_rn(__ldg(sims + (((size_t)b * n_src + v) * D + d) * HW + pix), w[v]));
+        out[((size_t)b * D + d) * HW + pix] = __fdiv_rn(num, den);
+    }
+}
+
+template <int C, int G>
+int launch_agg(const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
+               const float* interval, const float* weights, int B, int H, int W, int D, float* sim_out,
+               float* hyp_out, cudaStream_t st) {
+    dim3 block(32, DT), grid(ceil_div(H * W, 32), ceil_div(D, DT), B);
+    warp_corr_agg_kernel<C, G><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, C, H, W,
+                                                       D, sim_out, hyp_out);
+    return check_launch("warp_corr_agg_kernel");
+}
+
+template <int C>
+int dispatch_g(int G, const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp,
+               int hyp_mode, const float* interval, const float* weights, int B, int H, int W, int D,
+               float* sim_out, float* hyp_out, cudaStream_t st) {
+    switch (G) {
+        case 1: return launch_agg<C, 1>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+        case 2: return launch_agg<C, 2>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+        case 4: return launch_agg<C, 4>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+        case 8: return launch_agg<C, 8>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+    }
+    set_error("warp_corr_agg: G=%d not in {1,2,4,8}", G);
+    return EFFIMVS_EUNSUPPORTED;
+}
+
+int fill_srcs(SrcPtrs& s, const float* const* src_fea, int n_src) {
+    EFFI_REQUIRE(src_fea && n_src >= 1 && n_src <= EFFIMVS_MAX_SRC_VIEWS, EFFIMVS_EINVAL,
+                 "n_src=%d must be in [1,%d]", n_src, EFFIMVS_MAX_SRC_VIEWS);
+    for (int i = 0; i < EFFIMVS_MAX_SRC_VIEWS; ++i) s.p[i] = i < n_src ? src_fea[i] : nullptr;
+    for (int i = 0; i < n_src; ++i) EFFI_REQUIRE(s.p[i], EFFIMVS_EINVAL, "src_fea[%d] is NULL", i);
+    return EFFIMVS_OK;
+}
+
+}  // namespace
+}  // namespace effimvs
+
+using namespace effimvs;
+
+extern "C" int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* const* src_fea, int n_src,
+                                         const float* proj, const float* hyp, int hyp_mode, const float* interval,
+                                         const float* weights, int B, int C, int H, int W, int D, int G,
+                                         float* sim_out, float* hyp_out, void* stream) {
+    EFFI_REQUIRE(ref_fea && proj && hyp && sim_out, EFFIMVS_EINVAL, "warp_corr_agg: null pointer");
+    EFFI_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1 && D > 0 && G > 0, EFFIMVS_EINVAL, "warp_corr_agg: bad sizes");
+    EFFI_REQUIRE(hyp_mode >= 0 && hyp_mode <= 2, EFFIMVS_EINVAL, "warp_corr_agg: hyp_mode=%d", hyp_mode);
+    EFFI_REQUIRE(hyp_mode != EFFIMVS_HYP_LOCAL || (interval && D > 1), EFFIMVS_EINVAL,
+                 "warp_corr_agg: HYP_LOCAL needs interval and D > 1");
+    EFFI_REQUIRE(C % G == 0, EFFIMVS_EINVAL, "warp_corr_agg: C=%d not divisible by G=%d", C, G);
+    EFFI_REQUIRE(B <= 65535, EFFIMVS_EUNSUPPORTED, "warp_corr_agg: B too large");
+    SrcPtrs s;
+    int rc = fill_srcs(s, src_fea, n_src);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (C) {
+        case 8: return dispatch_g<8>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+        case 16: return dispatch_g<16>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+        case 32: return dispatch_g<32>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+    }
+    set_error("warp_corr_agg: C=%d not in {8,16,32}", C);
+    return EFFIMVS_EUNSUPPORTED;
+}
+
+extern "C" int effimvs_warp_corr_views_f32(const float* ref_fea, const float* const* src_fea, int n_src,
+                                           const float* proj, const float* hyp, int hyp_mode,
+                                           int B, int C, int H, int W, int D,
+                                           float* sims_out, float* entropy_out, void* stream) {
+    EFFI_REQUIRE(ref_fea && proj && hyp && sims_out && entropy_out, EFFIMVS_EINVAL, "warp_corr_views: null pointer");
+    EFFI_REQUIRE(B > 0 && H > 1 && W > 1 && D > 0, EFFIMVS_EINVAL, "warp_corr_views: bad sizes");
+    EFFI_REQUIRE(hyp_mode == EFFIMVS_HYP_TENSOR || hyp_mode == EFFIMVS_HYP_PLANES, EFFIMVS_EINVAL,
+                 "warp_corr_views: hyp_mode=%d", hyp_mode);
+    EFFI_REQUIRE(D <= 1024 && B <= 65535, EFFIMVS_EUNSUPPORTED, "warp_corr_views: D=%d > 1024", D);
+    SrcPtrs s;
+    int rc = fill_srcs(s, src_fea, n_src);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 block(32, DT), grid(ceil_div(H * W, 32), n_src, B);
+    size_t smem = (size_t)D * 32 * sizeof(float);
+    switch (C) {
+        case 8:
+            if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            warp_corr_views_kernel<8><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out);
+            break;
+        case 16:
+            if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            warp_corr_views_kernel<16><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out);
+            break;
+        case 32:
+            if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            warp_corr_views_kernel<32><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out);
+            break;
+        default:
+            set_error("warp_corr_views: C=%d not in {8,16,32}", C);
+            return EFFIMVS_EUNSUPPORTED;
+    }
+    return check_launch("warp_corr_views_kernel");
+}
+
+extern "C" int effimvs_weighted_agg_f32(const float* sims, const float* weights, int B, int n_src, int D, int H, int W,
+                                        float* out, void* stream) {
+    EFFI_REQUIRE(sims && weights && out, EFFIMVS_EINVAL, "weighted_agg: null pointer");
+    EFFI_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && n_src >= 1 && n_src <= EFFIMVS_MAX_SRC_VIEWS, EFFIMVS_EINVAL,
+                 "weighted_agg: bad sizes");
+    dim3 block(256), grid(ceil_div(H * W, 256), D < 8 ? D : 8, B);
+    weighted_agg_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(sims, weights, n_src, D, H * W, out);
+    return check_launch("weighted_agg_kernel");
+}

@@ -1,0 +1,168 @@
+"""CudaHotPath: the hot-path table (stage1 / local_volume / volume_lookup / cross_scale /
+dynamic_cost) backed by the hand-written sm_100a kernels through ``effimvs::*`` custom ops.
+
+The same table shape is implemented by the test oracle; ``net.EffiMVSPlus`` and the upstream
+drop-ins in ``dropin.py`` are written against it.  Nothing here falls back to PyTorch math: if
+libeffimvs.so is missing the import of ``capi`` raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import capi, ops
+
+
+def fold_bn(block, transposed: bool):
+    """Eval-mode BatchNorm folded into the preceding bias-free (de)conv
+    (upstream models/module.py:146-160, 189-203).  Returns fp32 (weight, bias)."""
+    bn = block.bn
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    shift = bn.bias - bn.running_mean * scale
+    w = block.conv.weight
+    w = w * (scale.reshape(1, -1, 1, 1, 1) if transposed else scale.reshape(-1, 1, 1, 1, 1))
+    return w.detach().float().contiguous(), shift.detach().float().contiguous()
+
+
+class _FoldCache:
+    """Folded weights per module, invalidated when a parameter / buffer is replaced or updated in place."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, net, build):
+        key = id(net)
+        stamp = tuple((id(t), t._version, t.device) for t in list(net.parameters()) + list(net.buffers()))
+        hit = self._store.get(key)
+        if hit is None or hit[0] != stamp:
+            hit = (stamp, build(net))
+            self._store[key] = hit
+        return hit[1]
+
+
+def _is_planes(hyp: torch.Tensor) -> bool:
+    return hyp.dim() == 2 or (hyp.dim() == 4 and (hyp.shape[2:] == (1, 1) or (hyp.stride(2) == 0 and hyp.stride(3) == 0)))
+
+
+class CudaHotPath:
+    name = "cuda"
+
+    def __init__(self, precision: str = "f32", native_projection: bool = False):
+        """precision: 'f32' (CUDA-core exact-parity convs) or 'bf16' (tcgen05 implicit GEMM).
+        native_projection: compute P_src @ inverse(P_ref) with the library's fp64 kernel instead
+        of torch (needed under CUDA-graph capture; torch.linalg.inv may synchronise)."""
+        self.precision = {"f32": capi.PREC_F32, "bf16": capi.PREC_BF16}[precision]
+        self.native_projection = native_projection
+        self._folds = _FoldCache()
+
+    # -- a1 + module.py:314 -------------------------------------------------------------------
+    def relative_projection(self, cams: torch.Tensor) -> torch.Tensor:
+        """cams (B,V,2,4,4) -> (B,V-1,12) rot|trans of P_src @ inverse(P_ref)."""
+        if self.native_projection:
+            return ops.relative_projection(cams)
+        B, V = cams.shape[:2]
+        P = cams[:, :, 0].clone()
+        P[:, :, :3, :4] = torch.matmul(cams[:, :, 1, :3, :3], cams[:, :, 0, :3, :4])
+        inv_ref = torch.linalg.inv_ex(P[:, 0])[0]
+        rel = torch.matmul(P[:, 1:], inv_ref.unsqueeze(1))
+        return torch.cat([rel[:, :, :3, :3].reshape(B, V - 1, 9), rel[:, :, :3, 3]], dim=-1).contiguous()
+
+    # -- a2-a4, a9, a11, a12 ---------------------------------------------------------------------
+    def stage1(self, features, cams, depth_hyp, pixel_wise_net, reg_net, G):
+        if G != 1:
+            raise ValueError("stage-1 view weighting requires G == 1 (upstream squeezes the group axis, Effi_MVS_plus.py:43)")
+        ref, srcs = features[0], list(features[1:])
+        B, _, H, W = ref.shape
+        D = depth_hyp.shape[1]
+        proj = self.relative_projection(cams)
+        if _is_planes(depth_hyp):
+            hyp, mode = depth_hyp.reshape(B, D, -1)[:, :, 0].contiguous(), capi.HYP_PLANES
+        else:
+            hyp, mode = depth_hyp, capi.HYP_TENSOR
+        sims, ent = ops.warp_corr_views(ref, srcs, proj, hyp, mode, D)
+        n = len(srcs)
+        vw = pixel_wise_net(ent.reshape(B * n, 1, H, W)).reshape(B, n, H, W)
+        sim = ops.weighted_agg(sims, vw)
+        prob_pre = self.cost_regularization(reg_net, sim.unsqueeze(1)).squeeze(1)
+        depth, conf = ops.softmax_regress_conf(prob_pre, hyp, mode)
+        return {"depth": depth, "photometric_confidence": conf, "view_weights": vw,
+                "reg_volume": prob_pre, "volume": sim.unsqueeze(1)}
+
+    # -- a5 ---------------------------------------------------------------------------------------
+    def local_volume(self, cur_depth, features, cams, interval, view_weights, ndepth, G):
+        ref, srcs = features[0], list(features[1:])
+        B, _, H, W = ref.shape
+        proj = self.relative_projection(cams)
+        iv = interval.reshape(-1).expand(B) if torch.is_tensor(interval) else torch.full((B,), float(interval), device=ref.device)
+        sim, hyp = ops.warp_corr_agg(ref, srcs, proj, cur_depth, capi.HYP_LOCAL, iv.float().contiguous(), view_weights, ndepth, G, True)
+        return sim.reshape(B, G * ndepth, H, W), hyp
+
+    # -- a2 + a3 + aggregation with explicit hypotheses (config-2 microbench form) --------------------
+    def warp_corr_agg(self, features, cams, hyp, view_weights, G):
+        ref, srcs = features[0], list(features[1:])
+        D = hyp.shape[1]
+        proj = self.relative_projection(cams)
+        if _is_planes(hyp):
+            hyp, mode = hyp.reshape(hyp.shape[0], D, -1)[:, :, 0].contiguous(), capi.HYP_PLANES
+        else:
+            mode = capi.HYP_TENSOR
+        return ops.warp_corr_agg(ref, srcs, proj, hyp, mode, None, view_weights, D, G, False)[0]
+
+    # -- a6 / a8 ----------------------------------------------------------------------------------
+    def volume_lookup(self, volume, depth_sample, depth_min, depth_max):
+        """depth_sample may be a [::2, ::2] view of a full-resolution tensor (Effi_MVS_plus.py:514);
+        the stride-2 read is then fused into the kernel instead of materialising the view."""
+        B, D, H, W = volume.shape
+        base = getattr(depth_sample, "_base", None)
+        if (not depth_sample.is_contiguous() and base is not None and base.is_contiguous() and base.dim() == 4
+                and tuple(base.shape) == (B, depth_sample.shape[1], 2 * H, 2 * W)
+                and depth_sample.stride() == (base.stride(0), base.stride(1), 2 * base.stride(2), 2)
+                and depth_sample.storage_offset() == base.storage_offset()):
+            return ops.volume_lookup(volume, base, self._range(depth_min, B), self._range(depth_max, B), 2)
+        return ops.volume_lookup(volume, depth_sample, self._range(depth_min, B), self._range(depth_max, B), 1)
+
+    @staticmethod
+    def _range(t, B):
+        t = t.reshape(B, -1)
+        return t.contiguous()
+
+    # -- a7 ---------------------------------------------------------------------------------------
+    def dynamic_cost(self, cur_depth, raw_volume, reg_volume, interval, vmin, vmax, ndepth):
+        B = raw_volume.shape[0]
+        iv = interval.reshape(-1).expand(B) if torch.is_tensor(interval) else torch.full((B,), float(interval), device=raw_volume.device)
+        return ops.dynamic_cost(cur_depth, raw_volume, reg_volume, iv.float().contiguous(), self._range(vmin, B), self._range(vmax, B), ndepth)
+
+    # -- a9 / a10 ---------------------------------------------------------------------------------
+    def _reg_weights(self, net):
+        def build(n):
+            ws, bs = [], []
+            for name, tr in (("conv0", False), ("conv1", False), ("conv2", False), ("conv3", False), ("conv4", False),
+                             ("conv5", False), ("conv6", True), ("conv7", True)):
+                w, b = fold_bn(getattr(n, name), tr)
+                ws.append(w)
+                bs.append(b)
+            ws.append(n.prob.weight.detach().float().contiguous())
+            return ws, bs
+        return self._folds.get(net, build)
+
+    def _csp_weights(self, net):
+        def build(n):
+            pairs = [fold_bn(n.conv0, False), fold_bn(n.conv_cost, False), fold_bn(n.conv1, False), fold_bn(n.conv2, True)]
+            return [p[0] for p in pairs], [p[1] for p in pairs]
+        return self._folds.get(net, build)
+
+    def cost_regularization(self, net, x):
+        """x (B,1,D,H,W) -> prob_pre (B,1,D,H,W)   (upstream models/module.py:453-463)."""
+        ws, bs = self._reg_weights(net)
+        return ops.costreg_fpn3d(x, ws, bs, self.precision)
+
+    def cross_scale(self, net, cur_volume, prev_resampled):
+        """cur (B,1,D,H,W), prev (B,1,D,H/2,W/2) -> (B,1,D,H,W)   (upstream models/module.py:509-516)."""
+        ws, bs = self._csp_weights(net)
+        return ops.cost_up_small(cur_volume, prev_resampled, ws, bs, self.precision)
+
+    # -- a11 / a12 --------------------------------------------------------------------------------
+    def softmax_regress_conf(self, prob_pre, hyp):
+        if _is_planes(hyp):
+            B, D = prob_pre.shape[:2]
+            return ops.softmax_regress_conf(prob_pre, hyp.reshape(B, D, -1)[:, :, 0].contiguous(), capi.HYP_PLANES)
+        return ops.softmax_regress_conf(prob_pre, hyp, capi.HYP_TENSOR)

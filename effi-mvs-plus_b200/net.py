@@ -270,7 +270,7 @@ class EffiMVSPlus(nn.Module):
                 D = self.ndepths[0]
                 k = torch.arange(D, device=imgs.device, dtype=imgs.dtype).reshape(1, D)
                 inv_s = disp_min.reshape(B, 1) + k * ((disp_max - disp_min).reshape(B, 1) / (D - 1))
-                hyp = (1.0 / inv_s).reshape(B, D, 1, 1).expand(B, D, H, W).contiguous()
+                hyp = (1.0 / inv_s).reshape(B, D, 1, 1).expand(B, D, H, W)   # plane sweep: stride-0 view
                 out = hp.stage1(f, cams, hyp, self.PixelwiseNet, self.cost_regularization, self.G)
                 conf = F.interpolate(out["photometric_confidence"].unsqueeze(1), [H * 4, W * 4], mode="nearest").squeeze(1)
                 view_w = out["view_weights"]

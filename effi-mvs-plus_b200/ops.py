@@ -1,0 +1,337 @@
+"""``torch.library`` custom ops ``effimvs::*`` over the C-ABI (device pointers only).
+
+PyTorch is plumbing here: it owns the device buffers and the stream; every op forwards raw
+pointers to libeffimvs.so.  Inference only (no autograd formula).  CPU tensors are rejected --
+there is no fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import capi
+
+_lib = capi.lib
+
+# kernels of libeffimvs.so launched through this module since the caller last reset it (bench.py's
+# `gpu_launches`); every op adds the number of launches its C entry point enqueues.
+LAUNCHES = 0
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _dev(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("effimvs::{} got a CPU tensor; the hot path is CUDA-only (no fallback)".format(name))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _opt(t: Optional[Tensor]):
+    return t.data_ptr() if t is not None else None
+
+
+# -------------------------------------------------------------------------------------------
+@torch.library.custom_op("effimvs::relative_projection", mutates_args=())
+def relative_projection(cams: Tensor) -> Tensor:
+    cams = _dev(cams, "relative_projection")
+    B, V = cams.shape[0], cams.shape[1]
+    out = torch.empty(B, V - 1, 12, device=cams.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_relative_projection_f32(cams.data_ptr(), B, V, out.data_ptr(), _stream()))
+    return out
+
+
+@relative_projection.register_fake
+def _(cams):
+    return cams.new_empty(cams.shape[0], cams.shape[1] - 1, 12)
+
+
+# -------------------------------------------------------------------------------------------
+@torch.library.custom_op("effimvs::warp_corr_agg", mutates_args=())
+def warp_corr_agg(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hyp_mode: int,
+                  interval: Optional[Tensor], weights: Optional[Tensor], D: int, G: int,
+                  want_hyp: bool) -> Tuple[Tensor, Tensor]:
+    ref = _dev(ref, "warp_corr_agg")
+    srcs = [_dev(s, "warp_corr_agg") for s in srcs]
+    proj, hyp = _dev(proj, "warp_corr_agg"), _dev(hyp, "warp_corr_agg")
+    interval = _dev(interval, "warp_corr_agg") if interval is not None else None
+    weights = _dev(weights, "warp_corr_agg") if weights is not None else None
+    B, Cc, H, W = ref.shape
+    sim = torch.empty(B, G, D, H, W, device=ref.device, dtype=torch.float32)
+    hyp_out = torch.empty(B, D, H, W, device=ref.device, dtype=torch.float32) if want_hyp else ref.new_empty(0)
+    arr, keep = capi.ptr_array([s.data_ptr() for s in srcs])
+    _count(1)
+    capi.check(_lib.effimvs_warp_corr_agg_f32(ref.data_ptr(), arr, len(srcs), proj.data_ptr(), hyp.data_ptr(), hyp_mode,
+                                              _opt(interval), _opt(weights), B, Cc, H, W, D, G, sim.data_ptr(),
+                                              hyp_out.data_ptr() if want_hyp else None, _stream()))
+    del keep
+    return sim, hyp_out
+
+
+@warp_corr_agg.register_fake
+def _(ref, srcs, proj, hyp, hyp_mode, interval, weights, D, G, want_hyp):
+    B, _, H, W = ref.shape
+    return ref.new_empty(B, G, D, H, W), (ref.new_empty(B, D, H, W) if want_hyp else ref.new_empty(0))
+
+
+@torch.library.custom_op("effimvs::warp_corr_views", mutates_args=())
+def warp_corr_views(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hyp_mode: int, D: int) -> Tuple[Tensor, Tensor]:
+    ref = _dev(ref, "warp_corr_views")
+    srcs = [_dev(s, "warp_corr_views") for s in srcs]
+    proj, hyp = _dev(proj, "warp_corr_views"), _dev(hyp, "warp_corr_views")
+    B, Cc, H, W = ref.shape
+    n = len(srcs)
+    sims = torch.empty(B, n, D, H, W, device=ref.device, dtype=torch.float32)
+    ent = torch.empty(B, n, H, W, device=ref.device, dtype=torch.float32)
+    arr, keep = capi.ptr_array([s.data_ptr() for s in srcs])
+    _count(1)
+    capi.check(_lib.effimvs_warp_corr_views_f32(ref.data_ptr(), arr, n, proj.data_ptr(), hyp.data_ptr(), hyp_mode,
+                                                B, Cc, H, W, D, sims.data_ptr(), ent.data_ptr(), _stream()))
+    del keep
+    return sims, ent
+
+
+@warp_corr_views.register_fake
+def _(ref, srcs, proj, hyp, hyp_mode, D):
+    B, _, H, W = ref.shape
+    return ref.new_empty(B, len(srcs), D, H, W), ref.new_empty(B, len(srcs), H, W)
+
+
+@torch.library.custom_op("effimvs::weighted_agg", mutates_args=())
+def weighted_agg(sims: Tensor, weights: Tensor) -> Tensor:
+    sims, weights = _dev(sims, "weighted_agg"), _dev(weights, "weighted_agg")
+    B, n, D, H, W = sims.shape
+    out = torch.empty(B, D, H, W, device=sims.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_weighted_agg_f32(sims.data_ptr(), weights.data_ptr(), B, n, D, H, W, out.data_ptr(), _stream()))
+    return out
+
+
+@weighted_agg.register_fake
+def _(sims, weights):
+    B, n, D, H, W = sims.shape
+    return sims.new_empty(B, D, H, W)
+
+
+# -------------------------------------------------------------------------------------------
+def _range_mode(dmin: Tensor, B: int, H: int, W: int) -> int:
+    if dmin.numel() == B:
+        return capi.RANGE_SCALAR
+    if dmin.numel() == B * H * W:
+        return capi.RANGE_PIXEL
+    raise ValueError("depth range must have B or B*H*W elements, got {}".format(tuple(dmin.shape)))
+
+
+@torch.library.custom_op("effimvs::volume_lookup", mutates_args=())
+def volume_lookup(volume: Tensor, depth_sample: Tensor, depth_min: Tensor, depth_max: Tensor, sample_stride: int) -> Tensor:
+    volume, depth_sample = _dev(volume, "volume_lookup"), _dev(depth_sample, "volume_lookup")
+    depth_min, depth_max = _dev(depth_min, "volume_lookup"), _dev(depth_max, "volume_lookup")
+    B, D, H, W = volume.shape
+    d = depth_sample.shape[1]
+    if tuple(depth_sample.shape[2:]) != (H * sample_stride, W * sample_stride):
+        raise ValueError("depth_sample {} does not match volume {} with stride {}".format(tuple(depth_sample.shape), tuple(volume.shape), sample_stride))
+    mode = _range_mode(depth_min, B, H, W)
+    if _range_mode(depth_max, B, H, W) != mode:
+        raise ValueError("depth_min and depth_max must have the same shape")
+    out = torch.empty(B, d, H, W, device=volume.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_volume_lookup_f32(volume.data_ptr(), depth_sample.data_ptr(), depth_min.data_ptr(),
+                                              depth_max.data_ptr(), mode, sample_stride, B, D, d, H, W, out.data_ptr(), _stream()))
+    return out
+
+
+@volume_lookup.register_fake
+def _(volume, depth_sample, depth_min, depth_max, sample_stride):
+    B, D, H, W = volume.shape
+    return volume.new_empty(B, depth_sample.shape[1], H, W)
+
+
+@torch.library.custom_op("effimvs::dynamic_cost", mutates_args=())
+def dynamic_cost(cur_depth: Tensor, raw: Tensor, reg: Tensor, interval: Tensor, depth_min: Tensor, depth_max: Tensor,
+                 ndepth: int) -> Tensor:
+    cur_depth, raw, reg = _dev(cur_depth, "dynamic_cost"), _dev(raw, "dynamic_cost"), _dev(reg, "dynamic_cost")
+    interval, depth_min, depth_max = _dev(interval, "dynamic_cost"), _dev(depth_min, "dynamic_cost"), _dev(depth_max, "dynamic_cost")
+    B, D, H, W = raw.shape
+    if reg.shape != raw.shape or cur_depth.numel() != B * H * W or interval.numel() != B:
+        raise ValueError("dynamic_cost: inconsistent shapes")
+    mode = _range_mode(depth_min, B, H, W)
+    if _range_mode(depth_max, B, H, W) != mode:
+        raise ValueError("depth_min and depth_max must have the same shape")
+    out = torch.empty(B, 2 * ndepth, H, W, device=raw.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_dynamic_cost_f32(cur_depth.data_ptr(), raw.data_ptr(), reg.data_ptr(), interval.data_ptr(),
+                                             depth_min.data_ptr(), depth_max.data_ptr(), mode, ndepth, B, D, H, W,
+                                             out.data_ptr(), _stream()))
+    return out
+
+
+@dynamic_cost.register_fake
+def _(cur_depth, raw, reg, interval, depth_min, depth_max, ndepth):
+    B, D, H, W = raw.shape
+    return raw.new_empty(B, 2 * ndepth, H, W)
+
+
+@torch.library.custom_op("effimvs::softmax_regress_conf", mutates_args=())
+def softmax_regress_conf(prob_pre: Tensor, hyp: Tensor, hyp_mode: int) -> Tuple[Tensor, Tensor]:
+    prob_pre, hyp = _dev(prob_pre, "softmax_regress_conf"), _dev(hyp, "softmax_regress_conf")
+    B, D, H, W = prob_pre.shape
+    depth = torch.empty(B, H, W, device=prob_pre.device, dtype=torch.float32)
+    conf = torch.empty(B, H, W, device=prob_pre.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_softmax_regress_conf_f32(prob_pre.data_ptr(), hyp.data_ptr(), hyp_mode, B, D, H, W,
+                                                     depth.data_ptr(), conf.data_ptr(), _stream()))
+    return depth, conf
+
+
+@softmax_regress_conf.register_fake
+def _(prob_pre, hyp, hyp_mode):
+    B, D, H, W = prob_pre.shape
+    return prob_pre.new_empty(B, H, W), prob_pre.new_empty(B, H, W)
+
+
+# -------------------------------------------------------------------------------------------
+@torch.library.custom_op("effimvs::conv3d", mutates_args=())
+def conv3d(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], stride: List[int],
+           transposed: bool, relu: bool) -> Tensor:
+    x, weight = _dev(x, "conv3d"), _dev(weight, "conv3d")
+    bias = _dev(bias, "conv3d") if bias is not None else None
+    residual = _dev(residual, "conv3d") if residual is not None else None
+    B, Cin, D, H, W = x.shape
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    sd, sh, sw = stride
+    if transposed:
+        Do, Ho, Wo = D * sd, H * sh, W * sw
+    else:
+        Do, Ho, Wo = (D - 1) // sd + 1, (H - 1) // sh + 1, (W - 1) // sw + 1
+    y = torch.empty(B, Cout, Do, Ho, Wo, device=x.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_conv3d_f32(x.data_ptr(), weight.data_ptr(), _opt(bias), _opt(residual), B, Cin, Cout, D, H, W,
+                                       sd, sh, sw, int(transposed), int(relu), y.data_ptr(), 0, Cout, _stream()))
+    return y
+
+
+@conv3d.register_fake
+def _(x, weight, bias, residual, stride, transposed, relu):
+    B, Cin, D, H, W = x.shape
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    sd, sh, sw = stride
+    if transposed:
+        return x.new_empty(B, Cout, D * sd, H * sh, W * sw)
+    return x.new_empty(B, Cout, (D - 1) // sd + 1, (H - 1) // sh + 1, (W - 1) // sw + 1)
+
+
+@torch.library.custom_op("effimvs::costreg_fpn3d", mutates_args=())
+def costreg_fpn3d(x: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int) -> Tensor:
+    x = _dev(x, "costreg_fpn3d")
+    weights = [_dev(w, "costreg_fpn3d") for w in weights]
+    biases = [_dev(b, "costreg_fpn3d") for b in biases]
+    if len(weights) != 9 or len(biases) != 8:
+        raise ValueError("costreg_fpn3d wants 9 weights and 8 biases")
+    B, _, D, H, W = x.shape
+    need = _lib.effimvs_costreg_workspace_bytes(B, D, H, W, precision)
+    ws = torch.empty(max(need, 256), device=x.device, dtype=torch.uint8)
+    out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
+    wa, k1 = capi.ptr_array([w.data_ptr() for w in weights])
+    ba, k2 = capi.ptr_array([b.data_ptr() for b in biases])
+    _count(9)
+    capi.check(_lib.effimvs_costreg_fpn3d(x.data_ptr(), wa, ba, B, D, H, W, precision, ws.data_ptr(), ws.numel(),
+                                          out.data_ptr(), _stream()))
+    del k1, k2
+    return out
+
+
+@costreg_fpn3d.register_fake
+def _(x, weights, biases, precision):
+    return x.new_empty(x.shape)
+
+
+@torch.library.custom_op("effimvs::cost_up_small", mutates_args=())
+def cost_up_small(x: Tensor, prev: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int) -> Tensor:
+    x, prev = _dev(x, "cost_up_small"), _dev(prev, "cost_up_small")
+    weights = [_dev(w, "cost_up_small") for w in weights]
+    biases = [_dev(b, "cost_up_small") for b in biases]
+    if len(weights) != 4 or len(biases) != 4:
+        raise ValueError("cost_up_small wants 4 weights and 4 biases")
+    B, _, D, H, W = x.shape
+    if tuple(prev.shape) != (B, 1, D, H // 2, W // 2):
+        raise ValueError("cost_up_small: prev {} does not match x {}".format(tuple(prev.shape), tuple(x.shape)))
+    need = _lib.effimvs_cost_up_workspace_bytes(B, D, H, W, precision)
+    ws = torch.empty(max(need, 256), device=x.device, dtype=torch.uint8)
+    out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
+    wa, k1 = capi.ptr_array([w.data_ptr() for w in weights])
+    ba, k2 = capi.ptr_array([b.data_ptr() for b in biases])
+    _count(4)
+    capi.check(_lib.effimvs_cost_up_small(x.data_ptr(), prev.data_ptr(), wa, ba, B, D, H, W, precision, ws.data_ptr(),
+                                          ws.numel(), out.data_ptr(), _stream()))
+    del k1, k2
+    return out
+
+
+@cost_up_small.register_fake
+def _(x, prev, weights, biases, precision):
+    return x.new_empty(x.shape)
+
+
+# -------------------------------------------------------------------------------------------
+@torch.library.custom_op("effimvs::fusion_reproject", mutates_args=())
+def fusion_reproject(ref_depth: Tensor, srcs_depth: Tensor, ref_cam: Tensor, srcs_cam: Tensor,
+                     inv_cams: Optional[Tensor]) -> Tensor:
+    ref_depth, srcs_depth = _dev(ref_depth, "fusion_reproject"), _dev(srcs_depth, "fusion_reproject")
+    ref_cam, srcs_cam = _dev(ref_cam, "fusion_reproject"), _dev(srcs_cam, "fusion_reproject")
+    inv_cams = _dev(inv_cams, "fusion_reproject") if inv_cams is not None else None
+    n, v, _, h, w = srcs_depth.shape
+    out = torch.empty(n, v, 3, h, w, device=ref_depth.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_fusion_reproject_f32(ref_depth.data_ptr(), srcs_depth.data_ptr(), ref_cam.data_ptr(),
+                                                 srcs_cam.data_ptr(), _opt(inv_cams), n, v, h, w, out.data_ptr(), _stream()))
+    return out
+
+
+@fusion_reproject.register_fake
+def _(ref_depth, srcs_depth, ref_cam, srcs_cam, inv_cams):
+    n, v, _, h, w = srcs_depth.shape
+    return ref_depth.new_empty(n, v, 3, h, w)
+
+
+@torch.library.custom_op("effimvs::fusion_filter", mutates_args=())
+def fusion_filter(ref_depth: Tensor, srcs_depth: Tensor, conf: Tensor, ref_cam: Tensor, srcs_cam: Tensor,
+                  inv_cams: Optional[Tensor], dist_base: float, rel_diff_base: float, thres_view: int,
+                  prob_threshold: float, relative: bool, want_masks: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    ref_depth, srcs_depth, conf = _dev(ref_depth, "fusion_filter"), _dev(srcs_depth, "fusion_filter"), _dev(conf, "fusion_filter")
+    ref_cam, srcs_cam = _dev(ref_cam, "fusion_filter"), _dev(srcs_cam, "fusion_filter")
+    inv_cams = _dev(inv_cams, "fusion_filter") if inv_cams is not None else None
+    n, v, _, h, w = srcs_depth.shape
+    hc, wc = conf.shape[-2:]
+    dev = ref_depth.device
+    final = torch.empty(n, 1, h, w, device=dev, dtype=torch.uint8)
+    avg = torch.empty(n, 1, h, w, device=dev, dtype=torch.float32)
+    pts = torch.empty(n, 3, h, w, device=dev, dtype=torch.float32)
+    K = v - thres_view + 1
+    masks = torch.empty((n, v, K, h, w) if want_masks else (0,), device=dev, dtype=torch.uint8)
+    _count(1)
+    capi.check(_lib.effimvs_fusion_filter_f32(ref_depth.data_ptr(), srcs_depth.data_ptr(), conf.data_ptr(), ref_cam.data_ptr(),
+                                              srcs_cam.data_ptr(), _opt(inv_cams), n, v, h, w, hc, wc, dist_base, rel_diff_base,
+                                              thres_view, prob_threshold, int(relative), final.data_ptr(), avg.data_ptr(),
+                                              pts.data_ptr(), masks.data_ptr() if want_masks else None, _stream()))
+    return final, avg, pts, masks
+
+
+@fusion_filter.register_fake
+def _(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, dist_base, rel_diff_base, thres_view, prob_threshold,
+      relative, want_masks):
+    n, v, _, h, w = srcs_depth.shape
+    K = v - thres_view + 1
+    u8 = torch.uint8
+    return (ref_depth.new_empty(n, 1, h, w, dtype=u8), ref_depth.new_empty(n, 1, h, w), ref_depth.new_empty(n, 3, h, w),
+            ref_depth.new_empty((n, v, K, h, w) if want_masks else (0,), dtype=u8))

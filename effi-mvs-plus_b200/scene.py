@@ -1,0 +1,62 @@
+"""Per-scene runner: reference views sharded round-robin over ranks (one process per GPU), no
+collective during depth inference, ONE all-gather of the final depth maps before fusion
+(upstream hands depth maps over through PFM files, test_tank.py:304-373).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> List[int]:
+    """Reference views owned by `rank`: rank, rank+world, ..."""
+    return list(range(rank, n_views, world))
+
+
+def slots_per_rank(n_views: int, world: int) -> int:
+    return (n_views + world - 1) // world
+
+
+def gather_depths(local: Dict[int, torch.Tensor], n_views: int, rank: int, world: int, h: int, w: int, device) -> torch.Tensor:
+    """All-gather of the per-rank depth maps into one (n_views,h,w) tensor on every rank.
+
+    Each rank contributes a (slots,h,w) block (zero padded when n_views % world != 0); with the
+    round-robin sharding view i lives in slot i // world of rank i % world."""
+    slots = slots_per_rank(n_views, world)
+    mine = torch.zeros(slots, h, w, device=device, dtype=torch.float32)
+    for i, d in local.items():
+        mine[i // world] = d
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        full = mine.unsqueeze(0)
+    else:
+        full = torch.empty(world, slots, h, w, device=device, dtype=torch.float32)
+        dist.all_gather_into_tensor(full, mine)
+    # (world, slots) -> view index = slot * world + rank
+    return full.permute(1, 0, 2, 3).reshape(slots * world, h, w)[:n_views].contiguous()
+
+
+@torch.no_grad()
+def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Sequence[int]], rank: int = 0, world: int = 1,
+              device="cuda"):
+    """infer(ref_view, src_views) -> (depth (h,w), conf (hc,wc)) on `device`;
+    fuse(ref_view, ref_depth (1,1,h,w), conf (1,hc,wc), src_views, src_depths (1,v,1,h,w)) -> dict with
+    'final' (1,1,h,w) bool and 'points' (1,3,h,w).
+    Returns {ref_view: (points (k,3), depth (h,w))} for the views this rank owns."""
+    mine = shard_views(n_views, rank, world)
+    depths, confs = {}, {}
+    for i in mine:
+        d, c = infer(i, list(pairs[i]))
+        depths[i], confs[i] = d, c
+    if not depths:
+        raise ValueError("rank {} owns no reference view (n_views={} < world={})".format(rank, n_views, world))
+    h, w = next(iter(depths.values())).shape[-2:]
+    all_depths = gather_depths(depths, n_views, rank, world, h, w, device)
+    out = {}
+    for i in mine:
+        src = list(pairs[i])
+        res = fuse(i, depths[i].reshape(1, 1, h, w), confs[i].unsqueeze(0), src, all_depths[src].reshape(1, len(src), 1, h, w))
+        m = res["final"][0, 0]
+        out[i] = (res["points"][0][:, m].t().contiguous(), depths[i])
+    return out

@@ -1,0 +1,165 @@
+/*
+ * effimvs.h -- C-ABI of libeffimvs.so: the B200 (sm_100a) cost-volume hot path of Effi-MVS+.
+ *
+ * The upstream project (bdwsq1996/Effi-MVS-plus) has no FFI; its boundary is a set of
+ * Python call sites.  Each entry point below names the upstream call site it replaces
+ * (paths relative to the upstream tree).  INTEGRATION.md shows the ctypes binding and the
+ * monkey-patch a maintainer adds on the upstream side.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative EFFIMVS_E* code;
+ *     effimvs_last_error() returns a thread-local description of the last failure.
+ *   - all tensor pointers are DEVICE pointers owned by the caller, fp32, dense, in the
+ *     layouts written next to each argument (upstream's NCHW / NCDHW order).  Arrays
+ *     documented as "host array" are small host-side arrays of device pointers.
+ *   - the library never allocates persistent memory and never synchronises; work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - re-entrant; no mutable global state besides the thread-local error string.
+ */
+#ifndef EFFIMVS_H
+#define EFFIMVS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EFFIMVS_OK 0
+#define EFFIMVS_EINVAL (-1)       /* bad argument (null pointer, non-positive size, ...) */
+#define EFFIMVS_EUNSUPPORTED (-2) /* shape outside what the kernels are built for */
+#define EFFIMVS_ECUDA (-3)        /* CUDA runtime / launch error */
+#define EFFIMVS_EWORKSPACE (-4)   /* caller-provided workspace too small */
+
+#define EFFIMVS_MAX_SRC_VIEWS 16
+
+/* hypothesis source for the warp kernels */
+#define EFFIMVS_HYP_TENSOR 0 /* hyp = (B,D,H,W) depth per pixel and plane                */
+#define EFFIMVS_HYP_PLANES 1 /* hyp = (B,D) one depth per plane (stage-1 plane sweep)    */
+#define EFFIMVS_HYP_LOCAL 2  /* hyp = cur_depth (B,1,H,W); D inverse-depth samples around
+                                it are generated in-kernel (models/module.py:554-570)    */
+
+/* per-batch scalar (B) or per-pixel (B,H,W) depth range of a volume */
+#define EFFIMVS_RANGE_SCALAR 0
+#define EFFIMVS_RANGE_PIXEL 1
+
+/* precision of the 3-D regularization nets */
+#define EFFIMVS_PREC_F32 0  /* CUDA-core fp32 direct convolution (exact-parity path)     */
+#define EFFIMVS_PREC_BF16 1 /* bf16 operands, fp32 accumulate in TMEM (tcgen05 implicit GEMM) */
+
+const char* effimvs_last_error(void);
+int effimvs_version(void);
+
+/* a1 + models/module.py:314.  cams (B,V,2,4,4): [b,v,0]=extrinsic, [b,v,1,:3,:3]=intrinsic.
+ * proj_out (B,V-1,12): rows of rot (9) then trans (3) of  P_src @ inverse(P_ref),
+ * P = E with P[:3,:4] = K @ E[:3,:4]  (models/Effi_MVS_plus.py:34-37).  Computed in fp64,
+ * rounded once to fp32.  (The torch binding may instead pass upstream's own fp32
+ * torch.inverse result to the warp kernels; this entry point serves non-torch callers and
+ * CUDA-graph capture.) */
+int effimvs_relative_projection_f32(const float* cams, int B, int V, float* proj_out, void* stream);
+
+/* a2 + a3 + a5 + weighted aggregation in one pass; the warped (B,C,D,H,W) volume is never
+ * materialised.  Replaces, per source view, homo_warping_new (models/module.py:303-344) +
+ * the group-wise correlation (models/Effi_MVS_plus.py:39-40, :222-224) and the aggregation
+ * over views (:52-53/:67, :233-234/:244).
+ *   ref_fea   (B,C,H,W)
+ *   src_fea   host array of n_src device pointers, each (B,C,H,W)
+ *   proj      (B,n_src,12) from effimvs_relative_projection_f32 (or torch)
+ *   hyp       see EFFIMVS_HYP_*;  interval (B) inverse-depth step, only for HYP_LOCAL
+ *   weights   (B,n_src,H,W) view weights or NULL (plain mean over views)
+ *   sim_out   (B,G,D,H,W);  hyp_out (B,D,H,W) depth hypotheses actually used, or NULL */
+int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* const* src_fea, int n_src,
+                              const float* proj, const float* hyp, int hyp_mode, const float* interval,
+                              const float* weights, int B, int C, int H, int W, int D, int G,
+                              float* sim_out, float* hyp_out, void* stream);
+
+/* Stage-1 form (models/Effi_MVS_plus.py:32-46): per-view similarity (G must be 1) and the
+ * entropy of its softmax over D, which upstream feeds to PixelwiseNet.
+ *   sims_out (B,n_src,D,H,W), entropy_out (B,n_src,H,W) */
+int effimvs_warp_corr_views_f32(const float* ref_fea, const float* const* src_fea, int n_src,
+                                const float* proj, const float* hyp, int hyp_mode,
+                                int B, int C, int H, int W, int D,
+                                float* sims_out, float* entropy_out, void* stream);
+
+/* sum_v w_v * sim_v / (sum_v w_v + 1e-6)  (models/Effi_MVS_plus.py:52-53, :67).
+ *   sims (B,n_src,D,H,W), weights (B,n_src,H,W) -> out (B,D,H,W) */
+int effimvs_weighted_agg_f32(const float* sims, const float* weights, int B, int n_src, int D, int H, int W,
+                             float* out, void* stream);
+
+/* a6: pro_bilinear_sampler (models/Effi_MVS_plus.py:102-134) on the un-permuted volume.
+ *   volume (B,D,H,W); depth_sample (B,d,H,W); depth_min/depth_max per EFFIMVS_RANGE_*
+ *   out (B,d,H,W).  sample_stride: 1, or 2 to read depth_sample from a (B,d,2H,2W) tensor at
+ *   even pixels (the nearest x1/2 of Effi_MVS_plus.py:514 fused in; a8). */
+int effimvs_volume_lookup_f32(const float* volume, const float* depth_sample, const float* depth_min,
+                              const float* depth_max, int range_mode, int sample_stride,
+                              int B, int D, int d, int H, int W, float* out, void* stream);
+
+/* a7: GetCost.forward (models/Effi_MVS_plus.py:257-303): ndepth hypotheses around
+ * cur_depth (B,1,H,W), looked up in raw (pro[-1]) and reg (pro[0]) volumes (B,D,H,W).
+ *   out (B,2*ndepth,H,W): raw samples first, then reg samples. */
+int effimvs_dynamic_cost_f32(const float* cur_depth, const float* raw_volume, const float* reg_volume,
+                             const float* interval, const float* depth_min, const float* depth_max,
+                             int range_mode, int ndepth, int B, int D, int H, int W, float* out, void* stream);
+
+/* a11 + a12: softmax over D, depth expectation, 4-bin confidence
+ * (models/Effi_MVS_plus.py:78-88, models/module.py:518-524).
+ *   prob_pre (B,D,H,W); hyp per hyp_mode (TENSOR or PLANES) -> depth (B,H,W), conf (B,H,W) */
+int effimvs_softmax_regress_conf_f32(const float* prob_pre, const float* hyp, int hyp_mode,
+                                     int B, int D, int H, int W, float* depth_out, float* conf_out, void* stream);
+
+/* One 3x3x3 (de)convolution layer with eval-BatchNorm folded in, fp32 CUDA cores
+ * (models/module.py:124-209).  x (B,Cin,D,H,W) -> y (B,Cout,Do,Ho,Wo) written at channel
+ * offset y_coff of a tensor with y_ctot channels (fuses the torch.cat of module.py:513).
+ *   weight: conv (Cout,Cin,3,3,3), deconv (Cin,Cout,3,3,3), BN scale already multiplied in
+ *   bias (Cout) or NULL; relu 0/1; residual (B,Cout,Do,Ho,Wo) added after the ReLU, or NULL
+ *   stride s* in {1,2}; padding 1; for deconv output_padding = s-1 (so Do = s*D). */
+int effimvs_conv3d_f32(const float* x, const float* weight, const float* bias, const float* residual,
+                       int B, int Cin, int Cout, int D, int H, int W, int sd, int sh, int sw,
+                       int transposed, int relu, float* y, int y_coff, int y_ctot, void* stream);
+
+/* a9: CostRegNet_2_sample_FPN3D_Fast.forward (models/module.py:453-463).
+ *   x (B,1,D,H,W), D,H,W multiples of 4.  weights: host array of 9 device pointers
+ *   (conv0..conv7 BN-folded, prob), biases: host array of 8 device pointers (conv0..conv7).
+ *   workspace: effimvs_costreg_workspace_bytes() bytes of device memory.
+ *   prob_out (B,1,D,H,W).  precision: EFFIMVS_PREC_*. */
+size_t effimvs_costreg_workspace_bytes(int B, int D, int H, int W, int precision);
+int effimvs_costreg_fpn3d(const float* x, const float* const* weights, const float* const* biases,
+                          int B, int D, int H, int W, int precision, void* workspace, size_t workspace_bytes,
+                          float* prob_out, void* stream);
+
+/* a10: cost_up_small.forward (models/module.py:509-516).
+ *   x (B,1,D,H,W) full-res local volume, prev (B,1,D,H/2,W/2) resampled previous volume.
+ *   weights/biases: host arrays of 4 device pointers (conv0, conv_cost, conv1, conv2).
+ *   out (B,1,D,H,W). */
+size_t effimvs_cost_up_workspace_bytes(int B, int D, int H, int W, int precision);
+int effimvs_cost_up_small(const float* x, const float* prev, const float* const* weights,
+                          const float* const* biases, int B, int D, int H, int W, int precision,
+                          void* workspace, size_t workspace_bytes, float* out, void* stream);
+
+/* a13: get_reproj_dynamic (misc/fusion.py:117-154).
+ *   ref_depth (n,1,h,w), srcs_depth (n,v,1,h,w), ref_cam (n,2,4,4), srcs_cam (n,v,2,4,4)
+ *   -> reproj_xyd (n,v,3,h,w).  Camera inverses are taken in-kernel (fp32 adjugate/LU as
+ *   documented in DESIGN.md) unless inv_cams is given: (n,1+v,2,4,4) holding inverse(E) and
+ *   inverse(K) (padded to 4x4) for ref then sources, e.g. torch.inverse results. */
+int effimvs_fusion_reproject_f32(const float* ref_depth, const float* srcs_depth, const float* ref_cam,
+                                 const float* srcs_cam, const float* inv_cams, int n, int v, int h, int w,
+                                 float* reproj_xyd, void* stream);
+
+/* a13 + a14 + a15 fused: reprojection, threshold ladder, votes, masked average and
+ * back-projection for one reference view (misc/fusion.py:117-181, test_tank.py:473-515).
+ *   conf (n,hc,wc) nearest-resized to (h,w); thresholds k/dist_base px and k/rel_diff_base
+ *   for k = thres_view..v; final = (conf > prob_threshold) & OR_k(votes_k >= k).
+ *   -> final_mask (n,h,w) uint8, depth_avg (n,h,w), points (n,3,h,w);
+ *      optional masks_out (n,v,K,h,w) uint8 (K = v-thres_view+1) or NULL. */
+int effimvs_fusion_filter_f32(const float* ref_depth, const float* srcs_depth, const float* conf,
+                              const float* ref_cam, const float* srcs_cam, const float* inv_cams,
+                              int n, int v, int h, int w, int hc, int wc,
+                              float dist_base, float rel_diff_base, int thres_view, float prob_threshold,
+                              int relative, uint8_t* final_mask, float* depth_avg, float* points,
+                              uint8_t* masks_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFFIMVS_H */

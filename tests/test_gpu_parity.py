@@ -1,0 +1,303 @@
+"""GPU parity tests (``-m gpu``): the CUDA path, called through the C-ABI (ctypes ->
+torch.library ops), against (a) the oracle on the same seeded inputs on the same device and
+(b) the golden fixtures produced by upstream itself (tests/golden/make_golden.py).
+
+Tolerances (BASELINE.json north_star): fp32 cost volumes max|d| <= 1e-4 * max|ref|; depth maps
+|d depth| <= 1e-3 * (depth_max - depth_min) on >= 99.9 % of pixels; fusion masks identical except
+within 1e-5 (relative) of a threshold.
+"""
+import pytest
+import torch
+
+from util import cspnet, dtu_model, golden, pixelwise, regnet, rel_max
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+DEPTH_RANGE = 935.0 - 425.0
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _strict_fp32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_grad_enabled(False)
+    yield
+
+
+@pytest.fixture(scope="module")
+def hp():
+    from effimvs_b200 import hotpath
+    return hotpath.CudaHotPath("f32")
+
+
+@pytest.fixture(scope="module")
+def ohp():
+    from oracle import hotpath as o
+    return o
+
+
+def frac_within(a, b, tol):
+    return float(((a - b).abs() <= tol).float().mean())
+
+
+# ------------------------------------------------------------------------------------------
+# warp + correlation + aggregation
+# ------------------------------------------------------------------------------------------
+def test_warp_corr_agg_golden(hp):
+    g = golden("warp_corr", DEV)
+    feats = list(g["feats"])
+    got = hp.warp_corr_agg(feats, g["cams"], g["hyp"], g["wts"], g["G"])
+    assert rel_max(got, g["agg"]) < 1e-4
+
+
+@pytest.mark.parametrize("C,G,D,H,W", [(8, 1, 8, 37, 53), (8, 8, 16, 64, 80), (16, 4, 8, 40, 64), (16, 1, 48, 32, 40),
+                                       (32, 1, 48, 37, 50), (32, 8, 8, 64, 96), (32, 2, 3, 20, 31)])
+@pytest.mark.parametrize("weighted", [True, False])
+def test_warp_corr_agg_vs_oracle(hp, ohp, C, G, D, H, W, weighted):
+    from effimvs_b200 import synthetic
+    feats, cams, hyp, wts = synthetic.microbench_inputs(C, D, H, W, views=5, seed=C + D, device=DEV)
+    got = hp.warp_corr_agg(feats, cams, hyp, wts if weighted else None, G)
+    sims = [ohp.view_similarity(feats[0], feats[v], cams[:, 0], cams[:, v], hyp, G) for v in range(1, 5)]
+    want = ohp.weighted_aggregate(sims, [wts[:, i:i + 1] for i in range(4)]) if weighted else sum(sims) / 4
+    assert rel_max(got, want) < 1e-4
+
+
+def test_warp_corr_agg_per_pixel_hypotheses_and_edge_cases(hp, ohp):
+    """Per-pixel hypotheses (HYP_TENSOR), out-of-frustum planes, negative / zero / NaN depths, batch of 2."""
+    from effimvs_b200 import synthetic
+    gen = torch.Generator().manual_seed(7)
+    C, D, H, W = 16, 8, 36, 44
+    feats, cams, hyp, wts = synthetic.microbench_inputs(C, D, H, W, views=4, seed=11)
+    feats = [torch.cat([f, torch.randn(1, C, H, W, generator=gen)]).to(DEV) for f in feats]
+    cams = cams.repeat(2, 1, 1, 1, 1).to(DEV)
+    hyp = (hyp.repeat(2, 1, 1, 1) * (0.8 + 0.4 * torch.rand(2, D, H, W, generator=gen))).to(DEV)
+    hyp[0, 0] = 30.0
+    hyp[1, 1, :5] = -400.0
+    hyp[0, 2, 3, 3] = 0.0
+    hyp[1, 3, 4, 4] = float("nan")
+    wts = wts.repeat(2, 1, 1, 1).to(DEV)
+    got = hp.warp_corr_agg(feats, cams, hyp, wts, 2)
+    sims = [ohp.view_similarity(feats[0], feats[v], cams[:, 0], cams[:, v], hyp, 2) for v in range(1, 4)]
+    want = ohp.weighted_aggregate(sims, [wts[:, i:i + 1] for i in range(3)])
+    assert torch.isfinite(got).all()           # NaN coordinates contribute zero, like ATen's CUDA kernel
+    ok = torch.isfinite(want)
+    assert ok.float().mean() > 0.99
+    assert rel_max(got[ok], want[ok]) < 1e-4
+
+
+def test_local_volume_golden_and_oracle(hp, ohp):
+    g = golden("local_volume", DEV)
+    feats = list(g["feats"])
+    sim, hyp = hp.local_volume(g["cur"], feats, g["cams"], g["interval"], g["wts"], 8, 1)
+    assert float(((hyp - g["samples"]).abs() / g["samples"]).max()) < 1e-6
+    assert rel_max(sim, g["sim"]) < 1e-4
+    sim2, _ = hp.local_volume(g["cur"], feats, g["cams"], g["interval"], None, 8, 1)
+    assert rel_max(sim2, g["sim_noweights"]) < 1e-4
+    o_sim, o_hyp = ohp.local_volume(g["cur"], feats, g["cams"], g["interval"], g["wts"], 8, 1)
+    assert torch.equal(hyp, o_hyp)             # hypothesis generation is bit-exact against torch on the device
+    assert rel_max(sim, o_sim) < 1e-4
+
+
+def test_native_projection_matches_torch(hp):
+    from effimvs_b200 import hotpath, synthetic
+    s = synthetic.make_sample("plumbing", seed=3)
+    cams = s["proj_matrices"]["stage2"].to(DEV)
+    a = hp.relative_projection(cams)
+    b = hotpath.CudaHotPath("f32", native_projection=True).relative_projection(cams)
+    assert float(((a - b).abs() / a.abs().clamp(min=1.0)).max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# stage 1 (per-view sims + entropy, weighted aggregation, regularization, regression)
+# ------------------------------------------------------------------------------------------
+def test_stage1_golden(hp):
+    g, r = golden("stage1", DEV), golden("regnets", DEV)
+    out = hp.stage1(list(g["feats"]), g["cams"], g["hyp"], pixelwise(g, DEV), regnet(r, DEV), 1)
+    assert rel_max(out["volume"], g["volume"]) < 1e-4
+    assert rel_max(out["view_weights"], g["view_weights"]) < 1e-4
+    assert rel_max(out["reg_volume"], g["reg_volume"]) < 1e-4
+    assert frac_within(out["depth"], g["depth"], 1e-3 * DEPTH_RANGE) >= 0.999
+    assert float((out["photometric_confidence"] - g["conf"]).abs().max()) < 1e-4
+
+
+def test_stage1_views_entropy_vs_oracle(ohp):
+    from effimvs_b200 import capi, ops, synthetic, hotpath
+    feats, cams, hyp, _ = synthetic.microbench_inputs(32, 96, 33, 47, views=7, seed=5, device=DEV)
+    feats = [f * 0.4 for f in feats]
+    proj = hotpath.CudaHotPath().relative_projection(cams)
+    sims, ent = ops.warp_corr_views(feats[0], feats[1:], proj, hyp, capi.HYP_TENSOR, 96)
+    planes = hyp[:, :, 0, 0].contiguous()
+    sims_p, ent_p = ops.warp_corr_views(feats[0], feats[1:], proj, planes, capi.HYP_PLANES, 96)
+    assert torch.equal(sims, sims_p) and torch.equal(ent, ent_p)
+    for v in range(6):
+        want = ohp.view_similarity(feats[0], feats[v + 1], cams[:, 0], cams[:, v + 1], hyp, 1)
+        assert rel_max(sims[:, v], want[:, 0]) < 1e-4
+        assert float((ent[:, v:v + 1] - ohp.similarity_entropy(want)).abs().max()) < 1e-4
+
+
+def test_softmax_regress_conf_vs_oracle(hp, ohp):
+    gen = torch.Generator().manual_seed(3)
+    for D in (8, 48, 96):
+        logits = (3 * torch.randn(2, D, 19, 23, generator=gen)).to(DEV)
+        hyp = (425 + 510 * torch.rand(2, D, 19, 23, generator=gen)).to(DEV)
+        d, c = hp.softmax_regress_conf(logits, hyp)
+        od, oc = ohp.softmax_regress_confidence(logits, hyp)
+        assert float((d - od).abs().max()) < 1e-3 and float((c - oc).abs().max()) < 1e-5
+    # peaked distributions at the volume borders exercise the zero-padded 4-bin window
+    logits = torch.full((1, 8, 4, 4), -20.0, device=DEV)
+    logits[:, 0, :2] = 20.0
+    logits[:, 7, 2:] = 20.0
+    hyp = torch.linspace(500, 900, 8, device=DEV).reshape(1, 8, 1, 1).expand(1, 8, 4, 4)
+    d, c = hp.softmax_regress_conf(logits, hyp)
+    od, oc = ohp.softmax_regress_confidence(logits, hyp.contiguous())
+    assert float((d - od).abs().max()) < 1e-3 and float((c - oc).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# volume lookup / dynamic cost
+# ------------------------------------------------------------------------------------------
+def test_lookup_golden_and_oracle(hp, ohp):
+    g = golden("lookup", DEV)
+    out = hp.dynamic_cost(g["cur"], g["vol_raw"], g["vol_reg"], g["interval"], g["vmin"], g["vmax"], 3)
+    assert rel_max(out, g["out6"]) < 1e-4
+    gmin, gmax = torch.full((1, 1, 1, 1), 425.0, device=DEV), torch.full((1, 1, 1, 1), 935.0, device=DEV)
+    out = hp.dynamic_cost(g["cur"], g["vol_raw"], g["vol_reg"], g["interval"] * 6, gmin, gmax, 3)
+    assert rel_max(out, g["out6_global"]) < 1e-4
+    look = hp.volume_lookup(g["vol_raw"], g["samples"], gmin, gmax)
+    assert rel_max(look, g["look_global"]) < 1e-4
+    # samples far outside the volume's range -> zero contribution from out-of-range taps
+    far = torch.cat([g["samples"] * 3.0, g["samples"] * 0.3], dim=1)
+    assert rel_max(hp.volume_lookup(g["vol_raw"], far, gmin, gmax), ohp.volume_lookup(g["vol_raw"], far, gmin, gmax)) < 1e-4
+
+
+def test_lookup_fused_half_resolution_view(hp, ohp):
+    gen = torch.Generator().manual_seed(5)
+    vol = torch.randn(2, 48, 20, 28, generator=gen).to(DEV)
+    full = (450 + 450 * torch.rand(2, 8, 40, 56, generator=gen)).to(DEV)
+    gmin, gmax = torch.full((2, 1, 1, 1), 425.0, device=DEV), torch.full((2, 1, 1, 1), 935.0, device=DEV)
+    low = full[:, :, ::2, ::2]
+    got = hp.volume_lookup(vol, low, gmin, gmax)                 # takes the fused stride-2 path
+    want = ohp.volume_lookup(vol, low.contiguous(), gmin, gmax)
+    assert rel_max(got, want) < 1e-4
+    assert torch.equal(got, hp.volume_lookup(vol, low.contiguous(), gmin, gmax))
+
+
+# ------------------------------------------------------------------------------------------
+# 3-D regularization nets, fp32 path
+# ------------------------------------------------------------------------------------------
+def test_regnets_golden(hp):
+    g = golden("regnets", DEV)
+    y = hp.cost_regularization(regnet(g, DEV), g["x"])
+    assert rel_max(y, g["y"]) < 1e-4
+    up = hp.cross_scale(cspnet(g, DEV), g["xs"], g["prev"])
+    assert rel_max(up, g["up"]) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,stride,transposed", [(1, 8, (1, 1, 1), False), (8, 16, (2, 2, 2), False), (16, 16, (1, 1, 1), False),
+                                                        (32, 32, (1, 1, 1), False), (1, 8, (1, 2, 2), False), (32, 16, (2, 2, 2), True),
+                                                        (8, 1, (1, 2, 2), True), (8, 1, (1, 1, 1), False)])
+def test_conv3d_layer_vs_aten(cin, cout, stride, transposed):
+    import torch.nn.functional as F
+    from effimvs_b200 import ops
+    gen = torch.Generator().manual_seed(cin * 100 + cout)
+    x = torch.randn(2, cin, 8, 10, 12, generator=gen).to(DEV)
+    w = (torch.randn((cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3), generator=gen) * 0.2).to(DEV)
+    b = torch.randn(cout, generator=gen).to(DEV)
+    if transposed:
+        ref = F.conv_transpose3d(x, w, b, stride=stride, padding=1, output_padding=tuple(s - 1 for s in stride))
+    else:
+        ref = F.conv3d(x, w, b, stride=stride, padding=1)
+    res = torch.randn(ref.shape, generator=gen).to(DEV)
+    got = ops.conv3d(x, w, b, res, list(stride), transposed, True)
+    assert rel_max(got, torch.relu(ref) + res) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# whole cascade
+# ------------------------------------------------------------------------------------------
+def test_model_forward_golden(hp):
+    from effimvs_b200 import synthetic
+    g = golden("model_forward")
+    s = synthetic.make_sample("plumbing", seed=g["seed"], width=g["width"], height=g["height"], device=DEV)
+    out = dtu_model(hp, DEV)(s["imgs"], s["proj_matrices"], s["depth_values"])
+    for i, d in enumerate(out["depth"]):
+        assert frac_within(d.cpu(), g["depth{:02d}".format(i)], 1e-3 * DEPTH_RANGE) >= 0.999, i
+    assert frac_within(out["photometric_confidence"].cpu(), g["conf"], 1e-3) >= 0.999
+
+
+@pytest.mark.parametrize("shape,ndepths", [("plumbing", "48,8,8")])
+def test_model_forward_vs_oracle_on_device(hp, ohp, shape, ndepths):
+    from effimvs_b200 import synthetic
+    s = synthetic.make_sample(shape, seed=1, device=DEV)
+    cuda_model = dtu_model(hp, DEV, ndepths)
+    want = dtu_model(ohp.OracleHotPath(), DEV, ndepths)(s["imgs"], s["proj_matrices"], s["depth_values"])
+    got = cuda_model(s["imgs"], s["proj_matrices"], s["depth_values"])
+    for i, (a, b) in enumerate(zip(got["depth"], want["depth"])):
+        assert frac_within(a, b, 1e-3 * DEPTH_RANGE) >= 0.999, i
+
+
+# ------------------------------------------------------------------------------------------
+# fusion
+# ------------------------------------------------------------------------------------------
+def _near_threshold(xyd, ref_depth, cx, cy, ks, dist_base, rel_base, ulps=8):
+    """Pixels whose reprojection distance / depth error lies within a few fp32 ulps of a ladder
+    threshold.  The north_star allows masks to differ within 1e-5 (relative) of a threshold; the
+    quantities compared are differences of pixel coordinates (<= w, ulp(1600) = 1.2e-4 px) and of
+    depths (ulp(935) = 6.1e-5), so the band is stated in ulps of those magnitudes."""
+    e_xy = ((xyd[:, :, 0] - cx) ** 2 + (xyd[:, :, 1] - cy) ** 2).sqrt()
+    e_d = (ref_depth - xyd[:, :, 2]).abs()
+    eps = 2.0 ** -23
+    band_xy = ulps * eps * max(float(cx.max()), float(cy.max()))
+    band_d = ulps * eps * float(ref_depth.abs().max())
+    near = torch.zeros_like(e_xy, dtype=torch.bool)
+    for k in ks:
+        near |= ((e_xy - k / dist_base).abs() <= band_xy + 1e-5 * k / dist_base) | ((e_d - k / rel_base).abs() <= band_d + 1e-5 * k / rel_base)
+    return near.any(dim=1, keepdim=True)
+
+
+@pytest.mark.parametrize("tag", ["mm", "tank"])
+@pytest.mark.parametrize("torch_inverse", [True, False])
+def test_fusion_golden(tag, torch_inverse):
+    from effimvs_b200 import fusion
+    g = golden("fusion_" + tag, DEV)
+    xyd, _, _ = fusion.get_reproj_dynamic(g["ref_depth"], g["srcs_depth"], g["ref_cam"], g["srcs_cam"], torch_inverse)
+    want = g["reproj_xyd"]
+    sane = torch.isfinite(want) & (want.abs() < 1e6)
+    assert rel_max(xyd[sane], want[sane]) < 1e-4
+    out = fusion.filter_view(g["ref_depth"], g["conf"], g["srcs_depth"], g["ref_cam"], g["srcs_cam"], g["dist_base"],
+                             g["rel_diff_base"], g["thres_view"], g["prob_threshold"], want_masks=True, torch_inverse=torch_inverse)
+    n, v, _, h, w = g["srcs_depth"].shape
+    cx = (torch.arange(w, device=DEV) + 0.5).reshape(1, 1, 1, w)
+    cy = (torch.arange(h, device=DEV) + 0.5).reshape(1, 1, h, 1)
+    near = _near_threshold(want, g["ref_depth"], cx, cy, range(g["thres_view"], v + 1), g["dist_base"], g["rel_diff_base"])
+    gm = g["masks"].bool()
+    diff = (out["masks"] != gm).any(dim=2).any(dim=1, keepdim=True)
+    assert not (diff & ~near).any(), "masks differ away from thresholds"
+    keep = ~near
+    assert torch.equal(out["final"][keep], g["final"].bool()[keep])
+    same = ~diff
+    assert rel_max(out["depth_avg"][same], g["depth_avg"][same]) < 1e-5
+    assert rel_max(out["points"][same.expand(-1, 3, -1, -1)], g["points"][same.expand(-1, 3, -1, -1)]) < 1e-4
+
+
+def test_fusion_vs_oracle_full_size():
+    """1600x1184 with 10 source views against the oracle on the device (size-independent property:
+    identical final masks away from thresholds, averaged depth equal where masks agree)."""
+    from effimvs_b200 import fusion, synthetic
+    from oracle import fusion as ofu
+    h, w, v = 1184, 1600, 10
+    E, K = synthetic.camera_ring(v + 1, w, h)
+    depths = synthetic.render_plane_scene(E, K, w, h, noise=0.15, seed=4).to(DEV)
+    cams = synthetic.stage_cameras(E, K, 1)["stage4"].to(DEV)
+    conf = torch.rand(1, h // 2, w // 2, device=DEV)
+    args = (depths[0][None, None], conf, depths[1:][None, :, None], cams[:, 0], cams[:, 1:], 2, 6, 2, 0.3)
+    got = fusion.filter_view(*args)
+    want = ofu.fuse_view(*args)
+    cx = (torch.arange(w, device=DEV) + 0.5).reshape(1, 1, 1, w)
+    cy = (torch.arange(h, device=DEV) + 0.5).reshape(1, 1, h, 1)
+    near = _near_threshold(want["reproj_xyd"], args[0], cx, cy, range(2, v + 1), 2, 6)
+    assert float(near.float().mean()) < 0.02
+    assert torch.equal(got["final"][~near], want["final"][~near])
+    agree = (got["final"] == want["final"]) & ~near
+    assert rel_max(got["depth_avg"][agree], want["depth_avg"][agree]) < 1e-5
+    assert 0.3 < float(want["final"].float().mean()) < 0.99
