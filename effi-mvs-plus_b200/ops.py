@@ -231,6 +231,38 @@ def _(x, weight, bias, residual, stride, transposed, relu):
     return x.new_empty(B, Cout, (D - 1) // sd + 1, (H - 1) // sh + 1, (W - 1) // sw + 1)
 
 
+@torch.library.custom_op("effimvs::conv3d_bf16", mutates_args=())
+def conv3d_bf16(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], sd: int,
+                transposed: bool, relu: bool) -> Tensor:
+    """One (de)conv layer on the tensor cores (tcgen05), fp32 NCDHW in/out.  Conv: stride sd in all
+    dims (1 or 2); transposed conv: stride (sd,2,2)."""
+    x, weight = _dev(x, "conv3d_bf16"), _dev(weight, "conv3d_bf16")
+    bias = _dev(bias, "conv3d_bf16") if bias is not None else None
+    residual = _dev(residual, "conv3d_bf16") if residual is not None else None
+    B, Cin, D, H, W = x.shape
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    if transposed:
+        Do, Ho, Wo = D * sd, H * 2, W * 2
+    else:
+        Do, Ho, Wo = D // sd, H // sd, W // sd
+    need = _lib.effimvs_conv3d_bf16_workspace_bytes(B, Cin, Cout, D, H, W, sd, int(transposed))
+    ws = torch.empty(max(need, 256), device=x.device, dtype=torch.uint8)
+    y = torch.empty(B, Cout, Do, Ho, Wo, device=x.device, dtype=torch.float32)
+    _count(5)
+    capi.check(_lib.effimvs_conv3d_bf16(x.data_ptr(), weight.data_ptr(), _opt(bias), _opt(residual), B, Cin, Cout, D, H, W,
+                                        sd, int(transposed), int(relu), ws.data_ptr(), ws.numel(), y.data_ptr(), _stream()))
+    return y
+
+
+@conv3d_bf16.register_fake
+def _(x, weight, bias, residual, sd, transposed, relu):
+    B, Cin, D, H, W = x.shape
+    Cout = weight.shape[1] if transposed else weight.shape[0]
+    if transposed:
+        return x.new_empty(B, Cout, D * sd, H * 2, W * 2)
+    return x.new_empty(B, Cout, D // sd, H // sd, W // sd)
+
+
 @torch.library.custom_op("effimvs::costreg_fpn3d", mutates_args=())
 def costreg_fpn3d(x: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int) -> Tensor:
     x = _dev(x, "costreg_fpn3d")
@@ -244,7 +276,7 @@ def costreg_fpn3d(x: Tensor, weights: List[Tensor], biases: List[Tensor], precis
     out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
     wa, k1 = capi.ptr_array([w.data_ptr() for w in weights])
     ba, k2 = capi.ptr_array([b.data_ptr() for b in biases])
-    _count(9)
+    _count(9 if precision == capi.PREC_F32 else 17)   # bf16: 8 weight packs + 1 CUDA-core conv + 8 tcgen05 layers
     capi.check(_lib.effimvs_costreg_fpn3d(x.data_ptr(), wa, ba, B, D, H, W, precision, ws.data_ptr(), ws.numel(),
                                           out.data_ptr(), _stream()))
     del k1, k2
@@ -271,7 +303,7 @@ def cost_up_small(x: Tensor, prev: Tensor, weights: List[Tensor], biases: List[T
     out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
     wa, k1 = capi.ptr_array([w.data_ptr() for w in weights])
     ba, k2 = capi.ptr_array([b.data_ptr() for b in biases])
-    _count(4)
+    _count(4 if precision == capi.PREC_F32 else 6)    # bf16: 2 weight packs + 2 CUDA-core convs + 2 tcgen05 layers
     capi.check(_lib.effimvs_cost_up_small(x.data_ptr(), prev.data_ptr(), wa, ba, B, D, H, W, precision, ws.data_ptr(),
                                           ws.numel(), out.data_ptr(), _stream()))
     del k1, k2

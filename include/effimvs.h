@@ -118,6 +118,17 @@ int effimvs_conv3d_f32(const float* x, const float* weight, const float* bias, c
                        int B, int Cin, int Cout, int D, int H, int W, int sd, int sh, int sw,
                        int transposed, int relu, float* y, int y_coff, int y_ctot, void* stream);
 
+/* The same layer on the tensor cores: bf16 operands, fp32 accumulation in TMEM (tcgen05 implicit
+ * GEMM, operands staged by bulk TMA copies).  Supported: convolution stride 1 or (2,2,2);
+ * transposed convolution stride (sd,2,2) with sd in {1,2}.  Cin in {8,16,32}, Cout <= 32.
+ * x, residual and y are fp32 NCDHW (converted to / from the kernel's channel-planar bf16 layout
+ * inside the call; the net-level entry points below keep activations in that layout between
+ * layers).  workspace: effimvs_conv3d_bf16_workspace_bytes() bytes. */
+size_t effimvs_conv3d_bf16_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int sd, int transposed);
+int effimvs_conv3d_bf16(const float* x, const float* weight, const float* bias, const float* residual, int B, int Cin,
+                        int Cout, int D, int H, int W, int sd, int transposed, int relu, void* workspace,
+                        size_t workspace_bytes, float* y, void* stream);
+
 /* a9: CostRegNet_2_sample_FPN3D_Fast.forward (models/module.py:453-463).
  *   x (B,1,D,H,W), D,H,W multiples of 4.  weights: host array of 9 device pointers
  *   (conv0..conv7 BN-folded, prob), biases: host array of 8 device pointers (conv0..conv7).
