@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("EFFIMVS_PRECISION", "f32"), choices=["f32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("EFFIMVS_PRECISION", "f32"), choices=["f32", "bf16", "bf16x3"])
     ap.add_argument("--shape", default="dtu", choices=["dtu", "tanks", "plumbing"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -62,7 +62,10 @@ def build_model(hotpath, device, ndepths):
         from util import load_dtu_weights
         load_dtu_weights(model)
         data = "synthetic images/cameras (seeded); weights = upstream model_dtu.ckpt values (tests/golden/dtu_weights.pt)"
-    return model.to(device).eval(), data
+    model = model.to(device).eval()
+    if torch.device(device).type == "cuda":
+        model = model.to(memory_format=torch.channels_last)     # 4-D conv weights NHWC: cuDNN tensor-core kernels without layout round trips
+    return model, data
 
 
 class ClockSampler:
@@ -378,7 +381,8 @@ def run_ours(a, rank, world, local_rank):
     e2e = world * a.steps / (ms_e2e / 1e3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if a.precision == "f32" else "bf16 (3-D regularization) / f32 (warp, lookup, regression)",
+            "dtype": {"f32": "f32", "bf16": "bf16 MMA, f32 accumulate (3-D regularization) / f32 (warp, lookup, regression)",
+                      "bf16x3": "hi+lo bf16 MMA x3, f32 accumulate (3-D regularization, fp32-grade) / f32 (warp, lookup, regression)"}[a.precision],
             "data": data,
             "config": {"workload": WORKLOAD, "shape": a.shape, "views": int(stat["imgs"].shape[1]), "ndepths": ndepths,
                        "sharding": "one reference view per rank per step, no collective", "cuda_graph": graph is not None,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libeffimvs.so")
 OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
 HYP_TENSOR, HYP_PLANES, HYP_LOCAL = 0, 1, 2
 RANGE_SCALAR, RANGE_PIXEL = 0, 1
-PREC_F32, PREC_BF16 = 0, 1
+PREC_F32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 MAX_SRC_VIEWS = 16
 
 
@@ -44,8 +44,8 @@ SIGNATURES = {
     "effimvs_dynamic_cost_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "effimvs_softmax_regress_conf_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_conv3d_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
-    "effimvs_conv3d_bf16_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
-    "effimvs_conv3d_bf16": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "effimvs_conv3d_bf16_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i, _i]),
+    "effimvs_conv3d_bf16": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "effimvs_costreg_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "effimvs_costreg_fpn3d": (_i, [_p, _pp, _pp, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "effimvs_cost_up_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),

@@ -7,17 +7,23 @@
 //
 // Data layout ("c8 planar, padded"): an activation tensor with C channels on a (D,H,W) grid is
 // stored as C/8 channel planes; a plane is a zero-padded (D+2,H+2,W+2) volume of 16-byte voxels
-// (8 bf16 channels), preceded and followed by a guard of Px+8 voxels.  A tile is 128 consecutive
-// padded positions q = yp*Px + xp of one z plane.  For a tap (a,b,c) the 128 input voxels of the
-// tile are again 128 consecutive voxels, i.e. exactly the canonical K-major / no-swizzle UMMA
-// operand (8 rows x 16 bytes per core matrix, SBO = 128 B) at a shifted shared-memory address:
-// the im2col matrix is never built, the MMA descriptors just point into the staged rows, and the
-// x-taps (c = 0,1,2) share one staged row.  K = 16 per MMA is two 8-channel chunks whose distance
-// is the descriptor's LBO: two taps for an 8-channel input, two channel planes otherwise.
+// (8 bf16 channels), preceded and followed by a guard.  A tile is 128 consecutive padded positions
+// q = yp*Px + xp of one z plane.  For a tap (a,b,c) the 128 input voxels of the tile are again 128
+// consecutive voxels, i.e. exactly the canonical K-major / no-swizzle UMMA operand (8 rows x 16
+// bytes per core matrix, SBO = 128 B) at a shifted shared-memory address: the im2col matrix is
+// never built, the MMA descriptors just point into the staged rows, and the x-taps (c = 0,1,2)
+// share one staged row.  K = 16 per MMA is two 8-channel chunks whose distance is the descriptor's
+// LBO: two taps for an 8-channel input, two channel planes otherwise.
 // Stride-2 convolutions read a parity-split copy of their input (8 sub-volumes, each a padded
 // half-resolution volume), which the producing layer's epilogue writes directly; transposed
 // convolutions accumulate the 8 (or 4) output parity classes in separate TMEM column ranges.
 // The positions of a tile that fall on the halo compute garbage that is never stored.
+//
+// Precision modes.  EFFIMVS_PREC_BF16: one bf16 MMA per K chunk pair.  EFFIMVS_PREC_BF16X3:
+// activations and weights are carried as hi + lo bf16 pairs (x = hi + lo to 16 mantissa bits) and
+// every product is formed as hi*hi + hi*lo + lo*hi in three bf16 MMAs with fp32 accumulation --
+// fp32-grade results (needed for the 1e-3 depth tolerance) at tensor-core rate.  32-channel inputs
+// are then processed in two K phases (channel-plane pairs) through the same shared-memory slab.
 //
 // One tile per CTA: warp 4 lane 0 issues the bulk copies, waits on the mbarrier, issues the
 // tcgen05.mma sequence and commits; warps 0-3 own TMEM lanes 32w..32w+31 (= tile rows) and run
@@ -26,6 +32,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -36,22 +43,27 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int SEG_VOX = 136;  // 128 + 2 (x halo) + 1 (dummy chunk) rounded up to a multiple of 8
 constexpr int SEG_BYTES = SEG_VOX * 16;
-constexpr int MAX_SEGS = 36;
-constexpr int MAX_OPS = 54;
+constexpr int MAX_SEGS = 72;
+constexpr int MAX_OPS = 168;
+constexpr int MAX_BLOCKS = 112;  // packed weight blocks (one K chunk pair each)
+constexpr int MAX_PHASES = 2;
 
 enum { L_REG = 0, L_SPLIT = 1 };
 
 struct ActLayout {
-    int kind, planes, D, H, W;  // logical dims of the tensor
+    int kind, planes, D, H, W;  // logical dims of the tensor; planes counts hi and lo halves
+    int lo_off;                 // plane offset of the lo half (0: plain bf16 tensor)
     int Py, Px, guard;          // padded dims of one (sub-)volume
     long long zstride;          // Py * Px
     long long vs;               // voxels per (sub-)volume including both guards
     long long batch_stride;     // voxels per batch item
 };
 
-ActLayout make_layout(int kind, int C, int D, int H, int W) {
+ActLayout make_layout(int kind, int C, int D, int H, int W, bool hilo) {
     ActLayout L;
-    L.kind = kind; L.planes = C / 8; L.D = D; L.H = H; L.W = W;
+    L.kind = kind; L.D = D; L.H = H; L.W = W;
+    L.lo_off = hilo ? C / 8 : 0;
+    L.planes = (C / 8) * (hilo ? 2 : 1);
     int d = D, h = H, w = W;
     if (kind == L_SPLIT) { d /= 2; h /= 2; w /= 2; }
     L.Py = h + 2; L.Px = w + 2; L.guard = L.Px + 136;  // a tile may over-read up to 129 voxels past the last plane
@@ -71,21 +83,23 @@ __host__ __device__ inline long long act_index(const ActLayout& L, int b, int pl
            (long long)((z >> 1) + 1) * L.zstride + (long long)((y >> 1) + 1) * L.Px + ((x >> 1) + 1);
 }
 
-struct Seg { long long src_off; int copy_vox; int pad_; };
-struct Op { uint32_t a_off, a_lbo, b_off; uint16_t d_col, accum; };
-struct Chunk { short tap, cbase; };  // weight source of one 8-wide K chunk (tap < 0: zeros)
+struct Seg { long long src_off; int copy_vox; int slot; };          // slot: shared-memory segment index within its phase
+struct Op { uint32_t a_off, a_lbo, b_off; uint16_t d_col; uint8_t accum, pad_; };
+struct Phase { int seg_begin, seg_end, op_begin, op_end, w_off, w_bytes; };
+struct Block { short tap0, cb0, tap1, cb1, lo, pad_; };               // weight source of one packed K chunk pair
 
 struct ConvProgram {
-    int n_segs, n_ops;
-    int N, n_classes, cout, w_bytes, tmem_cols;
+    int n_phases;
+    int N, n_classes, cout, tmem_cols;
     int gD, gH, gW, gPx;          // tile grid (output grid for conv, input grid for transposed conv)
     long long zstride;            // voxels per padded z plane of the input (sub-)volumes
     int up_z, up_y, up_x;         // output coordinate = grid coordinate * up + class bit
-    int relu, transposed;
+    int relu, w_smem_off;         // weights live at this byte offset of dynamic shared memory
+    Phase ph[MAX_PHASES];
     Seg segs[MAX_SEGS];
     Op ops[MAX_OPS];
 };
-struct PackTable { int n_ops, N, cout, cin, transposed; Chunk ch[MAX_OPS][2]; };
+struct PackTable { int n_blocks, N, cout, cin, transposed; Block blk[MAX_BLOCKS]; };
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -153,28 +167,69 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ uint4 pack_bf16x8(const float (&v)[8]) {
+    uint4 o;
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    return o;
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& r, float (&v)[8]) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(p[j]);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+    }
+}
+// store 8 channels of one voxel; hi/lo layouts get the bf16 value and the bf16 of the remainder
+__device__ __forceinline__ void store_voxel(uint4* __restrict__ out, const ActLayout& L, int b, int g, int z, int y, int x,
+                                            const float (&v)[8]) {
+    const uint4 hi = pack_bf16x8(v);
+    out[act_index(L, b, g, z, y, x)] = hi;
+    if (L.lo_off) {
+        float h[8], r[8];
+        unpack_bf16x8(hi, h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = v[j] - h[j];
+        out[act_index(L, b, g + L.lo_off, z, y, x)] = pack_bf16x8(r);
+    }
+}
+__device__ __forceinline__ void load_voxel(const uint4* __restrict__ in, const ActLayout& L, int b, int g, int z, int y, int x,
+                                           float (&v)[8]) {
+    unpack_bf16x8(__ldg(in + act_index(L, b, g, z, y, x)), v);
+    if (L.lo_off) {
+        float l[8];
+        unpack_bf16x8(__ldg(in + act_index(L, b, g + L.lo_off, z, y, x)), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += l[j];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the tile kernel
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(160)
 conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ in, long long in_batch_stride,
-               const uint4* __restrict__ wpk, const float* __restrict__ bias, const ActLayout OL, uint4* __restrict__ out,
+               const uint8_t* __restrict__ wpk, const float* __restrict__ bias, const ActLayout OL, uint4* __restrict__ out,
                const ActLayout RL, const uint4* __restrict__ res, float* __restrict__ out_f32) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_load, bar_mma;
+    __shared__ __align__(8) uint64_t bar_load, bar_step, bar_done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.y, b = blockIdx.z;
     const long long q0 = (long long)P.gPx + (long long)blockIdx.x * TILE_M;  // first tile starts at padded row yp = 1
     uint8_t* slab = smem;
-    uint8_t* wsm = smem + (size_t)P.n_segs * SEG_BYTES;
+    uint8_t* wsm = smem + P.w_smem_off;
 
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)P.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         if (lane == 0) {
             mbar_init(&bar_load, 1);
-            mbar_init(&bar_mma, 1);
+            mbar_init(&bar_step, 1);
+            mbar_init(&bar_done, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -185,23 +240,30 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
 
     if (warp == 4) {
         if (lane == 0) {
-            uint32_t bytes = (uint32_t)P.w_bytes;
-            for (int s = 0; s < P.n_segs; ++s) bytes += (uint32_t)P.segs[s].copy_vox * 16u;
-            mbar_expect_tx(&bar_load, bytes);
             const uint4* base = in + (long long)b * in_batch_stride + (long long)z * P.zstride + q0;
-            for (int s = 0; s < P.n_segs; ++s)
-                bulk_g2s(slab + (size_t)s * SEG_BYTES, base + P.segs[s].src_off, (uint32_t)P.segs[s].copy_vox * 16u, &bar_load);
-            bulk_g2s(wsm, wpk, (uint32_t)P.w_bytes, &bar_load);
-            mbar_wait(&bar_load, 0);
-            tc_fence_after();
             const uint32_t a0 = smem_u32(slab), b0 = smem_u32(wsm);
             const uint32_t idesc = umma_idesc(P.N);
-            for (int i = 0; i < P.n_ops; ++i) {
-                const Op op = P.ops[i];
-                umma_bf16(tmem + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, (uint32_t)P.N * 16u, 128),
-                          idesc, op.accum);
+            for (int p = 0; p < P.n_phases; ++p) {
+                const Phase ph = P.ph[p];
+                if (p > 0) {                       // the previous phase's MMAs must have consumed the slab
+                    mbar_wait(&bar_step, (uint32_t)((p - 1) & 1));
+                    tc_fence_after();
+                }
+                uint32_t bytes = (uint32_t)ph.w_bytes;
+                for (int s = ph.seg_begin; s < ph.seg_end; ++s) bytes += (uint32_t)P.segs[s].copy_vox * 16u;
+                mbar_expect_tx(&bar_load, bytes);
+                for (int s = ph.seg_begin; s < ph.seg_end; ++s)
+                    bulk_g2s(slab + (size_t)P.segs[s].slot * SEG_BYTES, base + P.segs[s].src_off, (uint32_t)P.segs[s].copy_vox * 16u, &bar_load);
+                bulk_g2s(wsm, wpk + ph.w_off, (uint32_t)ph.w_bytes, &bar_load);
+                mbar_wait(&bar_load, (uint32_t)(p & 1));
+                tc_fence_after();
+                for (int i = ph.op_begin; i < ph.op_end; ++i) {
+                    const Op op = P.ops[i];
+                    umma_bf16(tmem + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, (uint32_t)P.N * 16u, 128),
+                              idesc, op.accum);
+                }
+                umma_commit(p + 1 < P.n_phases ? &bar_step : &bar_done);
             }
-            umma_commit(&bar_mma);
         }
         __syncwarp();
     } else {
@@ -210,7 +272,7 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
         const int yp = (int)(q / P.gPx), xp = (int)(q - (long long)yp * P.gPx);
         const bool interior = yp >= 1 && yp <= P.gH && xp >= 1 && xp <= P.gW;
         const int gy = yp - 1, gx = xp - 1;
-        mbar_wait(&bar_mma, 0);
+        mbar_wait(&bar_done, 0);
         tc_fence_after();
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         const int groups = (P.cout + 7) / 8;
@@ -233,20 +295,12 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                     continue;
                 }
                 if (res) {
-                    const uint4 r = __ldg(res + act_index(RL, b, g, oz, oy, ox));
-                    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
+                    float r[8];
+                    load_voxel(res, RL, b, g, oz, oy, ox, r);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = __bfloat1622float2(rp[j]);
-                        v[2 * j] += f.x;
-                        v[2 * j + 1] += f.y;
-                    }
+                    for (int j = 0; j < 8; ++j) v[j] += r[j];
                 }
-                uint4 o;
-                __nv_bfloat162* op2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) op2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                out[act_index(OL, b, g, oz, oy, ox)] = o;
+                store_voxel(out, OL, b, g, oz, oy, ox, v);
             }
         }
     }
@@ -259,18 +313,21 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // helper kernels: weight packing, single-input-channel convolution (CUDA cores), layout conversion
 // ------------------------------------------------------------------------------------------------
-// packed B operand of op i: [chunk j][row n][8 k] bf16; row n = output channel (zero beyond cout)
+// packed block: [chunk j][row n][8 k] bf16; row n = output channel (zero beyond cout).  lo blocks hold
+// bf16(w - bf16(w)).
 __global__ void pack_weights_kernel(const __grid_constant__ PackTable T, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
-    const int total = T.n_ops * 2 * T.N * 8;
+    const int total = T.n_blocks * 2 * T.N * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int kk = i & 7, n = (i >> 3) % T.N, j = (i / (8 * T.N)) & 1, op = i / (16 * T.N);
-        const Chunk c = T.ch[op][j];
+        const int kk = i & 7, n = (i >> 3) % T.N, j = (i / (8 * T.N)) & 1, blk = i / (16 * T.N);
+        const Block c = T.blk[blk];
+        const int tap = j ? c.tap1 : c.tap0, cb = j ? c.cb1 : c.cb0;
         float v = 0.0f;
-        if (c.tap >= 0 && n < T.cout) {
-            const int ci = c.cbase + kk;
-            v = T.transposed ? w[((size_t)ci * T.cout + n) * 27 + c.tap] : w[((size_t)n * T.cin + ci) * 27 + c.tap];
+        if (tap >= 0 && n < T.cout) {
+            const int ci = cb + kk;
+            v = T.transposed ? w[((size_t)ci * T.cout + n) * 27 + tap] : w[((size_t)n * T.cin + ci) * 27 + tap];
         }
-        dst[i] = __float2bfloat16(v);
+        __nv_bfloat16 hi = __float2bfloat16(v);
+        dst[i] = c.lo ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
     }
 }
 
@@ -279,7 +336,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable T, const f
 __global__ void __launch_bounds__(128)
 conv_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int D, int H, int W,
                  int s, const ActLayout OL, int plane, uint4* __restrict__ out) {
-    __shared__ float sw[27 * 8 + 8];
+    __shared__ __align__(16) float sw[27 * 8 + 8];
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];  // [tap][co]
     if (threadIdx.x < 8) sw[216 + threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
@@ -312,96 +369,145 @@ conv_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w, const
             }
         }
     }
-    uint4 r;
-    __nv_bfloat162* rp = reinterpret_cast<__nv_bfloat162*>(&r);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) rp[j] = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.0f), fmaxf(acc[2 * j + 1], 0.0f));
-    out[act_index(OL, b, plane, oz, oy, ox)] = r;
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.0f);
+    store_voxel(out, OL, b, plane, oz, oy, ox, acc);
 }
 
 // fp32 NCDHW <-> c8 layouts (single-layer entry point and tests)
 __global__ void to_c8_kernel(const float* __restrict__ x, int C, const ActLayout L, uint4* __restrict__ out) {
     const int b = blockIdx.y;
+    const int groups = (C + 7) / 8;
     const size_t vox = (size_t)L.D * L.H * L.W;
     const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= vox * L.planes) return;
-    const int plane = (int)(o / vox);
+    if (o >= vox * groups) return;
+    const int g = (int)(o / vox);
     const size_t r = o % vox;
     const int xx = (int)(r % L.W), yy = (int)((r / L.W) % L.H), zz = (int)(r / ((size_t)L.W * L.H));
-    uint4 v;
-    __nv_bfloat16* vp = reinterpret_cast<__nv_bfloat16*>(&v);
+    float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = plane * 8 + j;
-        vp[j] = __float2bfloat16(c < C ? x[((size_t)b * C + c) * vox + r] : 0.0f);
+        const int c = g * 8 + j;
+        v[j] = c < C ? x[((size_t)b * C + c) * vox + r] : 0.0f;
     }
-    out[act_index(L, b, plane, zz, yy, xx)] = v;
+    store_voxel(out, L, b, g, zz, yy, xx, v);
 }
 __global__ void from_c8_kernel(const uint4* __restrict__ in, int C, const ActLayout L, float* __restrict__ y) {
     const int b = blockIdx.y;
+    const int groups = (C + 7) / 8;
     const size_t vox = (size_t)L.D * L.H * L.W;
     const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= vox * L.planes) return;
-    const int plane = (int)(o / vox);
+    if (o >= vox * groups) return;
+    const int g = (int)(o / vox);
     const size_t r = o % vox;
     const int xx = (int)(r % L.W), yy = (int)((r / L.W) % L.H), zz = (int)(r / ((size_t)L.W * L.H));
-    const uint4 v = in[act_index(L, b, plane, zz, yy, xx)];
-    const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(&v);
+    float v[8];
+    load_voxel(in, L, b, g, zz, yy, xx, v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int c = plane * 8 + j;
-        if (c < C) y[((size_t)b * C + c) * vox + r] = __bfloat162float(vp[j]);
+        const int c = g * 8 + j;
+        if (c < C) y[((size_t)b * C + c) * vox + r] = v[j];
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host: program builders
 // ------------------------------------------------------------------------------------------------
-struct Term { int seg, byte_off, tap, cls; };  // seg: index within plane 0's segments
+struct Term { int seg, byte_off, tap, cls; };      // seg: index within one plane's segments
+struct PlaneSeg { long long off; int copy_vox; };  // per-plane segment: source offset relative to the plane base
 
 int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
-// Turns the tap terms into MMA ops.  NP = Cin / 8 channel planes, SPP = segments per plane.
-bool emit_ops(ConvProgram& P, PackTable& T, std::vector<Term> terms, int NP, int SPP) {
+// Assembles segments, MMA ops and packed-weight blocks.
+//   NP channel planes (Cin / 8), segments per plane `pseg`, `plane_stride` voxels between planes,
+//   hilo: operands carried as hi + lo bf16 (three MMA products per K chunk pair).
+// Shared-memory slot of (half h, local plane pl, plane segment k) inside a phase: (h * NPph + pl) * SPP + k.
+bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, const std::vector<PlaneSeg>& pseg, int NP,
+              long long plane_stride, long long lo_plane_off, bool hilo) {
+    const int SPP = (int)pseg.size();
+    const int halves = hilo ? 2 : 1;
+    // K phases: hi/lo with 4 planes does not fit one slab -> one phase per plane pair
+    const int n_phases = (hilo && NP == 4) ? 2 : 1;
+    const int NPph = NP / n_phases;
+    if (n_phases > MAX_PHASES) return false;
+    P.n_phases = n_phases;
+    int n_seg = 0, n_op = 0, n_blk = 0;
     std::vector<bool> started(P.n_classes, false);
-    int n = 0;
-    auto push = [&](uint32_t a_off, uint32_t lbo, int cls, Chunk c0, Chunk c1) {
-        if (n >= MAX_OPS) return false;
-        Op& op = P.ops[n];
-        op.a_off = a_off; op.a_lbo = lbo; op.b_off = (uint32_t)n * 2u * P.N * 16u;
-        op.d_col = (uint16_t)(cls * P.N); op.accum = started[cls] ? 1 : 0;
-        started[cls] = true;
-        T.ch[n][0] = c0; T.ch[n][1] = c1;
-        ++n;
-        return true;
-    };
-    if (NP == 1) {
-        // pair taps of the same class in ascending shared-memory address (LBO must be positive)
-        for (int cls = 0; cls < P.n_classes; ++cls) {
-            std::vector<Term> v;
-            for (auto& t : terms) if (t.cls == cls) v.push_back(t);
-            std::sort(v.begin(), v.end(), [](const Term& x, const Term& y) { return x.seg * SEG_BYTES + x.byte_off < y.seg * SEG_BYTES + y.byte_off; });
-            for (size_t i = 0; i < v.size(); i += 2) {
-                uint32_t a0 = (uint32_t)(v[i].seg * SEG_BYTES + v[i].byte_off);
-                if (i + 1 < v.size()) {
-                    uint32_t a1 = (uint32_t)(v[i + 1].seg * SEG_BYTES + v[i + 1].byte_off);
-                    if (!push(a0, a1 - a0, cls, Chunk{(short)v[i].tap, 0}, Chunk{(short)v[i + 1].tap, 0})) return false;
-                } else {
-                    if (!push(a0, 16, cls, Chunk{(short)v[i].tap, 0}, Chunk{-1, 0})) return false;  // zero-weight dummy chunk
+    size_t max_slab = 0;
+    struct Base { uint32_t a_off, lbo; int cls; Block blk; };
+    for (int ph = 0; ph < n_phases; ++ph) {
+        Phase& F = P.ph[ph];
+        F.seg_begin = n_seg; F.op_begin = n_op;
+        const int blk_begin = n_blk;
+        for (int h = 0; h < halves; ++h)
+            for (int pl = 0; pl < NPph; ++pl)
+                for (int k = 0; k < SPP; ++k) {
+                    if (n_seg >= MAX_SEGS) return false;
+                    Seg& s = P.segs[n_seg++];
+                    s.src_off = (long long)(ph * NPph + pl) * plane_stride + (h ? lo_plane_off : 0) + pseg[k].off;
+                    s.copy_vox = pseg[k].copy_vox;
+                    s.slot = (h * NPph + pl) * SPP + k;
+                }
+        const uint32_t lo_smem = (uint32_t)(NPph * SPP * SEG_BYTES);  // hi -> lo distance in the slab
+        const uint32_t blk_bytes = 2u * P.N * 16u;
+        std::vector<Base> bases;
+        if (NP == 1) {
+            // 8 input channels: pair taps of the same class in ascending shared-memory address (LBO > 0)
+            for (int cls = 0; cls < P.n_classes; ++cls) {
+                std::vector<Term> v;
+                for (auto& t : terms) if (t.cls == cls) v.push_back(t);
+                std::sort(v.begin(), v.end(), [](const Term& x, const Term& y) { return x.seg * SEG_BYTES + x.byte_off < y.seg * SEG_BYTES + y.byte_off; });
+                for (size_t i = 0; i < v.size(); i += 2) {
+                    const uint32_t a0 = (uint32_t)(v[i].seg * SEG_BYTES + v[i].byte_off);
+                    if (i + 1 < v.size()) {
+                        const uint32_t a1 = (uint32_t)(v[i + 1].seg * SEG_BYTES + v[i + 1].byte_off);
+                        bases.push_back(Base{a0, a1 - a0, cls, Block{(short)v[i].tap, 0, (short)v[i + 1].tap, 0, 0, 0}});
+                    } else {
+                        bases.push_back(Base{a0, 16, cls, Block{(short)v[i].tap, 0, -1, 0, 0, 0}});  // zero-weight dummy chunk
+                    }
                 }
             }
+        } else {
+            for (auto& t : terms)
+                for (int pl = 0; pl < NPph; pl += 2) {
+                    const int cb = (ph * NPph + pl) * 8;
+                    bases.push_back(Base{(uint32_t)((pl * SPP + t.seg) * SEG_BYTES + t.byte_off), (uint32_t)(SPP * SEG_BYTES), t.cls,
+                                         Block{(short)t.tap, (short)cb, (short)t.tap, (short)(cb + 8), 0, 0}});
+                }
         }
-    } else {
-        for (auto& t : terms)
-            for (int p = 0; p < NP; p += 2)
-                if (!push((uint32_t)((p * SPP + t.seg) * SEG_BYTES + t.byte_off), (uint32_t)(SPP * SEG_BYTES), t.cls,
-                          Chunk{(short)t.tap, (short)(p * 8)}, Chunk{(short)t.tap, (short)(p * 8 + 8)}))
-                    return false;
+        for (auto& bs : bases) {
+            if (n_blk + halves > MAX_BLOCKS || n_op + (hilo ? 3 : 1) > MAX_OPS) return false;
+            const uint32_t b_hi = (uint32_t)(n_blk - blk_begin) * blk_bytes;
+            T.blk[n_blk] = bs.blk; T.blk[n_blk].lo = 0; ++n_blk;
+            uint32_t b_lo = 0;
+            if (hilo) { b_lo = (uint32_t)(n_blk - blk_begin) * blk_bytes; T.blk[n_blk] = bs.blk; T.blk[n_blk].lo = 1; ++n_blk; }
+            auto push = [&](uint32_t a_off, uint32_t b_off) {
+                Op& op = P.ops[n_op++];
+                op.a_off = a_off; op.a_lbo = bs.lbo; op.b_off = b_off;
+                op.d_col = (uint16_t)(bs.cls * P.N); op.accum = started[bs.cls] ? 1 : 0; op.pad_ = 0;
+                started[bs.cls] = true;
+            };
+            push(bs.a_off, b_hi);                 // x_hi * w_hi
+            if (hilo) {
+                push(bs.a_off, b_lo);             // x_hi * w_lo
+                push(bs.a_off + lo_smem, b_hi);   // x_lo * w_hi
+            }
+        }
+        F.seg_end = n_seg; F.op_end = n_op;
+        F.w_off = (int)((size_t)blk_begin * blk_bytes); F.w_bytes = (int)((size_t)(n_blk - blk_begin) * blk_bytes);
+        max_slab = std::max(max_slab, (size_t)halves * NPph * SPP * SEG_BYTES);
     }
-    P.n_ops = T.n_ops = n;
-    P.w_bytes = n * 2 * P.N * 16;
+    T.n_blocks = n_blk;
+    P.w_smem_off = (int)max_slab;
     return true;
 }
+
+size_t program_smem(const ConvProgram& P) {
+    size_t w = 0;
+    for (int p = 0; p < P.n_phases; ++p) w = std::max(w, (size_t)P.ph[p].w_bytes);
+    return (size_t)P.w_smem_off + w;
+}
+size_t program_weight_bytes(const PackTable& T) { return (size_t)T.n_blocks * 2 * T.N * 16; }
 
 void init_program(ConvProgram& P, PackTable& T, int Cin, int Cout, int n_classes, int gD, int gH, int gW, const ActLayout& IL,
                   int relu, int transposed) {
@@ -410,97 +516,77 @@ void init_program(ConvProgram& P, PackTable& T, int Cin, int Cout, int n_classes
     P.N = std::max(16, (Cout + 15) / 16 * 16);
     P.n_classes = n_classes; P.cout = Cout; P.tmem_cols = pow2_cols(P.N * n_classes);
     P.gD = gD; P.gH = gH; P.gW = gW; P.gPx = IL.Px; P.zstride = IL.zstride;
-    P.up_z = P.up_y = P.up_x = 1; P.relu = relu; P.transposed = transposed;
+    P.up_z = P.up_y = P.up_x = 1; P.relu = relu;
     T.N = P.N; T.cout = Cout; T.cin = Cin; T.transposed = transposed;
 }
 
 // stride-1 convolution, input REGULAR on the output grid
 bool build_conv_s1(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLayout& IL, int relu) {
     init_program(P, T, Cin, Cout, 1, IL.D, IL.H, IL.W, IL, relu, 0);
-    const int NP = Cin / 8, SPP = 9;
-    if (NP * SPP > MAX_SEGS) return false;
-    for (int p = 0; p < NP; ++p)
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) {
-                Seg& s = P.segs[(p * 3 + a) * 3 + b];
-                s.src_off = (long long)p * IL.vs + IL.guard + (long long)a * IL.zstride + (long long)(b - 1) * IL.Px - 1;
-                s.copy_vox = TILE_M + 3;
-            }
-    P.n_segs = NP * SPP;
+    std::vector<PlaneSeg> pseg;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            pseg.push_back(PlaneSeg{IL.guard + (long long)a * IL.zstride + (long long)(b - 1) * IL.Px - 1, TILE_M + 3});
     std::vector<Term> terms;
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
             for (int c = 0; c < 3; ++c) terms.push_back(Term{a * 3 + b, c * 16, a * 9 + b * 3 + c, 0});
-    return emit_ops(P, T, terms, NP, SPP);
+    return assemble(P, T, terms, pseg, Cin / 8, IL.vs, (long long)IL.lo_off * IL.vs, IL.lo_off != 0);
 }
 
 // stride-(2,2,2) convolution, input PARITY-SPLIT (its sub-volumes live on the output grid)
 bool build_conv_s2(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLayout& IL, int relu) {
     init_program(P, T, Cin, Cout, 1, IL.D / 2, IL.H / 2, IL.W / 2, IL, relu, 0);
-    const int NP = Cin / 8, SPP = 18;
-    if (NP * SPP > MAX_SEGS) return false;
-    for (int p = 0; p < NP; ++p)
-        for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b)
-                for (int ex = 0; ex < 2; ++ex) {
-                    const int sub = ((a != 1) << 2) | ((b != 1) << 1) | ex;
-                    Seg& s = P.segs[p * SPP + (a * 3 + b) * 2 + ex];
-                    s.src_off = (long long)(p * 8 + sub) * IL.vs + IL.guard + (long long)(a == 0 ? 0 : 1) * IL.zstride +
-                                (long long)(b == 0 ? -1 : 0) * IL.Px - ex;
-                    s.copy_vox = TILE_M + 2;
-                }
-    P.n_segs = NP * SPP;
+    std::vector<PlaneSeg> pseg;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            for (int ex = 0; ex < 2; ++ex) {
+                // input coordinate 2o + k - 1: k = 1 -> even sub-volume, index o; k = 0 / 2 -> odd sub-volume, index o - 1 / o
+                const int sub = ((a != 1) << 2) | ((b != 1) << 1) | ex;
+                pseg.push_back(PlaneSeg{(long long)sub * IL.vs + IL.guard + (long long)(a == 0 ? 0 : 1) * IL.zstride +
+                                            (long long)(b == 0 ? -1 : 0) * IL.Px - ex, TILE_M + 2});
+            }
     std::vector<Term> terms;
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
-            for (int c = 0; c < 3; ++c) {
-                const int ex = (c != 1);
-                terms.push_back(Term{(a * 3 + b) * 2 + ex, c == 2 ? 16 : 0, a * 9 + b * 3 + c, 0});
-            }
-    return emit_ops(P, T, terms, NP, SPP);
+            for (int c = 0; c < 3; ++c) terms.push_back(Term{(a * 3 + b) * 2 + (c != 1), c == 2 ? 16 : 0, a * 9 + b * 3 + c, 0});
+    return assemble(P, T, terms, pseg, Cin / 8, 8 * IL.vs, (long long)IL.lo_off * 8 * IL.vs, IL.lo_off != 0);
 }
 
 // transposed convolution, stride (sz,2,2) with sz in {1,2}; input REGULAR; tile grid = input grid
 bool build_deconv(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLayout& IL, int sz, int relu) {
-    const int n_classes = sz == 2 ? 8 : 4;
-    init_program(P, T, Cin, Cout, n_classes, IL.D, IL.H, IL.W, IL, relu, 1);
+    init_program(P, T, Cin, Cout, sz == 2 ? 8 : 4, IL.D, IL.H, IL.W, IL, relu, 1);
     P.up_z = sz; P.up_y = 2; P.up_x = 2;
-    const int NP = Cin / 8, NZ = sz == 2 ? 2 : 3, SPP = NZ * 2;
-    if (NP * SPP > MAX_SEGS) return false;
-    // z slot k holds padded input plane z + (sz == 2 ? 1 + k : k), i.e. input z + k or z - 1 + k
-    for (int p = 0; p < NP; ++p)
-        for (int k = 0; k < NZ; ++k)
-            for (int dy = 0; dy < 2; ++dy) {
-                Seg& s = P.segs[p * SPP + k * 2 + dy];
-                s.src_off = (long long)p * IL.vs + IL.guard + (long long)(sz == 2 ? 1 + k : k) * IL.zstride + (long long)dy * IL.Px;
-                s.copy_vox = TILE_M + 2;
-            }
-    P.n_segs = NP * SPP;
+    const int NZ = sz == 2 ? 2 : 3;
+    // z slot k holds padded input plane z + (sz == 2 ? 1 + k : k), i.e. input z + k (stride 2) or z - 1 + k (stride 1)
+    std::vector<PlaneSeg> pseg;
+    for (int k = 0; k < NZ; ++k)
+        for (int dy = 0; dy < 2; ++dy)
+            pseg.push_back(PlaneSeg{IL.guard + (long long)(sz == 2 ? 1 + k : k) * IL.zstride + (long long)dy * IL.Px, TILE_M + 2});
     std::vector<Term> terms;
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
             for (int c = 0; c < 3; ++c) {
-                // output o = s*i + k - 1:  stride 2: class bit = (k != 1), input offset +1 when k == 0;  stride 1: i = o + 1 - k
+                // output o = s*i + k - 1.  stride 2: class bit = (k != 1), input offset +1 when k == 0.  stride 1: i = o + 1 - k.
                 const int kz = sz == 2 ? (a == 0) : (2 - a);
-                const int pz = sz == 2 ? (a != 1) : 0;
-                const int cls = sz == 2 ? ((pz << 2) | ((b != 1) << 1) | (c != 1)) : (((b != 1) << 1) | (c != 1));
+                const int cls = sz == 2 ? (((a != 1) << 2) | ((b != 1) << 1) | (c != 1)) : (((b != 1) << 1) | (c != 1));
                 terms.push_back(Term{kz * 2 + (b == 0), (c == 0) * 16, a * 9 + b * 3 + c, cls});
             }
-    return emit_ops(P, T, terms, NP, SPP);
+    return assemble(P, T, terms, pseg, Cin / 8, IL.vs, (long long)IL.lo_off * IL.vs, IL.lo_off != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host: launches
 // ------------------------------------------------------------------------------------------------
 int run_pack(const PackTable& T, const float* w, void* dst, cudaStream_t st) {
-    int total = T.n_ops * 2 * T.N * 8;
+    int total = T.n_blocks * 2 * T.N * 8;
     pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(T, w, (__nv_bfloat16*)dst);
     return check_launch("pack_weights_kernel");
 }
 
 int run_tile_kernel(const ConvProgram& P, int B, const void* in, const ActLayout& IL, const void* wpk, const float* bias,
                     const ActLayout& OL, void* out, const ActLayout* RL, const void* res, float* out_f32, cudaStream_t st) {
-    size_t smem = (size_t)P.n_segs * SEG_BYTES + P.w_bytes;
+    size_t smem = program_smem(P);
     EFFI_REQUIRE(smem <= 220 * 1024, EFFIMVS_EUNSUPPORTED, "conv_tc: tile needs %zu bytes of shared memory", smem);
     static bool attr_set = false;
     if (!attr_set) {
@@ -511,7 +597,7 @@ int run_tile_kernel(const ConvProgram& P, int B, const void* in, const ActLayout
     int tiles = ceil_div(P.gH * P.gPx, TILE_M);
     dim3 grid(tiles, P.gD, B), block(160);
     ActLayout rl = RL ? *RL : OL;
-    conv_tc_kernel<<<grid, block, smem, st>>>(P, (const uint4*)in, IL.batch_stride, (const uint4*)wpk, bias, OL, (uint4*)out, rl,
+    conv_tc_kernel<<<grid, block, smem, st>>>(P, (const uint4*)in, IL.batch_stride, (const uint8_t*)wpk, bias, OL, (uint4*)out, rl,
                                               (const uint4*)res, out_f32);
     return check_launch("conv_tc_kernel");
 }
@@ -529,29 +615,29 @@ struct Carver {
     void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; }
 };
 
-constexpr size_t W_SLOT = 64 * 1024;  // packed weights of one layer (<= 54 ops * 2 * 32 * 16 B = 55 KiB)
+constexpr size_t W_SLOT = 128 * 1024;  // packed weights of one layer (<= 108 blocks * 2 * 32 * 16 B)
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // a9 on tensor cores
 // ------------------------------------------------------------------------------------------------
-size_t costreg_bf16_workspace_bytes(int B, int D, int H, int W) {
-    ActLayout c0 = make_layout(L_REG, 8, D, H, W), c1 = make_layout(L_SPLIT, 8, D, H, W);
-    ActLayout c2 = make_layout(L_REG, 16, D / 2, H / 2, W / 2), c3 = make_layout(L_SPLIT, 16, D / 2, H / 2, W / 2);
-    ActLayout c4 = make_layout(L_REG, 32, D / 4, H / 4, W / 4);
+size_t costreg_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo) {
+    ActLayout c0 = make_layout(L_REG, 8, D, H, W, hilo), c1 = make_layout(L_SPLIT, 8, D, H, W, hilo);
+    ActLayout c2 = make_layout(L_REG, 16, D / 2, H / 2, W / 2, hilo), c3 = make_layout(L_SPLIT, 16, D / 2, H / 2, W / 2, hilo);
+    ActLayout c4 = make_layout(L_REG, 32, D / 4, H / 4, W / 4, hilo);
     return layout_bytes(c0, B) * 2 + layout_bytes(c1, B) + layout_bytes(c2, B) * 2 + layout_bytes(c3, B) + layout_bytes(c4, B) * 2 +
            8 * W_SLOT + 4096;
 }
 
-int costreg_bf16(const float* x, const float* const* weights, const float* const* biases, int B, int D, int H, int W, void* ws,
-                 size_t ws_bytes, float* prob_out, cudaStream_t st) {
+int costreg_bf16(const float* x, const float* const* weights, const float* const* biases, int B, int D, int H, int W, bool hilo,
+                 void* ws, size_t ws_bytes, float* prob_out, cudaStream_t st) {
     EFFI_REQUIRE(D % 4 == 0 && H % 4 == 0 && W % 4 == 0, EFFIMVS_EUNSUPPORTED, "costreg bf16: D, H, W must be multiples of 4");
-    EFFI_REQUIRE(D / 4 <= 65535 && B <= 65535, EFFIMVS_EUNSUPPORTED, "costreg bf16: D or B too large");
+    EFFI_REQUIRE(D <= 65535 && B <= 65535, EFFIMVS_EUNSUPPORTED, "costreg bf16: D or B too large");
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2, D4 = D / 4, H4 = H / 4, W4 = W / 4;
-    ActLayout L0 = make_layout(L_REG, 8, D, H, W), L1 = make_layout(L_SPLIT, 8, D, H, W);
-    ActLayout L2 = make_layout(L_REG, 16, D2, H2, W2), L3 = make_layout(L_SPLIT, 16, D2, H2, W2);
-    ActLayout L4 = make_layout(L_REG, 32, D4, H4, W4), L5 = L4, L6 = L2, L7 = L0;
+    ActLayout L0 = make_layout(L_REG, 8, D, H, W, hilo), L1 = make_layout(L_SPLIT, 8, D, H, W, hilo);
+    ActLayout L2 = make_layout(L_REG, 16, D2, H2, W2, hilo), L3 = make_layout(L_SPLIT, 16, D2, H2, W2, hilo);
+    ActLayout L4 = make_layout(L_REG, 32, D4, H4, W4, hilo), L5 = L4, L6 = L2, L7 = L0;
     Carver cv{(char*)ws, 0, ws_bytes};
     void* c0 = cv.take(layout_bytes(L0, B)); void* c7 = cv.take(layout_bytes(L7, B)); void* c1 = cv.take(layout_bytes(L1, B));
     void* c2 = cv.take(layout_bytes(L2, B)); void* c6 = cv.take(layout_bytes(L6, B)); void* c3 = cv.take(layout_bytes(L3, B));
@@ -563,16 +649,18 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
     // halos and guards must read as zero
     if (cudaMemsetAsync(ws, 0, act_bytes, st) != cudaSuccess) { set_error("costreg bf16: memset failed"); return EFFIMVS_ECUDA; }
 
-    ConvProgram P[8];
-    PackTable T[8];
+    static thread_local ConvProgram P[8];
+    static thread_local PackTable T[8];
     bool ok = build_conv_s1(P[0], T[0], 8, 8, L0, 1) && build_conv_s2(P[1], T[1], 8, 16, L1, 1) &&
               build_conv_s1(P[2], T[2], 16, 16, L2, 1) && build_conv_s2(P[3], T[3], 16, 32, L3, 1) &&
               build_conv_s1(P[4], T[4], 32, 32, L4, 1) && build_deconv(P[5], T[5], 32, 16, L5, 2, 1) &&
               build_deconv(P[6], T[6], 16, 8, L6, 2, 1) && build_conv_s1(P[7], T[7], 8, 1, L7, 0);
     EFFI_REQUIRE(ok, EFFIMVS_EUNSUPPORTED, "costreg bf16: program does not fit");
     int rc;
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i) {
+        EFFI_REQUIRE(program_weight_bytes(T[i]) <= W_SLOT, EFFIMVS_EUNSUPPORTED, "costreg bf16: packed weights of layer %d too large", i + 1);
         if ((rc = run_pack(T[i], weights[i + 1], wp[i], st))) return rc;
+    }
     if ((rc = run_cin1(x, weights[0], biases[0], B, D, H, W, 1, L0, 0, c0, st))) return rc;
     if ((rc = run_tile_kernel(P[0], B, c0, L0, wp[0], biases[1], L1, c1, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[1], B, c1, L1, wp[1], biases[2], L2, c2, nullptr, nullptr, nullptr, st))) return rc;
@@ -581,78 +669,78 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
     if ((rc = run_tile_kernel(P[4], B, c4, L4, wp[4], biases[5], L5, c5, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[5], B, c5, L5, wp[5], biases[6], L6, c6, &L3, c3, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[6], B, c6, L6, wp[6], biases[7], L7, c7, &L1, c1, nullptr, st))) return rc;
-    ActLayout LO = L7;  // fp32 output indexed with the logical dims
-    return run_tile_kernel(P[7], B, c7, L7, wp[7], nullptr, LO, nullptr, nullptr, nullptr, prob_out, st);
+    return run_tile_kernel(P[7], B, c7, L7, wp[7], nullptr, L7, nullptr, nullptr, nullptr, prob_out, st);  // fp32 out, logical dims of L7
 }
 
 // ------------------------------------------------------------------------------------------------
 // a10 on tensor cores
 // ------------------------------------------------------------------------------------------------
-size_t cost_up_bf16_workspace_bytes(int B, int D, int H, int W) {
-    ActLayout cat = make_layout(L_REG, 16, D, H / 2, W / 2), c1 = make_layout(L_REG, 8, D, H / 2, W / 2);
+size_t cost_up_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo) {
+    ActLayout cat = make_layout(L_REG, 16, D, H / 2, W / 2, hilo), c1 = make_layout(L_REG, 8, D, H / 2, W / 2, hilo);
     return layout_bytes(cat, B) + layout_bytes(c1, B) + 2 * W_SLOT + 4096;
 }
 
 int cost_up_bf16(const float* x, const float* prev, const float* const* weights, const float* const* biases, int B, int D, int H,
-                 int W, void* ws, size_t ws_bytes, float* out, cudaStream_t st) {
+                 int W, bool hilo, void* ws, size_t ws_bytes, float* out, cudaStream_t st) {
     EFFI_REQUIRE(D <= 65535 && B <= 65535, EFFIMVS_EUNSUPPORTED, "cost_up bf16: D or B too large");
     const int H2 = H / 2, W2 = W / 2;
-    ActLayout Lcat = make_layout(L_REG, 16, D, H2, W2), L1 = make_layout(L_REG, 8, D, H2, W2);
+    ActLayout Lcat = make_layout(L_REG, 16, D, H2, W2, hilo), L1 = make_layout(L_REG, 8, D, H2, W2, hilo);
     Carver cv{(char*)ws, 0, ws_bytes};
     void* cat = cv.take(layout_bytes(Lcat, B)); void* c1 = cv.take(layout_bytes(L1, B));
     const size_t act_bytes = cv.off;
     void* wp1 = cv.take(W_SLOT); void* wp2 = cv.take(W_SLOT);
     EFFI_REQUIRE(cv.off <= ws_bytes, EFFIMVS_EWORKSPACE, "cost_up bf16: workspace %zu < %zu", ws_bytes, cv.off);
     if (cudaMemsetAsync(ws, 0, act_bytes, st) != cudaSuccess) { set_error("cost_up bf16: memset failed"); return EFFIMVS_ECUDA; }
-    ConvProgram P1, P2;
-    PackTable T1, T2;
+    static thread_local ConvProgram P1, P2;
+    static thread_local PackTable T1, T2;
     bool ok = build_conv_s1(P1, T1, 16, 8, Lcat, 1) && build_deconv(P2, T2, 8, 1, L1, 1, 1);
     EFFI_REQUIRE(ok, EFFIMVS_EUNSUPPORTED, "cost_up bf16: program does not fit");
     int rc;
     if ((rc = run_pack(T1, weights[2], wp1, st))) return rc;
     if ((rc = run_pack(T2, weights[3], wp2, st))) return rc;
+    // in a hi/lo layout the concatenated tensor has planes [conv0 hi, conv_cost hi, conv0 lo, conv_cost lo]
     if ((rc = run_cin1(x, weights[0], biases[0], B, D, H, W, 2, Lcat, 0, cat, st))) return rc;
     if ((rc = run_cin1(prev, weights[1], biases[1], B, D, H2, W2, 1, Lcat, 1, cat, st))) return rc;
     if ((rc = run_tile_kernel(P1, B, cat, Lcat, wp1, biases[2], L1, c1, nullptr, nullptr, nullptr, st))) return rc;
-    ActLayout LO = make_layout(L_REG, 8, D, H, W);  // fp32 output indexed with the logical (full-resolution) dims
+    ActLayout LO = make_layout(L_REG, 8, D, H, W, false);  // fp32 output indexed with the logical (full-resolution) dims
     return run_tile_kernel(P2, B, c1, L1, wp2, biases[3], LO, nullptr, nullptr, nullptr, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------
 // single layer (tests, other callers): fp32 NCDHW in/out around one tensor-core layer
 // ------------------------------------------------------------------------------------------------
-size_t conv3d_bf16_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int sd, int transposed) {
+size_t conv3d_bf16_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int sd, int transposed, bool hilo) {
     int Do = D, Ho = H, Wo = W;
     if (transposed) { Do = D * sd; Ho = H * 2; Wo = W * 2; }
     else if (sd == 2) { Do = D / 2; Ho = H / 2; Wo = W / 2; }
-    ActLayout LI = make_layout(!transposed && sd == 2 ? L_SPLIT : L_REG, (Cin + 7) / 8 * 8, D, H, W);
-    ActLayout LO = make_layout(L_REG, (Cout + 7) / 8 * 8, Do, Ho, Wo);
+    ActLayout LI = make_layout(!transposed && sd == 2 ? L_SPLIT : L_REG, (Cin + 7) / 8 * 8, D, H, W, hilo);
+    ActLayout LO = make_layout(L_REG, (Cout + 7) / 8 * 8, Do, Ho, Wo, hilo);
     return layout_bytes(LI, B) + 2 * layout_bytes(LO, B) + W_SLOT + 4096;
 }
 
 int conv3d_bf16(const float* x, const float* weight, const float* bias, const float* residual, int B, int Cin, int Cout, int D,
-                int H, int W, int sd, int transposed, int relu, void* ws, size_t ws_bytes, float* y, cudaStream_t st) {
-    EFFI_REQUIRE(Cin % 8 == 0 && Cin <= 32 && Cout >= 1 && Cout <= 32, EFFIMVS_EUNSUPPORTED, "conv3d_bf16: Cin in {8,16,32}, Cout <= 32");
-    EFFI_REQUIRE(Cin != 24, EFFIMVS_EUNSUPPORTED, "conv3d_bf16: Cin = 24 not supported");
+                int H, int W, int sd, int transposed, int relu, bool hilo, void* ws, size_t ws_bytes, float* y, cudaStream_t st) {
+    EFFI_REQUIRE((Cin == 8 || Cin == 16 || Cin == 32) && Cout >= 1 && Cout <= 32, EFFIMVS_EUNSUPPORTED,
+                 "conv3d_bf16: Cin in {8,16,32}, Cout <= 32");
     int Do = D, Ho = H, Wo = W;
     if (transposed) { Do = D * sd; Ho = H * 2; Wo = W * 2; }
     else if (sd == 2) { EFFI_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, EFFIMVS_EUNSUPPORTED, "conv3d_bf16: stride 2 needs even dims"); Do = D / 2; Ho = H / 2; Wo = W / 2; }
     const int Cop = (Cout + 7) / 8 * 8;
-    ActLayout LI = make_layout(!transposed && sd == 2 ? L_SPLIT : L_REG, Cin, D, H, W);
-    ActLayout LO = make_layout(L_REG, Cop, Do, Ho, Wo);
+    ActLayout LI = make_layout(!transposed && sd == 2 ? L_SPLIT : L_REG, Cin, D, H, W, hilo);
+    ActLayout LO = make_layout(L_REG, Cop, Do, Ho, Wo, hilo);
     Carver cv{(char*)ws, 0, ws_bytes};
     void* xin = cv.take(layout_bytes(LI, B)); void* yout = cv.take(layout_bytes(LO, B)); void* rin = cv.take(layout_bytes(LO, B));
     const size_t act_bytes = cv.off;
     void* wp = cv.take(W_SLOT);
     EFFI_REQUIRE(cv.off <= ws_bytes, EFFIMVS_EWORKSPACE, "conv3d_bf16: workspace %zu < %zu", ws_bytes, cv.off);
     if (cudaMemsetAsync(ws, 0, act_bytes, st) != cudaSuccess) { set_error("conv3d_bf16: memset failed"); return EFFIMVS_ECUDA; }
-    ConvProgram P;
-    PackTable T;
+    static thread_local ConvProgram P;
+    static thread_local PackTable T;
     bool ok = transposed ? build_deconv(P, T, Cin, Cout, LI, sd, relu) : (sd == 2 ? build_conv_s2(P, T, Cin, Cout, LI, relu) : build_conv_s1(P, T, Cin, Cout, LI, relu));
-    EFFI_REQUIRE(ok, EFFIMVS_EUNSUPPORTED, "conv3d_bf16: program does not fit");
+    EFFI_REQUIRE(ok && program_weight_bytes(T) <= W_SLOT, EFFIMVS_EUNSUPPORTED, "conv3d_bf16: program does not fit");
     int rc;
     if ((rc = run_pack(T, weight, wp, st))) return rc;
-    size_t n_in = (size_t)D * H * W * LI.planes, n_out = (size_t)Do * Ho * Wo * LO.planes;
+    size_t n_in = (size_t)D * H * W * (Cin / 8), n_out = (size_t)Do * Ho * Wo * (Cop / 8);
     to_c8_kernel<<<dim3((unsigned)((n_in + 255) / 256), B), 256, 0, st>>>(x, Cin, LI, (uint4*)xin);
     if (residual) to_c8_kernel<<<dim3((unsigned)((n_out + 255) / 256), B), 256, 0, st>>>(residual, Cout, LO, (uint4*)rin);
     if ((rc = check_launch("to_c8_kernel"))) return rc;
@@ -663,14 +751,15 @@ int conv3d_bf16(const float* x, const float* weight, const float* bias, const fl
 
 }  // namespace effimvs
 
-extern "C" size_t effimvs_conv3d_bf16_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int sd, int transposed) {
-    return effimvs::conv3d_bf16_workspace_bytes(B, Cin, Cout, D, H, W, sd, transposed);
+extern "C" size_t effimvs_conv3d_bf16_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int sd, int transposed, int precision) {
+    return effimvs::conv3d_bf16_workspace_bytes(B, Cin, Cout, D, H, W, sd, transposed, precision == EFFIMVS_PREC_BF16X3);
 }
 extern "C" int effimvs_conv3d_bf16(const float* x, const float* weight, const float* bias, const float* residual, int B, int Cin,
-                                   int Cout, int D, int H, int W, int sd, int transposed, int relu, void* workspace,
+                                   int Cout, int D, int H, int W, int sd, int transposed, int relu, int precision, void* workspace,
                                    size_t workspace_bytes, float* y, void* stream) {
     EFFI_REQUIRE(x && weight && y && workspace, EFFIMVS_EINVAL, "conv3d_bf16: null pointer");
     EFFI_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && (sd == 1 || sd == 2), EFFIMVS_EINVAL, "conv3d_bf16: bad sizes");
-    return effimvs::conv3d_bf16(x, weight, bias, residual, B, Cin, Cout, D, H, W, sd, transposed, relu, workspace, workspace_bytes, y,
-                                (cudaStream_t)stream);
+    EFFI_REQUIRE(precision == EFFIMVS_PREC_BF16 || precision == EFFIMVS_PREC_BF16X3, EFFIMVS_EINVAL, "conv3d_bf16: precision=%d", precision);
+    return effimvs::conv3d_bf16(x, weight, bias, residual, B, Cin, Cout, D, H, W, sd, transposed, relu, precision == EFFIMVS_PREC_BF16X3,
+                                workspace, workspace_bytes, y, (cudaStream_t)stream);
 }

@@ -13,12 +13,12 @@ int conv3d_f32(const float* x, const float* weight, const float* bias, const flo
                cudaStream_t st);
 
 // bf16 tcgen05 implementations (conv3d_tc.cu)
-size_t costreg_bf16_workspace_bytes(int B, int D, int H, int W);
+size_t costreg_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo);
 int costreg_bf16(const float* x, const float* const* weights, const float* const* biases, int B, int D, int H, int W,
-                 void* ws, size_t ws_bytes, float* prob_out, cudaStream_t st);
-size_t cost_up_bf16_workspace_bytes(int B, int D, int H, int W);
+                 bool hilo, void* ws, size_t ws_bytes, float* prob_out, cudaStream_t st);
+size_t cost_up_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo);
 int cost_up_bf16(const float* x, const float* prev, const float* const* weights, const float* const* biases, int B,
-                 int D, int H, int W, void* ws, size_t ws_bytes, float* out, cudaStream_t st);
+                 int D, int H, int W, bool hilo, void* ws, size_t ws_bytes, float* out, cudaStream_t st);
 
 namespace {
 size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -30,7 +30,7 @@ using namespace effimvs;
 
 extern "C" size_t effimvs_costreg_workspace_bytes(int B, int D, int H, int W, int precision) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
-    if (precision == EFFIMVS_PREC_BF16) return costreg_bf16_workspace_bytes(B, D, H, W);
+    if (precision != EFFIMVS_PREC_F32) return costreg_bf16_workspace_bytes(B, D, H, W, precision == EFFIMVS_PREC_BF16X3);
     size_t v = (size_t)B * D * H * W;
     // c0, c1 (8 ch, full) + c2, c3, c6 (16 ch, 1/8 of the voxels) + c4, c5 (32 ch, 1/64); c7 reuses c0
     return align256(8 * v * 4) * 2 + align256(16 * (v / 8) * 4) * 3 + align256(32 * (v / 64) * 4) * 2;
@@ -47,7 +47,8 @@ extern "C" int effimvs_costreg_fpn3d(const float* x, const float* const* weights
     size_t need = effimvs_costreg_workspace_bytes(B, D, H, W, precision);
     EFFI_REQUIRE(workspace_bytes >= need, EFFIMVS_EWORKSPACE, "costreg_fpn3d: workspace %zu < %zu bytes", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == EFFIMVS_PREC_BF16) return costreg_bf16(x, weights, biases, B, D, H, W, workspace, workspace_bytes, prob_out, st);
+    if (precision == EFFIMVS_PREC_BF16 || precision == EFFIMVS_PREC_BF16X3)
+        return costreg_bf16(x, weights, biases, B, D, H, W, precision == EFFIMVS_PREC_BF16X3, workspace, workspace_bytes, prob_out, st);
     EFFI_REQUIRE(precision == EFFIMVS_PREC_F32, EFFIMVS_EINVAL, "costreg_fpn3d: precision=%d", precision);
 
     size_t v = (size_t)B * D * H * W;
@@ -75,7 +76,7 @@ extern "C" int effimvs_costreg_fpn3d(const float* x, const float* const* weights
 
 extern "C" size_t effimvs_cost_up_workspace_bytes(int B, int D, int H, int W, int precision) {
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
-    if (precision == EFFIMVS_PREC_BF16) return cost_up_bf16_workspace_bytes(B, D, H, W);
+    if (precision != EFFIMVS_PREC_F32) return cost_up_bf16_workspace_bytes(B, D, H, W, precision == EFFIMVS_PREC_BF16X3);
     size_t v = (size_t)B * D * (H / 2) * (W / 2);
     return align256(16 * v * 4) + align256(8 * v * 4);
 }
@@ -91,7 +92,8 @@ extern "C" int effimvs_cost_up_small(const float* x, const float* prev, const fl
     size_t need = effimvs_cost_up_workspace_bytes(B, D, H, W, precision);
     EFFI_REQUIRE(workspace_bytes >= need, EFFIMVS_EWORKSPACE, "cost_up_small: workspace %zu < %zu bytes", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == EFFIMVS_PREC_BF16) return cost_up_bf16(x, prev, weights, biases, B, D, H, W, workspace, workspace_bytes, out, st);
+    if (precision == EFFIMVS_PREC_BF16 || precision == EFFIMVS_PREC_BF16X3)
+        return cost_up_bf16(x, prev, weights, biases, B, D, H, W, precision == EFFIMVS_PREC_BF16X3, workspace, workspace_bytes, out, st);
     EFFI_REQUIRE(precision == EFFIMVS_PREC_F32, EFFIMVS_EINVAL, "cost_up_small: precision=%d", precision);
 
     const int H2 = H / 2, W2 = W / 2;

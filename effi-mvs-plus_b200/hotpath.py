@@ -47,10 +47,11 @@ class CudaHotPath:
     name = "cuda"
 
     def __init__(self, precision: str = "f32", native_projection: bool = False):
-        """precision: 'f32' (CUDA-core exact-parity convs) or 'bf16' (tcgen05 implicit GEMM).
+        """precision of the 3-D regularization: 'f32' (CUDA-core direct convs), 'bf16' (tcgen05 implicit
+        GEMM, one bf16 MMA per product) or 'bf16x3' (tcgen05, hi/lo split operands, fp32-grade).
         native_projection: compute P_src @ inverse(P_ref) with the library's fp64 kernel instead
         of torch (needed under CUDA-graph capture; torch.linalg.inv may synchronise)."""
-        self.precision = {"f32": capi.PREC_F32, "bf16": capi.PREC_BF16}[precision]
+        self.precision = {"f32": capi.PREC_F32, "bf16": capi.PREC_BF16, "bf16x3": capi.PREC_BF16X3}[precision]
         self.native_projection = native_projection
         self._folds = _FoldCache()
 

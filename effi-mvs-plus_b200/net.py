@@ -24,15 +24,38 @@ import torch.nn.functional as F
 # building blocks (attribute names .conv / .bn are the checkpoint format)
 # ----------------------------------------------------------------------------
 class ConvBNReLU2d(nn.Module):
-    """conv2d(bias-free) + BatchNorm2d + ReLU  (upstream Conv2d / ConvBnReLU)."""
+    """conv2d(bias-free) + BatchNorm2d + ReLU  (upstream Conv2d / ConvBnReLU).
+
+    In eval mode the BatchNorm is folded into the convolution (the standard PyTorch inference
+    fusion, cf. torch.nn.utils.fusion.fuse_conv_bn_eval): one cuDNN convolution with bias instead
+    of convolution + a separate normalisation pass over the full-resolution map.  The fold is
+    cached and rebuilt when a parameter or buffer changes.
+    """
 
     def __init__(self, cin, cout, k, stride=1, padding=0):
         super().__init__()
         self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=False)
         self.bn = nn.BatchNorm2d(cout)
+        self._fold = None
+
+    def _folded(self):
+        bn = self.bn
+        ts = (self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        stamp = tuple((id(t), t._version, t.device) for t in ts)
+        if self._fold is None or self._fold[0] != stamp:
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = (self.conv.weight * scale.reshape(-1, 1, 1, 1)).detach()
+            b = (bn.bias - bn.running_mean * scale).detach()
+            if w.is_cuda:
+                w = w.contiguous(memory_format=torch.channels_last)
+            self._fold = (stamp, w, b)
+        return self._fold[1], self._fold[2]
 
     def forward(self, x):
-        return F.relu(self.bn(self.conv(x)), inplace=True)
+        if self.training:
+            return F.relu(self.bn(self.conv(x)), inplace=True)
+        w, b = self._folded()
+        return F.relu(F.conv2d(x, w, b, self.conv.stride, self.conv.padding), inplace=True)
 
 
 class ConvBN3d(nn.Module):
@@ -237,7 +260,10 @@ class EffiMVSPlus(nn.Module):
     def encode(self, imgs):
         """FPN over all V views in one batch -> per stage a list of V (B,C,h,w) maps."""
         B, V = imgs.shape[:2]
-        pyr = self.feature(imgs.reshape(B * V, *imgs.shape[2:]))
+        x = imgs.reshape(B * V, *imgs.shape[2:])
+        if x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)   # cuDNN NHWC kernels, no layout round trips
+        pyr = self.feature(x)
         return [[p.reshape(B, V, *p.shape[1:])[:, v] for v in range(V)] for p in pyr]
 
     def forward(self, imgs, proj_matrices, depth_values):
@@ -254,7 +280,8 @@ class EffiMVSPlus(nn.Module):
             return 1.0 / (lo_disp + (hi_disp - lo_disp) * inv).clamp(min=1e-4)
 
         feats = self.encode(imgs)
-        ctx_pyr = self.cnet_depth(imgs[:, 0])
+        ref_img = imgs[:, 0]
+        ctx_pyr = self.cnet_depth(ref_img.contiguous(memory_format=torch.channels_last) if ref_img.is_cuda else ref_img)
 
         preds = []
         conf = None

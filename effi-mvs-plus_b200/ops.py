@@ -233,7 +233,7 @@ def _(x, weight, bias, residual, stride, transposed, relu):
 
 @torch.library.custom_op("effimvs::conv3d_bf16", mutates_args=())
 def conv3d_bf16(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], sd: int,
-                transposed: bool, relu: bool) -> Tensor:
+                transposed: bool, relu: bool, precision: int) -> Tensor:
     """One (de)conv layer on the tensor cores (tcgen05), fp32 NCDHW in/out.  Conv: stride sd in all
     dims (1 or 2); transposed conv: stride (sd,2,2)."""
     x, weight = _dev(x, "conv3d_bf16"), _dev(weight, "conv3d_bf16")
@@ -245,17 +245,17 @@ def conv3d_bf16(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Opt
         Do, Ho, Wo = D * sd, H * 2, W * 2
     else:
         Do, Ho, Wo = D // sd, H // sd, W // sd
-    need = _lib.effimvs_conv3d_bf16_workspace_bytes(B, Cin, Cout, D, H, W, sd, int(transposed))
+    need = _lib.effimvs_conv3d_bf16_workspace_bytes(B, Cin, Cout, D, H, W, sd, int(transposed), precision)
     ws = torch.empty(max(need, 256), device=x.device, dtype=torch.uint8)
     y = torch.empty(B, Cout, Do, Ho, Wo, device=x.device, dtype=torch.float32)
     _count(5)
     capi.check(_lib.effimvs_conv3d_bf16(x.data_ptr(), weight.data_ptr(), _opt(bias), _opt(residual), B, Cin, Cout, D, H, W,
-                                        sd, int(transposed), int(relu), ws.data_ptr(), ws.numel(), y.data_ptr(), _stream()))
+                                        sd, int(transposed), int(relu), precision, ws.data_ptr(), ws.numel(), y.data_ptr(), _stream()))
     return y
 
 
 @conv3d_bf16.register_fake
-def _(x, weight, bias, residual, sd, transposed, relu):
+def _(x, weight, bias, residual, sd, transposed, relu, precision):
     B, Cin, D, H, W = x.shape
     Cout = weight.shape[1] if transposed else weight.shape[0]
     if transposed:

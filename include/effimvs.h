@@ -47,6 +47,8 @@ extern "C" {
 /* precision of the 3-D regularization nets */
 #define EFFIMVS_PREC_F32 0  /* CUDA-core fp32 direct convolution (exact-parity path)     */
 #define EFFIMVS_PREC_BF16 1 /* bf16 operands, fp32 accumulate in TMEM (tcgen05 implicit GEMM) */
+#define EFFIMVS_PREC_BF16X3 2 /* operands split into hi + lo bf16, three tcgen05 MMAs per product
+                                 (hi*hi + hi*lo + lo*hi): fp32-grade results on the tensor cores */
 
 const char* effimvs_last_error(void);
 int effimvs_version(void);
@@ -124,10 +126,11 @@ int effimvs_conv3d_f32(const float* x, const float* weight, const float* bias, c
  * x, residual and y are fp32 NCDHW (converted to / from the kernel's channel-planar bf16 layout
  * inside the call; the net-level entry points below keep activations in that layout between
  * layers).  workspace: effimvs_conv3d_bf16_workspace_bytes() bytes. */
-size_t effimvs_conv3d_bf16_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int sd, int transposed);
+size_t effimvs_conv3d_bf16_workspace_bytes(int B, int Cin, int Cout, int D, int H, int W, int sd, int transposed,
+                                           int precision);
 int effimvs_conv3d_bf16(const float* x, const float* weight, const float* bias, const float* residual, int B, int Cin,
-                        int Cout, int D, int H, int W, int sd, int transposed, int relu, void* workspace,
-                        size_t workspace_bytes, float* y, void* stream);
+                        int Cout, int D, int H, int W, int sd, int transposed, int relu, int precision /* BF16 | BF16X3 */,
+                        void* workspace, size_t workspace_bytes, float* y, void* stream);
 
 /* a9: CostRegNet_2_sample_FPN3D_Fast.forward (models/module.py:453-463).
  *   x (B,1,D,H,W), D,H,W multiples of 4.  weights: host array of 9 device pointers

@@ -399,6 +399,9 @@ class OracleHotPath:
     def volume_lookup(self, volume, depth_sample, depth_min, depth_max):
         return volume_lookup(volume, depth_sample, depth_min, depth_max)
 
+    def cost_regularization(self, net, x):
+        return cost_regularization(net, x)[0]
+
     def cross_scale(self, net, cur_volume, prev_resampled):
         out, _ = cross_scale_net(net, cur_volume, prev_resampled)
         return out
