@@ -64,7 +64,9 @@ def build_model(hotpath, device, ndepths):
         data = "synthetic images/cameras (seeded); weights = upstream model_dtu.ckpt values (tests/golden/dtu_weights.pt)"
     model = model.to(device).eval()
     if torch.device(device).type == "cuda":
-        model = model.to(memory_format=torch.channels_last)     # 4-D conv weights NHWC: cuDNN tensor-core kernels without layout round trips
+        for m in model.modules():                               # 4-D conv weights NHWC: cuDNN tensor-core kernels without layout round trips
+            if isinstance(m, torch.nn.Conv2d):
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
     return model, data
 
 

@@ -31,8 +31,9 @@ def gather_depths(local: Dict[int, torch.Tensor], n_views: int, rank: int, world
     if world == 1 or not (dist.is_available() and dist.is_initialized()):
         full = mine.unsqueeze(0)
     else:
-        full = torch.empty(world, slots, h, w, device=device, dtype=torch.float32)
-        dist.all_gather_into_tensor(full, mine)
+        flat = torch.empty(world * slots, h, w, device=device, dtype=torch.float32)   # rank-major concatenation
+        dist.all_gather_into_tensor(flat, mine)
+        full = flat.reshape(world, slots, h, w)
     # (world, slots) -> view index = slot * world + rank
     return full.permute(1, 0, 2, 3).reshape(slots * world, h, w)[:n_views].contiguous()
 
