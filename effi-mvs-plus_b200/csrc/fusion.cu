@@ -23,6 +23,9 @@ struct Cam {       // one camera in shared memory
     float Ei[16];  // inverse(E)
     float K[9];
     float Ki[9];
+    // last row exactly (0,0,0,1) / (0,0,1): the homogeneous coordinate is then exactly 1 and
+    // x / (1 + 1e-9f) == x bit for bit, so upstream's renormalising divisions can be skipped
+    int affE, affEi, affK, affKi;
 };
 
 __device__ bool invert_n(const double* A, double* inv, int n) {
@@ -71,6 +74,10 @@ __device__ void load_cam(Cam& c, const float* __restrict__ cam, const float* __r
         ok = invert_n(A, I, 3);
         for (int i = 0; i < 9; ++i) c.Ki[i] = ok ? (float)I[i] : __int_as_float(0x7fc00000);
     }
+    c.affE = c.E[12] == 0.0f && c.E[13] == 0.0f && c.E[14] == 0.0f && c.E[15] == 1.0f;
+    c.affEi = c.Ei[12] == 0.0f && c.Ei[13] == 0.0f && c.Ei[14] == 0.0f && c.Ei[15] == 1.0f;
+    c.affK = c.K[6] == 0.0f && c.K[7] == 0.0f && c.K[8] == 1.0f;
+    c.affKi = c.Ki[6] == 0.0f && c.Ki[7] == 0.0f && c.Ki[8] == 1.0f;
 }
 
 __device__ __forceinline__ void mat3(const float* M, float x, float y, float z, float o[3]) {
@@ -87,30 +94,50 @@ __device__ __forceinline__ void mat4(const float* M, const float p[4], float o[4
 __device__ __forceinline__ void img_to_world(const Cam& c, float u, float v, float depth, float pw[4]) {
     float k[3];
     mat3(c.Ki, u, v, 1.0f, k);
-    float zz = __fadd_rn(k[2], 1e-9f);
-    float pc[4] = {__fmul_rn(__fdiv_rn(k[0], zz), depth), __fmul_rn(__fdiv_rn(k[1], zz), depth),
-                   __fmul_rn(__fdiv_rn(k[2], zz), depth), 1.0f};
+    float pc[4];
+    if (c.affKi) {   // k[2] == 1 exactly
+        pc[0] = __fmul_rn(k[0], depth); pc[1] = __fmul_rn(k[1], depth); pc[2] = depth;
+    } else {
+        float zz = __fadd_rn(k[2], 1e-9f);
+        pc[0] = __fmul_rn(__fdiv_rn(k[0], zz), depth); pc[1] = __fmul_rn(__fdiv_rn(k[1], zz), depth);
+        pc[2] = __fmul_rn(__fdiv_rn(k[2], zz), depth);
+    }
+    pc[3] = 1.0f;
     float w[4];
     mat4(c.Ei, pc, w);
-    float ww = __fadd_rn(w[3], 1e-9f);
+    if (c.affEi) {   // w[3] == 1 exactly
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pw[i] = __fdiv_rn(w[i], ww);
+        for (int i = 0; i < 4; ++i) pw[i] = w[i];
+    } else {
+        float ww = __fadd_rn(w[3], 1e-9f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pw[i] = __fdiv_rn(w[i], ww);
+    }
 }
 
 // idx_world2cam (fusion.py:37-40)
 __device__ __forceinline__ void world_to_cam(const Cam& c, const float pw[4], float pc[4]) {
     float t[4];
     mat4(c.E, pw, t);
-    float ww = __fadd_rn(t[3], 1e-9f);
+    if (c.affE && pw[3] == 1.0f) {   // t[3] == 1 exactly
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pc[i] = __fdiv_rn(t[i], ww);
+        for (int i = 0; i < 4; ++i) pc[i] = t[i];
+    } else {
+        float ww = __fadd_rn(t[3], 1e-9f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pc[i] = __fdiv_rn(t[i], ww);
+    }
 }
 
 // idx_cam2img (fusion.py:43-47)
 __device__ __forceinline__ void cam_to_img(const Cam& c, const float pc[4], float& u, float& v) {
-    float ww = __fadd_rn(pc[3], 1e-9f);
     float k[3];
-    mat3(c.K, __fdiv_rn(pc[0], ww), __fdiv_rn(pc[1], ww), __fdiv_rn(pc[2], ww), k);
+    if (pc[3] == 1.0f) {             // (1 + 1e-9f) == 1: the division is the identity
+        mat3(c.K, pc[0], pc[1], pc[2], k);
+    } else {
+        float ww = __fadd_rn(pc[3], 1e-9f);
+        mat3(c.K, __fdiv_rn(pc[0], ww), __fdiv_rn(pc[1], ww), __fdiv_rn(pc[2], ww), k);
+    }
     float zz = __fadd_rn(k[2], 1e-9f);
     u = __fdiv_rn(k[0], zz);
     v = __fdiv_rn(k[1], zz);

@@ -15,9 +15,26 @@ duplicate registrations ``update_block_depth1`` / ``update_block.0`` etc.) so th
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+# cuDNN's fused convolution + bias + ReLU (aten::cudnn_convolution_relu, stock PyTorch) for the
+# inference path on CUDA; EFFIMVS_FUSED_CONV_RELU=0 falls back to conv2d followed by relu_.
+_FUSED_CONV_RELU = os.environ.get("EFFIMVS_FUSED_CONV_RELU", "1") == "1"
+
+
+def conv_relu(x, weight, bias, stride=(1, 1), padding=(0, 0)):
+    """relu(conv2d(x) + bias) -- one fused cuDNN call on CUDA in no-grad mode."""
+    if _FUSED_CONV_RELU and x.is_cuda and bias is not None and not torch.is_grad_enabled():
+        return torch.cudnn_convolution_relu(x, weight, bias, stride, padding, (1, 1), 1)
+    return F.relu(F.conv2d(x, weight, bias, stride, padding), inplace=True)
+
+
+def _conv_relu_mod(conv: nn.Conv2d, x):
+    return conv_relu(x, conv.weight, conv.bias, conv.stride, conv.padding)
 
 
 # ----------------------------------------------------------------------------
@@ -55,7 +72,7 @@ class ConvBNReLU2d(nn.Module):
         if self.training:
             return F.relu(self.bn(self.conv(x)), inplace=True)
         w, b = self._folded()
-        return F.relu(F.conv2d(x, w, b, self.conv.stride, self.conv.padding), inplace=True)
+        return conv_relu(x, w, b, self.conv.stride, self.conv.padding)
 
 
 class ConvBN3d(nn.Module):
@@ -143,10 +160,10 @@ class CostEncoder(nn.Module):
         self.convc = nn.Conv2d(hidden, hidden, 1)
 
     def forward(self, inv_depth, cost, context):
-        c = F.relu(self.convc2(F.relu(self.convc1(cost))))
-        d = F.relu(self.convd2(F.relu(self.convd1(inv_depth))))
+        c = _conv_relu_mod(self.convc2, _conv_relu_mod(self.convc1, cost))
+        d = _conv_relu_mod(self.convd2, _conv_relu_mod(self.convd1, inv_depth))
         m = self.convd(torch.cat([c, d], dim=1))
-        return F.relu(self.convc(torch.cat([m, context], dim=1)))
+        return _conv_relu_mod(self.convc, torch.cat([m, context], dim=1))
 
 
 class GRUCell2d(nn.Module):
@@ -175,7 +192,7 @@ class DeltaHead(nn.Module):
         self.conv2 = nn.Conv2d(hidden, 1, 3, padding=1)
 
     def forward(self, x):
-        return torch.tanh(self.conv2(F.relu(self.conv1(x))))
+        return torch.tanh(self.conv2(_conv_relu_mod(self.conv1, x)))
 
 
 class UpdateBlock(nn.Module):
@@ -198,7 +215,7 @@ class UpdateBlock(nn.Module):
             net = self.depth_gru(net, x)
             inv_depth = inv_depth + self.depth_head(net)
             inv_seq.append(inv_depth)
-        return net, 0.25 * self.mask(net), inv_seq
+        return net, 0.25 * self.mask[2](_conv_relu_mod(self.mask[0], net)), inv_seq
 
 
 def convex_upsample(x, mask, ratio):
