@@ -21,9 +21,12 @@
 //
 // Precision modes.  EFFIMVS_PREC_BF16: one bf16 MMA per K chunk pair.  EFFIMVS_PREC_BF16X3:
 // activations and weights are carried as hi + lo bf16 pairs (x = hi + lo to 16 mantissa bits) and
-// every product is formed as hi*hi + hi*lo + lo*hi in three bf16 MMAs with fp32 accumulation --
-// fp32-grade results (needed for the 1e-3 depth tolerance) at tensor-core rate.  32-channel inputs
-// are then processed in two K phases (channel-plane pairs) through the same shared-memory slab.
+// every product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation -- fp32-grade results
+// (needed for the 1e-3 depth tolerance) on the tensor cores.  The layers are bound by the A-operand
+// fetch of the tensor pipe, so x_hi is streamed once against the stacked B block [w_hi ; w_lo]
+// (one MMA of width 2N, the epilogue adds the two column halves) and x_lo once against w_hi: two
+// A reads per product instead of three.  32-channel inputs are processed in two K phases
+// (channel-plane pairs) through the same shared-memory slab.
 //
 // One tile per CTA: warp 4 lane 0 issues the bulk copies, waits on the mbarrier, issues the
 // tcgen05.mma sequence and commits; warps 0-3 own TMEM lanes 32w..32w+31 (= tile rows) and run
@@ -44,8 +47,8 @@ constexpr int TILE_M = 128;
 constexpr int SEG_VOX = 136;  // 128 + 2 (x halo) + 1 (dummy chunk) rounded up to a multiple of 8
 constexpr int SEG_BYTES = SEG_VOX * 16;
 constexpr int MAX_SEGS = 72;
-constexpr int MAX_OPS = 168;
-constexpr int MAX_BLOCKS = 112;  // packed weight blocks (one K chunk pair each)
+constexpr int MAX_OPS = 112;
+constexpr int MAX_BLOCKS = 56;   // packed weight blocks (one K chunk pair each)
 constexpr int MAX_PHASES = 2;
 
 enum { L_REG = 0, L_SPLIT = 1 };
@@ -84,13 +87,14 @@ __host__ __device__ inline long long act_index(const ActLayout& L, int b, int pl
 }
 
 struct Seg { long long src_off; int copy_vox; int slot; };          // slot: shared-memory segment index within its phase
-struct Op { uint32_t a_off, a_lbo, b_off; uint16_t d_col; uint8_t accum, pad_; };
+struct Op { uint32_t a_off, a_lbo, b_off; uint16_t d_col; uint8_t accum, n8; };   // n8: MMA N / 8
 struct Phase { int seg_begin, seg_end, op_begin, op_end, w_off, w_bytes; };
-struct Block { short tap0, cb0, tap1, cb1, lo, pad_; };               // weight source of one packed K chunk pair
+struct Block { short tap0, cb0, tap1, cb1; };                         // weight source of one packed K chunk pair
 
 struct ConvProgram {
     int n_phases;
     int N, n_classes, cout, tmem_cols;
+    int b_rows;                   // rows of a packed weight block: N, or 2N in hi/lo mode ([w_hi ; w_lo])
     int gD, gH, gW, gPx;          // tile grid (output grid for conv, input grid for transposed conv)
     long long zstride;            // voxels per padded z plane of the input (sub-)volumes
     int up_z, up_y, up_x;         // output coordinate = grid coordinate * up + class bit
@@ -99,7 +103,7 @@ struct ConvProgram {
     Seg segs[MAX_SEGS];
     Op ops[MAX_OPS];
 };
-struct PackTable { int n_blocks, N, cout, cin, transposed; Block blk[MAX_BLOCKS]; };
+struct PackTable { int n_blocks, N, rows, cout, cin, transposed; Block blk[MAX_BLOCKS]; };
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -242,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
         if (lane == 0) {
             const uint4* base = in + (long long)b * in_batch_stride + (long long)z * P.zstride + q0;
             const uint32_t a0 = smem_u32(slab), b0 = smem_u32(wsm);
-            const uint32_t idesc = umma_idesc(P.N);
+            const uint32_t b_lbo = (uint32_t)P.b_rows * 16u;
             for (int p = 0; p < P.n_phases; ++p) {
                 const Phase ph = P.ph[p];
                 if (p > 0) {                       // the previous phase's MMAs must have consumed the slab
@@ -259,8 +263,8 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                 tc_fence_after();
                 for (int i = ph.op_begin; i < ph.op_end; ++i) {
                     const Op op = P.ops[i];
-                    umma_bf16(tmem + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, (uint32_t)P.N * 16u, 128),
-                              idesc, op.accum);
+                    umma_bf16(tmem + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, b_lbo, 128),
+                              umma_idesc(op.n8 * 8), op.accum);
                 }
                 umma_commit(p + 1 < P.n_phases ? &bar_step : &bar_done);
             }
@@ -283,7 +287,13 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
             const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
             for (int g = 0; g < groups; ++g) {
                 float v[8];
-                tmem_ld8(lane_base + (uint32_t)(cls * P.N + g * 8), v);
+                tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + g * 8), v);
+                if (P.b_rows != P.N) {   // hi/lo mode: columns [N, 2N) hold x_hi * w_lo
+                    float u[8];
+                    tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + P.N + g * 8), u);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += u[j];
+                }
                 if (!interior) continue;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -313,12 +323,14 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // helper kernels: weight packing, single-input-channel convolution (CUDA cores), layout conversion
 // ------------------------------------------------------------------------------------------------
-// packed block: [chunk j][row n][8 k] bf16; row n = output channel (zero beyond cout).  lo blocks hold
-// bf16(w - bf16(w)).
+// packed block: [chunk j][row][8 k] bf16; rows [0,N) = output channels (zero beyond cout) of bf16(w);
+// in hi/lo mode rows [N,2N) hold bf16(w - bf16(w)).
 __global__ void pack_weights_kernel(const __grid_constant__ PackTable T, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
-    const int total = T.n_blocks * 2 * T.N * 8;
+    const int total = T.n_blocks * 2 * T.rows * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int kk = i & 7, n = (i >> 3) % T.N, j = (i / (8 * T.N)) & 1, blk = i / (16 * T.N);
+        const int kk = i & 7, row = (i >> 3) % T.rows, j = (i / (8 * T.rows)) & 1, blk = i / (16 * T.rows);
+        const bool lo = row >= T.N;
+        const int n = lo ? row - T.N : row;
         const Block c = T.blk[blk];
         const int tap = j ? c.tap1 : c.tap0, cb = j ? c.cb1 : c.cb0;
         float v = 0.0f;
@@ -327,7 +339,52 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackTable T, const f
             v = T.transposed ? w[((size_t)ci * T.cout + n) * 27 + tap] : w[((size_t)n * T.cin + ci) * 27 + tap];
         }
         __nv_bfloat16 hi = __float2bfloat16(v);
-        dst[i] = c.lo ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
+        dst[i] = lo ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
+    }
+}
+
+struct PackJobs { int n; PackTable T[8]; const float* w[8]; __nv_bfloat16* dst[8]; };
+__global__ void pack_weights_multi_kernel(const __grid_constant__ PackJobs J) {
+    const PackTable& T = J.T[blockIdx.y];
+    const float* __restrict__ w = J.w[blockIdx.y];
+    __nv_bfloat16* __restrict__ dst = J.dst[blockIdx.y];
+    const int total = T.n_blocks * 2 * T.rows * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kk = i & 7, row = (i >> 3) % T.rows, j = (i / (8 * T.rows)) & 1, blk = i / (16 * T.rows);
+        const bool lo = row >= T.N;
+        const int n = lo ? row - T.N : row;
+        const Block c = T.blk[blk];
+        const int tap = j ? c.tap1 : c.tap0, cb = j ? c.cb1 : c.cb0;
+        float v = 0.0f;
+        if (tap >= 0 && n < T.cout) {
+            const int ci = cb + kk;
+            v = T.transposed ? w[((size_t)ci * T.cout + n) * 27 + tap] : w[((size_t)n * T.cin + ci) * 27 + tap];
+        }
+        __nv_bfloat16 hi = __float2bfloat16(v);
+        dst[i] = lo ? __float2bfloat16(v - __bfloat162float(hi)) : hi;
+    }
+}
+
+// Zeroes guards and halos of up to 8 activation buffers (the interiors are fully overwritten by the
+// layers; tiles read halos as the zero padding of the convolution).
+struct HaloJobs { int n; uint4* ptr[8]; ActLayout L[8]; };
+__global__ void zero_halo_kernel(const __grid_constant__ HaloJobs J, int B) {
+    const ActLayout& L = J.L[blockIdx.y];
+    uint4* __restrict__ p = J.ptr[blockIdx.y];
+    const int d = L.kind == L_SPLIT ? L.D / 2 : L.D, h = L.Py - 2, w = L.Px - 2;
+    const long long total = L.batch_stride * B;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i % L.vs;
+        bool halo = r < L.guard || r >= L.vs - L.guard;
+        if (!halo) {
+            const long long q = r - L.guard;
+            const int zp = (int)(q / L.zstride);
+            const int rem = (int)(q - (long long)zp * L.zstride);
+            const int yp = rem / L.Px, xp = rem - yp * L.Px;
+            halo = zp < 1 || zp > d || yp < 1 || yp > h || xp < 1 || xp > w;
+        }
+        if (halo) p[i] = zero;
     }
 }
 
@@ -431,6 +488,9 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
     const int NPph = NP / n_phases;
     if (n_phases > MAX_PHASES) return false;
     P.n_phases = n_phases;
+    P.b_rows = T.rows = hilo ? 2 * P.N : P.N;
+    P.tmem_cols = pow2_cols(P.b_rows * P.n_classes);
+    if (P.tmem_cols > 512) return false;
     int n_seg = 0, n_op = 0, n_blk = 0;
     std::vector<bool> started(P.n_classes, false);
     size_t max_slab = 0;
@@ -449,7 +509,7 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
                     s.slot = (h * NPph + pl) * SPP + k;
                 }
         const uint32_t lo_smem = (uint32_t)(NPph * SPP * SEG_BYTES);  // hi -> lo distance in the slab
-        const uint32_t blk_bytes = 2u * P.N * 16u;
+        const uint32_t blk_bytes = 2u * P.b_rows * 16u;
         std::vector<Base> bases;
         if (NP == 1) {
             // 8 input channels: pair taps of the same class in ascending shared-memory address (LBO > 0)
@@ -461,9 +521,9 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
                     const uint32_t a0 = (uint32_t)(v[i].seg * SEG_BYTES + v[i].byte_off);
                     if (i + 1 < v.size()) {
                         const uint32_t a1 = (uint32_t)(v[i + 1].seg * SEG_BYTES + v[i + 1].byte_off);
-                        bases.push_back(Base{a0, a1 - a0, cls, Block{(short)v[i].tap, 0, (short)v[i + 1].tap, 0, 0, 0}});
+                        bases.push_back(Base{a0, a1 - a0, cls, Block{(short)v[i].tap, 0, (short)v[i + 1].tap, 0}});
                     } else {
-                        bases.push_back(Base{a0, 16, cls, Block{(short)v[i].tap, 0, -1, 0, 0, 0}});  // zero-weight dummy chunk
+                        bases.push_back(Base{a0, 16, cls, Block{(short)v[i].tap, 0, -1, 0}});  // zero-weight dummy chunk
                     }
                 }
             }
@@ -472,26 +532,21 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
                 for (int pl = 0; pl < NPph; pl += 2) {
                     const int cb = (ph * NPph + pl) * 8;
                     bases.push_back(Base{(uint32_t)((pl * SPP + t.seg) * SEG_BYTES + t.byte_off), (uint32_t)(SPP * SEG_BYTES), t.cls,
-                                         Block{(short)t.tap, (short)cb, (short)t.tap, (short)(cb + 8), 0, 0}});
+                                         Block{(short)t.tap, (short)cb, (short)t.tap, (short)(cb + 8)}});
                 }
         }
         for (auto& bs : bases) {
-            if (n_blk + halves > MAX_BLOCKS || n_op + (hilo ? 3 : 1) > MAX_OPS) return false;
-            const uint32_t b_hi = (uint32_t)(n_blk - blk_begin) * blk_bytes;
-            T.blk[n_blk] = bs.blk; T.blk[n_blk].lo = 0; ++n_blk;
-            uint32_t b_lo = 0;
-            if (hilo) { b_lo = (uint32_t)(n_blk - blk_begin) * blk_bytes; T.blk[n_blk] = bs.blk; T.blk[n_blk].lo = 1; ++n_blk; }
-            auto push = [&](uint32_t a_off, uint32_t b_off) {
+            if (n_blk + 1 > MAX_BLOCKS || n_op + halves > MAX_OPS) return false;
+            const uint32_t b_off = (uint32_t)(n_blk - blk_begin) * blk_bytes;
+            T.blk[n_blk++] = bs.blk;
+            auto push = [&](uint32_t a_off, int n) {
                 Op& op = P.ops[n_op++];
                 op.a_off = a_off; op.a_lbo = bs.lbo; op.b_off = b_off;
-                op.d_col = (uint16_t)(bs.cls * P.N); op.accum = started[bs.cls] ? 1 : 0; op.pad_ = 0;
+                op.d_col = (uint16_t)(bs.cls * P.b_rows); op.accum = started[bs.cls] ? 1 : 0; op.n8 = (uint8_t)(n / 8);
                 started[bs.cls] = true;
             };
-            push(bs.a_off, b_hi);                 // x_hi * w_hi
-            if (hilo) {
-                push(bs.a_off, b_lo);             // x_hi * w_lo
-                push(bs.a_off + lo_smem, b_hi);   // x_lo * w_hi
-            }
+            push(bs.a_off, P.b_rows);                      // x_hi * [w_hi ; w_lo]  (or x * w)
+            if (hilo) push(bs.a_off + lo_smem, P.N);        // x_lo * w_hi, into the first N columns
         }
         F.seg_end = n_seg; F.op_end = n_op;
         F.w_off = (int)((size_t)blk_begin * blk_bytes); F.w_bytes = (int)((size_t)(n_blk - blk_begin) * blk_bytes);
@@ -507,7 +562,7 @@ size_t program_smem(const ConvProgram& P) {
     for (int p = 0; p < P.n_phases; ++p) w = std::max(w, (size_t)P.ph[p].w_bytes);
     return (size_t)P.w_smem_off + w;
 }
-size_t program_weight_bytes(const PackTable& T) { return (size_t)T.n_blocks * 2 * T.N * 16; }
+size_t program_weight_bytes(const PackTable& T) { return (size_t)T.n_blocks * 2 * T.rows * 16; }
 
 void init_program(ConvProgram& P, PackTable& T, int Cin, int Cout, int n_classes, int gD, int gH, int gW, const ActLayout& IL,
                   int relu, int transposed) {
@@ -579,9 +634,29 @@ bool build_deconv(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLayo
 // host: launches
 // ------------------------------------------------------------------------------------------------
 int run_pack(const PackTable& T, const float* w, void* dst, cudaStream_t st) {
-    int total = T.n_blocks * 2 * T.N * 8;
+    int total = T.n_blocks * 2 * T.rows * 8;
     pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(T, w, (__nv_bfloat16*)dst);
     return check_launch("pack_weights_kernel");
+}
+
+int run_pack_multi(int n, const PackTable* T, const float* const* w, void* const* dst, cudaStream_t st) {
+    static thread_local PackJobs J;
+    J.n = n;
+    int most = 0;
+    for (int i = 0; i < n; ++i) {
+        J.T[i] = T[i]; J.w[i] = w[i]; J.dst[i] = (__nv_bfloat16*)dst[i];
+        most = std::max(most, T[i].n_blocks * 2 * T[i].rows * 8);
+    }
+    pack_weights_multi_kernel<<<dim3(ceil_div(most, 256), n), 256, 0, st>>>(J);
+    return check_launch("pack_weights_multi_kernel");
+}
+
+int run_zero_halo(int n, void* const* ptr, const ActLayout* L, int B, cudaStream_t st) {
+    static thread_local HaloJobs J;
+    J.n = n;
+    for (int i = 0; i < n; ++i) { J.ptr[i] = (uint4*)ptr[i]; J.L[i] = L[i]; }
+    zero_halo_kernel<<<dim3(2 * kNumSMs, n), 256, 0, st>>>(J, B);
+    return check_launch("zero_halo_kernel");
 }
 
 int run_tile_kernel(const ConvProgram& P, int B, const void* in, const ActLayout& IL, const void* wpk, const float* bias,
@@ -646,8 +721,13 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
     void* wp[8];
     for (int i = 0; i < 8; ++i) wp[i] = cv.take(W_SLOT);
     EFFI_REQUIRE(cv.off <= ws_bytes, EFFIMVS_EWORKSPACE, "costreg bf16: workspace %zu < %zu", ws_bytes, cv.off);
-    // halos and guards must read as zero
-    if (cudaMemsetAsync(ws, 0, act_bytes, st) != cudaSuccess) { set_error("costreg bf16: memset failed"); return EFFIMVS_ECUDA; }
+    (void)act_bytes;
+    int rc;
+    {   // halos and guards must read as zero
+        void* bufs[8] = {c0, c7, c1, c2, c6, c3, c4, c5};
+        ActLayout lays[8] = {L0, L7, L1, L2, L6, L3, L4, L5};
+        if ((rc = run_zero_halo(8, bufs, lays, B, st))) return rc;
+    }
 
     static thread_local ConvProgram P[8];
     static thread_local PackTable T[8];
@@ -656,11 +736,9 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
               build_conv_s1(P[4], T[4], 32, 32, L4, 1) && build_deconv(P[5], T[5], 32, 16, L5, 2, 1) &&
               build_deconv(P[6], T[6], 16, 8, L6, 2, 1) && build_conv_s1(P[7], T[7], 8, 1, L7, 0);
     EFFI_REQUIRE(ok, EFFIMVS_EUNSUPPORTED, "costreg bf16: program does not fit");
-    int rc;
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 8; ++i)
         EFFI_REQUIRE(program_weight_bytes(T[i]) <= W_SLOT, EFFIMVS_EUNSUPPORTED, "costreg bf16: packed weights of layer %d too large", i + 1);
-        if ((rc = run_pack(T[i], weights[i + 1], wp[i], st))) return rc;
-    }
+    if ((rc = run_pack_multi(8, T, weights + 1, wp, st))) return rc;
     if ((rc = run_cin1(x, weights[0], biases[0], B, D, H, W, 1, L0, 0, c0, st))) return rc;
     if ((rc = run_tile_kernel(P[0], B, c0, L0, wp[0], biases[1], L1, c1, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[1], B, c1, L1, wp[1], biases[2], L2, c2, nullptr, nullptr, nullptr, st))) return rc;
@@ -690,14 +768,22 @@ int cost_up_bf16(const float* x, const float* prev, const float* const* weights,
     const size_t act_bytes = cv.off;
     void* wp1 = cv.take(W_SLOT); void* wp2 = cv.take(W_SLOT);
     EFFI_REQUIRE(cv.off <= ws_bytes, EFFIMVS_EWORKSPACE, "cost_up bf16: workspace %zu < %zu", ws_bytes, cv.off);
-    if (cudaMemsetAsync(ws, 0, act_bytes, st) != cudaSuccess) { set_error("cost_up bf16: memset failed"); return EFFIMVS_ECUDA; }
+    (void)act_bytes;
+    int rc;
+    {
+        void* bufs[2] = {cat, c1};
+        ActLayout lays[2] = {Lcat, L1};
+        if ((rc = run_zero_halo(2, bufs, lays, B, st))) return rc;
+    }
     static thread_local ConvProgram P1, P2;
-    static thread_local PackTable T1, T2;
+    static thread_local PackTable T12[2];
+    PackTable &T1 = T12[0], &T2 = T12[1];
     bool ok = build_conv_s1(P1, T1, 16, 8, Lcat, 1) && build_deconv(P2, T2, 8, 1, L1, 1, 1);
     EFFI_REQUIRE(ok, EFFIMVS_EUNSUPPORTED, "cost_up bf16: program does not fit");
-    int rc;
-    if ((rc = run_pack(T1, weights[2], wp1, st))) return rc;
-    if ((rc = run_pack(T2, weights[3], wp2, st))) return rc;
+    {
+        void* dsts[2] = {wp1, wp2};
+        if ((rc = run_pack_multi(2, T12, weights + 2, dsts, st))) return rc;
+    }
     // in a hi/lo layout the concatenated tensor has planes [conv0 hi, conv_cost hi, conv0 lo, conv_cost lo]
     if ((rc = run_cin1(x, weights[0], biases[0], B, D, H, W, 2, Lcat, 0, cat, st))) return rc;
     if ((rc = run_cin1(prev, weights[1], biases[1], B, D, H2, W2, 1, Lcat, 1, cat, st))) return rc;

@@ -276,7 +276,7 @@ def costreg_fpn3d(x: Tensor, weights: List[Tensor], biases: List[Tensor], precis
     out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
     wa, k1 = capi.ptr_array([w.data_ptr() for w in weights])
     ba, k2 = capi.ptr_array([b.data_ptr() for b in biases])
-    _count(9 if precision == capi.PREC_F32 else 17)   # bf16: 8 weight packs + 1 CUDA-core conv + 8 tcgen05 layers
+    _count(9 if precision == capi.PREC_F32 else 11)   # tensor-core modes: halo zeroing + weight pack + 1 CUDA-core conv + 8 tcgen05 layers
     capi.check(_lib.effimvs_costreg_fpn3d(x.data_ptr(), wa, ba, B, D, H, W, precision, ws.data_ptr(), ws.numel(),
                                           out.data_ptr(), _stream()))
     del k1, k2
@@ -303,7 +303,7 @@ def cost_up_small(x: Tensor, prev: Tensor, weights: List[Tensor], biases: List[T
     out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
     wa, k1 = capi.ptr_array([w.data_ptr() for w in weights])
     ba, k2 = capi.ptr_array([b.data_ptr() for b in biases])
-    _count(4 if precision == capi.PREC_F32 else 6)    # bf16: 2 weight packs + 2 CUDA-core convs + 2 tcgen05 layers
+    _count(4 if precision == capi.PREC_F32 else 6)    # tensor-core modes: halo zeroing + weight pack + 2 CUDA-core convs + 2 tcgen05 layers
     capi.check(_lib.effimvs_cost_up_small(x.data_ptr(), prev.data_ptr(), wa, ba, B, D, H, W, precision, ws.data_ptr(),
                                           ws.numel(), out.data_ptr(), _stream()))
     del k1, k2
