@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libeffimvs.so")
 OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
 HYP_TENSOR, HYP_PLANES, HYP_LOCAL = 0, 1, 2
 RANGE_SCALAR, RANGE_PIXEL = 0, 1
+FEA_NCHW, FEA_NHWC = 0, 1
 PREC_F32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 MAX_SRC_VIEWS = 16
 
@@ -37,8 +38,8 @@ SIGNATURES = {
     "effimvs_last_error": (C.c_char_p, []),
     "effimvs_version": (_i, []),
     "effimvs_relative_projection_f32": (_i, [_p, _i, _i, _p, _p]),
-    "effimvs_warp_corr_agg_f32": (_i, [_p, _pp, _i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "effimvs_warp_corr_views_f32": (_i, [_p, _pp, _i, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "effimvs_warp_corr_agg_f32": (_i, [_p, _pp, _i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "effimvs_warp_corr_views_f32": (_i, [_p, _pp, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_weighted_agg_f32": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "effimvs_volume_lookup_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "effimvs_dynamic_cost_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -28,10 +28,12 @@
 // A reads per product instead of three.  32-channel inputs are processed in two K phases
 // (channel-plane pairs) through the same shared-memory slab.
 //
-// One tile per CTA: warp 4 lane 0 issues the bulk copies, waits on the mbarrier, issues the
-// tcgen05.mma sequence and commits; warps 0-3 own TMEM lanes 32w..32w+31 (= tile rows) and run
-// the epilogue (tcgen05.ld -> bias, ReLU, residual -> bf16 -> one 16-byte store per 8 channels).
-// Several CTAs are resident per SM, so loads, MMAs and epilogues of different tiles overlap.
+// Persistent CTAs (one or two per SM) loop over tiles with warp-specialised roles: a TMA producer
+// warp, an MMA issuer warp (one elected lane each) and four epilogue warps that own TMEM lanes
+// 32w..32w+31 (= tile rows).  The operand slab is double buffered (full/empty mbarriers, the
+// empty arrive comes from tcgen05.commit) and so is the TMEM accumulator (tmem_full / tmem_empty),
+// so the loads of tile k+2, the MMAs of tile k+1 and the epilogue of tile k overlap; the packed
+// weights are loaded once per CTA.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -98,7 +100,10 @@ struct ConvProgram {
     int gD, gH, gW, gPx;          // tile grid (output grid for conv, input grid for transposed conv)
     long long zstride;            // voxels per padded z plane of the input (sub-)volumes
     int up_z, up_y, up_x;         // output coordinate = grid coordinate * up + class bit
-    int relu, w_smem_off;         // weights live at this byte offset of dynamic shared memory
+    int relu;
+    int w_smem_bytes;             // packed weights of all phases (resident in shared memory, loaded once per CTA)
+    int slab_bytes, n_stages;     // operand slab of one load unit; number of slab stages (1 or 2)
+    int tile_cols;                // TMEM columns of one accumulator stage (two stages are allocated)
     Phase ph[MAX_PHASES];
     Seg segs[MAX_SEGS];
     Op ops[MAX_OPS];
@@ -212,30 +217,37 @@ __device__ __forceinline__ void load_voxel(const uint4* __restrict__ in, const A
 }
 
 // ------------------------------------------------------------------------------------------------
-// the tile kernel
+// the tile kernel: persistent, warp-specialised, software-pipelined over tiles
+//   warp 4 (one lane)  TMA producer : bulk copies of the next load unit (tile x K phase) into slab stage
+//   warp 5 (one lane)  MMA issuer   : tcgen05.mma sequence of a unit into TMEM accumulator stage k % 2
+//   warps 0-3          epilogue     : TMEM -> registers -> bias / ReLU / residual -> bf16 -> global
+// mbarriers: full[s] / empty[s] per slab stage (TMA <-> MMA), tmem_full[a] / tmem_empty[a] per
+// accumulator stage (MMA <-> epilogue), wbar for the weights (loaded once per CTA).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(160)
+constexpr int MAX_STAGES = 2;
+constexpr int CTA_THREADS = 192;
+
+__global__ void __launch_bounds__(CTA_THREADS)
 conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ in, long long in_batch_stride,
                const uint8_t* __restrict__ wpk, const float* __restrict__ bias, const ActLayout OL, uint4* __restrict__ out,
-               const ActLayout RL, const uint4* __restrict__ res, float* __restrict__ out_f32) {
+               const ActLayout RL, const uint4* __restrict__ res, float* __restrict__ out_f32, int n_tiles, int tiles_per_plane) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bar_load, bar_step, bar_done;
+    __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2], bar_w;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int z = blockIdx.y, b = blockIdx.z;
-    const long long q0 = (long long)P.gPx + (long long)blockIdx.x * TILE_M;  // first tile starts at padded row yp = 1
-    uint8_t* slab = smem;
-    uint8_t* wsm = smem + P.w_smem_off;
+    uint8_t* wsm = smem;                              // all phases' weights, resident for the CTA's lifetime
+    uint8_t* slab = smem + P.w_smem_bytes;            // n_stages slabs of slab_bytes
+    const int S = P.n_stages;
 
-    if (warp == 4) {
+    if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)P.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        if (lane == 0) {
-            mbar_init(&bar_load, 1);
-            mbar_init(&bar_step, 1);
-            mbar_init(&bar_done, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
+    }
+    if (tid == 128) {
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], 4); }
+        mbar_init(&bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -243,80 +255,115 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
     const uint32_t tmem = tmem_base_s;
 
     if (warp == 4) {
+        // ---------------- TMA producer ----------------
         if (lane == 0) {
-            const uint4* base = in + (long long)b * in_batch_stride + (long long)z * P.zstride + q0;
-            const uint32_t a0 = smem_u32(slab), b0 = smem_u32(wsm);
-            const uint32_t b_lbo = (uint32_t)P.b_rows * 16u;
-            for (int p = 0; p < P.n_phases; ++p) {
-                const Phase ph = P.ph[p];
-                if (p > 0) {                       // the previous phase's MMAs must have consumed the slab
-                    mbar_wait(&bar_step, (uint32_t)((p - 1) & 1));
-                    tc_fence_after();
+            mbar_expect_tx(&bar_w, (uint32_t)P.w_smem_bytes);
+            bulk_g2s(wsm, wpk, (uint32_t)P.w_smem_bytes, &bar_w);
+            uint32_t u = 0;                                          // load unit counter
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int t = tile % tiles_per_plane, z = (tile / tiles_per_plane) % P.gD, b = tile / (tiles_per_plane * P.gD);
+                const long long q0 = (long long)P.gPx + (long long)t * TILE_M;
+                const uint4* base = in + (long long)b * in_batch_stride + (long long)z * P.zstride + q0;
+                for (int p = 0; p < P.n_phases; ++p, ++u) {
+                    const Phase ph = P.ph[p];
+                    const uint32_t s = u % S, n = u / S;
+                    mbar_wait(&bar_empty[s], (n & 1) ^ 1);          // slab stage free (first use passes)
+                    uint32_t bytes = 0;
+                    for (int i = ph.seg_begin; i < ph.seg_end; ++i) bytes += (uint32_t)P.segs[i].copy_vox * 16u;
+                    mbar_expect_tx(&bar_full[s], bytes);
+                    uint8_t* dst = slab + (size_t)s * P.slab_bytes;
+                    for (int i = ph.seg_begin; i < ph.seg_end; ++i)
+                        bulk_g2s(dst + (size_t)P.segs[i].slot * SEG_BYTES, base + P.segs[i].src_off, (uint32_t)P.segs[i].copy_vox * 16u, &bar_full[s]);
                 }
-                uint32_t bytes = (uint32_t)ph.w_bytes;
-                for (int s = ph.seg_begin; s < ph.seg_end; ++s) bytes += (uint32_t)P.segs[s].copy_vox * 16u;
-                mbar_expect_tx(&bar_load, bytes);
-                for (int s = ph.seg_begin; s < ph.seg_end; ++s)
-                    bulk_g2s(slab + (size_t)P.segs[s].slot * SEG_BYTES, base + P.segs[s].src_off, (uint32_t)P.segs[s].copy_vox * 16u, &bar_load);
-                bulk_g2s(wsm, wpk + ph.w_off, (uint32_t)ph.w_bytes, &bar_load);
-                mbar_wait(&bar_load, (uint32_t)(p & 1));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t w0 = smem_u32(wsm), b_lbo = (uint32_t)P.b_rows * 16u;
+            mbar_wait(&bar_w, 0);
+            uint32_t u = 0, k = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+                const uint32_t acc = k & 1;
+                mbar_wait(&bar_tempty[acc], ((k >> 1) & 1) ^ 1);    // epilogue drained this accumulator stage
                 tc_fence_after();
-                for (int i = ph.op_begin; i < ph.op_end; ++i) {
-                    const Op op = P.ops[i];
-                    umma_bf16(tmem + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, b_lbo, 128),
-                              umma_idesc(op.n8 * 8), op.accum);
+                const uint32_t d0 = tmem + acc * (uint32_t)P.tile_cols;
+                for (int p = 0; p < P.n_phases; ++p, ++u) {
+                    const Phase ph = P.ph[p];
+                    const uint32_t s = u % S, n = u / S;
+                    mbar_wait(&bar_full[s], n & 1);                  // operands landed
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(slab + (size_t)s * P.slab_bytes), b0 = w0 + (uint32_t)ph.w_off;
+                    for (int i = ph.op_begin; i < ph.op_end; ++i) {
+                        const Op op = P.ops[i];
+                        umma_bf16(d0 + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, b_lbo, 128),
+                                  umma_idesc(op.n8 * 8), op.accum);
+                    }
+                    umma_commit(&bar_empty[s]);                      // slab stage reusable once these MMAs retire
                 }
-                umma_commit(p + 1 < P.n_phases ? &bar_step : &bar_done);
+                umma_commit(&bar_tfull[acc]);                        // accumulator complete
             }
         }
         __syncwarp();
     } else {
-        // ---- epilogue: thread <-> tile row <-> TMEM lane ----
-        const long long q = q0 + tid;
-        const int yp = (int)(q / P.gPx), xp = (int)(q - (long long)yp * P.gPx);
-        const bool interior = yp >= 1 && yp <= P.gH && xp >= 1 && xp <= P.gW;
-        const int gy = yp - 1, gx = xp - 1;
-        mbar_wait(&bar_done, 0);
-        tc_fence_after();
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        // ---------------- epilogue: thread <-> tile row <-> TMEM lane ----------------
         const int groups = (P.cout + 7) / 8;
-        for (int cls = 0; cls < P.n_classes; ++cls) {
-            int pz = 0, py = 0, px = 0;
-            if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
-            else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
-            const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
-            for (int g = 0; g < groups; ++g) {
-                float v[8];
-                tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + g * 8), v);
-                if (P.b_rows != P.N) {   // hi/lo mode: columns [N, 2N) hold x_hi * w_lo
-                    float u[8];
-                    tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + P.N + g * 8), u);
+        uint32_t k = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int t = tile % tiles_per_plane, z = (tile / tiles_per_plane) % P.gD, b = tile / (tiles_per_plane * P.gD);
+            const int q = P.gPx + t * TILE_M + tid;
+            const int yp = q / P.gPx, xp = q - yp * P.gPx;
+            const bool interior = yp >= 1 && yp <= P.gH && xp >= 1 && xp <= P.gW;
+            const int gy = yp - 1, gx = xp - 1;
+            const uint32_t acc = k & 1;
+            mbar_wait(&bar_tfull[acc], (k >> 1) & 1);
+            tc_fence_after();
+            const uint32_t lane_base = tmem + acc * (uint32_t)P.tile_cols + ((uint32_t)(warp * 32) << 16);
+            for (int cls = 0; cls < P.n_classes; ++cls) {
+                int pz = 0, py = 0, px = 0;
+                if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
+                else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
+                const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
+                for (int g = 0; g < groups; ++g) {
+                    float v[8];
+                    tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + g * 8), v);
+                    if (P.b_rows != P.N) {   // hi/lo mode: columns [N, 2N) hold x_hi * w_lo
+                        float w2[8];
+                        tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + P.N + g * 8), w2);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += u[j];
-                }
-                if (!interior) continue;
+                        for (int j = 0; j < 8; ++j) v[j] += w2[j];
+                    }
+                    if (cls == P.n_classes - 1 && g == groups - 1) {
+                        // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_tempty[acc])) : "memory");
+                    }
+                    if (!interior) continue;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (bias && g * 8 + j < P.cout) v[j] += __ldg(bias + g * 8 + j);
-                    if (P.relu) v[j] = fmaxf(v[j], 0.0f);
-                }
-                if (out_f32) {  // single-channel fp32 NCDHW output
-                    out_f32[(((size_t)b * OL.D + oz) * OL.H + oy) * OL.W + ox] = v[0];
-                    continue;
-                }
-                if (res) {
-                    float r[8];
-                    load_voxel(res, RL, b, g, oz, oy, ox, r);
+                    for (int j = 0; j < 8; ++j) {
+                        if (bias && g * 8 + j < P.cout) v[j] += __ldg(bias + g * 8 + j);
+                        if (P.relu) v[j] = fmaxf(v[j], 0.0f);
+                    }
+                    if (out_f32) {  // single-channel fp32 NCDHW output
+                        out_f32[(((size_t)b * OL.D + oz) * OL.H + oy) * OL.W + ox] = v[0];
+                        continue;
+                    }
+                    if (res) {
+                        float r[8];
+                        load_voxel(res, RL, b, g, oz, oy, ox, r);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] += r[j];
+                        for (int j = 0; j < 8; ++j) v[j] += r[j];
+                    }
+                    store_voxel(out, OL, b, g, oz, oy, ox, v);
                 }
-                store_voxel(out, OL, b, g, oz, oy, ox, v);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4)
+    if (warp == 5)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)P.tmem_cols) : "memory");
 }
 
@@ -489,8 +536,6 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
     if (n_phases > MAX_PHASES) return false;
     P.n_phases = n_phases;
     P.b_rows = T.rows = hilo ? 2 * P.N : P.N;
-    P.tmem_cols = pow2_cols(P.b_rows * P.n_classes);
-    if (P.tmem_cols > 512) return false;
     int n_seg = 0, n_op = 0, n_blk = 0;
     std::vector<bool> started(P.n_classes, false);
     size_t max_slab = 0;
@@ -553,15 +598,18 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
         max_slab = std::max(max_slab, (size_t)halves * NPph * SPP * SEG_BYTES);
     }
     T.n_blocks = n_blk;
-    P.w_smem_off = (int)max_slab;
+    P.w_smem_bytes = (int)((size_t)n_blk * 2u * P.b_rows * 16u);
+    P.slab_bytes = (int)max_slab;
+    const size_t budget = 220 * 1024;
+    if ((size_t)P.w_smem_bytes + P.slab_bytes > budget) return false;
+    P.n_stages = ((size_t)P.w_smem_bytes + 2 * (size_t)P.slab_bytes <= budget) ? 2 : 1;
+    P.tile_cols = P.b_rows * P.n_classes;
+    P.tmem_cols = pow2_cols(2 * P.tile_cols);
+    if (P.tmem_cols > 512) return false;
     return true;
 }
 
-size_t program_smem(const ConvProgram& P) {
-    size_t w = 0;
-    for (int p = 0; p < P.n_phases; ++p) w = std::max(w, (size_t)P.ph[p].w_bytes);
-    return (size_t)P.w_smem_off + w;
-}
+size_t program_smem(const ConvProgram& P) { return (size_t)P.w_smem_bytes + (size_t)P.n_stages * P.slab_bytes; }
 size_t program_weight_bytes(const PackTable& T) { return (size_t)T.n_blocks * 2 * T.rows * 16; }
 
 void init_program(ConvProgram& P, PackTable& T, int Cin, int Cout, int n_classes, int gD, int gH, int gW, const ActLayout& IL,
@@ -669,11 +717,15 @@ int run_tile_kernel(const ConvProgram& P, int B, const void* in, const ActLayout
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return EFFIMVS_ECUDA; }
         attr_set = true;
     }
-    int tiles = ceil_div(P.gH * P.gPx, TILE_M);
-    dim3 grid(tiles, P.gD, B), block(160);
+    const int tiles_per_plane = ceil_div(P.gH * P.gPx, TILE_M);
+    const long long n_tiles = (long long)tiles_per_plane * P.gD * B;
+    EFFI_REQUIRE(n_tiles < (1ll << 31) && (long long)P.gPx * (P.gH + 2) < (1ll << 30), EFFIMVS_EUNSUPPORTED, "conv_tc: volume too large");
+    // persistent CTAs: as many per SM as shared memory and TMEM (512 columns) allow, at most 2
+    const int per_sm = (smem <= 110 * 1024 && P.tmem_cols <= 256) ? 2 : 1;
+    const int grid = (int)std::min<long long>(n_tiles, (long long)kNumSMs * per_sm);
     ActLayout rl = RL ? *RL : OL;
-    conv_tc_kernel<<<grid, block, smem, st>>>(P, (const uint4*)in, IL.batch_stride, (const uint8_t*)wpk, bias, OL, (uint4*)out, rl,
-                                              (const uint4*)res, out_f32);
+    conv_tc_kernel<<<grid, CTA_THREADS, smem, st>>>(P, (const uint4*)in, IL.batch_stride, (const uint8_t*)wpk, bias, OL, (uint4*)out, rl,
+                                                    (const uint4*)res, out_f32, (int)n_tiles, tiles_per_plane);
     return check_launch("conv_tc_kernel");
 }
 

@@ -96,6 +96,59 @@ __device__ __forceinline__ void correlate(const float* __restrict__ src, int HW,
     }
 }
 
+// Channels-last (NHWC) feature maps -- what cuDNN's channels_last FPN emits: the C values of a tap
+// are contiguous, so a tap is C/4 128-bit loads at immediate offsets from one address and the
+// correlation is formed per tap (dot over the channels of a group, then one FMA with the bilinear
+// weight): 4x fewer load and address instructions than the planar path.
+template <int C, int G>
+__device__ __forceinline__ void tap_dot(const float4* __restrict__ p, const float (&ref)[C], float w, float (&sim)[G]) {
+    constexpr int CG = C / G;
+    float dot[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) dot[g] = 0.0f;
+#pragma unroll
+    for (int cq = 0; cq < C / 4; ++cq) {
+        const float4 v = __ldg(p + cq);
+        dot[(cq * 4 + 0) / CG] = fmaf(v.x, ref[cq * 4 + 0], dot[(cq * 4 + 0) / CG]);
+        dot[(cq * 4 + 1) / CG] = fmaf(v.y, ref[cq * 4 + 1], dot[(cq * 4 + 1) / CG]);
+        dot[(cq * 4 + 2) / CG] = fmaf(v.z, ref[cq * 4 + 2], dot[(cq * 4 + 2) / CG]);
+        dot[(cq * 4 + 3) / CG] = fmaf(v.w, ref[cq * 4 + 3], dot[(cq * 4 + 3) / CG]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) sim[g] = fmaf(dot[g], w, sim[g]);
+}
+
+template <int C, int G>
+__device__ __forceinline__ void correlate_nhwc(const float* __restrict__ src, int W, const Taps& t, const float (&ref)[C],
+                                               float (&sim)[G]) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) sim[g] = 0.0f;
+    if (!t.any) return;
+    const float4* p = reinterpret_cast<const float4*>(src) + (ptrdiff_t)t.o_nw * (C / 4);
+    if (t.v_nw) tap_dot<C, G>(p, ref, t.w_nw, sim);
+    if (t.v_ne) tap_dot<C, G>(p + C / 4, ref, t.w_ne, sim);
+    if (t.v_sw) tap_dot<C, G>(p + (ptrdiff_t)W * (C / 4), ref, t.w_sw, sim);
+    if (t.v_se) tap_dot<C, G>(p + (ptrdiff_t)(W + 1) * (C / 4), ref, t.w_se, sim);
+#pragma unroll
+    for (int g = 0; g < G; ++g) sim[g] *= (1.0f / (C / G));
+}
+
+template <int C, bool NHWC>
+__device__ __forceinline__ void load_ref(const float* __restrict__ ref_fea, int b, int pix, int HW, float (&ref)[C]) {
+    if (NHWC) {
+        const float4* rp = reinterpret_cast<const float4*>(ref_fea + ((size_t)b * HW + pix) * C);
+#pragma unroll
+        for (int cq = 0; cq < C / 4; ++cq) {
+            const float4 v = __ldg(rp + cq);
+            ref[cq * 4] = v.x; ref[cq * 4 + 1] = v.y; ref[cq * 4 + 2] = v.z; ref[cq * 4 + 3] = v.w;
+        }
+    } else {
+        const float* rp = ref_fea + (size_t)b * C * HW + pix;
+#pragma unroll
+        for (int c = 0; c < C; ++c) ref[c] = __ldg(rp + (size_t)c * HW);
+    }
+}
+
 // inverse-depth samples around cur_depth, exactly the op sequence of models/module.py:558-570
 __device__ __forceinline__ float local_hypothesis(float cur_depth, float interval, int D, int d) {
     float inv = __fdiv_rn(1.0f, cur_depth);
@@ -114,7 +167,7 @@ __device__ __forceinline__ float fetch_hypothesis(const float* __restrict__ hyp,
     return local_hypothesis(__ldg(hyp + (size_t)b * HW + pix), __ldg(interval + b), D, d);
 }
 
-template <int C, int G>
+template <int C, int G, bool NHWC>
 __global__ void __launch_bounds__(32 * DT)
 warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
                      const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval,
@@ -137,9 +190,7 @@ warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src,
     const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
 
     float ref[C];
-    const float* rp = ref_fea + (size_t)b * C * HW + pix;
-#pragma unroll
-    for (int c = 0; c < C; ++c) ref[c] = __ldg(rp + (size_t)c * HW);
+    load_ref<C, NHWC>(ref_fea, b, pix, HW, ref);
 
     const float depth = fetch_hypothesis(hyp, hyp_mode, interval, b, d, D, pix, HW);
     if (hyp_out) hyp_out[((size_t)b * D + d) * HW + pix] = depth;
@@ -151,7 +202,8 @@ warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src,
     for (int v = 0; v < n_src; ++v) {
         Taps t = make_taps(sP + v * 12, x, y, depth, H, W, inv_half_w, inv_half_h);
         float sim[G];
-        correlate<C, G>(sSrc[v] + (size_t)b * C * HW, HW, W, t, ref, sim);
+        if (NHWC) correlate_nhwc<C, G>(sSrc[v] + (size_t)b * C * HW, W, t, ref, sim);
+        else correlate<C, G>(sSrc[v] + (size_t)b * C * HW, HW, W, t, ref, sim);
         if (weights) {
             float w = __ldg(weights + ((size_t)b * n_src + v) * HW + pix);
 #pragma unroll
@@ -170,7 +222,7 @@ warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src,
 
 // Stage-1 form: one source view per blockIdx.y; all D planes of 32 pixels per block so that the
 // softmax entropy over D can be reduced on chip.
-template <int C>
+template <int C, bool NHWC>
 __global__ void __launch_bounds__(32 * DT)
 warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
                        const float* __restrict__ hyp, int hyp_mode, int H, int W, int D,
@@ -192,16 +244,15 @@ warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_sr
         const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
         const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
         float ref[C];
-        const float* rp = ref_fea + (size_t)b * C * HW + pix;
-#pragma unroll
-        for (int c = 0; c < C; ++c) ref[c] = __ldg(rp + (size_t)c * HW);
+        load_ref<C, NHWC>(ref_fea, b, pix, HW, ref);
         const float* src = sSrc + (size_t)b * C * HW;
         float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
         for (int d = threadIdx.y; d < D; d += DT) {
             const float depth = fetch_hypothesis(hyp, hyp_mode, nullptr, b, d, D, pix, HW);
             Taps t = make_taps(sP, x, y, depth, H, W, inv_half_w, inv_half_h);
             float sim[1];
-            correlate<C, 1>(src, HW, W, t, ref, sim);
+            if (NHWC) correlate_nhwc<C, 1>(src, W, t, ref, sim);
+            else correlate<C, 1>(src, HW, W, t, ref, sim);
             out[(size_t)d * HW] = sim[0];
             s_sim[d * 32 + threadIdx.x] = sim[0];
         }
@@ -247,23 +298,27 @@ __global__ void weighted_agg_kernel(const float* __restrict__ sims, const float*
 
 template <int C, int G>
 int launch_agg(const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
-               const float* interval, const float* weights, int B, int H, int W, int D, float* sim_out,
+               const float* interval, const float* weights, int B, int H, int W, int D, int nhwc, float* sim_out,
                float* hyp_out, cudaStream_t st) {
     dim3 block(32, DT), grid(ceil_div(H * W, 32), ceil_div(D, DT), B);
-    warp_corr_agg_kernel<C, G><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, C, H, W,
-                                                       D, sim_out, hyp_out);
+    if (nhwc)
+        warp_corr_agg_kernel<C, G, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, C, H, W,
+                                                                 D, sim_out, hyp_out);
+    else
+        warp_corr_agg_kernel<C, G, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, C, H, W,
+                                                                  D, sim_out, hyp_out);
     return check_launch("warp_corr_agg_kernel");
 }
 
 template <int C>
 int dispatch_g(int G, const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp,
-               int hyp_mode, const float* interval, const float* weights, int B, int H, int W, int D,
+               int hyp_mode, const float* interval, const float* weights, int B, int H, int W, int D, int nhwc,
                float* sim_out, float* hyp_out, cudaStream_t st) {
     switch (G) {
-        case 1: return launch_agg<C, 1>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
-        case 2: return launch_agg<C, 2>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
-        case 4: return launch_agg<C, 4>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
-        case 8: return launch_agg<C, 8>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+        case 1: return launch_agg<C, 1>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
+        case 2: return launch_agg<C, 2>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
+        case 4: return launch_agg<C, 4>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
+        case 8: return launch_agg<C, 8>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
     }
     set_error("warp_corr_agg: G=%d not in {1,2,4,8}", G);
     return EFFIMVS_EUNSUPPORTED;
@@ -285,22 +340,24 @@ using namespace effimvs;
 extern "C" int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* const* src_fea, int n_src,
                                          const float* proj, const float* hyp, int hyp_mode, const float* interval,
                                          const float* weights, int B, int C, int H, int W, int D, int G,
-                                         float* sim_out, float* hyp_out, void* stream) {
+                                         int fea_layout, float* sim_out, float* hyp_out, void* stream) {
     EFFI_REQUIRE(ref_fea && proj && hyp && sim_out, EFFIMVS_EINVAL, "warp_corr_agg: null pointer");
     EFFI_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1 && D > 0 && G > 0, EFFIMVS_EINVAL, "warp_corr_agg: bad sizes");
     EFFI_REQUIRE(hyp_mode >= 0 && hyp_mode <= 2, EFFIMVS_EINVAL, "warp_corr_agg: hyp_mode=%d", hyp_mode);
     EFFI_REQUIRE(hyp_mode != EFFIMVS_HYP_LOCAL || (interval && D > 1), EFFIMVS_EINVAL,
                  "warp_corr_agg: HYP_LOCAL needs interval and D > 1");
     EFFI_REQUIRE(C % G == 0, EFFIMVS_EINVAL, "warp_corr_agg: C=%d not divisible by G=%d", C, G);
+    EFFI_REQUIRE(fea_layout == EFFIMVS_FEA_NCHW || fea_layout == EFFIMVS_FEA_NHWC, EFFIMVS_EINVAL, "warp_corr_agg: fea_layout=%d", fea_layout);
+    const int nhwc = fea_layout == EFFIMVS_FEA_NHWC;
     EFFI_REQUIRE(B <= 65535, EFFIMVS_EUNSUPPORTED, "warp_corr_agg: B too large");
     SrcPtrs s;
     int rc = fill_srcs(s, src_fea, n_src);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
-        case 8: return dispatch_g<8>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
-        case 16: return dispatch_g<16>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
-        case 32: return dispatch_g<32>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, sim_out, hyp_out, st);
+        case 8: return dispatch_g<8>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
+        case 16: return dispatch_g<16>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
+        case 32: return dispatch_g<32>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
     }
     set_error("warp_corr_agg: C=%d not in {8,16,32}", C);
     return EFFIMVS_EUNSUPPORTED;
@@ -308,36 +365,35 @@ extern "C" int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* cons
 
 extern "C" int effimvs_warp_corr_views_f32(const float* ref_fea, const float* const* src_fea, int n_src,
                                            const float* proj, const float* hyp, int hyp_mode,
-                                           int B, int C, int H, int W, int D,
+                                           int B, int C, int H, int W, int D, int fea_layout,
                                            float* sims_out, float* entropy_out, void* stream) {
     EFFI_REQUIRE(ref_fea && proj && hyp && sims_out && entropy_out, EFFIMVS_EINVAL, "warp_corr_views: null pointer");
     EFFI_REQUIRE(B > 0 && H > 1 && W > 1 && D > 0, EFFIMVS_EINVAL, "warp_corr_views: bad sizes");
     EFFI_REQUIRE(hyp_mode == EFFIMVS_HYP_TENSOR || hyp_mode == EFFIMVS_HYP_PLANES, EFFIMVS_EINVAL,
                  "warp_corr_views: hyp_mode=%d", hyp_mode);
     EFFI_REQUIRE(D <= 1024 && B <= 65535, EFFIMVS_EUNSUPPORTED, "warp_corr_views: D=%d > 1024", D);
+    EFFI_REQUIRE(fea_layout == EFFIMVS_FEA_NCHW || fea_layout == EFFIMVS_FEA_NHWC, EFFIMVS_EINVAL, "warp_corr_views: fea_layout=%d", fea_layout);
     SrcPtrs s;
     int rc = fill_srcs(s, src_fea, n_src);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 block(32, DT), grid(ceil_div(H * W, 32), n_src, B);
     size_t smem = (size_t)D * 32 * sizeof(float);
+#define EFFI_VIEWS_CASE(CC, L)                                                                                                   \
+    {                                                                                                                            \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<CC, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        warp_corr_views_kernel<CC, L><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out); \
+    }
+    const bool nhwc = fea_layout == EFFIMVS_FEA_NHWC;
     switch (C) {
-        case 8:
-            if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            warp_corr_views_kernel<8><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out);
-            break;
-        case 16:
-            if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            warp_corr_views_kernel<16><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out);
-            break;
-        case 32:
-            if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            warp_corr_views_kernel<32><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out);
-            break;
+        case 8: if (nhwc) EFFI_VIEWS_CASE(8, true) else EFFI_VIEWS_CASE(8, false) break;
+        case 16: if (nhwc) EFFI_VIEWS_CASE(16, true) else EFFI_VIEWS_CASE(16, false) break;
+        case 32: if (nhwc) EFFI_VIEWS_CASE(32, true) else EFFI_VIEWS_CASE(32, false) break;
         default:
             set_error("warp_corr_views: C=%d not in {8,16,32}", C);
             return EFFIMVS_EUNSUPPORTED;
     }
+#undef EFFI_VIEWS_CASE
     return check_launch("warp_corr_views_kernel");
 }
 

@@ -33,6 +33,18 @@ def _dev(t: Tensor, name: str) -> Tensor:
     return t.contiguous()
 
 
+def _features(ref: Tensor, srcs: List[Tensor], name: str):
+    """Feature maps as the kernels read them: all NCHW-contiguous or all channels-last (NHWC).
+    Channels-last maps (what the channels_last FPN emits) are passed through without a copy."""
+    for t in [ref] + list(srcs):
+        if not t.is_cuda:
+            raise RuntimeError("effimvs::{} got a CPU tensor; the hot path is CUDA-only (no fallback)".format(name))
+    nhwc = ref.dim() == 4 and ref.shape[1] > 1 and not ref.is_contiguous() and ref.is_contiguous(memory_format=torch.channels_last)
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    fix = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous(memory_format=fmt)   # noqa: E731
+    return fix(ref), [fix(s) for s in srcs], (capi.FEA_NHWC if nhwc else capi.FEA_NCHW)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -62,8 +74,7 @@ def _(cams):
 def warp_corr_agg(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hyp_mode: int,
                   interval: Optional[Tensor], weights: Optional[Tensor], D: int, G: int,
                   want_hyp: bool) -> Tuple[Tensor, Tensor]:
-    ref = _dev(ref, "warp_corr_agg")
-    srcs = [_dev(s, "warp_corr_agg") for s in srcs]
+    ref, srcs, layout = _features(ref, srcs, "warp_corr_agg")
     proj, hyp = _dev(proj, "warp_corr_agg"), _dev(hyp, "warp_corr_agg")
     interval = _dev(interval, "warp_corr_agg") if interval is not None else None
     weights = _dev(weights, "warp_corr_agg") if weights is not None else None
@@ -73,7 +84,7 @@ def warp_corr_agg(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hy
     arr, keep = capi.ptr_array([s.data_ptr() for s in srcs])
     _count(1)
     capi.check(_lib.effimvs_warp_corr_agg_f32(ref.data_ptr(), arr, len(srcs), proj.data_ptr(), hyp.data_ptr(), hyp_mode,
-                                              _opt(interval), _opt(weights), B, Cc, H, W, D, G, sim.data_ptr(),
+                                              _opt(interval), _opt(weights), B, Cc, H, W, D, G, layout, sim.data_ptr(),
                                               hyp_out.data_ptr() if want_hyp else None, _stream()))
     del keep
     return sim, hyp_out
@@ -87,8 +98,7 @@ def _(ref, srcs, proj, hyp, hyp_mode, interval, weights, D, G, want_hyp):
 
 @torch.library.custom_op("effimvs::warp_corr_views", mutates_args=())
 def warp_corr_views(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hyp_mode: int, D: int) -> Tuple[Tensor, Tensor]:
-    ref = _dev(ref, "warp_corr_views")
-    srcs = [_dev(s, "warp_corr_views") for s in srcs]
+    ref, srcs, layout = _features(ref, srcs, "warp_corr_views")
     proj, hyp = _dev(proj, "warp_corr_views"), _dev(hyp, "warp_corr_views")
     B, Cc, H, W = ref.shape
     n = len(srcs)
@@ -97,7 +107,7 @@ def warp_corr_views(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, 
     arr, keep = capi.ptr_array([s.data_ptr() for s in srcs])
     _count(1)
     capi.check(_lib.effimvs_warp_corr_views_f32(ref.data_ptr(), arr, n, proj.data_ptr(), hyp.data_ptr(), hyp_mode,
-                                                B, Cc, H, W, D, sims.data_ptr(), ent.data_ptr(), _stream()))
+                                                B, Cc, H, W, D, layout, sims.data_ptr(), ent.data_ptr(), _stream()))
     del keep
     return sims, ent
 

@@ -40,6 +40,10 @@ extern "C" {
 #define EFFIMVS_HYP_LOCAL 2  /* hyp = cur_depth (B,1,H,W); D inverse-depth samples around
                                 it are generated in-kernel (models/module.py:554-570)    */
 
+/* memory layout of the feature maps handed to the warp kernels */
+#define EFFIMVS_FEA_NCHW 0 /* (B,C,H,W) planar, upstream's default                               */
+#define EFFIMVS_FEA_NHWC 1 /* (B,H,W,C) channels-last, what a channels_last cuDNN FPN emits      */
+
 /* per-batch scalar (B) or per-pixel (B,H,W) depth range of a volume */
 #define EFFIMVS_RANGE_SCALAR 0
 #define EFFIMVS_RANGE_PIXEL 1
@@ -65,15 +69,15 @@ int effimvs_relative_projection_f32(const float* cams, int B, int V, float* proj
  * materialised.  Replaces, per source view, homo_warping_new (models/module.py:303-344) +
  * the group-wise correlation (models/Effi_MVS_plus.py:39-40, :222-224) and the aggregation
  * over views (:52-53/:67, :233-234/:244).
- *   ref_fea   (B,C,H,W)
- *   src_fea   host array of n_src device pointers, each (B,C,H,W)
+ *   ref_fea   (B,C,H,W), or (B,H,W,C) with fea_layout = EFFIMVS_FEA_NHWC
+ *   src_fea   host array of n_src device pointers, each laid out like ref_fea
  *   proj      (B,n_src,12) from effimvs_relative_projection_f32 (or torch)
  *   hyp       see EFFIMVS_HYP_*;  interval (B) inverse-depth step, only for HYP_LOCAL
  *   weights   (B,n_src,H,W) view weights or NULL (plain mean over views)
  *   sim_out   (B,G,D,H,W);  hyp_out (B,D,H,W) depth hypotheses actually used, or NULL */
 int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* const* src_fea, int n_src,
                               const float* proj, const float* hyp, int hyp_mode, const float* interval,
-                              const float* weights, int B, int C, int H, int W, int D, int G,
+                              const float* weights, int B, int C, int H, int W, int D, int G, int fea_layout,
                               float* sim_out, float* hyp_out, void* stream);
 
 /* Stage-1 form (models/Effi_MVS_plus.py:32-46): per-view similarity (G must be 1) and the
@@ -81,7 +85,7 @@ int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* const* src_fea,
  *   sims_out (B,n_src,D,H,W), entropy_out (B,n_src,H,W) */
 int effimvs_warp_corr_views_f32(const float* ref_fea, const float* const* src_fea, int n_src,
                                 const float* proj, const float* hyp, int hyp_mode,
-                                int B, int C, int H, int W, int D,
+                                int B, int C, int H, int W, int D, int fea_layout,
                                 float* sims_out, float* entropy_out, void* stream);
 
 /* sum_v w_v * sim_v / (sum_v w_v + 1e-6)  (models/Effi_MVS_plus.py:52-53, :67).

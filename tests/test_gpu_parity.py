@@ -53,9 +53,12 @@ def test_warp_corr_agg_golden(hp):
 @pytest.mark.parametrize("C,G,D,H,W", [(8, 1, 8, 37, 53), (8, 8, 16, 64, 80), (16, 4, 8, 40, 64), (16, 1, 48, 32, 40),
                                        (32, 1, 48, 37, 50), (32, 8, 8, 64, 96), (32, 2, 3, 20, 31)])
 @pytest.mark.parametrize("weighted", [True, False])
-def test_warp_corr_agg_vs_oracle(hp, ohp, C, G, D, H, W, weighted):
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_warp_corr_agg_vs_oracle(hp, ohp, C, G, D, H, W, weighted, channels_last):
     from effimvs_b200 import synthetic
     feats, cams, hyp, wts = synthetic.microbench_inputs(C, D, H, W, views=5, seed=C + D, device=DEV)
+    if channels_last:          # NHWC kernels: the maps are read in place, as a channels_last FPN emits them
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
     got = hp.warp_corr_agg(feats, cams, hyp, wts if weighted else None, G)
     sims = [ohp.view_similarity(feats[0], feats[v], cams[:, 0], cams[:, v], hyp, G) for v in range(1, 5)]
     want = ohp.weighted_aggregate(sims, [wts[:, i:i + 1] for i in range(4)]) if weighted else sum(sims) / 4
@@ -126,6 +129,9 @@ def test_stage1_views_entropy_vs_oracle(ohp):
     feats = [f * 0.4 for f in feats]
     proj = hotpath.CudaHotPath().relative_projection(cams)
     sims, ent = ops.warp_corr_views(feats[0], feats[1:], proj, hyp, capi.HYP_TENSOR, 96)
+    cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    sims_cl, ent_cl = ops.warp_corr_views(cl[0], cl[1:], proj, hyp, capi.HYP_TENSOR, 96)
+    assert rel_max(sims_cl, sims) < 1e-5 and float((ent_cl - ent).abs().max()) < 1e-5
     planes = hyp[:, :, 0, 0].contiguous()
     sims_p, ent_p = ops.warp_corr_views(feats[0], feats[1:], proj, planes, capi.HYP_PLANES, 96)
     assert torch.equal(sims, sims_p) and torch.equal(ent, ent_p)
