@@ -194,6 +194,22 @@ class TimedHotPath:
         return getattr(self.inner, name)
 
 
+def ncu_traffic(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel whose label contains `tag`,
+    from the committed `ncu --set full` summary (profiles/r1_kernels_ncu_full.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_kernels_ncu_full.json")) as f:
+            for k in json.load(f):
+                if tag in k["label"] and "warp_corr" in k["label"]:
+                    def mb(v):
+                        num, unit = v.split()[:2]
+                        return float(num) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+                    return mb(k["dram__bytes_read.sum"]) + mb(k["dram__bytes_write.sum"])
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
     """Per-kernel device time of the hot-path launches at the bench shape, timed in isolation with
     CUDA events on the launching stream, an L2 flush (256 MiB memset) before every launch."""
@@ -225,7 +241,11 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
     planes = (1.0 / torch.linspace(1 / 935.0, 1 / 425.0, D, device=dev)).reshape(1, D).repeat(B, 1)
     ms = timed(lambda: ops.warp_corr_views(f[0], f[1:], proj, planes, capi.HYP_PLANES, D))
     by = 4.0 * (V * C * H * W + D + (V - 1) * D * H * W + (V - 1) * H * W)
-    out["warp_corr_views_stage1"] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6}
+    out["warp_corr_views_stage1"] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6,
+                                     "feature_layout": "NHWC" if not f[0].is_contiguous() else "NCHW"}
+    fp = [t.contiguous() for t in f]
+    ms = timed(lambda: ops.warp_corr_views(fp[0], fp[1:], proj, planes, capi.HYP_PLANES, D))
+    out["warp_corr_views_stage1_nchw"] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6, "feature_layout": "NCHW"}
     # stages 2, 3: fused warp + correlation + aggregation with in-kernel hypotheses
     for s in (1, 2):
         f = feats[s]
@@ -238,7 +258,11 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
         wts = torch.rand(B, V - 1, H, W, device=dev)
         ms = timed(lambda: ops.warp_corr_agg(f[0], f[1:], proj, cur, capi.HYP_LOCAL, iv, wts, D, 1, True))
         by = 4.0 * (V * C * H * W + H * W + (V - 1) * H * W + D * H * W + D * H * W)
-        out["warp_corr_agg_stage{}".format(s + 1)] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6}
+        out["warp_corr_agg_stage{}".format(s + 1)] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6,
+                                                      "feature_layout": "NHWC" if not f[0].is_contiguous() else "NCHW"}
+        fp = [t.contiguous() for t in f]
+        ms = timed(lambda: ops.warp_corr_agg(fp[0], fp[1:], proj, cur, capi.HYP_LOCAL, iv, wts, D, 1, True))
+        out["warp_corr_agg_stage{}_nchw".format(s + 1)] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6, "feature_layout": "NCHW"}
     # regularization nets
     Hs, Ws = feats[0][0].shape[2:]
     x = torch.randn(B, 1, model.ndepths[0], Hs, Ws, device=dev)
@@ -257,7 +281,7 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
         out["cost_up_small_stage{}".format(s + 1)] = {"ms": ms, "flops": fl, "tflops": fl / ms / 1e9}
     dom = out["warp_corr_agg_stage3"]
     roof = {"kernel": "warp_corr_agg_kernel<8,1> (stage 3, 800x592, D=8, 4 source views)", "bound": "hbm",
-            "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak, "traffic": None,
+            "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak, "traffic": ncu_traffic("stage3"),
             "peak_source": peak_src, "algorithmic_bytes": dom["bytes"], "ms": dom["ms"]}
     reg_ms = out["costreg_fpn3d"]["ms"] + 2 * out["cost_up_small_stage2"]["ms"] + 2 * out["cost_up_small_stage3"]["ms"]
     reg_fl = out["costreg_fpn3d"]["flops"] + 2 * out["cost_up_small_stage2"]["flops"] + 2 * out["cost_up_small_stage3"]["flops"]
