@@ -37,6 +37,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -104,6 +105,7 @@ struct ConvProgram {
     int w_smem_bytes;             // packed weights of all phases (resident in shared memory, loaded once per CTA)
     int slab_bytes, n_stages;     // operand slab of one load unit; number of slab stages (1 or 2)
     int tile_cols;                // TMEM columns of one accumulator stage (two stages are allocated)
+    int debug;                    // EFFIMVS_TC_DEBUG bits (profiling only): 1 no MMA, 2 no operand copies, 4 no epilogue body, 8 no stores
     Phase ph[MAX_PHASES];
     Seg segs[MAX_SEGS];
     Op ops[MAX_OPS];
@@ -269,11 +271,13 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                     const uint32_t s = u % S, n = u / S;
                     mbar_wait(&bar_empty[s], (n & 1) ^ 1);          // slab stage free (first use passes)
                     uint32_t bytes = 0;
-                    for (int i = ph.seg_begin; i < ph.seg_end; ++i) bytes += (uint32_t)P.segs[i].copy_vox * 16u;
+                    if (!(P.debug & 2))
+                        for (int i = ph.seg_begin; i < ph.seg_end; ++i) bytes += (uint32_t)P.segs[i].copy_vox * 16u;
                     mbar_expect_tx(&bar_full[s], bytes);
                     uint8_t* dst = slab + (size_t)s * P.slab_bytes;
-                    for (int i = ph.seg_begin; i < ph.seg_end; ++i)
-                        bulk_g2s(dst + (size_t)P.segs[i].slot * SEG_BYTES, base + P.segs[i].src_off, (uint32_t)P.segs[i].copy_vox * 16u, &bar_full[s]);
+                    if (!(P.debug & 2))
+                        for (int i = ph.seg_begin; i < ph.seg_end; ++i)
+                            bulk_g2s(dst + (size_t)P.segs[i].slot * SEG_BYTES, base + P.segs[i].src_off, (uint32_t)P.segs[i].copy_vox * 16u, &bar_full[s]);
                 }
             }
         }
@@ -295,7 +299,7 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                     mbar_wait(&bar_full[s], n & 1);                  // operands landed
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(slab + (size_t)s * P.slab_bytes), b0 = w0 + (uint32_t)ph.w_off;
-                    for (int i = ph.op_begin; i < ph.op_end; ++i) {
+                    for (int i = ph.op_begin; i < ph.op_end && !(P.debug & 1); ++i) {
                         const Op op = P.ops[i];
                         umma_bf16(d0 + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, b_lbo, 128),
                                   umma_idesc(op.n8 * 8), op.accum);
@@ -340,14 +344,14 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                         __syncwarp();
                         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_tempty[acc])) : "memory");
                     }
-                    if (!interior) continue;
+                    if (!interior || (P.debug & 4)) continue;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (bias && g * 8 + j < P.cout) v[j] += __ldg(bias + g * 8 + j);
                         if (P.relu) v[j] = fmaxf(v[j], 0.0f);
                     }
                     if (out_f32) {  // single-channel fp32 NCDHW output
-                        out_f32[(((size_t)b * OL.D + oz) * OL.H + oy) * OL.W + ox] = v[0];
+                        if (!(P.debug & 8)) out_f32[(((size_t)b * OL.D + oz) * OL.H + oy) * OL.W + ox] = v[0];
                         continue;
                     }
                     if (res) {
@@ -356,7 +360,7 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] += r[j];
                     }
-                    store_voxel(out, OL, b, g, oz, oy, ox, v);
+                    if (!(P.debug & 8)) store_voxel(out, OL, b, g, oz, oy, ox, v);
                 }
             }
         }
@@ -724,6 +728,7 @@ int run_tile_kernel(const ConvProgram& P, int B, const void* in, const ActLayout
     const int per_sm = (smem <= 110 * 1024 && P.tmem_cols <= 256) ? 2 : 1;
     const int grid = (int)std::min<long long>(n_tiles, (long long)kNumSMs * per_sm);
     ActLayout rl = RL ? *RL : OL;
+    if (const char* dbg = getenv("EFFIMVS_TC_DEBUG")) const_cast<ConvProgram&>(P).debug = atoi(dbg);
     conv_tc_kernel<<<grid, CTA_THREADS, smem, st>>>(P, (const uint4*)in, IL.batch_stride, (const uint8_t*)wpk, bias, OL, (uint4*)out, rl,
                                                     (const uint4*)res, out_f32, (int)n_tiles, tiles_per_plane);
     return check_launch("conv_tc_kernel");
