@@ -166,7 +166,7 @@ def run_reference(a, rank, world):
             "vs_baseline": None, "dtype": "f32", "data": data, "config": {"workload": WORKLOAD, "device": "cpu"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -419,7 +419,7 @@ def run_ours(a, rank, world, local_rank):
             "clocks": clk.summary(), "roofline": roof, "roofline_regularization": roof_reg, "kernels": kern}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
 
 
 def cpu_baseline(a, ndepths):
@@ -445,7 +445,28 @@ def cpu_baseline(a, ndepths):
                 len(timed), a.shape, len(ts) - len(timed), cores)}
 
 
+class _QuietStdout:
+    """Everything written to fd 1 by libraries (NCCL prints its version banner there) goes to stderr
+    while the benchmark runs; `emit` restores stdout for the ONE JSON line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
+OUT = None
+
+
 def main():
+    global OUT
+    OUT = _QuietStdout()
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -324,12 +324,30 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
             mbar_wait(&bar_tfull[acc], (k >> 1) & 1);
             tc_fence_after();
             const uint32_t lane_base = tmem + acc * (uint32_t)P.tile_cols + ((uint32_t)(warp * 32) << 16);
-            for (int cls = 0; cls < P.n_classes; ++cls) {
-                int pz = 0, py = 0, px = 0;
-                if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
-                else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
-                const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
-                for (int g = 0; g < groups; ++g) {
+            for (int g = 0; g < groups; ++g) {
+                // residual voxels of all output classes of this channel group: issued up front so that their
+                // global-memory latency overlaps the TMEM reads instead of serialising class by class
+                uint4 rhi[8], rlo[8];
+                if (res && interior && !(P.debug & 4)) {
+#pragma unroll
+                    for (int cls = 0; cls < 8; ++cls) {
+                        if (cls < P.n_classes) {
+                            int pz = 0, py = 0, px = 0;
+                            if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
+                            else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
+                            const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
+                            rhi[cls] = __ldg(res + act_index(RL, b, g, oz, oy, ox));
+                            if (RL.lo_off) rlo[cls] = __ldg(res + act_index(RL, b, g + RL.lo_off, oz, oy, ox));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int cls = 0; cls < 8; ++cls) {
+                    if (cls >= P.n_classes) break;
+                    int pz = 0, py = 0, px = 0;
+                    if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
+                    else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
+                    const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
                     float v[8];
                     tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + g * 8), v);
                     if (P.b_rows != P.N) {   // hi/lo mode: columns [N, 2N) hold x_hi * w_lo
@@ -356,9 +374,14 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                     }
                     if (res) {
                         float r[8];
-                        load_voxel(res, RL, b, g, oz, oy, ox, r);
+                        unpack_bf16x8(rhi[cls], r);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] += r[j];
+                        if (RL.lo_off) {
+                            unpack_bf16x8(rlo[cls], r);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] += r[j];
+                        }
                     }
                     if (!(P.debug & 8)) store_voxel(out, OL, b, g, oz, oy, ox, v);
                 }
@@ -417,25 +440,28 @@ __global__ void pack_weights_multi_kernel(const __grid_constant__ PackJobs J) {
 }
 
 // Zeroes guards and halos of up to 8 activation buffers (the interiors are fully overwritten by the
-// layers; tiles read halos as the zero padding of the convolution).
-struct HaloJobs { int n; uint4* ptr[8]; ActLayout L[8]; };
+// layers; tiles read halos as the zero padding of the convolution).  One block per padded z plane of
+// a (sub-)volume: halo planes and the two guards are cleared whole, interior planes only get their
+// first / last row and first / last column cleared.
+struct HaloJobs { int n; uint4* ptr[8]; ActLayout L[8]; int planes_before[9]; };
 __global__ void zero_halo_kernel(const __grid_constant__ HaloJobs J, int B) {
-    const ActLayout& L = J.L[blockIdx.y];
-    uint4* __restrict__ p = J.ptr[blockIdx.y];
-    const int d = L.kind == L_SPLIT ? L.D / 2 : L.D, h = L.Py - 2, w = L.Px - 2;
-    const long long total = L.batch_stride * B;
+    int job = 0;
+    while (job + 1 < J.n && (int)blockIdx.x >= J.planes_before[job + 1]) ++job;
+    const ActLayout& L = J.L[job];
+    const int d = L.kind == L_SPLIT ? L.D / 2 : L.D, Pz = d + 2;
+    const int local = blockIdx.x - J.planes_before[job];       // (volume index, zp)
+    const int vol = local / Pz, zp = local - vol * Pz;
+    uint4* __restrict__ base = J.ptr[job] + (long long)vol * L.vs;
     const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i % L.vs;
-        bool halo = r < L.guard || r >= L.vs - L.guard;
-        if (!halo) {
-            const long long q = r - L.guard;
-            const int zp = (int)(q / L.zstride);
-            const int rem = (int)(q - (long long)zp * L.zstride);
-            const int yp = rem / L.Px, xp = rem - yp * L.Px;
-            halo = zp < 1 || zp > d || yp < 1 || yp > h || xp < 1 || xp > w;
-        }
-        if (halo) p[i] = zero;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (zp == 0) for (int i = tid; i < L.guard; i += nt) base[i] = zero;                                     // front guard
+    if (zp == Pz - 1) for (int i = tid; i < L.guard; i += nt) base[L.vs - L.guard + i] = zero;               // back guard
+    uint4* __restrict__ plane = base + L.guard + (long long)zp * L.zstride;
+    if (zp == 0 || zp == Pz - 1) {
+        for (int i = tid; i < (int)L.zstride; i += nt) plane[i] = zero;
+    } else {
+        for (int i = tid; i < L.Px; i += nt) { plane[i] = zero; plane[(long long)(L.Py - 1) * L.Px + i] = zero; }
+        for (int y = 1 + tid; y < L.Py - 1; y += nt) { plane[(long long)y * L.Px] = zero; plane[(long long)y * L.Px + L.Px - 1] = zero; }
     }
 }
 
@@ -706,8 +732,15 @@ int run_pack_multi(int n, const PackTable* T, const float* const* w, void* const
 int run_zero_halo(int n, void* const* ptr, const ActLayout* L, int B, cudaStream_t st) {
     static thread_local HaloJobs J;
     J.n = n;
-    for (int i = 0; i < n; ++i) { J.ptr[i] = (uint4*)ptr[i]; J.L[i] = L[i]; }
-    zero_halo_kernel<<<dim3(2 * kNumSMs, n), 256, 0, st>>>(J, B);
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        J.ptr[i] = (uint4*)ptr[i]; J.L[i] = L[i];
+        J.planes_before[i] = total;
+        const int d = L[i].kind == L_SPLIT ? L[i].D / 2 : L[i].D;
+        total += B * L[i].planes * (L[i].kind == L_SPLIT ? 8 : 1) * (d + 2);
+    }
+    J.planes_before[n] = total;
+    zero_halo_kernel<<<total, 128, 0, st>>>(J, B);
     return check_launch("zero_halo_kernel");
 }
 
