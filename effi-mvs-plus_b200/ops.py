@@ -39,10 +39,11 @@ def _features(ref: Tensor, srcs: List[Tensor], name: str):
     for t in [ref] + list(srcs):
         if not t.is_cuda:
             raise RuntimeError("effimvs::{} got a CPU tensor; the hot path is CUDA-only (no fallback)".format(name))
-    # NHWC pays off up to 16 channels (measured on B200: C=8 1.26x, C=16 1.06x faster than planar);
-    # at C=32 a lane's 128-byte pixel makes every 128-bit load touch 32 cache lines (2.2x slower),
-    # so 32-channel maps are converted to planar once instead
-    nhwc = (ref.dim() == 4 and 1 < ref.shape[1] <= 16 and not ref.is_contiguous()
+    # NHWC pays off for 8-channel maps only (measured on B200 at the DTU stage shapes: C=8 1.11x faster
+    # than planar and no conversion copy; C=16 1.3x slower; C=32 2.2x slower -- a lane's 64/128-byte
+    # pixel makes every 128-bit load of a warp touch 16/32 cache lines), so wider maps are converted
+    # to planar once instead
+    nhwc = (ref.dim() == 4 and 1 < ref.shape[1] <= 8 and not ref.is_contiguous()
             and ref.is_contiguous(memory_format=torch.channels_last))
     fmt = torch.channels_last if nhwc else torch.contiguous_format
     fix = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous(memory_format=fmt)   # noqa: E731
