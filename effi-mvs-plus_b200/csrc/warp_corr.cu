@@ -7,10 +7,10 @@
 //   softmax entropy of a view        upstream models/Effi_MVS_plus.py:43-44
 //   local hypothesis generation      upstream models/module.py:554-570
 //
-// Thread mapping: blockDim = (32 pixels, DT depth lanes).  A warp owns 32 consecutive reference
-// pixels of one depth plane, so every bilinear tap of a channel is one (nearly) contiguous
-// 128-byte request on the NCHW source map; the C reference-feature values of the pixel live in
-// registers and are reused across source views (and depth planes in the stage-1 kernel).
+// Thread mapping: a warp owns 32 consecutive reference pixels, so every bilinear tap of a channel is
+// one (nearly) contiguous 128-byte request on a planar (NCHW) source map, or C/4 128-bit loads per
+// lane on a channels-last map; the C reference-feature values of the pixel live in registers and
+// are reused across source views and depth planes.
 // Reductions over the channels of a group and over the views stay in registers; the stage-1
 // kernel reduces softmax statistics over D through shared memory.
 #include "common.cuh"
@@ -32,14 +32,21 @@ struct Taps {
 // z == 0 -> z + 1e-8, u = px / pz, normalise u * (1 / ((W-1)/2)) - 1 (torch's CUDA div-by-scalar
 // multiplies by the reciprocal), ATen un-normalise ((g + 1) / 2) * (W - 1), bilinear corner
 // weights as in ATen's grid_sampler_2d (zeros padding, align_corners=True).
-__device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float x, float y, float depth,
-                                          int H, int W, float inv_half_w, float inv_half_h) {
-    float rx = fmaf(P[2], 1.0f, fmaf(P[1], y, __fmul_rn(P[0], x)));
-    float ry = fmaf(P[5], 1.0f, fmaf(P[4], y, __fmul_rn(P[3], x)));
-    float rz = fmaf(P[8], 1.0f, fmaf(P[7], y, __fmul_rn(P[6], x)));
-    float px = __fadd_rn(__fmul_rn(rx, depth), P[9]);
-    float py = __fadd_rn(__fmul_rn(ry, depth), P[10]);
-    float pz = __fadd_rn(__fmul_rn(rz, depth), P[11]);
+struct Ray { float rx, ry, rz, tx, ty, tz; };   // rot @ (x, y, 1) and trans of one (pixel, source view)
+
+__device__ __forceinline__ Ray make_ray(const float* __restrict__ P, float x, float y) {
+    Ray r;
+    r.rx = fmaf(P[2], 1.0f, fmaf(P[1], y, __fmul_rn(P[0], x)));
+    r.ry = fmaf(P[5], 1.0f, fmaf(P[4], y, __fmul_rn(P[3], x)));
+    r.rz = fmaf(P[8], 1.0f, fmaf(P[7], y, __fmul_rn(P[6], x)));
+    r.tx = P[9]; r.ty = P[10]; r.tz = P[11];
+    return r;
+}
+
+__device__ __forceinline__ Taps make_taps(const Ray& r, float depth, int H, int W, float inv_half_w, float inv_half_h) {
+    float px = __fadd_rn(__fmul_rn(r.rx, depth), r.tx);
+    float py = __fadd_rn(__fmul_rn(r.ry, depth), r.ty);
+    float pz = __fadd_rn(__fmul_rn(r.rz, depth), r.tz);
     if (pz == 0.0f) pz = __fadd_rn(pz, 1e-8f);
     float u = __fdiv_rn(px, pz);
     float v = __fdiv_rn(py, pz);
@@ -167,23 +174,30 @@ __device__ __forceinline__ float fetch_hypothesis(const float* __restrict__ hyp,
     return local_hypothesis(__ldg(hyp + (size_t)b * HW + pix), __ldg(interval + b), D, d);
 }
 
+// One thread owns one reference pixel and DPT consecutive depth planes (8 for G = 1): the reference
+// features, the per-view ray rot @ (x,y,1), the view weight and the whole prologue are amortised over
+// the planes, and the planes' independent tap loads give the memory system work to overlap.
+constexpr int AGG_THREADS = 128;
+template <int G> struct PlanesPerThread { static constexpr int value = G >= 8 ? 1 : 8 / G; };
+
 template <int C, int G, bool NHWC>
-__global__ void __launch_bounds__(32 * DT)
+__global__ void __launch_bounds__(AGG_THREADS)
 warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
                      const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval,
                      const float* __restrict__ weights, int C_rt, int H, int W, int D,
                      float* __restrict__ sim_out, float* __restrict__ hyp_out) {
+    constexpr int DPT = PlanesPerThread<G>::value;
     __shared__ float sP[EFFIMVS_MAX_SRC_VIEWS * 12];
     __shared__ const float* sSrc[EFFIMVS_MAX_SRC_VIEWS];
     const int b = blockIdx.z;
     const int HW = H * W;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < n_src * 12; i += 32 * DT) sP[i] = proj[(size_t)b * n_src * 12 + i];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_src * 12; i += AGG_THREADS) sP[i] = proj[(size_t)b * n_src * 12 + i];
     if (tid < EFFIMVS_MAX_SRC_VIEWS) sSrc[tid] = srcs.p[tid];
     __syncthreads();
-    const int pix = blockIdx.x * 32 + threadIdx.x;
-    const int d = blockIdx.y * DT + threadIdx.y;
-    if (pix >= HW || d >= D) return;
+    const int pix = blockIdx.x * AGG_THREADS + tid;
+    const int d0 = blockIdx.y * DPT;
+    if (pix >= HW) return;
     const int yi = pix / W, xi = pix - yi * W;
     const float x = (float)xi, y = (float)yi;
     const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
@@ -192,32 +206,41 @@ warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src,
     float ref[C];
     load_ref<C, NHWC>(ref_fea, b, pix, HW, ref);
 
-    const float depth = fetch_hypothesis(hyp, hyp_mode, interval, b, d, D, pix, HW);
-    if (hyp_out) hyp_out[((size_t)b * D + d) * HW + pix] = depth;
-
-    float num[G];
+    float depth[DPT], num[DPT][G];
 #pragma unroll
-    for (int g = 0; g < G; ++g) num[g] = 0.0f;
+    for (int k = 0; k < DPT; ++k) {
+        depth[k] = (d0 + k < D) ? fetch_hypothesis(hyp, hyp_mode, interval, b, d0 + k, D, pix, HW) : 1.0f;
+        if (hyp_out && d0 + k < D) hyp_out[((size_t)b * D + d0 + k) * HW + pix] = depth[k];
+#pragma unroll
+        for (int g = 0; g < G; ++g) num[k][g] = 0.0f;
+    }
     float den = 0.0f;
     for (int v = 0; v < n_src; ++v) {
-        Taps t = make_taps(sP + v * 12, x, y, depth, H, W, inv_half_w, inv_half_h);
-        float sim[G];
-        if (NHWC) correlate_nhwc<C, G>(sSrc[v] + (size_t)b * C * HW, W, t, ref, sim);
-        else correlate<C, G>(sSrc[v] + (size_t)b * C * HW, HW, W, t, ref, sim);
-        if (weights) {
-            float w = __ldg(weights + ((size_t)b * n_src + v) * HW + pix);
+        const Ray ray = make_ray(sP + v * 12, x, y);
+        const float* src = sSrc[v] + (size_t)b * C * HW;
+        const float w = weights ? __ldg(weights + ((size_t)b * n_src + v) * HW + pix) : 1.0f;
 #pragma unroll
-            for (int g = 0; g < G; ++g) num[g] = __fadd_rn(num[g], __fmul_rn(sim[g], w));
-            den = __fadd_rn(den, w);
-        } else {
+        for (int k = 0; k < DPT; ++k) {
+            if (d0 + k < D) {
+                Taps t = make_taps(ray, depth[k], H, W, inv_half_w, inv_half_h);
+                float sim[G];
+                if (NHWC) correlate_nhwc<C, G>(src, W, t, ref, sim);
+                else correlate<C, G>(src, HW, W, t, ref, sim);
 #pragma unroll
-            for (int g = 0; g < G; ++g) num[g] = __fadd_rn(num[g], sim[g]);
+                for (int g = 0; g < G; ++g)
+                    num[k][g] = weights ? __fadd_rn(num[k][g], __fmul_rn(sim[g], w)) : __fadd_rn(num[k][g], sim[g]);
+            }
         }
+        den = __fadd_rn(den, w);
     }
     const float div = weights ? __fadd_rn(den, 1e-6f) : (float)n_src;
 #pragma unroll
-    for (int g = 0; g < G; ++g)
-        sim_out[(((size_t)b * G + g) * D + d) * HW + pix] = __fdiv_rn(num[g], div);
+    for (int k = 0; k < DPT; ++k)
+        if (d0 + k < D) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                sim_out[(((size_t)b * G + g) * D + d0 + k) * HW + pix] = __fdiv_rn(num[k][g], div);
+        }
 }
 
 // Stage-1 form: one source view per blockIdx.y; all D planes of 32 pixels per block so that the
@@ -247,9 +270,10 @@ warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_sr
         load_ref<C, NHWC>(ref_fea, b, pix, HW, ref);
         const float* src = sSrc + (size_t)b * C * HW;
         float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
+        const Ray ray = make_ray(sP, x, y);
         for (int d = threadIdx.y; d < D; d += DT) {
             const float depth = fetch_hypothesis(hyp, hyp_mode, nullptr, b, d, D, pix, HW);
-            Taps t = make_taps(sP, x, y, depth, H, W, inv_half_w, inv_half_h);
+            Taps t = make_taps(ray, depth, H, W, inv_half_w, inv_half_h);
             float sim[1];
             if (NHWC) correlate_nhwc<C, 1>(src, W, t, ref, sim);
             else correlate<C, 1>(src, HW, W, t, ref, sim);
@@ -300,7 +324,7 @@ template <int C, int G>
 int launch_agg(const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
                const float* interval, const float* weights, int B, int H, int W, int D, int nhwc, float* sim_out,
                float* hyp_out, cudaStream_t st) {
-    dim3 block(32, DT), grid(ceil_div(H * W, 32), ceil_div(D, DT), B);
+    dim3 block(AGG_THREADS), grid(ceil_div(H * W, AGG_THREADS), ceil_div(D, PlanesPerThread<G>::value), B);
     if (nhwc)
         warp_corr_agg_kernel<C, G, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, C, H, W,
                                                                  D, sim_out, hyp_out);
