@@ -466,46 +466,68 @@ __global__ void zero_halo_kernel(const __grid_constant__ HaloJobs J, int B) {
 }
 
 // 1 -> 8 channel 3x3x3 convolution (BN folded, + bias + ReLU), fp32 NCDHW in, one c8 plane out.
-// stride (1, s, s) with s in {1, 2}.  CUDA cores: K = 27 is too thin for an MMA tile.
+// stride (1, s, s) with s in {1, 2}.  CUDA cores: K = 27 is too thin for an MMA tile.  A thread
+// computes CIN1_X consecutive outputs of a row so that the input row segments and the broadcast
+// weight reads are shared between them.
+constexpr int CIN1_X = 4;
+template <int S>
 __global__ void __launch_bounds__(128)
 conv_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int D, int H, int W,
-                 int s, const ActLayout OL, int plane, uint4* __restrict__ out) {
+                 const ActLayout OL, int plane, uint4* __restrict__ out) {
     __shared__ __align__(16) float sw[27 * 8 + 8];
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];  // [tap][co]
     if (threadIdx.x < 8) sw[216 + threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
     const int b = blockIdx.y;
     const int Ho = OL.H, Wo = OL.W;
+    const int Wq = (Wo + CIN1_X - 1) / CIN1_X;
     const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= (size_t)D * Ho * Wo) return;
-    const int ox = (int)(o % Wo), oy = (int)((o / Wo) % Ho), oz = (int)(o / ((size_t)Wo * Ho));
-    float acc[8];
+    if (o >= (size_t)D * Ho * Wq) return;
+    const int ox0 = (int)(o % Wq) * CIN1_X, oy = (int)((o / Wq) % Ho), oz = (int)(o / ((size_t)Wq * Ho));
+    constexpr int NIN = (CIN1_X - 1) * S + 3;   // input columns feeding CIN1_X outputs
+    float acc[CIN1_X][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = sw[216 + c];
+    for (int i = 0; i < CIN1_X; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = sw[216 + c];
     const float* xb = x + (size_t)b * D * H * W;
+    const int ix0 = ox0 * S - 1;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         const int iz = oz + a - 1;
 #pragma unroll
         for (int bb = 0; bb < 3; ++bb) {
-            const int iy = oy * s + bb - 1;
+            const int iy = oy * S + bb - 1;
+            const bool row_ok = iz >= 0 && iz < D && iy >= 0 && iy < H;
+            const float* row = xb + ((size_t)(row_ok ? iz : 0) * H + (row_ok ? iy : 0)) * W;
+            float in[NIN];
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) {
+                const int ix = ix0 + j;
+                in[j] = (row_ok && ix >= 0 && ix < W) ? __ldg(row + ix) : 0.0f;
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const int ix = ox * s + c - 1;
-                const bool ok = iz >= 0 && iz < D && iy >= 0 && iy < H && ix >= 0 && ix < W;
-                const float v = ok ? __ldg(xb + ((size_t)iz * H + iy) * W + ix) : 0.0f;
                 const float4 w0 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8);
                 const float4 w1 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8 + 4);
-                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-                acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-                acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+#pragma unroll
+                for (int i = 0; i < CIN1_X; ++i) {
+                    const float v = in[i * S + c];
+                    acc[i][0] = fmaf(v, w0.x, acc[i][0]); acc[i][1] = fmaf(v, w0.y, acc[i][1]);
+                    acc[i][2] = fmaf(v, w0.z, acc[i][2]); acc[i][3] = fmaf(v, w0.w, acc[i][3]);
+                    acc[i][4] = fmaf(v, w1.x, acc[i][4]); acc[i][5] = fmaf(v, w1.y, acc[i][5]);
+                    acc[i][6] = fmaf(v, w1.z, acc[i][6]); acc[i][7] = fmaf(v, w1.w, acc[i][7]);
+                }
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.0f);
-    store_voxel(out, OL, b, plane, oz, oy, ox, acc);
+    for (int i = 0; i < CIN1_X; ++i) {
+        if (ox0 + i >= Wo) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaxf(acc[i][j], 0.0f);
+        store_voxel(out, OL, b, plane, oz, oy, ox0 + i, acc[i]);
+    }
 }
 
 // fp32 NCDHW <-> c8 layouts (single-layer entry point and tests)
@@ -769,9 +791,10 @@ int run_tile_kernel(const ConvProgram& P, int B, const void* in, const ActLayout
 
 int run_cin1(const float* x, const float* w, const float* bias, int B, int D, int H, int W, int s, const ActLayout& OL, int plane,
              void* out, cudaStream_t st) {
-    size_t vox = (size_t)D * OL.H * OL.W;
-    dim3 grid((unsigned)((vox + 127) / 128), B);
-    conv_cin1_kernel<<<grid, 128, 0, st>>>(x, w, bias, D, H, W, s, OL, plane, (uint4*)out);
+    size_t work = (size_t)D * OL.H * ((OL.W + CIN1_X - 1) / CIN1_X);
+    dim3 grid((unsigned)((work + 127) / 128), B);
+    if (s == 2) conv_cin1_kernel<2><<<grid, 128, 0, st>>>(x, w, bias, D, H, W, OL, plane, (uint4*)out);
+    else conv_cin1_kernel<1><<<grid, 128, 0, st>>>(x, w, bias, D, H, W, OL, plane, (uint4*)out);
     return check_launch("conv_cin1_kernel");
 }
 

@@ -270,10 +270,9 @@ warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_sr
         load_ref<C, NHWC>(ref_fea, b, pix, HW, ref);
         const float* src = sSrc + (size_t)b * C * HW;
         float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
-        const Ray ray = make_ray(sP, x, y);
         for (int d = threadIdx.y; d < D; d += DT) {
             const float depth = fetch_hypothesis(hyp, hyp_mode, nullptr, b, d, D, pix, HW);
-            Taps t = make_taps(ray, depth, H, W, inv_half_w, inv_half_h);
+            Taps t = make_taps(make_ray(sP, x, y), depth, H, W, inv_half_w, inv_half_h);
             float sim[1];
             if (NHWC) correlate_nhwc<C, 1>(src, W, t, ref, sim);
             else correlate<C, 1>(src, HW, W, t, ref, sim);
