@@ -403,3 +403,27 @@ def test_model_forward_tensor_core_depth_tolerance():
     err = float((low["depth"][-1] - want["depth"][-1]).abs().mean())
     print("plain bf16 vs f32 fraction within tolerance per output:", ["%.4f" % f for f in fl], "mean |d| final = %.3f mm" % err)
     assert err < 1e-2 * DEPTH_RANGE
+
+
+# ------------------------------------------------------------------------------------------
+# end-to-end pipeline (host in, host out; H2D of sample k+1 overlapped with the forward of sample k)
+# ------------------------------------------------------------------------------------------
+def test_pipeline_matches_direct_forward(hp):
+    from effimvs_b200 import pipeline, synthetic
+    model = dtu_model(hp, DEV)
+    samples = [synthetic.make_sample("plumbing", seed=s, width=256, height=192) for s in (0, 1, 2)]
+    host = [{"imgs": s["imgs"].pin_memory(), "depth_values": s["depth_values"].pin_memory(),
+             "proj_matrices": {k: v.pin_memory() for k, v in s["proj_matrices"].items()}} for s in samples]
+    pipe = pipeline.DepthMapPipeline(model, host[0], slots=2)
+    tickets, got = [], []
+    for i, h in enumerate(host):                       # 3 samples through 2 slots: slot 0 is reused
+        tickets.append(pipe.submit(h))
+        if i >= 1:
+            d, c = pipe.result(tickets[i - 1])
+            got.append((d.clone(), c.clone()))
+    d, c = pipe.result(tickets[-1])
+    got.append((d.clone(), c.clone()))
+    for s, (d, c) in zip(samples, got):
+        want = model(s["imgs"].to(DEV), {k: v.to(DEV) for k, v in s["proj_matrices"].items()}, s["depth_values"].to(DEV))
+        assert frac_within(d, want["depth"][-1].cpu(), 1e-3 * DEPTH_RANGE) >= 0.999
+        assert frac_within(c, want["photometric_confidence"].cpu(), 1e-3) >= 0.999
