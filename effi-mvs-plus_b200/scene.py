@@ -40,11 +40,14 @@ def gather_depths(local: Dict[int, torch.Tensor], n_views: int, rank: int, world
 
 @torch.no_grad()
 def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Sequence[int]], rank: int = 0, world: int = 1,
-              device="cuda"):
+              device="cuda", fuse_pairs: Sequence[Sequence[int]] = None, timings: dict = None):
     """infer(ref_view, src_views) -> (depth (h,w), conf (hc,wc)) on `device`;
     fuse(ref_view, ref_depth (1,1,h,w), conf (1,hc,wc), src_views, src_depths (1,v,1,h,w)) -> dict with
     'final' (1,1,h,w) bool and 'points' (1,3,h,w).
+    pairs[i]: source views used for the depth map of view i; fuse_pairs[i] (default: pairs[i]): source
+    views whose depth maps the consistency filter of view i reads (upstream: 4 and up to 10).
     Returns {ref_view: (points (k,3), depth (h,w))} for the views this rank owns."""
+    fuse_pairs = pairs if fuse_pairs is None else fuse_pairs
     mine = shard_views(n_views, rank, world)
     depths, confs = {}, {}
     for i in mine:
@@ -53,11 +56,41 @@ def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Seq
     if not depths:
         raise ValueError("rank {} owns no reference view (n_views={} < world={})".format(rank, n_views, world))
     h, w = next(iter(depths.values())).shape[-2:]
+    ev = None
+    if timings is not None and torch.cuda.is_available() and str(device).startswith("cuda"):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
     all_depths = gather_depths(depths, n_views, rank, world, h, w, device)
+    if ev:
+        ev[1].record()
     out = {}
     for i in mine:
-        src = list(pairs[i])
+        src = list(fuse_pairs[i])
         res = fuse(i, depths[i].reshape(1, 1, h, w), confs[i].unsqueeze(0), src, all_depths[src].reshape(1, len(src), 1, h, w))
         m = res["final"][0, 0]
         out[i] = (res["points"][0][:, m].t().contiguous(), depths[i])
+    if ev:
+        ev[2].record()
+        torch.cuda.synchronize()
+        timings["all_gather_ms"] = ev[0].elapsed_time(ev[1])
+        timings["fusion_ms"] = ev[1].elapsed_time(ev[2])
     return out
+
+
+def cuda_scene_callables(model, imgs: torch.Tensor, cams: Dict[str, torch.Tensor], depth_values: torch.Tensor,
+                         dist_base: float, rel_diff_base: float, thres_view: int, prob_threshold: float):
+    """infer / fuse callables for `run_scene` on the CUDA path.
+    imgs (Nv,3,H,W) on the device; cams {"stage1".."stage4": (Nv,2,4,4)}; depth_values (Dv)."""
+    from . import fusion
+
+    def infer(i, srcs):
+        idx = [i] + list(srcs)
+        out = model(imgs[idx].unsqueeze(0), {k: v[idx].unsqueeze(0) for k, v in cams.items() if k != "stage4"},
+                    depth_values.unsqueeze(0))
+        return out["depth"][-1][0], out["photometric_confidence"][0]
+
+    def fuse(i, ref_depth, conf, srcs, src_depths):
+        full = cams["stage4"]
+        return fusion.filter_view(ref_depth, conf, src_depths, full[i].unsqueeze(0), full[list(srcs)].unsqueeze(0),
+                                  dist_base, rel_diff_base, thres_view, prob_threshold, torch_inverse=False)
+    return infer, fuse

@@ -52,6 +52,21 @@ def camera_ring(views: int, width: int, height: int, focus: float = 680.0):
     return E, K
 
 
+def camera_arc(views: int, width: int, height: int, step: float = 0.02, focus: float = 680.0):
+    """Scene-sized camera set: `views` cameras on an arc about the y axis (`step` rad apart, centred on
+    view views//2), all aimed at (0,0,focus) -- neighbouring views overlap like a DTU scan."""
+    f = 1.8075 * width
+    K = torch.tensor([[f, 0.0, width / 2.0], [0.0, f, height / 2.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    E = torch.eye(4, dtype=torch.float64).repeat(views, 1, 1)
+    target = torch.tensor([0.0, 0.0, focus], dtype=torch.float64)
+    for v in range(views):
+        a = step * (v - views // 2)
+        R = _rot_y(a) @ _rot_x(0.01 * ((v % 3) - 1))
+        E[v, :3, :3] = R
+        E[v, :3, 3] = target - R @ target + torch.tensor([1.5 * (v % 2), 1.0 * (v % 3), 0.5 * (v % 5)], dtype=torch.float64)
+    return E, K
+
+
 def stage_cameras(E: torch.Tensor, K: torch.Tensor, batch: int = 1, dtype=torch.float32):
     """{"stage1".."stage4"}: (B,V,2,4,4), intrinsic rows 0-1 scaled by 1/8, 1/4, 1/2, 1."""
     V = E.shape[0]

@@ -231,10 +231,12 @@ def test_model_forward_golden(hp):
     assert frac_within(out["photometric_confidence"].cpu(), g["conf"], 1e-3) >= 0.999
 
 
-@pytest.mark.parametrize("shape,ndepths", [("plumbing", "48,8,8")])
-def test_model_forward_vs_oracle_on_device(hp, ohp, shape, ndepths):
+@pytest.mark.parametrize("shape,ndepths,size", [("plumbing", "48,8,8", None), ("tanks", "96,8,8", (480, 288))])
+def test_model_forward_vs_oracle_on_device(hp, ohp, shape, ndepths, size):
+    """640x512 x 5 views (config 1) and a Tanks&Temples-like case: 7 views, 96 stage-1 planes."""
     from effimvs_b200 import synthetic
-    s = synthetic.make_sample(shape, seed=1, device=DEV)
+    kw = {} if size is None else {"width": size[0], "height": size[1]}
+    s = synthetic.make_sample(shape, seed=1, device=DEV, **kw)
     cuda_model = dtu_model(hp, DEV, ndepths)
     want = dtu_model(ohp.OracleHotPath(), DEV, ndepths)(s["imgs"], s["proj_matrices"], s["depth_values"])
     got = cuda_model(s["imgs"], s["proj_matrices"], s["depth_values"])
@@ -384,6 +386,16 @@ def test_regnets_tensor_core_vs_fp32(prec, tol):
     assert rel_max(hb.cost_regularization(reg, x), hf.cost_regularization(reg, x)) < tol
     xs, prev = torch.randn(2, 1, 8, 40, 56, generator=gen).to(DEV), torch.randn(2, 1, 8, 20, 28, generator=gen).to(DEV)
     assert rel_max(hb.cross_scale(csp, xs, prev), hf.cross_scale(csp, xs, prev)) < tol
+
+
+def test_model_forward_tensor_core_tanks_shape():
+    """7 views, 96 stage-1 planes through the tcgen05 (bf16x3) regularization against the fp32 CUDA-core nets."""
+    from effimvs_b200 import hotpath, synthetic
+    s = synthetic.make_sample("tanks", seed=2, device=DEV, width=480, height=288)
+    want = dtu_model(hotpath.CudaHotPath("f32"), DEV, "96,8,8")(s["imgs"], s["proj_matrices"], s["depth_values"])
+    got = dtu_model(hotpath.CudaHotPath("bf16x3"), DEV, "96,8,8")(s["imgs"], s["proj_matrices"], s["depth_values"])
+    fr = [frac_within(a, b, 1e-3 * DEPTH_RANGE) for a, b in zip(got["depth"], want["depth"])]
+    assert min(fr) >= 0.999, fr
 
 
 def test_model_forward_tensor_core_depth_tolerance():
