@@ -259,6 +259,28 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
     points[((size_t)n * 3 + 2) * hw + pix] = pw[2];
 }
 
+// vis_filter_dynamic (misc/fusion.py:157-181) on an existing reproj_xyd (n,v,3,h,w) -> masks (n,v,K,h,w)
+__global__ void fusion_masks_kernel(const float* __restrict__ ref_depth, const float* __restrict__ xyd, int v, int h, int w,
+                                    float dist_base, float rel_diff_base, int thres_view, int relative, uint8_t* __restrict__ masks) {
+    const int n = blockIdx.z, s = blockIdx.y;
+    const int hw = h * w;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= hw) return;
+    const int yi = pix / w, xi = pix - yi * w;
+    const float cx = (float)xi + 0.5f, cy = (float)yi + 0.5f;
+    const float* p = xyd + (((size_t)n * v + s) * 3) * hw + pix;
+    const float dref = __ldg(ref_depth + (size_t)n * hw + pix);
+    const float ex = __fsub_rn(__ldg(p), cx), ey = __fsub_rn(__ldg(p + hw), cy);
+    const float e_xy = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
+    float e_d = fabsf(__fsub_rn(dref, __ldg(p + 2 * (size_t)hw)));
+    if (relative) e_d = __fdiv_rn(e_d, dref);
+    const int K = v - thres_view + 1;
+    for (int k = 0; k < K; ++k) {
+        const float kk = (float)(thres_view + k);
+        masks[(((size_t)n * v + s) * K + k) * hw + pix] = (e_xy < __fdiv_rn(kk, dist_base)) && (e_d < __fdiv_rn(kk, rel_diff_base));
+    }
+}
+
 }  // namespace
 }  // namespace effimvs
 
@@ -292,4 +314,16 @@ extern "C" int effimvs_fusion_filter_f32(const float* ref_depth, const float* sr
                                                            dist_base, rel_diff_base, thres_view, prob_threshold, relative,
                                                            nullptr, final_mask, depth_avg, points, masks_out);
     return check_launch("fusion_kernel(filter)");
+}
+
+extern "C" int effimvs_fusion_masks_f32(const float* ref_depth, const float* reproj_xyd, int n, int v, int h, int w,
+                                        float dist_base, float rel_diff_base, int thres_view, int relative,
+                                        uint8_t* masks_out, void* stream) {
+    EFFI_REQUIRE(ref_depth && reproj_xyd && masks_out, EFFIMVS_EINVAL, "fusion_masks: null pointer");
+    EFFI_REQUIRE(n > 0 && v >= 1 && v <= 65535 && h > 0 && w > 0 && thres_view >= 1 && thres_view <= v, EFFIMVS_EINVAL, "fusion_masks: bad sizes");
+    EFFI_REQUIRE(dist_base > 0.0f && rel_diff_base > 0.0f, EFFIMVS_EINVAL, "fusion_masks: thresholds must be positive");
+    dim3 block(128), grid(ceil_div(h * w, 128), v, n);
+    fusion_masks_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, reproj_xyd, v, h, w, dist_base, rel_diff_base, thres_view,
+                                                                relative, masks_out);
+    return check_launch("fusion_masks_kernel");
 }

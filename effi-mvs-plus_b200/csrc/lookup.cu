@@ -136,6 +136,22 @@ __device__ __forceinline__ float local_hypothesis(float cur_depth, float interva
     return __fdiv_rn(1.0f, s);
 }
 
+// get_cur_depth_range_samples (models/module.py:554-570) on its own: `cur` (B,H,W) in whatever space the
+// caller works in (upstream passes inverse depth), `interval` (B) -> samples (B,ndepth,H,W), no reciprocal.
+__global__ void range_samples_kernel(const float* __restrict__ cur, const float* __restrict__ interval, int ndepth, int HW,
+                                     float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const float c = __ldg(cur + (size_t)b * HW + pix);
+    const float half = __fmul_rn((float)(ndepth / 2), __ldg(interval + b));
+    const float lo = fmaxf(__fsub_rn(c, half), 1e-4f);
+    const float hi = fminf(fmaxf(__fadd_rn(c, half), 1e-4f), 1e4f);
+    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(ndepth - 1));
+    for (int d = 0; d < ndepth; ++d)
+        out[((size_t)b * ndepth + d) * HW + pix] = fmaxf(__fadd_rn(lo, __fmul_rn((float)d, step)), 1e-5f);
+}
+
 __global__ void dynamic_cost_kernel(const float* __restrict__ cur_depth, const float* __restrict__ raw,
                                     const float* __restrict__ reg, const float* __restrict__ interval,
                                     const float* __restrict__ dmin, const float* __restrict__ dmax, int range_mode,
@@ -237,4 +253,13 @@ extern "C" int effimvs_softmax_regress_conf_f32(const float* prob_pre, const flo
     dim3 block(128), grid(ceil_div(H * W, 128), B);
     softmax_regress_conf_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(prob_pre, hyp, hyp_mode, D, H * W, depth_out, conf_out);
     return check_launch("softmax_regress_conf_kernel");
+}
+
+extern "C" int effimvs_depth_range_samples_f32(const float* cur, const float* interval, int B, int ndepth, int H, int W,
+                                               float* samples_out, void* stream) {
+    EFFI_REQUIRE(cur && interval && samples_out, EFFIMVS_EINVAL, "depth_range_samples: null pointer");
+    EFFI_REQUIRE(B > 0 && ndepth > 1 && H > 0 && W > 0 && B <= 65535, EFFIMVS_EINVAL, "depth_range_samples: bad sizes");
+    dim3 block(128), grid(ceil_div(H * W, 128), B);
+    range_samples_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(cur, interval, ndepth, H * W, samples_out);
+    return check_launch("range_samples_kernel");
 }

@@ -295,6 +295,37 @@ warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_sr
     }
 }
 
+// homo_warping_new itself (models/module.py:303-344): materialises the warped volume (B,C,D,H,W).  Only
+// for callers that need upstream's intermediate; the fused kernels above never write it.
+__global__ void __launch_bounds__(128)
+homo_warp_kernel(const float* __restrict__ src_fea, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode,
+                 int C, int H, int W, int D, float* __restrict__ out) {
+    __shared__ float sP[12];
+    const int b = blockIdx.z, d = blockIdx.y;
+    const int HW = H * W;
+    if (threadIdx.x < 12) sP[threadIdx.x] = proj[(size_t)b * 12 + threadIdx.x];
+    __syncthreads();
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const int yi = pix / W, xi = pix - yi * W;
+    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
+    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
+    const float depth = fetch_hypothesis(hyp, hyp_mode, nullptr, b, d, D, pix, HW);
+    const Taps t = make_taps(make_ray(sP, (float)xi, (float)yi), depth, H, W, inv_half_w, inv_half_h);
+    const float* p = src_fea + (size_t)b * C * HW + t.o_nw;
+    float* o = out + (((size_t)b * C) * D + d) * HW + pix;
+    for (int c = 0; c < C; ++c) {
+        float v = 0.0f;
+        if (t.any) {
+            const float* q = p + (size_t)c * HW;
+            const float a = t.v_nw ? __ldg(q) : 0.0f, e = t.v_ne ? __ldg(q + 1) : 0.0f;
+            const float f = t.v_sw ? __ldg(q + W) : 0.0f, g = t.v_se ? __ldg(q + W + 1) : 0.0f;
+            v = fmaf(g, t.w_se, fmaf(f, t.w_sw, fmaf(e, t.w_ne, a * t.w_nw)));
+        }
+        o[(size_t)c * D * HW] = v;
+    }
+}
+
 __global__ void weighted_agg_kernel(const float* __restrict__ sims, const float* __restrict__ weights,
                                     int n_src, int D, int HW, float* __restrict__ out) {
     const int b = blockIdx.z;
@@ -428,4 +459,14 @@ extern "C" int effimvs_weighted_agg_f32(const float* sims, const float* weights,
     dim3 block(256), grid(ceil_div(H * W, 256), D < 8 ? D : 8, B);
     weighted_agg_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(sims, weights, n_src, D, H * W, out);
     return check_launch("weighted_agg_kernel");
+}
+
+extern "C" int effimvs_homo_warp_f32(const float* src_fea, const float* proj, const float* hyp, int hyp_mode,
+                                     int B, int C, int H, int W, int D, float* warped_out, void* stream) {
+    EFFI_REQUIRE(src_fea && proj && hyp && warped_out, EFFIMVS_EINVAL, "homo_warp: null pointer");
+    EFFI_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1 && D > 0 && D <= 65535 && B <= 65535, EFFIMVS_EINVAL, "homo_warp: bad sizes");
+    EFFI_REQUIRE(hyp_mode == EFFIMVS_HYP_TENSOR || hyp_mode == EFFIMVS_HYP_PLANES, EFFIMVS_EINVAL, "homo_warp: hyp_mode=%d", hyp_mode);
+    dim3 block(128), grid(ceil_div(H * W, 128), D, B);
+    homo_warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src_fea, proj, hyp, hyp_mode, C, H, W, D, warped_out);
+    return check_launch("homo_warp_kernel");
 }

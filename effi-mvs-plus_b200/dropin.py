@@ -68,6 +68,35 @@ def make_pro_bilinear_sampler(hotpath=None):
     return pro_bilinear_sampler
 
 
+def homo_warping_new(src_fea, src_proj, ref_proj, depth_values):
+    """Drop-in for models/module.py:303 (materialises the warped (B,C,D,H,W) volume; CUDA only).
+    depth_values (B,D) or (B,D,H,W)."""
+    from . import capi, ops
+    B = src_fea.shape[0]
+    rel = torch.matmul(src_proj, torch.linalg.inv_ex(ref_proj)[0])
+    proj = torch.cat([rel[:, :3, :3].reshape(B, 9), rel[:, :3, 3]], dim=-1).contiguous()
+    D = depth_values.shape[1]
+    mode = capi.HYP_PLANES if depth_values.dim() == 2 else capi.HYP_TENSOR
+    return ops.homo_warp(src_fea, proj, depth_values, mode, D)
+
+
+def get_depth_range_samples(cur_depth, ndepth, depth_inteval_pixel, device=None, dtype=None, shape=None, max_depth=192.0, min_depth=0.0):
+    """Drop-in for models/module.py:572 (both branches).  The 2-D branch is upstream's own three torch
+    expressions; the per-pixel branch runs the library kernel."""
+    if cur_depth.dim() == 2:
+        lo, hi = cur_depth[:, 0], cur_depth[:, -1]
+        step = (hi - lo) / (ndepth - 1)
+        k = torch.arange(0, ndepth, device=cur_depth.device, dtype=cur_depth.dtype).reshape(1, -1)
+        s = lo.unsqueeze(1) + k * step.unsqueeze(1)
+        return s.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, shape[1], shape[2])
+    from . import ops
+    B = cur_depth.shape[0]
+    assert cur_depth.shape == torch.Size(shape), "cur_depth:{}, input shape:{}".format(cur_depth.shape, shape)
+    iv = depth_inteval_pixel.reshape(-1).expand(B) if torch.is_tensor(depth_inteval_pixel) else \
+        torch.full((B,), float(depth_inteval_pixel), device=cur_depth.device)
+    return ops.depth_range_samples(cur_depth, iv.float().contiguous(), ndepth)
+
+
 def make_depth_regression(hotpath=None):
     def depth_regression(p, depth_values):
         """Drop-in for models/module.py:518 (p is already a probability volume): kept as the one

@@ -26,6 +26,14 @@ def get_reproj_dynamic(ref_depth, srcs_depth, ref_cam, srcs_cam, torch_inverse: 
     return ops.fusion_reproject(ref_depth, srcs_depth, ref_cam, srcs_cam, inv), None, None
 
 
+def vis_filter_dynamic(ref_depth, reproj_xyd, ref_idx_world=None, src2ref_idx_cam=None, dist_base=4, rel_diff_base=1300,
+                       thres_view=2, relative=False):
+    """Drop-in for misc/fusion.py:157 ``vis_filter_dynamic``: (masks (n,v,K,h,w) bool, mask (n,v,1,h,w) bool).
+    The two camera-space arguments are accepted and ignored, as upstream's own arithmetic ignores them."""
+    masks = ops.fusion_masks(ref_depth, reproj_xyd, float(dist_base), float(rel_diff_base), int(thres_view), bool(relative)).bool()
+    return masks, masks[:, :, -1:]
+
+
 def filter_view(ref_depth, ref_conf, srcs_depth, ref_cam, srcs_cam, dist_base, rel_diff_base, thres_view,
                 prob_threshold, relative: bool = False, want_masks: bool = False, torch_inverse: bool = True):
     """One reference view of ``dynamic_filter_depth`` (test_tank.py:470-515) in a single kernel.

@@ -75,6 +75,59 @@ def _(cams):
 
 
 # -------------------------------------------------------------------------------------------
+@torch.library.custom_op("effimvs::homo_warp", mutates_args=())
+def homo_warp(src_fea: Tensor, proj: Tensor, hyp: Tensor, hyp_mode: int, D: int) -> Tensor:
+    src_fea, proj, hyp = _dev(src_fea, "homo_warp"), _dev(proj, "homo_warp"), _dev(hyp, "homo_warp")
+    B, Cc, H, W = src_fea.shape
+    out = torch.empty(B, Cc, D, H, W, device=src_fea.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_homo_warp_f32(src_fea.data_ptr(), proj.data_ptr(), hyp.data_ptr(), hyp_mode, B, Cc, H, W, D,
+                                          out.data_ptr(), _stream()))
+    return out
+
+
+@homo_warp.register_fake
+def _(src_fea, proj, hyp, hyp_mode, D):
+    B, Cc, H, W = src_fea.shape
+    return src_fea.new_empty(B, Cc, D, H, W)
+
+
+@torch.library.custom_op("effimvs::depth_range_samples", mutates_args=())
+def depth_range_samples(cur: Tensor, interval: Tensor, ndepth: int) -> Tensor:
+    cur, interval = _dev(cur, "depth_range_samples"), _dev(interval, "depth_range_samples")
+    B, H, W = cur.shape
+    out = torch.empty(B, ndepth, H, W, device=cur.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_depth_range_samples_f32(cur.data_ptr(), interval.data_ptr(), B, ndepth, H, W, out.data_ptr(), _stream()))
+    return out
+
+
+@depth_range_samples.register_fake
+def _(cur, interval, ndepth):
+    B, H, W = cur.shape
+    return cur.new_empty(B, ndepth, H, W)
+
+
+@torch.library.custom_op("effimvs::fusion_masks", mutates_args=())
+def fusion_masks(ref_depth: Tensor, reproj_xyd: Tensor, dist_base: float, rel_diff_base: float, thres_view: int,
+                 relative: bool) -> Tensor:
+    ref_depth, reproj_xyd = _dev(ref_depth, "fusion_masks"), _dev(reproj_xyd, "fusion_masks")
+    n, v, _, h, w = reproj_xyd.shape
+    K = v - thres_view + 1
+    out = torch.empty(n, v, K, h, w, device=ref_depth.device, dtype=torch.uint8)
+    _count(1)
+    capi.check(_lib.effimvs_fusion_masks_f32(ref_depth.data_ptr(), reproj_xyd.data_ptr(), n, v, h, w, dist_base, rel_diff_base,
+                                             thres_view, int(relative), out.data_ptr(), _stream()))
+    return out
+
+
+@fusion_masks.register_fake
+def _(ref_depth, reproj_xyd, dist_base, rel_diff_base, thres_view, relative):
+    n, v, _, h, w = reproj_xyd.shape
+    return ref_depth.new_empty(n, v, v - thres_view + 1, h, w, dtype=torch.uint8)
+
+
+# -------------------------------------------------------------------------------------------
 @torch.library.custom_op("effimvs::warp_corr_agg", mutates_args=())
 def warp_corr_agg(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hyp_mode: int,
                   interval: Optional[Tensor], weights: Optional[Tensor], D: int, G: int,

@@ -65,6 +65,19 @@ int effimvs_version(void);
  * CUDA-graph capture.) */
 int effimvs_relative_projection_f32(const float* cams, int B, int V, float* proj_out, void* stream);
 
+/* a2 alone: homo_warping_new (models/module.py:303-344), materialising the warped volume.
+ *   src_fea (B,C,H,W) planar, proj (B,12) for this source view, hyp TENSOR (B,D,H,W) or PLANES (B,D)
+ *   -> warped_out (B,C,D,H,W).  Provided for call-site parity; the fused entry points below never
+ *   write this volume. */
+int effimvs_homo_warp_f32(const float* src_fea, const float* proj, const float* hyp, int hyp_mode,
+                          int B, int C, int H, int W, int D, float* warped_out, void* stream);
+
+/* get_cur_depth_range_samples (models/module.py:554-570): ndepth samples around cur (B,H,W) in the
+ * caller's space (upstream: inverse depth), half-width (ndepth/2)*interval[b], clamped like upstream.
+ *   -> samples_out (B,ndepth,H,W) */
+int effimvs_depth_range_samples_f32(const float* cur, const float* interval, int B, int ndepth, int H, int W,
+                                    float* samples_out, void* stream);
+
 /* a2 + a3 + a5 + weighted aggregation in one pass; the warped (B,C,D,H,W) volume is never
  * materialised.  Replaces, per source view, homo_warping_new (models/module.py:303-344) +
  * the group-wise correlation (models/Effi_MVS_plus.py:39-40, :222-224) and the aggregation
@@ -163,6 +176,12 @@ int effimvs_cost_up_small(const float* x, const float* prev, const float* const*
 int effimvs_fusion_reproject_f32(const float* ref_depth, const float* srcs_depth, const float* ref_cam,
                                  const float* srcs_cam, const float* inv_cams, int n, int v, int h, int w,
                                  float* reproj_xyd, void* stream);
+
+/* a14 alone: vis_filter_dynamic (misc/fusion.py:157-181) on an existing reproj_xyd (n,v,3,h,w).
+ *   -> masks_out (n,v,K,h,w) uint8, K = v-thres_view+1 (the last ladder step is upstream's `mask`). */
+int effimvs_fusion_masks_f32(const float* ref_depth, const float* reproj_xyd, int n, int v, int h, int w,
+                             float dist_base, float rel_diff_base, int thres_view, int relative,
+                             uint8_t* masks_out, void* stream);
 
 /* a13 + a14 + a15 fused: reprojection, threshold ladder, votes, masked average and
  * back-projection for one reference view (misc/fusion.py:117-181, test_tank.py:473-515).

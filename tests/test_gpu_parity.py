@@ -439,3 +439,45 @@ def test_pipeline_matches_direct_forward(hp):
         want = model(s["imgs"].to(DEV), {k: v.to(DEV) for k, v in s["proj_matrices"].items()}, s["depth_values"].to(DEV))
         assert frac_within(d, want["depth"][-1].cpu(), 1e-3 * DEPTH_RANGE) >= 0.999
         assert frac_within(c, want["photometric_confidence"].cpu(), 1e-3) >= 0.999
+
+
+# ------------------------------------------------------------------------------------------
+# remaining upstream-named call sites: homo_warping_new, get_depth_range_samples,
+# vis_filter_dynamic
+# ------------------------------------------------------------------------------------------
+def test_homo_warping_new_dropin_golden_and_oracle(ohp):
+    from effimvs_b200 import dropin
+    g = golden("warp_corr", DEV)
+    feats, cams, hyp = list(g["feats"]), g["cams"], g["hyp"]
+    P = [ohp.compose_projection(cams[:, v]) for v in range(len(feats))]
+    got = dropin.homo_warping_new(feats[1], P[1], P[0], hyp)
+    assert got.shape == (1, 8, 6, 20, 28)
+    assert rel_max(got.reshape(g["warped1"].shape), g["warped1"]) < 1e-4
+    planes = (1.0 / torch.linspace(1 / 935.0, 1 / 425.0, 5, device=DEV)).reshape(1, 5)
+    a = dropin.homo_warping_new(feats[2], P[2], P[0], planes)
+    b = ohp.homo_warp(feats[2], P[2], P[0], planes.reshape(1, 5, 1, 1).expand(1, 5, 20, 28).contiguous())
+    assert rel_max(a, b) < 1e-4
+
+
+def test_get_depth_range_samples_dropin_bit_exact(ohp):
+    from effimvs_b200 import dropin
+    gen = torch.Generator().manual_seed(1)
+    inv = (1.0 / (430 + 500 * torch.rand(2, 30, 44, generator=gen))).to(DEV)
+    inv[0, 0, :3] = torch.tensor([1e-6, 2e4, 5e-5], device=DEV)            # exercise the clamps
+    interval = torch.tensor([1e-5, 3e-6], device=DEV).reshape(2, 1, 1, 1)
+    for nd in (3, 8):
+        got = dropin.get_depth_range_samples(inv, nd, interval.squeeze(1), shape=[2, 30, 44])
+        want = ohp.local_inverse_depth_samples(inv, nd, interval.squeeze(1))
+        assert torch.equal(got, want)
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384, device=DEV).unsqueeze(0)
+    assert torch.equal(dropin.get_depth_range_samples(dv, 48, None, shape=[1, 6, 7]), ohp.uniform_inverse_depth_samples(dv, 48, 6, 7))
+
+
+@pytest.mark.parametrize("tag", ["mm", "tank"])
+def test_vis_filter_dynamic_dropin_golden(tag):
+    from effimvs_b200 import fusion
+    g = golden("fusion_" + tag, DEV)
+    masks, mask = fusion.vis_filter_dynamic(g["ref_depth"], g["reproj_xyd"], None, None, dist_base=g["dist_base"],
+                                            rel_diff_base=g["rel_diff_base"], thres_view=g["thres_view"])
+    assert torch.equal(masks, g["masks"].bool())          # same reproj_xyd in -> identical masks
+    assert torch.equal(mask, g["masks"].bool()[:, :, -1:])
