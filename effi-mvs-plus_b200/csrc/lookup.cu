@@ -131,7 +131,7 @@ __device__ __forceinline__ float local_hypothesis(float cur_depth, float interva
     float half = __fmul_rn((float)(D / 2), interval);
     float lo = fmaxf(__fsub_rn(inv, half), 1e-4f);
     float hi = fminf(fmaxf(__fadd_rn(inv, half), 1e-4f), 1e4f);
-    float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1));
+    float step = __fmul_rn(__fsub_rn(hi, lo), __fdiv_rn(1.0f, (float)(D - 1)));   // torch (CUDA) divides by a Python scalar as a * (1/b)
     float s = fmaxf(__fadd_rn(lo, __fmul_rn((float)d, step)), 1e-5f);
     return __fdiv_rn(1.0f, s);
 }
@@ -147,7 +147,7 @@ __global__ void range_samples_kernel(const float* __restrict__ cur, const float*
     const float half = __fmul_rn((float)(ndepth / 2), __ldg(interval + b));
     const float lo = fmaxf(__fsub_rn(c, half), 1e-4f);
     const float hi = fminf(fmaxf(__fadd_rn(c, half), 1e-4f), 1e4f);
-    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(ndepth - 1));
+    const float step = __fmul_rn(__fsub_rn(hi, lo), __fdiv_rn(1.0f, (float)(ndepth - 1)));   // torch (CUDA): a * (1/b)
     for (int d = 0; d < ndepth; ++d)
         out[((size_t)b * ndepth + d) * HW + pix] = fmaxf(__fadd_rn(lo, __fmul_rn((float)d, step)), 1e-5f);
 }

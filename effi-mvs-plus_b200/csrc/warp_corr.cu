@@ -162,7 +162,7 @@ __device__ __forceinline__ float local_hypothesis(float cur_depth, float interva
     float half = __fmul_rn((float)(D / 2), interval);
     float lo = fmaxf(__fsub_rn(inv, half), 1e-4f);
     float hi = fminf(fmaxf(__fadd_rn(inv, half), 1e-4f), 1e4f);
-    float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1));
+    float step = __fmul_rn(__fsub_rn(hi, lo), __fdiv_rn(1.0f, (float)(D - 1)));   // torch (CUDA) divides by a Python scalar as a * (1/b)
     float s = fmaxf(__fadd_rn(lo, __fmul_rn((float)d, step)), 1e-5f);
     return __fdiv_rn(1.0f, s);
 }
