@@ -1,0 +1,66 @@
+"""CPU tests of the C-ABI boundary: the library loads without a GPU, exports every function that
+include/effimvs.h declares, the ctypes table covers all of them, argument validation returns the
+documented error codes (no compute is launched), and CPU tensors are rejected (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import effimvs_b200  # noqa: F401
+from effimvs_b200 import capi, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "effimvs.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(effimvs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(capi.lib, n), "libeffimvs.so does not export " + n
+        assert n in capi.SIGNATURES, "capi.SIGNATURES has no binding for " + n
+    assert sorted(capi.SIGNATURES) == names          # and nothing is bound that the header does not declare
+
+
+def test_argument_validation_returns_error_codes():
+    lib = capi.lib
+    assert lib.effimvs_version() >= 100
+    # null pointers / bad sizes are rejected before any launch
+    assert lib.effimvs_weighted_agg_f32(None, None, 1, 1, 1, 1, 1, None, None) == capi.EINVAL
+    assert "null pointer" in capi.last_error()
+    one = ctypes.c_void_p(16)
+    assert lib.effimvs_volume_lookup_f32(one, one, one, one, 0, 3, 1, 8, 3, 4, 4, one, None) == capi.EINVAL
+    assert "sample_stride" in capi.last_error()
+    arr, keep = capi.ptr_array([16] * 4)
+    assert lib.effimvs_warp_corr_agg_f32(one, arr, 4, one, one, 0, None, None, 1, 12, 8, 8, 4, 1, 0, one, None, None) == capi.EUNSUPPORTED
+    assert "C=12" in capi.last_error()
+    assert lib.effimvs_warp_corr_agg_f32(one, arr, 4, one, one, 0, None, None, 1, 8, 8, 8, 4, 3, 0, one, None, None) == capi.EINVAL
+    assert lib.effimvs_costreg_fpn3d(one, arr, arr, 1, 6, 8, 8, 0, one, 1 << 30, one, None) == capi.EUNSUPPORTED   # D not a multiple of 4
+    assert lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_F32) > 0
+    assert lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16X3) > lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16)
+    with pytest.raises(capi.EffiMVSError):
+        capi.check(capi.EWORKSPACE)
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ops.volume_lookup(torch.zeros(1, 8, 4, 4), torch.ones(1, 3, 4, 4), torch.ones(1), torch.ones(1), 1)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        ops.warp_corr_agg(torch.zeros(1, 8, 4, 4), [torch.zeros(1, 8, 4, 4)], torch.zeros(1, 1, 12), torch.ones(1, 2, 4, 4), 0, None, None, 2, 1, False)
+
+
+def test_fake_implementations_give_shapes_without_a_device():
+    with torch.device("meta"):
+        ref = torch.empty(2, 16, 24, 32)
+        sim, hyp = torch.ops.effimvs.warp_corr_agg(ref, [ref, ref], torch.empty(2, 2, 12), torch.empty(2, 1, 24, 32), 2,
+                                                   torch.empty(2), None, 8, 1, True)
+        assert sim.shape == (2, 1, 8, 24, 32) and hyp.shape == (2, 8, 24, 32)
+        out = torch.ops.effimvs.conv3d_bf16(torch.empty(1, 16, 4, 6, 8), torch.empty(16, 8, 3, 3, 3), None, None, 2, True, True, 2)
+        assert out.shape == (1, 8, 8, 12, 16)
