@@ -178,7 +178,7 @@ __device__ __forceinline__ float fetch_hypothesis(const float* __restrict__ hyp,
 // features, the per-view ray rot @ (x,y,1), the view weight and the whole prologue are amortised over
 // the planes, and the planes' independent tap loads give the memory system work to overlap.
 constexpr int AGG_THREADS = 128;
-template <int G> struct PlanesPerThread { static constexpr int value = G >= 8 ? 1 : 8 / G; };
+template <int G> struct PlanesPerThread { static constexpr int value = G >= 4 ? 4 : 8; };   // accumulators: planes x G <= 32
 
 template <int C, int G, bool NHWC>
 __global__ void __launch_bounds__(AGG_THREADS)

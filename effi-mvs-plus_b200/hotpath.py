@@ -60,12 +60,21 @@ class CudaHotPath:
         """cams (B,V,2,4,4) -> (B,V-1,12) rot|trans of P_src @ inverse(P_ref)."""
         if self.native_projection:
             return ops.relative_projection(cams)
+        # the same torch calls, with the same operand shapes, as upstream issues per source view
+        # (Effi_MVS_plus.py:34-37, module.py:314): a batched formulation can differ from it by an ulp in
+        # the entries of proj, which is 1e-4 px at 1600-pixel coordinates
         B, V = cams.shape[:2]
-        P = cams[:, :, 0].clone()
-        P[:, :, :3, :4] = torch.matmul(cams[:, :, 1, :3, :3], cams[:, :, 0, :3, :4])
-        inv_ref = torch.linalg.inv_ex(P[:, 0])[0]
-        rel = torch.matmul(P[:, 1:], inv_ref.unsqueeze(1))
-        return torch.cat([rel[:, :, :3, :3].reshape(B, V - 1, 9), rel[:, :, :3, 3]], dim=-1).contiguous()
+
+        def compose(c):
+            P = c[:, 0].clone()
+            P[:, :3, :4] = torch.matmul(c[:, 1, :3, :3], c[:, 0, :3, :4])
+            return P
+        inv_ref = torch.linalg.inv_ex(compose(cams[:, 0]))[0]       # torch.inverse minus the host-side error check
+        rows = []
+        for v in range(1, V):
+            rel = torch.matmul(compose(cams[:, v]), inv_ref)
+            rows.append(torch.cat([rel[:, :3, :3].reshape(B, 9), rel[:, :3, 3]], dim=-1))
+        return torch.stack(rows, dim=1).contiguous()
 
     # -- a2-a4, a9, a11, a12 ---------------------------------------------------------------------
     def stage1(self, features, cams, depth_hyp, pixel_wise_net, reg_net, G):
