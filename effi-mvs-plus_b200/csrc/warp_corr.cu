@@ -13,7 +13,10 @@
 // are reused across source views and depth planes.
 // Reductions over the channels of a group and over the views stay in registers; the stage-1
 // kernel reduces softmax statistics over D through shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "warp_coords.cuh"
 
 namespace effimvs {
 namespace {
@@ -27,33 +30,9 @@ struct Taps {
     bool any;
 };
 
-// Coordinates exactly as upstream computes them on a CUDA device (no FMA contraction where torch
-// issues separate kernels): ray = rot @ (x,y,1) [matmul: fma chain], p = ray * depth + trans,
-// z == 0 -> z + 1e-8, u = px / pz, normalise u * (1 / ((W-1)/2)) - 1 (torch's CUDA div-by-scalar
-// multiplies by the reciprocal), ATen un-normalise ((g + 1) / 2) * (W - 1), bilinear corner
-// weights as in ATen's grid_sampler_2d (zeros padding, align_corners=True).
-struct Ray { float rx, ry, rz, tx, ty, tz; };   // rot @ (x, y, 1) and trans of one (pixel, source view)
-
-__device__ __forceinline__ Ray make_ray(const float* __restrict__ P, float x, float y) {
-    Ray r;
-    r.rx = fmaf(P[2], 1.0f, fmaf(P[1], y, __fmul_rn(P[0], x)));
-    r.ry = fmaf(P[5], 1.0f, fmaf(P[4], y, __fmul_rn(P[3], x)));
-    r.rz = fmaf(P[8], 1.0f, fmaf(P[7], y, __fmul_rn(P[6], x)));
-    r.tx = P[9]; r.ty = P[10]; r.tz = P[11];
-    return r;
-}
-
 __device__ __forceinline__ Taps make_taps(const Ray& r, float depth, int H, int W, float inv_half_w, float inv_half_h) {
-    float px = __fadd_rn(__fmul_rn(r.rx, depth), r.tx);
-    float py = __fadd_rn(__fmul_rn(r.ry, depth), r.ty);
-    float pz = __fadd_rn(__fmul_rn(r.rz, depth), r.tz);
-    if (pz == 0.0f) pz = __fadd_rn(pz, 1e-8f);
-    float u = __fdiv_rn(px, pz);
-    float v = __fdiv_rn(py, pz);
-    float gx = __fsub_rn(__fmul_rn(u, inv_half_w), 1.0f);
-    float gy = __fsub_rn(__fmul_rn(v, inv_half_h), 1.0f);
-    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
-    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
+    float ix, iy;
+    sample_coords(r, depth, H, W, inv_half_w, inv_half_h, ix, iy);
     float fx = floorf(ix), fy = floorf(iy);
     Taps t;
     // comparisons are false for NaN/inf -> every corner contributes zero (ATen CUDA behaviour)
@@ -156,24 +135,6 @@ __device__ __forceinline__ void load_ref(const float* __restrict__ ref_fea, int 
     }
 }
 
-// inverse-depth samples around cur_depth, exactly the op sequence of models/module.py:558-570
-__device__ __forceinline__ float local_hypothesis(float cur_depth, float interval, int D, int d) {
-    float inv = __fdiv_rn(1.0f, cur_depth);
-    float half = __fmul_rn((float)(D / 2), interval);
-    float lo = fmaxf(__fsub_rn(inv, half), 1e-4f);
-    float hi = fminf(fmaxf(__fadd_rn(inv, half), 1e-4f), 1e4f);
-    float step = __fmul_rn(__fsub_rn(hi, lo), __fdiv_rn(1.0f, (float)(D - 1)));   // torch (CUDA) divides by a Python scalar as a * (1/b)
-    float s = fmaxf(__fadd_rn(lo, __fmul_rn((float)d, step)), 1e-5f);
-    return __fdiv_rn(1.0f, s);
-}
-
-__device__ __forceinline__ float fetch_hypothesis(const float* __restrict__ hyp, int mode, const float* __restrict__ interval,
-                                                  int b, int d, int D, int pix, int HW) {
-    if (mode == EFFIMVS_HYP_TENSOR) return __ldg(hyp + ((size_t)b * D + d) * HW + pix);
-    if (mode == EFFIMVS_HYP_PLANES) return __ldg(hyp + b * D + d);
-    return local_hypothesis(__ldg(hyp + (size_t)b * HW + pix), __ldg(interval + b), D, d);
-}
-
 // One thread owns one reference pixel and DPT consecutive depth planes (8 for G = 1): the reference
 // features, the per-view ray rot @ (x,y,1), the view weight and the whole prologue are amortised over
 // the planes, and the planes' independent tap loads give the memory system work to overlap.
@@ -184,7 +145,7 @@ template <int C, int G, bool NHWC>
 __global__ void __launch_bounds__(AGG_THREADS)
 warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
                      const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval,
-                     const float* __restrict__ weights, int C_rt, int H, int W, int D,
+                     const float* __restrict__ weights, int ray_unfused, int H, int W, int D,
                      float* __restrict__ sim_out, float* __restrict__ hyp_out) {
     constexpr int DPT = PlanesPerThread<G>::value;
     __shared__ float sP[EFFIMVS_MAX_SRC_VIEWS * 12];
@@ -216,7 +177,7 @@ warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src,
     }
     float den = 0.0f;
     for (int v = 0; v < n_src; ++v) {
-        const Ray ray = make_ray(sP + v * 12, x, y);
+        const Ray ray = make_ray(sP + v * 12, x, y, ray_unfused != 0);
         const float* src = sSrc[v] + (size_t)b * C * HW;
         const float w = weights ? __ldg(weights + ((size_t)b * n_src + v) * HW + pix) : 1.0f;
 #pragma unroll
@@ -248,7 +209,7 @@ warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src,
 template <int C, bool NHWC>
 __global__ void __launch_bounds__(32 * DT)
 warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
-                       const float* __restrict__ hyp, int hyp_mode, int H, int W, int D,
+                       const float* __restrict__ hyp, int hyp_mode, int ray_unfused, int H, int W, int D,
                        float* __restrict__ sims_out, float* __restrict__ entropy_out) {
     extern __shared__ float s_sim[];  // [D][32]
     __shared__ float sP[12];
@@ -272,7 +233,7 @@ warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_sr
         float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
         for (int d = threadIdx.y; d < D; d += DT) {
             const float depth = fetch_hypothesis(hyp, hyp_mode, nullptr, b, d, D, pix, HW);
-            Taps t = make_taps(make_ray(sP, x, y), depth, H, W, inv_half_w, inv_half_h);
+            Taps t = make_taps(make_ray(sP, x, y, ray_unfused != 0), depth, H, W, inv_half_w, inv_half_h);
             float sim[1];
             if (NHWC) correlate_nhwc<C, 1>(src, W, t, ref, sim);
             else correlate<C, 1>(src, HW, W, t, ref, sim);
@@ -299,7 +260,7 @@ warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_sr
 // for callers that need upstream's intermediate; the fused kernels above never write it.
 __global__ void __launch_bounds__(128)
 homo_warp_kernel(const float* __restrict__ src_fea, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode,
-                 int C, int H, int W, int D, float* __restrict__ out) {
+                 int ray_unfused, int C, int H, int W, int D, float* __restrict__ out) {
     __shared__ float sP[12];
     const int b = blockIdx.z, d = blockIdx.y;
     const int HW = H * W;
@@ -311,7 +272,7 @@ homo_warp_kernel(const float* __restrict__ src_fea, const float* __restrict__ pr
     const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
     const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
     const float depth = fetch_hypothesis(hyp, hyp_mode, nullptr, b, d, D, pix, HW);
-    const Taps t = make_taps(make_ray(sP, (float)xi, (float)yi), depth, H, W, inv_half_w, inv_half_h);
+    const Taps t = make_taps(make_ray(sP, (float)xi, (float)yi, ray_unfused != 0), depth, H, W, inv_half_w, inv_half_h);
     const float* p = src_fea + (size_t)b * C * HW + t.o_nw;
     float* o = out + (((size_t)b * C) * D + d) * HW + pix;
     for (int c = 0; c < C; ++c) {
@@ -356,11 +317,11 @@ int launch_agg(const float* ref, const SrcPtrs& srcs, int n_src, const float* pr
                float* hyp_out, cudaStream_t st) {
     dim3 block(AGG_THREADS), grid(ceil_div(H * W, AGG_THREADS), ceil_div(D, PlanesPerThread<G>::value), B);
     if (nhwc)
-        warp_corr_agg_kernel<C, G, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, C, H, W,
-                                                                 D, sim_out, hyp_out);
+        warp_corr_agg_kernel<C, G, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights,
+                                                                 ray_unfused_for(H, W), H, W, D, sim_out, hyp_out);
     else
-        warp_corr_agg_kernel<C, G, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, C, H, W,
-                                                                  D, sim_out, hyp_out);
+        warp_corr_agg_kernel<C, G, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights,
+                                                                  ray_unfused_for(H, W), H, W, D, sim_out, hyp_out);
     return check_launch("warp_corr_agg_kernel");
 }
 
@@ -389,6 +350,12 @@ int fill_srcs(SrcPtrs& s, const float* const* src_fea, int n_src) {
 }  // namespace
 }  // namespace effimvs
 
+namespace effimvs {
+int warp_corr_agg_tile(const float* ref_fea, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
+                       const float* interval, const float* weights, int B, int C, int H, int W, int D, int G, float* sim_out,
+                       float* hyp_out, cudaStream_t st);
+}
+
 using namespace effimvs;
 
 extern "C" int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* const* src_fea, int n_src,
@@ -408,6 +375,12 @@ extern "C" int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* cons
     int rc = fill_srcs(s, src_fea, n_src);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (nhwc && (C == 8 || C == 16 || C == 32) && ((uintptr_t)ref_fea & 15) == 0 && !getenv("EFFIMVS_WARP_NO_TILE")) {
+        bool aligned = true;
+        for (int i = 0; i < n_src; ++i) aligned = aligned && ((uintptr_t)s.p[i] & 15) == 0;
+        if (aligned)
+            return warp_corr_agg_tile(ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, C, H, W, D, G, sim_out, hyp_out, st);
+    }
     switch (C) {
         case 8: return dispatch_g<8>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
         case 16: return dispatch_g<16>(G, ref_fea, s, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, nhwc, sim_out, hyp_out, st);
@@ -436,7 +409,7 @@ extern "C" int effimvs_warp_corr_views_f32(const float* ref_fea, const float* co
 #define EFFI_VIEWS_CASE(CC, L)                                                                                                   \
     {                                                                                                                            \
         if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<CC, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        warp_corr_views_kernel<CC, L><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, H, W, D, sims_out, entropy_out); \
+        warp_corr_views_kernel<CC, L><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, ray_unfused_for(H, W), H, W, D, sims_out, entropy_out); \
     }
     const bool nhwc = fea_layout == EFFIMVS_FEA_NHWC;
     switch (C) {
@@ -467,6 +440,6 @@ extern "C" int effimvs_homo_warp_f32(const float* src_fea, const float* proj, co
     EFFI_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1 && D > 0 && D <= 65535 && B <= 65535, EFFIMVS_EINVAL, "homo_warp: bad sizes");
     EFFI_REQUIRE(hyp_mode == EFFIMVS_HYP_TENSOR || hyp_mode == EFFIMVS_HYP_PLANES, EFFIMVS_EINVAL, "homo_warp: hyp_mode=%d", hyp_mode);
     dim3 block(128), grid(ceil_div(H * W, 128), D, B);
-    homo_warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src_fea, proj, hyp, hyp_mode, C, H, W, D, warped_out);
+    homo_warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src_fea, proj, hyp, hyp_mode, ray_unfused_for(H, W), C, H, W, D, warped_out);
     return check_launch("homo_warp_kernel");
 }

@@ -6,6 +6,7 @@ there is no fallback.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -14,6 +15,7 @@ from torch import Tensor
 from . import capi
 
 _lib = capi.lib
+_NHWC_MAXC = int(os.environ.get("EFFIMVS_NHWC_MAXC", "32"))
 
 # kernels of libeffimvs.so launched through this module since the caller last reset it (bench.py's
 # `gpu_launches`); every op adds the number of launches its C entry point enqueues.
@@ -39,11 +41,9 @@ def _features(ref: Tensor, srcs: List[Tensor], name: str):
     for t in [ref] + list(srcs):
         if not t.is_cuda:
             raise RuntimeError("effimvs::{} got a CPU tensor; the hot path is CUDA-only (no fallback)".format(name))
-    # NHWC pays off for 8-channel maps only (measured on B200 at the DTU stage shapes: C=8 1.11x faster
-    # than planar and no conversion copy; C=16 1.3x slower; C=32 2.2x slower -- a lane's 64/128-byte
-    # pixel makes every 128-bit load of a warp touch 16/32 cache lines), so wider maps are converted
-    # to planar once instead
-    nhwc = (ref.dim() == 4 and 1 < ref.shape[1] <= 8 and not ref.is_contiguous()
+    # channels-last maps go to the tiled kernel (csrc/warp_tile.cu: TMA-staged source tiles, any C in {8,16,32});
+    # EFFIMVS_NHWC_MAXC caps the channel count that takes that path (wider maps are converted to planar once)
+    nhwc = (ref.dim() == 4 and 1 < ref.shape[1] <= _NHWC_MAXC and not ref.is_contiguous()
             and ref.is_contiguous(memory_format=torch.channels_last))
     fmt = torch.channels_last if nhwc else torch.contiguous_format
     fix = lambda t: (t if t.dtype == torch.float32 else t.float()).contiguous(memory_format=fmt)   # noqa: E731
