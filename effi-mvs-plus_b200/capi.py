@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeffimvs.so")
+LIB_PATH = os.environ.get("EFFIMVS_LIB") or os.path.join(_HERE, "libeffimvs.so")   # EFFIMVS_LIB: kernel-tuning builds
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, EWORKSPACE = 0, -1, -2, -3, -4
 HYP_TENSOR, HYP_PLANES, HYP_LOCAL = 0, 1, 2

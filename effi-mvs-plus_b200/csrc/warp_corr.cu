@@ -354,6 +354,8 @@ namespace effimvs {
 int warp_corr_agg_tile(const float* ref_fea, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
                        const float* interval, const float* weights, int B, int C, int H, int W, int D, int G, float* sim_out,
                        float* hyp_out, cudaStream_t st);
+int warp_corr_views_tile(const float* ref_fea, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
+                         int B, int C, int H, int W, int D, float* sims_out, float* entropy_out, cudaStream_t st);
 }
 
 using namespace effimvs;
@@ -404,6 +406,11 @@ extern "C" int effimvs_warp_corr_views_f32(const float* ref_fea, const float* co
     int rc = fill_srcs(s, src_fea, n_src);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (fea_layout == EFFIMVS_FEA_NHWC && (C == 8 || C == 16 || C == 32) && ((uintptr_t)ref_fea & 15) == 0 && !getenv("EFFIMVS_WARP_NO_TILE")) {
+        bool aligned = true;
+        for (int i = 0; i < n_src; ++i) aligned = aligned && ((uintptr_t)s.p[i] & 15) == 0;
+        if (aligned) return warp_corr_views_tile(ref_fea, s, n_src, proj, hyp, hyp_mode, B, C, H, W, D, sims_out, entropy_out, st);
+    }
     dim3 block(32, DT), grid(ceil_div(H * W, 32), n_src, B);
     size_t smem = (size_t)D * 32 * sizeof(float);
 #define EFFI_VIEWS_CASE(CC, L)                                                                                                   \

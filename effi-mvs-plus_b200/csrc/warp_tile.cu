@@ -1,22 +1,28 @@
-// Tiled fused homography warp + group-wise correlation + view aggregation for channels-last feature
-// maps: the source footprint of a block's reference tile is staged in shared memory by TMA and the
-// bilinear taps are read from there.
+// Tiled fused homography warp + group-wise correlation (+ view aggregation / softmax entropy) for
+// channels-last feature maps: the source footprint of a block's reference tile is staged in shared
+// memory by TMA and the bilinear taps are read from there.
 //
 // Replaces the same upstream code as warp_corr.cu (models/module.py:303-344, 554-570;
 // models/Effi_MVS_plus.py:39-53, 65-67, 222-244); this file is the fast path for EFFIMVS_FEA_NHWC.
 //
 // Why a tile: the 4 taps x C channels of every (pixel, plane, view) sample are 16*C bytes of gather
-// for 4*(C + 1) bytes of HBM traffic, so the kernel is bound by the on-chip gather rate, not HBM.
+// for 4*(C + 1) bytes of HBM traffic, so the kernels are bound by the on-chip gather rate, not HBM.
 // Measured on B200: a warp-wide global load pays ~2 cycles per 128-byte line it touches (~64 B/clk/SM
-// through L1), shared memory delivers 128 B/clk/SM when conflict free.  So per source view the block
-//   1. computes the sample coordinates of its 32x4 reference pixels x DPT planes exactly as upstream
-//      does on a CUDA device (same op order, no contraction) and reduces their bounding box,
-//   2. has one thread issue a TMA box load (8 channels x BW x BH source pixels, 32-byte swizzle, zero
-//      fill outside the image = grid_sample's zeros padding) per 8-channel block,
-//   3. samples from shared memory with 128-bit loads (the swizzle spreads the 32-byte pixels of
-//      neighbouring lanes over all banks) and packed fp32 FMAs (FFMA2).
-// A (block, view) whose footprint does not fit the box (depth discontinuities, wild hypotheses)
-// gathers from global memory with 256-bit loads instead -- same arithmetic, same results.
+// through L1), shared memory delivers 128 B/clk/SM when conflict free.  So per round (a source view,
+// and in the stage-1 kernel a group of planes) the block
+//   1. computes the sample positions of its 32x4 reference pixels x DPT planes exactly as upstream
+//      does on a CUDA device (same op order, no contraction), keeps only (ix, iy) per sample in
+//      registers and reduces the bounding box of the live 2x2 cells,
+//   2. has one thread issue the TMA box loads of ALL channels at once (C/8 sub-boxes of 8 channels x BW
+//      x BH source pixels, 32-byte swizzle, zero fill outside the image = grid_sample's zeros
+//      padding) on one mbarrier,
+//   3. re-derives cell and weights from (ix, iy) and samples from shared memory with 128-bit loads at
+//      immediate offsets (the swizzle spreads the 32-byte pixels of neighbouring lanes over all
+//      banks) and packed fp32 FMAs (FFMA2).
+// Several blocks are resident per SM, so the TMA round trip of one block hides behind the sampling
+// of the others.  A round whose footprint does not fit the box (depth discontinuities, wild
+// hypotheses, strong in-plane rotation) gathers from global memory with 256-bit loads instead --
+// same arithmetic, same results.
 #include <cuda.h>  // CUtensorMap types only; the encoder is resolved through cudaGetDriverEntryPoint
 
 #include <limits.h>
@@ -32,11 +38,28 @@ namespace {
 
 constexpr int TW = 32, TH = 4;            // reference tile of a block: one warp per tile row
 constexpr int TILE_THREADS = TW * TH;
-constexpr int BW = 64, BH = 12;           // staged source box in pixels (one 8-channel block of it)
-constexpr int BOX_BYTES = BW * BH * 32;
-constexpr int ROW_BYTES = BW * 32;        // multiple of 256: the swizzle bit (address bit 7) is row independent
 constexpr int FLAG_FORCE_GATHER = 1;      // debugging / tests: never stage, always gather from global
 constexpr int FLAG_RAY_UNFUSED = 2;       // ray = (r0*x + r1*y) + r2 without contraction (see warp_coords.cuh)
+
+// staged source box in pixels, per channel count (one sub-box holds 8 channels = 32 bytes per pixel).
+// BW * 32 is a multiple of 256 so that the swizzle bit (address bit 7) does not depend on the row.
+template <int C> struct Box { static constexpr int W = 64, H = 12; };
+template <> struct Box<32> { static constexpr int W = 64, H = 8; };
+template <int C> struct BoxBytes {
+    static constexpr int ROW = Box<C>::W * 32;
+    static constexpr int SUB = Box<C>::W * Box<C>::H * 32;
+    static constexpr int ALL = SUB * (C / 8);
+};
+#ifndef EFFI_TILE_BPS8
+#define EFFI_TILE_BPS8 5
+#endif
+#ifndef EFFI_TILE_BPS16
+#define EFFI_TILE_BPS16 4
+#endif
+#ifndef EFFI_TILE_BPS32
+#define EFFI_TILE_BPS32 3
+#endif
+template <int C> struct BlocksPerSM { static constexpr int value = C == 8 ? EFFI_TILE_BPS8 : (C == 16 ? EFFI_TILE_BPS16 : EFFI_TILE_BPS32); };
 
 struct TileMaps {
     CUtensorMap m[EFFIMVS_MAX_SRC_VIEWS];
@@ -85,12 +108,6 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* ma
                  : "memory");
 }
 
-struct Q2 { u64 a, b; };                 // four consecutive channels as two packed pairs
-__device__ __forceinline__ Q2 lds_q2(uint32_t addr) {
-    Q2 q;
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(q.a), "=l"(q.b) : "r"(addr));
-    return q;
-}
 struct O2 { u64 a, b, c, d; };           // eight consecutive channels
 __device__ __forceinline__ O2 ldg_o2(const float* p) {
     O2 o;
@@ -98,36 +115,10 @@ __device__ __forceinline__ O2 ldg_o2(const float* p) {
     return o;
 }
 
-// One sample: where its 2x2 cell sits and its four axis weights (products formed at use, in
-// upstream's operand order).  Non-live samples (no corner inside the image, or NaN/inf coordinates:
-// ATen's CUDA kernel gives zero) carry zero weights.
-struct Cell {
-    int x0, y0;
-    float ex, dx, ey, dy;
-    bool live;
-};
-
-__device__ __forceinline__ Cell make_cell(const Ray& r, float depth, int H, int W, float inv_half_w, float inv_half_h) {
-    float ix, iy;
-    sample_coords(r, depth, H, W, inv_half_w, inv_half_h, ix, iy);
-    const float fx = floorf(ix), fy = floorf(iy);
-    Cell c;
-    c.live = (fx >= -1.0f) && (fx <= (float)(W - 1)) && (fy >= -1.0f) && (fy <= (float)(H - 1));   // false for NaN/inf
-    c.x0 = c.live ? (int)fx : 0;
-    c.y0 = c.live ? (int)fy : 0;
-    c.ex = c.live ? __fsub_rn(__fadd_rn(fx, 1.0f), ix) : 0.0f;
-    c.dx = c.live ? __fsub_rn(ix, fx) : 0.0f;
-    c.ey = c.live ? __fsub_rn(__fadd_rn(fy, 1.0f), iy) : 0.0f;
-    c.dy = c.live ? __fsub_rn(iy, fy) : 0.0f;
-    return c;
-}
-
 // interpolate 8 channels (4 packed pairs) of one sample and multiply-accumulate with the reference
 template <int NACC, int ACC0, int PPA>
 __device__ __forceinline__ void accumulate8(const u64 (&t00)[4], const u64 (&t01)[4], const u64 (&t10)[4], const u64 (&t11)[4],
-                                            float w00, float w01, float w10, float w11, const u64* __restrict__ ref2,
-                                            u64 (&acc)[NACC]) {
-    const u64 W00 = pack2(w00, w00), W01 = pack2(w01, w01), W10 = pack2(w10, w10), W11 = pack2(w11, w11);
+                                            u64 W00, u64 W01, u64 W10, u64 W11, const u64* __restrict__ ref2, u64 (&acc)[NACC]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         u64 s = mul2(t00[j], W00);
@@ -149,33 +140,252 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 template <int G> struct TilePlanes { static constexpr int value = G >= 4 ? 4 : 8; };
 
+// Shared state of a block: projection rows, the double-buffered bounding box and the TMA barrier.
+struct TileShared {
+    float P[EFFIMVS_MAX_SRC_VIEWS * 12];
+    int box[2][4];                         // min x, min y, max x, max y of the live cells
+    alignas(8) uint64_t bar;
+};
+
+// One sample re-derived from its position: the 2x2 cell and the four axis weights (products formed at
+// use, in upstream's operand order).  Non-live samples (no corner inside the image, or NaN/inf
+// coordinates: ATen's CUDA kernel gives zero) contribute a similarity of exactly zero.
+struct Cell {
+    int x0, y0;
+    float ex, dx, ey, dy;
+    bool live;
+};
+__device__ __forceinline__ Cell cell_at(float ix, float iy, int H, int W) {
+    const float fx = floorf(ix), fy = floorf(iy);
+    Cell c;
+    c.live = (fx >= -1.0f) && (fx <= (float)(W - 1)) && (fy >= -1.0f) && (fy <= (float)(H - 1));   // false for NaN/inf
+    c.x0 = (int)fx;
+    c.y0 = (int)fy;
+    c.ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+    c.dx = __fsub_rn(ix, fx);
+    c.ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+    c.dy = __fsub_rn(iy, fy);
+    return c;
+}
+
+template <int C, int G> struct AccShape {
+    static constexpr int CG = C / G;
+    static constexpr int NACC = CG == 1 ? C / 2 : G;       // packed accumulators per plane
+    static constexpr int PPA = CG == 1 ? 1 : CG / 2;       // channel pairs per accumulator
+};
+
+template <int C, int G, class F>
+__device__ __forceinline__ void emit_sims(const u64 (&acc)[AccShape<C, G>::NACC], F&& consume) {
+    constexpr int CG = AccShape<C, G>::CG;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        float lo, hi, sim;
+        if (CG == 1) {
+            unpack2(acc[g / 2], lo, hi);
+            sim = (g & 1) ? hi : lo;
+        } else {
+            unpack2(acc[g], lo, hi);
+            sim = __fmul_rn(__fadd_rn(lo, hi), 1.0f / CG);
+        }
+        consume(g, sim);
+    }
+}
+
+// A live sample whose cell is not inside the staged box (depth discontinuities, wild hypotheses, a
+// footprint larger than the box): the same arithmetic on 256-bit global loads.  Rare, hence out of line;
+// the reference features are re-read from global memory so that no register array crosses the call.
 template <int C, int G>
-__global__ void __launch_bounds__(TILE_THREADS, C == 32 ? 3 : 4)
+__device__ __noinline__ void gather_cell(const float* __restrict__ src, const float* __restrict__ refp, int x0, int y0, float ex,
+                                         float dx, float ey, float dy, int H, int W, float* __restrict__ sims) {
+    constexpr int NACC = AccShape<C, G>::NACC, PPA = AccShape<C, G>::PPA, CG = AccShape<C, G>::CG;
+    // 2x2 block clamped into the image; the axis weights move with it (a corner outside the image
+    // gets weight zero, the inside one keeps upstream's weight)
+    const int xc = min(max(x0, 0), W - 2), yc = min(max(y0, 0), H - 2);
+    const float wl = x0 == xc ? ex : (x0 + 1 == xc ? dx : 0.0f);
+    const float wr = x0 == xc ? dx : (x0 == xc + 1 ? ex : 0.0f);
+    const float wt = y0 == yc ? ey : (y0 + 1 == yc ? dy : 0.0f);
+    const float wb = y0 == yc ? dy : (y0 == yc + 1 ? ey : 0.0f);
+    const float w00 = __fmul_rn(wl, wt), w01 = __fmul_rn(wr, wt), w10 = __fmul_rn(wl, wb), w11 = __fmul_rn(wr, wb);
+    const u64 W00 = pack2(w00, w00), W01 = pack2(w01, w01), W10 = pack2(w10, w10), W11 = pack2(w11, w11);
+    const float* p = src + ((size_t)yc * W + xc) * C;
+    u64 acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0ull;
+    static_for<0, C / 8>([&](auto cb_c) {
+        constexpr int cb = decltype(cb_c)::value;
+        u64 t00[4], t01[4], t10[4], t11[4], r2[4];
+        O2 o;
+        o = ldg_o2(p + cb * 8);                       t00[0] = o.a; t00[1] = o.b; t00[2] = o.c; t00[3] = o.d;
+        o = ldg_o2(p + C + cb * 8);                   t01[0] = o.a; t01[1] = o.b; t01[2] = o.c; t01[3] = o.d;
+        o = ldg_o2(p + (size_t)W * C + cb * 8);       t10[0] = o.a; t10[1] = o.b; t10[2] = o.c; t10[3] = o.d;
+        o = ldg_o2(p + (size_t)(W + 1) * C + cb * 8); t11[0] = o.a; t11[1] = o.b; t11[2] = o.c; t11[3] = o.d;
+        o = ldg_o2(refp + cb * 8);                    r2[0] = o.a; r2[1] = o.b; r2[2] = o.c; r2[3] = o.d;
+        accumulate8<NACC, (CG == 1 ? cb * 4 : (cb * 8) / CG), PPA>(t00, t01, t10, t11, W00, W01, W10, W11, r2, acc);
+    });
+    emit_sims<C, G>(acc, [&](int g, float sim) { sims[g] = sim; });
+}
+
+// One round (a source view, or a plane group of one) of a block:
+//   1. the two end planes of every pixel give its part of the block's source bounding box (the sample
+//      position is a Moebius function of the depth, monotonic along the epipolar line between planes on
+//      the same side of the camera); warp reduction + shared atomics, one block barrier;
+//   2. one thread issues the TMA loads of the box (anchored at its top-left corner; whatever extends past
+//      BW x BH is simply not staged);
+//   3. in the shadow of the copy the threads compute the exact sample positions of all their planes;
+//   4. per sample: cell inside the staged box -> shared memory, else -> gather_cell().  The box is an
+//      optimisation only: correctness never depends on step 1 having predicted it right.
+// consume(k, g, sim) receives the correlation of plane k and group g.
+template <int C, int G, int DPT, class F>
+__device__ __forceinline__ void run_round(TileShared& sh, const uint8_t* __restrict__ tile, const CUtensorMap* map,
+                                          const float* __restrict__ src, const float* __restrict__ refp, int round, uint32_t& phase,
+                                          int flags, int b, const Ray& ray, const float (&depth)[DPT], unsigned valid, int H, int W,
+                                          float inv_half_w, float inv_half_h, const u64* __restrict__ ref2, F&& consume) {
+    constexpr int BW = Box<C>::W, BH = Box<C>::H, ROW = BoxBytes<C>::ROW, SUB = BoxBytes<C>::SUB;
+    constexpr int NACC = AccShape<C, G>::NACC, PPA = AccShape<C, G>::PPA, CG = AccShape<C, G>::CG;
+    const int lane = threadIdx.x & 31;
+    float ix[DPT], iy[DPT];
+
+    // ---- 1. bounding box from the end planes
+    {
+        float dl = depth[0];
+#pragma unroll
+        for (int k = 1; k < DPT; ++k) dl = ((valid >> k) & 1u) ? depth[k] : dl;
+        float jx, jy;
+        sample_coords(ray, depth[0], H, W, inv_half_w, inv_half_h, ix[0], iy[0]);
+        sample_coords(ray, dl, H, W, inv_half_w, inv_half_h, jx, jy);
+        const float lx = floorf(fminf(ix[0], jx)), hx = floorf(fmaxf(ix[0], jx));
+        const float ly = floorf(fminf(iy[0], jy)), hy = floorf(fmaxf(iy[0], jy));
+        // the curve touches the image extended by the -1 border (false for NaN/inf and for absent pixels)
+        const bool on = (valid & 1u) && (lx <= (float)(W - 1)) && (hx >= -1.0f) && (ly <= (float)(H - 1)) && (hy >= -1.0f) &&
+                        (fabsf(lx) < 1e9f) && (fabsf(hx) < 1e9f) && (fabsf(ly) < 1e9f) && (fabsf(hy) < 1e9f);
+        int mnx = on ? (int)fmaxf(lx, -1.0f) : INT_MAX, mxx = on ? (int)fminf(hx, (float)(W - 1)) : INT_MIN;
+        int mny = on ? (int)fmaxf(ly, -1.0f) : INT_MAX, mxy = on ? (int)fminf(hy, (float)(H - 1)) : INT_MIN;
+        mnx = __reduce_min_sync(0xffffffffu, mnx);
+        mny = __reduce_min_sync(0xffffffffu, mny);
+        mxx = __reduce_max_sync(0xffffffffu, mxx);
+        mxy = __reduce_max_sync(0xffffffffu, mxy);
+        int* box = sh.box[round & 1];
+        if (lane == 0 && mnx <= mxx) {
+            atomicMin(&box[0], mnx);
+            atomicMin(&box[1], mny);
+            atomicMax(&box[2], mxx);
+            atomicMax(&box[3], mxy);
+        }
+    }
+    __syncthreads();   // box complete; every thread is also done with the tile of the previous round
+    const int bx = sh.box[round & 1][0], by = sh.box[round & 1][1];
+    const bool any = sh.box[round & 1][0] <= sh.box[round & 1][2] && !(flags & FLAG_FORCE_GATHER);
+
+    // ---- 2. stage the box
+    if (threadIdx.x == 0) {
+        int* nb = sh.box[(round + 1) & 1];   // last read in the previous round: reset it for the next one
+        nb[0] = INT_MAX; nb[1] = INT_MAX; nb[2] = INT_MIN; nb[3] = INT_MIN;
+        if (any) {
+            mbar_expect_tx(&sh.bar, BoxBytes<C>::ALL);
+#pragma unroll
+            for (int cb = 0; cb < C / 8; ++cb) tma_load_box(smem_u32(tile) + cb * SUB, map, &sh.bar, cb * 8, bx, by, b);
+        }
+    }
+
+    // ---- 3. exact positions of all planes (NaN for planes / pixels that do not exist)
+    if (!(valid & 1u)) ix[0] = __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int k = 1; k < DPT; ++k) {
+        sample_coords(ray, depth[k], H, W, inv_half_w, inv_half_h, ix[k], iy[k]);
+        if (!((valid >> k) & 1u)) ix[k] = __int_as_float(0x7fc00000);
+    }
+    if (any) {
+        mbar_wait(&sh.bar, phase);
+        phase ^= 1u;
+    }
+    __syncwarp();   // lanes leave the wait loop one by one: reconverge before the long sampling code
+
+    // ---- 4. sample
+    const int org = by * BW + bx;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const Cell c = cell_at(ix[k], iy[k], H, W);
+        u64 acc[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[a] = 0ull;
+        const bool staged = any && (unsigned)(c.x0 - bx) <= (unsigned)(BW - 2) && (unsigned)(c.y0 - by) <= (unsigned)(BH - 2);
+        if (c.live && staged) {
+            const uint32_t a0 = (uint32_t)(c.y0 * BW + c.x0 - org) * 32u, a1 = a0 + 32u;
+            // 32-byte swizzle: address bit 4 ^= bit 7 (the two 16-byte halves of a pixel swap in every other 128-byte line)
+            const uint32_t s0 = a0 ^ ((a0 >> 3) & 16u), s1 = a1 ^ ((a1 >> 3) & 16u);
+            const uint8_t* p00 = tile + s0;
+            const uint8_t* p01 = tile + s1;
+            const uint8_t* q00 = tile + (s0 ^ 16u);
+            const uint8_t* q01 = tile + (s1 ^ 16u);
+            const float w00 = __fmul_rn(c.ex, c.ey), w01 = __fmul_rn(c.dx, c.ey), w10 = __fmul_rn(c.ex, c.dy), w11 = __fmul_rn(c.dx, c.dy);
+            const u64 W00 = pack2(w00, w00), W01 = pack2(w01, w01), W10 = pack2(w10, w10), W11 = pack2(w11, w11);
+            static_for<0, C / 8>([&](auto cb_c) {
+                constexpr int cb = decltype(cb_c)::value;
+                u64 t00[4], t01[4], t10[4], t11[4];
+                ulonglong2 q;
+                q = *reinterpret_cast<const ulonglong2*>(p00 + cb * SUB);       t00[0] = q.x; t00[1] = q.y;
+                q = *reinterpret_cast<const ulonglong2*>(q00 + cb * SUB);       t00[2] = q.x; t00[3] = q.y;
+                q = *reinterpret_cast<const ulonglong2*>(p01 + cb * SUB);       t01[0] = q.x; t01[1] = q.y;
+                q = *reinterpret_cast<const ulonglong2*>(q01 + cb * SUB);       t01[2] = q.x; t01[3] = q.y;
+                q = *reinterpret_cast<const ulonglong2*>(p00 + cb * SUB + ROW); t10[0] = q.x; t10[1] = q.y;
+                q = *reinterpret_cast<const ulonglong2*>(q00 + cb * SUB + ROW); t10[2] = q.x; t10[3] = q.y;
+                q = *reinterpret_cast<const ulonglong2*>(p01 + cb * SUB + ROW); t11[0] = q.x; t11[1] = q.y;
+                q = *reinterpret_cast<const ulonglong2*>(q01 + cb * SUB + ROW); t11[2] = q.x; t11[3] = q.y;
+                accumulate8<NACC, (CG == 1 ? cb * 4 : (cb * 8) / CG), PPA>(t00, t01, t10, t11, W00, W01, W10, W11, ref2 + cb * 4, acc);
+            });
+            emit_sims<C, G>(acc, [&](int g, float sim) { consume(k, g, sim); });
+        } else if (c.live) {
+            float sims[G];
+            gather_cell<C, G>(src, refp, c.x0, c.y0, c.ex, c.dx, c.ey, c.dy, H, W, sims);
+#pragma unroll
+            for (int g = 0; g < G; ++g) consume(k, g, sims[g]);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) consume(k, g, 0.0f);
+        }
+    }
+}
+
+__device__ __forceinline__ const uint8_t* block_prologue(TileShared& sh, uint8_t* smem_raw, const float* __restrict__ proj, int n_proj) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_proj; i += TILE_THREADS) sh.P[i] = proj[i];
+    if (tid < 8) sh.box[tid >> 2][tid & 3] = (tid & 2) ? INT_MIN : INT_MAX;
+    if (tid == 0) {
+        mbar_init(&sh.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
+
+template <int C>
+__device__ __forceinline__ void load_ref2(const float* __restrict__ p, u64 (&ref2)[C / 2]) {
+    const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p);
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+        const ulonglong2 v = __ldg(rp + q);
+        ref2[2 * q] = v.x;
+        ref2[2 * q + 1] = v.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// aggregated form (stages 2 / 3, config-2 microbench): a round per source view, all views in one block
+// ------------------------------------------------------------------------------------------------
+template <int C, int G>
+__global__ void __launch_bounds__(TILE_THREADS, BlocksPerSM<C>::value)
 warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ ref_fea,
                       const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode,
                       const float* __restrict__ interval, const float* __restrict__ weights, int H, int W, int D, int tiles_x,
                       int flags, float* __restrict__ sim_out, float* __restrict__ hyp_out) {
     constexpr int DPT = TilePlanes<G>::value;
-    constexpr int CG = C / G;                              // channels per group
-    constexpr int NACC = CG == 1 ? C / 2 : G;              // packed accumulators per plane
-    constexpr int PPA = CG == 1 ? 1 : CG / 2;              // channel pairs per accumulator
     extern __shared__ uint8_t smem_raw[];
-    __shared__ float sP[EFFIMVS_MAX_SRC_VIEWS * 12];
-    __shared__ int s_box[2][4];                            // min x, min y, max x, max y of the live cells (double buffered over views)
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ TileShared sh;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int b = blockIdx.z;
     const int HW = H * W;
-    const uint32_t tile = (smem_u32(smem_raw) + 1023u) & ~1023u;
-
-    for (int i = tid; i < n_src * 12; i += TILE_THREADS) sP[i] = proj[(size_t)b * n_src * 12 + i];
-    if (tid < 8) s_box[tid >> 2][tid & 3] = (tid & 2) ? INT_MIN : INT_MAX;
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+    const uint8_t* tile = block_prologue(sh, smem_raw, proj + (size_t)b * n_src * 12, n_src * 12);
 
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int xi = tx * TW + lane, yi = ty * TH + (tid >> 5);
@@ -186,20 +396,15 @@ warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __rest
     const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
     const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
 
+    const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
     u64 ref2[C / 2];
-    {
-        const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(ref_fea + ((size_t)b * HW + pix) * C);
-#pragma unroll
-        for (int q = 0; q < C / 4; ++q) {
-            const ulonglong2 v = __ldg(rp + q);
-            ref2[2 * q] = v.x;
-            ref2[2 * q + 1] = v.y;
-        }
-    }
+    load_ref2<C>(refp, ref2);
     float depth[DPT], num[DPT][G];
+    unsigned valid = 0;
 #pragma unroll
     for (int k = 0; k < DPT; ++k) {
         const bool on = inimg && d0 + k < D;
+        valid |= on ? (1u << k) : 0u;
         depth[k] = on ? fetch_hypothesis(hyp, hyp_mode, interval, b, d0 + k, D, pix, HW) : 1.0f;
         if (hyp_out && on) hyp_out[((size_t)b * D + d0 + k) * HW + pix] = depth[k];
 #pragma unroll
@@ -209,135 +414,12 @@ warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __rest
     uint32_t phase = 0;
 
     for (int v = 0; v < n_src; ++v) {
-        const Ray ray = make_ray(sP + v * 12, x, y, (flags & FLAG_RAY_UNFUSED) != 0);
+        const Ray ray = make_ray(sh.P + v * 12, x, y, (flags & FLAG_RAY_UNFUSED) != 0);
         const float w = (weights && inimg) ? __ldg(weights + ((size_t)b * n_src + v) * HW + pix) : 1.0f;
-        Cell cell[DPT];
-        int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
-#pragma unroll
-        for (int k = 0; k < DPT; ++k) {
-            cell[k] = make_cell(ray, depth[k], H, W, inv_half_w, inv_half_h);
-            if (!(inimg && d0 + k < D)) {
-                cell[k].live = false;
-                cell[k].x0 = cell[k].y0 = 0;
-                cell[k].ex = cell[k].dx = cell[k].ey = cell[k].dy = 0.0f;
-            }
-            mnx = min(mnx, cell[k].live ? cell[k].x0 : INT_MAX);
-            mny = min(mny, cell[k].live ? cell[k].y0 : INT_MAX);
-            mxx = max(mxx, cell[k].live ? cell[k].x0 : INT_MIN);
-            mxy = max(mxy, cell[k].live ? cell[k].y0 : INT_MIN);
-        }
-        mnx = __reduce_min_sync(0xffffffffu, mnx);
-        mny = __reduce_min_sync(0xffffffffu, mny);
-        mxx = __reduce_max_sync(0xffffffffu, mxx);
-        mxy = __reduce_max_sync(0xffffffffu, mxy);
-        int* box = s_box[v & 1];
-        if (lane == 0 && mnx <= mxx) {
-            atomicMin(&box[0], mnx);
-            atomicMin(&box[1], mny);
-            atomicMax(&box[2], mxx);
-            atomicMax(&box[3], mxy);
-        }
-        __syncthreads();   // box complete; every thread is also done with the tile of the previous view
-        const int bx = box[0], by = box[1], ux = box[2], uy = box[3];
-        const bool any = bx <= ux;
-        const bool fits = any && (ux - bx + 2 <= BW) && (uy - by + 2 <= BH) && !(flags & FLAG_FORCE_GATHER);
-
-        u64 acc[DPT][NACC];
-#pragma unroll
-        for (int k = 0; k < DPT; ++k)
-#pragma unroll
-            for (int a = 0; a < NACC; ++a) acc[k][a] = 0ull;
-
-        if (fits) {
-            const int org = by * BW + bx;
-            uint32_t lin[DPT];   // byte offset of the cell's north-west pixel in the (unswizzled) box
-#pragma unroll
-            for (int k = 0; k < DPT; ++k)   // non-live samples have zero weights; keep their address inside the box
-                lin[k] = cell[k].live ? (uint32_t)(cell[k].y0 * BW + cell[k].x0 - org) * 32u : 0u;
-            static_for<0, C / 8>([&](auto cb_c) {
-                constexpr int cb = decltype(cb_c)::value;
-                if (cb > 0) __syncthreads();   // everyone has sampled the previous channel block
-                if (tid == 0) {
-                    if (cb == 0) {             // the other box buffer was last read in the previous view: reset it for the next one
-                        int* nb = s_box[(v + 1) & 1];
-                        nb[0] = INT_MAX; nb[1] = INT_MAX; nb[2] = INT_MIN; nb[3] = INT_MIN;
-                    }
-                    mbar_expect_tx(&s_bar, BOX_BYTES);
-                    tma_load_box(tile, &maps.m[v], &s_bar, cb * 8, bx, by, b);
-                }
-                mbar_wait(&s_bar, phase);
-                phase ^= 1u;
-#pragma unroll
-                for (int k = 0; k < DPT; ++k) {
-                    // 32-byte swizzle: address bit 4 ^= bit 7 (the two 16-byte halves of a pixel swap in every other 128-byte line)
-                    const uint32_t a0 = lin[k], a1 = a0 + 32u;
-                    const uint32_t p00 = tile + (a0 ^ ((a0 >> 3) & 16u)), p01 = tile + (a1 ^ ((a1 >> 3) & 16u));
-                    u64 t00[4], t01[4], t10[4], t11[4];
-                    Q2 q;
-                    q = lds_q2(p00);                     t00[0] = q.a; t00[1] = q.b;
-                    q = lds_q2(p00 ^ 16u);               t00[2] = q.a; t00[3] = q.b;
-                    q = lds_q2(p01);                     t01[0] = q.a; t01[1] = q.b;
-                    q = lds_q2(p01 ^ 16u);               t01[2] = q.a; t01[3] = q.b;
-                    q = lds_q2(p00 + ROW_BYTES);         t10[0] = q.a; t10[1] = q.b;
-                    q = lds_q2((p00 ^ 16u) + ROW_BYTES); t10[2] = q.a; t10[3] = q.b;
-                    q = lds_q2(p01 + ROW_BYTES);         t11[0] = q.a; t11[1] = q.b;
-                    q = lds_q2((p01 ^ 16u) + ROW_BYTES); t11[2] = q.a; t11[3] = q.b;
-                    accumulate8<NACC, (CG == 1 ? cb * 4 : (cb * 8) / CG), PPA>(
-                        t00, t01, t10, t11, __fmul_rn(cell[k].ex, cell[k].ey), __fmul_rn(cell[k].dx, cell[k].ey),
-                        __fmul_rn(cell[k].ex, cell[k].dy), __fmul_rn(cell[k].dx, cell[k].dy), ref2 + cb * 4, acc[k]);
-                }
-            });
-        } else {
-            if (tid == 0) {
-                int* nb = s_box[(v + 1) & 1];
-                nb[0] = INT_MAX; nb[1] = INT_MAX; nb[2] = INT_MIN; nb[3] = INT_MIN;
-            }
-            __syncthreads();
-            if (any) {
-                const float* src = srcs.p[v] + (size_t)b * C * HW;
-#pragma unroll
-                for (int k = 0; k < DPT; ++k) {
-                    // 2x2 block clamped into the image; the axis weights move with it (a corner outside the
-                    // image gets weight zero, the inside one keeps upstream's weight)
-                    const Cell& c = cell[k];
-                    const int xc = min(max(c.x0, 0), W - 2), yc = min(max(c.y0, 0), H - 2);
-                    const float wl = c.x0 == xc ? c.ex : (c.x0 + 1 == xc ? c.dx : 0.0f);
-                    const float wr = c.x0 == xc ? c.dx : (c.x0 == xc + 1 ? c.ex : 0.0f);
-                    const float wt = c.y0 == yc ? c.ey : (c.y0 + 1 == yc ? c.dy : 0.0f);
-                    const float wb = c.y0 == yc ? c.dy : (c.y0 == yc + 1 ? c.ey : 0.0f);
-                    const float* p = src + ((size_t)yc * W + xc) * C;
-                    if (c.live) {
-                        static_for<0, C / 8>([&](auto cb_c) {
-                            constexpr int cb = decltype(cb_c)::value;
-                            u64 t00[4], t01[4], t10[4], t11[4];
-                            O2 o;
-                            o = ldg_o2(p + cb * 8);                     t00[0] = o.a; t00[1] = o.b; t00[2] = o.c; t00[3] = o.d;
-                            o = ldg_o2(p + C + cb * 8);                 t01[0] = o.a; t01[1] = o.b; t01[2] = o.c; t01[3] = o.d;
-                            o = ldg_o2(p + (size_t)W * C + cb * 8);     t10[0] = o.a; t10[1] = o.b; t10[2] = o.c; t10[3] = o.d;
-                            o = ldg_o2(p + (size_t)(W + 1) * C + cb * 8); t11[0] = o.a; t11[1] = o.b; t11[2] = o.c; t11[3] = o.d;
-                            accumulate8<NACC, (CG == 1 ? cb * 4 : (cb * 8) / CG), PPA>(t00, t01, t10, t11, __fmul_rn(wl, wt), __fmul_rn(wr, wt),
-                                                                                       __fmul_rn(wl, wb), __fmul_rn(wr, wb), ref2 + cb * 4,
-                                                                                       acc[k]);
-                        });
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < DPT; ++k) {
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                float lo, hi, sim;
-                if (CG == 1) {
-                    unpack2(acc[k][g / 2], lo, hi);
-                    sim = (g & 1) ? hi : lo;
-                } else {
-                    unpack2(acc[k][g], lo, hi);
-                    sim = __fmul_rn(__fadd_rn(lo, hi), 1.0f / CG);
-                }
-                num[k][g] = weights ? __fadd_rn(num[k][g], __fmul_rn(sim, w)) : __fadd_rn(num[k][g], sim);
-            }
-        }
+        run_round<C, G, DPT>(sh, tile, &maps.m[v], srcs.p[v] + (size_t)b * C * HW, refp, v, phase, flags, b, ray, depth, valid, H, W,
+                             inv_half_w, inv_half_h, ref2, [&](int k, int g, float sim) {
+                                 num[k][g] = weights ? __fadd_rn(num[k][g], __fmul_rn(sim, w)) : __fadd_rn(num[k][g], sim);
+                             });
         den = __fadd_rn(den, w);
     }
     if (!inimg) return;
@@ -348,6 +430,70 @@ warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __rest
 #pragma unroll
             for (int g = 0; g < G; ++g) sim_out[(((size_t)b * G + g) * D + d0 + k) * HW + pix] = __fdiv_rn(num[k][g], div);
         }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage-1 form: per-view similarities (no aggregation); a block = (tile, group of 8 planes, source
+// view), one round.  The softmax entropy over D is a second, streaming kernel over the similarities.
+// ------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(TILE_THREADS, BlocksPerSM<C>::value)
+warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs,
+                       int n_src, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode, int H, int W, int D,
+                       int tiles_x, int flags, float* __restrict__ sims_out) {
+    constexpr int DPT = 8;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ TileShared sh;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.z, v = blockIdx.y % n_src, d0 = (blockIdx.y / n_src) * DPT;
+    const int HW = H * W;
+    const uint8_t* tile = block_prologue(sh, smem_raw, proj + ((size_t)b * n_src + v) * 12, 12);
+
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int xi = tx * TW + lane, yi = ty * TH + (tid >> 5);
+    const bool inimg = xi < W && yi < H;
+    const int pix = inimg ? yi * W + xi : 0;
+    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
+    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
+
+    const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
+    u64 ref2[C / 2];
+    load_ref2<C>(refp, ref2);
+    const Ray ray = make_ray(sh.P, (float)xi, (float)yi, (flags & FLAG_RAY_UNFUSED) != 0);
+    float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
+    uint32_t phase = 0;
+
+    float depth[DPT];
+    unsigned valid = 0;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const bool on = inimg && d0 + k < D;
+        valid |= on ? (1u << k) : 0u;
+        depth[k] = on ? fetch_hypothesis(hyp, hyp_mode, nullptr, b, d0 + k, D, pix, HW) : 1.0f;
+    }
+    run_round<C, 1, DPT>(sh, tile, &maps.m[v], srcs.p[v] + (size_t)b * C * HW, refp, 0, phase, flags, b, ray, depth, valid, H, W,
+                         inv_half_w, inv_half_h, ref2, [&](int k, int, float sim) {
+                             if ((valid >> k) & 1u) out[(size_t)(d0 + k) * HW] = sim;
+                         });
+}
+
+// softmax entropy over the D similarities of a (pixel, view) (models/Effi_MVS_plus.py:43-44); sims (N, D, HW)
+__global__ void __launch_bounds__(256)
+softmax_entropy_kernel(const float* __restrict__ sims, int D, int HW, float* __restrict__ entropy_out) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const float* mine = sims + (size_t)blockIdx.y * D * HW + pix;
+    float m = -INFINITY;
+    for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(mine + (size_t)d * HW));
+    float z = 0.0f;
+    for (int d = 0; d < D; ++d) z += expf(__ldg(mine + (size_t)d * HW) - m);
+    float ent = 0.0f;
+    for (int d = 0; d < D; ++d) {
+        const float p = __fdiv_rn(expf(__ldg(mine + (size_t)d * HW) - m), z);
+        ent -= p * logf(p + 1e-7f);
+    }
+    entropy_out[(size_t)blockIdx.y * HW + pix] = ent;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -366,12 +512,12 @@ EncodeTiledFn tensor_map_encoder() {
 }
 
 // (C, W, H, B) view of a channels-last map; box = 8 channels x BW x BH pixels, 32-byte swizzle, zero fill
-int encode_map(CUtensorMap* m, const float* base, int B, int C, int H, int W) {
+int encode_map(CUtensorMap* m, const float* base, int B, int C, int H, int W, int bw, int bh) {
     EncodeTiledFn enc = tensor_map_encoder();
     EFFI_REQUIRE(enc, EFFIMVS_ECUDA, "warp_corr: cuTensorMapEncodeTiled not available from the driver");
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    const cuuint32_t box[4] = {8, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+    const cuuint32_t box[4] = {8, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -380,13 +526,26 @@ int encode_map(CUtensorMap* m, const float* base, int B, int C, int H, int W) {
     return EFFIMVS_OK;
 }
 
+template <int C>
+int encode_maps(TileMaps& maps, const SrcPtrs& srcs, int n_src, int B, int H, int W) {
+    for (int v = 0; v < n_src; ++v) {
+        int rc = encode_map(&maps.m[v], srcs.p[v], B, C, H, W, Box<C>::W, Box<C>::H);
+        if (rc) return rc;
+    }
+    for (int v = n_src; v < EFFIMVS_MAX_SRC_VIEWS; ++v) maps.m[v] = maps.m[0];
+    return EFFIMVS_OK;
+}
+
 template <int C, int G>
-int launch_tile(const TileMaps& maps, const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp,
-                int hyp_mode, const float* interval, const float* weights, int B, int H, int W, int D, int flags, float* sim_out,
-                float* hyp_out, cudaStream_t st) {
+int launch_tile(const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
+                const float* interval, const float* weights, int B, int H, int W, int D, int flags, float* sim_out, float* hyp_out,
+                cudaStream_t st) {
+    TileMaps maps;
+    int rc = encode_maps<C>(maps, srcs, n_src, B, H, W);
+    if (rc) return rc;
     const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
     dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, ceil_div(D, TilePlanes<G>::value), B);
-    const size_t smem = BOX_BYTES + 1024;
+    const size_t smem = BoxBytes<C>::ALL + 1024;
     cudaFuncSetAttribute(warp_corr_tile_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     warp_corr_tile_kernel<C, G><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
                                                             tiles_x, flags, sim_out, hyp_out);
@@ -394,17 +553,33 @@ int launch_tile(const TileMaps& maps, const float* ref, const SrcPtrs& srcs, int
 }
 
 template <int C>
-int tile_dispatch_g(int G, const TileMaps& maps, const float* ref, const SrcPtrs& srcs, int n_src, const float* proj,
-                    const float* hyp, int hyp_mode, const float* interval, const float* weights, int B, int H, int W, int D,
-                    int flags, float* sim_out, float* hyp_out, cudaStream_t st) {
+int tile_dispatch_g(int G, const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
+                    const float* interval, const float* weights, int B, int H, int W, int D, int flags, float* sim_out,
+                    float* hyp_out, cudaStream_t st) {
     switch (G) {
-        case 1: return launch_tile<C, 1>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
-        case 2: return launch_tile<C, 2>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
-        case 4: return launch_tile<C, 4>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
-        case 8: return launch_tile<C, 8>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
+        case 1: return launch_tile<C, 1>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
+        case 2: return launch_tile<C, 2>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
+        case 4: return launch_tile<C, 4>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
+        case 8: return launch_tile<C, 8>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
     }
     set_error("warp_corr_agg: G=%d not in {1,2,4,8}", G);
     return EFFIMVS_EUNSUPPORTED;
+}
+
+template <int C>
+int launch_views(const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode, int B, int H,
+                 int W, int D, int flags, float* sims_out, float* entropy_out, cudaStream_t st) {
+    TileMaps maps;
+    int rc = encode_maps<C>(maps, srcs, n_src, B, H, W);
+    if (rc) return rc;
+    const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
+    dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, n_src * ceil_div(D, 8), B);
+    const size_t smem = BoxBytes<C>::ALL + 1024;
+    cudaFuncSetAttribute(warp_views_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    warp_views_tile_kernel<C><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
+    if ((rc = check_launch("warp_views_tile_kernel"))) return rc;
+    softmax_entropy_kernel<<<dim3(ceil_div(H * W, 256), B * n_src), 256, 0, st>>>(sims_out, D, H * W, entropy_out);
+    return check_launch("softmax_entropy_kernel");
 }
 
 }  // namespace
@@ -421,19 +596,26 @@ int warp_flags_from_env(int H, int W) {
 int warp_corr_agg_tile(const float* ref_fea, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
                        const float* interval, const float* weights, int B, int C, int H, int W, int D, int G, float* sim_out,
                        float* hyp_out, cudaStream_t st) {
-    TileMaps maps;
-    for (int v = 0; v < n_src; ++v) {
-        int rc = encode_map(&maps.m[v], srcs.p[v], B, C, H, W);
-        if (rc) return rc;
-    }
-    for (int v = n_src; v < EFFIMVS_MAX_SRC_VIEWS; ++v) maps.m[v] = maps.m[0];
     const int flags = warp_flags_from_env(H, W);
     switch (C) {
-        case 8: return tile_dispatch_g<8>(G, maps, ref_fea, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
-        case 16: return tile_dispatch_g<16>(G, maps, ref_fea, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
-        case 32: return tile_dispatch_g<32>(G, maps, ref_fea, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
+        case 8: return tile_dispatch_g<8>(G, ref_fea, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
+        case 16: return tile_dispatch_g<16>(G, ref_fea, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
+        case 32: return tile_dispatch_g<32>(G, ref_fea, srcs, n_src, proj, hyp, hyp_mode, interval, weights, B, H, W, D, flags, sim_out, hyp_out, st);
     }
     set_error("warp_corr_agg: C=%d not in {8,16,32}", C);
+    return EFFIMVS_EUNSUPPORTED;
+}
+
+// channels-last fast path of effimvs_warp_corr_views_f32
+int warp_corr_views_tile(const float* ref_fea, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
+                         int B, int C, int H, int W, int D, float* sims_out, float* entropy_out, cudaStream_t st) {
+    const int flags = warp_flags_from_env(H, W);
+    switch (C) {
+        case 8: return launch_views<8>(ref_fea, srcs, n_src, proj, hyp, hyp_mode, B, H, W, D, flags, sims_out, entropy_out, st);
+        case 16: return launch_views<16>(ref_fea, srcs, n_src, proj, hyp, hyp_mode, B, H, W, D, flags, sims_out, entropy_out, st);
+        case 32: return launch_views<32>(ref_fea, srcs, n_src, proj, hyp, hyp_mode, B, H, W, D, flags, sims_out, entropy_out, st);
+    }
+    set_error("warp_corr_views: C=%d not in {8,16,32}", C);
     return EFFIMVS_EUNSUPPORTED;
 }
 
