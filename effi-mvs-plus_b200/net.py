@@ -119,8 +119,26 @@ class CrossScaleNet3D(nn.Module):
         self.conv2 = ConvBN3d(base, 1, transposed=True)
 
 
+def _upsample2_nearest(t):
+    """Nearest x2 of a channels-last map as one strided copy (F.interpolate's NHWC kernel is ~4x slower)."""
+    N, C, h, w = t.shape
+    v = t.permute(0, 2, 3, 1)
+    v = v[:, :, None, :, None, :].expand(N, h, 2, w, 2, C).reshape(N, 2 * h, 2 * w, C)
+    return v.permute(0, 3, 1, 2)
+
+
 class FeaturePyramid(nn.Module):
-    """P_1to8_FeatureNet_Fast (models/module.py:346-412): strides 1,2,4,8; heads at 1/8, 1/4, 1/2."""
+    """P_1to8_FeatureNet_Fast (models/module.py:346-412): strides 1,2,4,8; heads at 1/8, 1/4, 1/2.
+
+    Inference on CUDA runs an algebraically identical top-down path that never materialises the
+    64-channel half-resolution map (upstream: nearest x2, 1x1 lateral conv, bias add, sum, 3x3 head =
+    five passes over 600 MB at the DTU shape).  The head is linear, so
+        out3(up(t) + inner2(l1)) = out3(up(t)) + (out3 o inner2)(l1) + out3(bias),
+    where out3(up(t)) is four phase-specific 3x3 convolutions on the quarter-resolution map (sub-pixel
+    form of a 3x3 convolution over a nearest-upsampled image; zero padding carries over exactly),
+    out3 o inner2 is one composed 16->8 3x3 convolution on l1 and out3(bias) is a constant map.
+    The quarter-resolution level adds the lateral 1x1 conv as one in-place addmm on the NHWC view.
+    """
 
     def __init__(self, chans, heads):
         super().__init__()
@@ -134,11 +152,74 @@ class FeaturePyramid(nn.Module):
         self.inner2 = nn.Conv2d(c1, c3, 1, bias=True)
         self.out2 = nn.Conv2d(c3, heads[1], 3, padding=1, bias=False)
         self.out3 = nn.Conv2d(c3, heads[2], 3, padding=1, bias=False)
+        self.fused_topdown = None     # None: on CUDA in eval mode; True / False force it
+        self._heads = None
+        self._bias_maps = {}
+
+    def _head_weights(self):
+        ts = (self.out3.weight, self.inner2.weight, self.inner2.bias, self.inner1.weight, self.inner1.bias)
+        stamp = tuple((id(t), t._version, t.device) for t in ts)
+        if self._heads is None or self._heads[0] != stamp:
+            w3 = self.out3.weight.detach()                      # (O, M, 3, 3)
+            O, M = w3.shape[:2]
+            lateral = torch.einsum("omyx,mi->oiyx", w3, self.inner2.weight.detach()[:, :, 0, 0]).contiguous()
+            # output row 2i+p reads input rows i-1, i, i+1 of the low-resolution map through kernel rows:
+            #   p = 0: {ky 0 -> i-1, ky 1 -> i, ky 2 -> i};   p = 1: {ky 0 -> i, ky 1 -> i, ky 2 -> i+1}
+            taps = {0: ((0, 0), (1, 1), (2, 1)), 1: ((0, 1), (1, 1), (2, 2))}
+            phase = w3.new_zeros(2, 2, O, M, 3, 3)
+            for py in (0, 1):
+                for px in (0, 1):
+                    for ky, dy in taps[py]:
+                        for kx, dx in taps[px]:
+                            phase[py, px, :, :, dy, dx] += w3[:, :, ky, kx]
+            phase = phase.reshape(4 * O, M, 3, 3)
+            w1t = self.inner1.weight.detach()[:, :, 0, 0].t().contiguous()      # (C2, M)
+            if w3.is_cuda:
+                lateral = lateral.contiguous(memory_format=torch.channels_last)
+                phase = phase.contiguous(memory_format=torch.channels_last)
+            self._heads = (stamp, lateral, phase, w1t)
+            self._bias_maps = {}
+        return self._heads[1:]
+
+    def _bias_map(self, H, W):
+        """out3 applied to the constant lateral bias: (1, O, H, W), differs from a constant only on the border."""
+        key = (H, W)
+        if key not in self._bias_maps:
+            b = self.inner2.bias.detach().reshape(1, -1, 1, 1).expand(1, -1, H, W)
+            self._bias_maps[key] = F.conv2d(b, self.out3.weight.detach(), padding=1)
+        return self._bias_maps[key]
+
+    def _topdown_fused(self, l1, l2, top):
+        lateral, phase, w1t = self._head_weights()
+        s1 = self.out1(top)
+        # 1/4 level: up(top) + inner1(l2) = up(top + bias) + l2 @ W1^T, accumulated in place on the NHWC view
+        t2 = _upsample2_nearest(top + self.inner1.bias.reshape(1, -1, 1, 1))
+        N, M, h, w = t2.shape
+        t2_rows = t2.permute(0, 2, 3, 1).reshape(-1, M)
+        t2_rows.addmm_(l2.permute(0, 2, 3, 1).reshape(-1, l2.shape[1]), w1t)
+        s2 = self.out2(t2)
+        # 1/2 level, never materialised
+        O = self.out3.weight.shape[0]
+        a = F.conv2d(t2, phase, padding=1)                               # (N, 4*O, h, w), channel = (py, px, o)
+        s3 = F.conv2d(l1, lateral, padding=1)                            # (N, O, 2h, 2w)
+        s3_view = s3.permute(0, 2, 3, 1).reshape(N, h, 2, w, 2, O)       # (n, i, py, j, px, o)
+        if s3_view.data_ptr() != s3.data_ptr():                          # not a view (unexpected layout): plain path
+            return None
+        s3_view += a.permute(0, 2, 3, 1).reshape(N, h, w, 2, 2, O).permute(0, 1, 3, 2, 4, 5)
+        s3 += self._bias_map(2 * h, 2 * w)
+        return [s1, s2, s3]
 
     def forward(self, x):
         l1 = self.conv1(self.conv0(x))
         l2 = self.conv2(l1)
         top = self.conv3(l2)
+        fused = self.fused_topdown
+        if fused is None:
+            fused = x.is_cuda and not self.training and not torch.is_grad_enabled()
+        if fused and l1.shape[2] == 2 * l2.shape[2] and l1.shape[3] == 2 * l2.shape[3]:
+            out = self._topdown_fused(l1, l2, top)
+            if out is not None:
+                return out
         s1 = self.out1(top)
         top = F.interpolate(top, scale_factor=2, mode="nearest") + self.inner1(l2)
         s2 = self.out2(top)
