@@ -54,6 +54,10 @@ SIGNATURES = {
     "effimvs_costreg_fpn3d": (_i, [_p, _pp, _pp, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "effimvs_cost_up_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "effimvs_cost_up_small": (_i, [_p, _p, _pp, _pp, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "effimvs_gru_reset_f32": (_i, [_p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
+    "effimvs_gru_update_f32": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
+    "effimvs_gru_delta_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "effimvs_convex_upsample_f32": (_i, [_p, _p, _f, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_fusion_reproject_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "effimvs_fusion_filter_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _i, _p, _p, _p, _p, _p]),
 }

@@ -1,0 +1,206 @@
+// Per-pixel glue of the ConvGRU update block and the convex upsampling: the
+// 2-D convolutions stay cuDNN (stock PyTorch); everything between them -- gate activations, the
+// reset product written straight into the next convolution's input, the state update, the inverse-
+// depth step with its depth conversion, and the softmax-weighted 3x3 upsampling -- is one pass each
+// instead of a chain of a dozen elementwise launches over the same maps.
+//
+//   ConvGRU.forward            upstream models/update.py:33-49
+//   DepthHead.forward (tail)   upstream models/update.py:19-27
+//   BasicUpdateBlock.forward   upstream models/update.py:114-127 (inv_depth + delta)
+//   disp_to_depth              upstream models/Effi_MVS_plus.py:138-148
+//   upsample_depth             upstream models/Effi_MVS_plus.py:167-178
+//
+// Multi-channel maps are channels-last (B,H,W,C), what cuDNN's NHWC convolutions emit; the arithmetic
+// repeats torch's elementwise kernels operation by operation (no contraction across torch ops):
+// sigmoid = 1 / (1 + exp(-x)), tanh = tanhf, reciprocal = 1 / x, bias added first as cuDNN's epilogue does.
+#include "common.cuh"
+
+namespace effimvs {
+namespace {
+
+__device__ __forceinline__ float sigmoid_t(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// disp_to_depth: 1 / clamp(lo + (hi - lo) * inv, 1e-4)
+__device__ __forceinline__ float to_depth(float inv, float lo, float hi) {
+    const float s = fmaxf(__fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), inv)), 1e-4f);
+    return __fdiv_rn(1.0f, s);
+}
+
+// rhx = [ sigmoid(r_pre + b_r) * h ; x ]   with zr_pre = (pixels, 2h) = [z_pre ; r_pre], hx = (pixels, h + cx) = [h ; x]
+__global__ void __launch_bounds__(256)
+gru_reset_kernel(const float4* __restrict__ zr_pre, const float* __restrict__ bias_r, const float4* __restrict__ hx, long long n_pix, int h,
+                 int cx, float4* __restrict__ rhx) {
+    const int ct4 = (h + cx) >> 2, h4 = h >> 2;
+    const long long total = n_pix * ct4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / ct4;
+        const int c4 = (int)(i - p * ct4);
+        float4 v = __ldg(hx + i);
+        if (c4 < h4) {
+            const float4 r = __ldg(zr_pre + p * (2 * h4) + h4 + c4);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias_r) + c4);
+            v.x = __fmul_rn(sigmoid_t(__fadd_rn(r.x, b.x)), v.x);
+            v.y = __fmul_rn(sigmoid_t(__fadd_rn(r.y, b.y)), v.y);
+            v.z = __fmul_rn(sigmoid_t(__fadd_rn(r.z, b.z)), v.z);
+            v.w = __fmul_rn(sigmoid_t(__fadd_rn(r.w, b.w)), v.w);
+        }
+        rhx[i] = v;
+    }
+}
+
+__device__ __forceinline__ float gru_mix(float zp, float bz, float qp, float bq, float hv) {
+    const float z = sigmoid_t(__fadd_rn(zp, bz));
+    const float q = tanhf(__fadd_rn(qp, bq));
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, z), hv), __fmul_rn(z, q));   // (1 - z) * h + z * q
+}
+
+// h' = (1 - z) * h + z * tanh(q_pre + b_q), z = sigmoid(z_pre + b_z); written to hx[:, :h] in place and to net (pixels, h)
+__global__ void __launch_bounds__(256)
+gru_update_kernel(const float4* __restrict__ zr_pre, const float* __restrict__ bias_z, const float4* __restrict__ q_pre,
+                  const float* __restrict__ bias_q, float4* __restrict__ hx, long long n_pix, int h, int cx, float4* __restrict__ net) {
+    const int ct4 = (h + cx) >> 2, h4 = h >> 2;
+    const long long total = n_pix * h4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / h4;
+        const int c4 = (int)(i - p * h4);
+        const float4 zp = __ldg(zr_pre + p * (2 * h4) + c4), qp = __ldg(q_pre + i);
+        const float4 bz = __ldg(reinterpret_cast<const float4*>(bias_z) + c4), bq = __ldg(reinterpret_cast<const float4*>(bias_q) + c4);
+        const float4 hv = hx[p * ct4 + c4];
+        float4 o;
+        o.x = gru_mix(zp.x, bz.x, qp.x, bq.x, hv.x);
+        o.y = gru_mix(zp.y, bz.y, qp.y, bq.y, hv.y);
+        o.z = gru_mix(zp.z, bz.z, qp.z, bq.z, hv.z);
+        o.w = gru_mix(zp.w, bz.w, qp.w, bq.w, hv.w);
+        hx[p * ct4 + c4] = o;
+        net[i] = o;
+    }
+}
+
+// inv' = inv + tanh(pre + b)  (pre == nullptr: inv' = inv), depth = disp_to_depth(inv')
+__global__ void __launch_bounds__(256)
+gru_delta_kernel(const float* __restrict__ pre, const float* __restrict__ bias, const float* __restrict__ inv, const float* __restrict__ lo,
+                 const float* __restrict__ hi, int HW, float* __restrict__ inv_out, float* __restrict__ depth_out) {
+    const int b = blockIdx.y;
+    const float l = __ldg(lo + b), hh = __ldg(hi + b);
+    const float bv = pre ? __ldg(bias) : 0.0f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)b * HW + i;
+        float v = __ldg(inv + o);
+        if (pre) v = __fadd_rn(v, tanhf(__fadd_rn(__ldg(pre + o), bv)));
+        if (inv_out) inv_out[o] = v;
+        depth_out[o] = to_depth(v, l, hh);
+    }
+}
+
+// upsample_depth with ratio R (2): mask (B,H,W,9*R*R) = scale * (mask_pre + bias), channel = (k*R + ry)*R + rx;
+// softmax over the 9 neighbours k, weighted sum of the zero-padded 3x3 neighbourhood of inv.
+template <int R>
+__global__ void __launch_bounds__(128)
+convex_upsample_kernel(const float* __restrict__ mask_pre, const float* __restrict__ mask_bias, float scale, const float* __restrict__ inv,
+                       const float* __restrict__ lo, const float* __restrict__ hi, int H, int W, float* __restrict__ up_out,
+                       float* __restrict__ depth_out) {
+    constexpr int CH = 9 * R * R;
+    __shared__ float sb[CH];
+    for (int i = threadIdx.x; i < CH; i += blockDim.x) sb[i] = mask_bias ? mask_bias[i] : 0.0f;
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= H * W) return;
+    const int y = pix / W, x = pix - y * W;
+    const float l = __ldg(lo + b), hh = __ldg(hi + b);
+    const float* ib = inv + (size_t)b * H * W;
+    float nb[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        nb[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ib + (size_t)yy * W + xx) : 0.0f;
+    }
+    const float4* mp = reinterpret_cast<const float4*>(mask_pre + ((size_t)b * H * W + pix) * CH);
+    float m[CH];
+#pragma unroll
+    for (int q = 0; q < CH / 4; ++q) {
+        const float4 v = __ldg(mp + q);
+        m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) m[c] = __fmul_rn(scale, __fadd_rn(m[c], sb[c]));
+    const int WO = W * R;
+#pragma unroll
+    for (int ry = 0; ry < R; ++ry) {
+        float res[R];
+#pragma unroll
+        for (int rx = 0; rx < R; ++rx) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) mx = fmaxf(mx, m[(k * R + ry) * R + rx]);
+            float e[9], z = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                e[k] = expf(__fsub_rn(m[(k * R + ry) * R + rx], mx));
+                z = __fadd_rn(z, e[k]);
+            }
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc = __fadd_rn(acc, __fmul_rn(__fdiv_rn(e[k], z), nb[k]));
+            res[rx] = acc;
+        }
+        const size_t o = ((size_t)b * H * R + (size_t)y * R + ry) * WO + (size_t)x * R;
+#pragma unroll
+        for (int rx = 0; rx < R; ++rx) {
+            if (up_out) up_out[o + rx] = res[rx];
+            if (depth_out) depth_out[o + rx] = to_depth(res[rx], l, hh);
+        }
+    }
+}
+
+int grid_for(long long work, int block) {
+    long long g = (work + block - 1) / block;
+    const long long cap = (long long)kNumSMs * 16;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+}  // namespace effimvs
+
+using namespace effimvs;
+
+extern "C" int effimvs_gru_reset_f32(const float* zr_pre, const float* bias_r, const float* hx, long long n_pix, int h, int cx,
+                                     float* rhx, void* stream) {
+    EFFI_REQUIRE(zr_pre && bias_r && hx && rhx, EFFIMVS_EINVAL, "gru_reset: null pointer");
+    EFFI_REQUIRE(n_pix > 0 && h > 0 && cx >= 0 && h % 4 == 0 && cx % 4 == 0, EFFIMVS_EINVAL, "gru_reset: h=%d, cx=%d must be multiples of 4", h, cx);
+    const long long work = n_pix * ((h + cx) / 4);
+    gru_reset_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)zr_pre, bias_r, (const float4*)hx, n_pix, h, cx,
+                                                                           (float4*)rhx);
+    return check_launch("gru_reset_kernel");
+}
+
+extern "C" int effimvs_gru_update_f32(const float* zr_pre, const float* bias_z, const float* q_pre, const float* bias_q, float* hx,
+                                      long long n_pix, int h, int cx, float* net_out, void* stream) {
+    EFFI_REQUIRE(zr_pre && bias_z && q_pre && bias_q && hx && net_out, EFFIMVS_EINVAL, "gru_update: null pointer");
+    EFFI_REQUIRE(n_pix > 0 && h > 0 && cx >= 0 && h % 4 == 0 && cx % 4 == 0, EFFIMVS_EINVAL, "gru_update: h=%d, cx=%d must be multiples of 4", h, cx);
+    const long long work = n_pix * (h / 4);
+    gru_update_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)zr_pre, bias_z, (const float4*)q_pre, bias_q,
+                                                                            (float4*)hx, n_pix, h, cx, (float4*)net_out);
+    return check_launch("gru_update_kernel");
+}
+
+extern "C" int effimvs_gru_delta_f32(const float* pre, const float* bias, const float* inv, const float* lo_disp, const float* hi_disp,
+                                     int B, int HW, float* inv_out, float* depth_out, void* stream) {
+    EFFI_REQUIRE(inv && lo_disp && hi_disp && depth_out && (!pre || bias), EFFIMVS_EINVAL, "gru_delta: null pointer");
+    EFFI_REQUIRE(B > 0 && B <= 65535 && HW > 0, EFFIMVS_EINVAL, "gru_delta: bad sizes");
+    dim3 grid(grid_for(HW, 256), B);
+    gru_delta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pre, bias, inv, lo_disp, hi_disp, HW, inv_out, depth_out);
+    return check_launch("gru_delta_kernel");
+}
+
+extern "C" int effimvs_convex_upsample_f32(const float* mask_pre, const float* mask_bias, float mask_scale, const float* inv,
+                                           const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio, float* up_out,
+                                           float* depth_out, void* stream) {
+    EFFI_REQUIRE(mask_pre && inv && lo_disp && hi_disp && (up_out || depth_out), EFFIMVS_EINVAL, "convex_upsample: null pointer");
+    EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "convex_upsample: bad sizes");
+    EFFI_REQUIRE(ratio == 2, EFFIMVS_EUNSUPPORTED, "convex_upsample: ratio=%d (only 2, the value upstream uses, is built)", ratio);
+    dim3 grid(ceil_div(H * W, 128), B);
+    convex_upsample_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(mask_pre, mask_bias, mask_scale, inv, lo_disp, hi_disp, H, W, up_out,
+                                                                     depth_out);
+    return check_launch("convex_upsample_kernel");
+}

@@ -45,6 +45,7 @@ def _is_planes(hyp: torch.Tensor) -> bool:
 
 class CudaHotPath:
     name = "cuda"
+    fused_update = True      # net.UpdateBlock.forward_fused: GRU / upsampling glue kernels
 
     def __init__(self, precision: str = "f32", native_projection: bool = False):
         """precision of the 3-D regularization: 'f32' (CUDA-core direct convs), 'bf16' (tcgen05 implicit
@@ -169,6 +170,12 @@ class CudaHotPath:
         """cur (B,1,D,H,W), prev (B,1,D,H/2,W/2) -> (B,1,D,H,W)   (upstream models/module.py:509-516)."""
         ws, bs = self._csp_weights(net)
         return ops.cost_up_small(cur_volume, prev_resampled, ws, bs, self.precision)
+
+    # -- section 8(f) row 3: update-block glue (upstream models/update.py:33-49, 114-127; Effi_MVS_plus.py:138-178) ---
+    gru_reset = staticmethod(ops.gru_reset)
+    gru_update = staticmethod(ops.gru_update)
+    gru_delta = staticmethod(ops.gru_delta)
+    convex_upsample = staticmethod(ops.convex_upsample)
 
     # -- a11 / a12 --------------------------------------------------------------------------------
     def softmax_regress_conf(self, prob_pre, hyp):

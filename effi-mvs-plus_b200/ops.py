@@ -435,3 +435,98 @@ def _(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, dist_base, rel_d
     u8 = torch.uint8
     return (ref_depth.new_empty(n, 1, h, w, dtype=u8), ref_depth.new_empty(n, 1, h, w), ref_depth.new_empty(n, 3, h, w),
             ref_depth.new_empty((n, v, K, h, w) if want_masks else (0,), dtype=u8))
+
+
+# -------------------------------------------------------------------------------------------
+# ConvGRU / convex-upsampling glue (csrc/update_glue.cu).  Multi-channel maps
+# are channels-last; (B,1,H,W) maps are plain dense.
+def _nhwc(t: Tensor, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("effimvs::{} got a CPU tensor; the hot path is CUDA-only (no fallback)".format(name))
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+@torch.library.custom_op("effimvs::gru_reset", mutates_args=())
+def gru_reset(zr_pre: Tensor, bias_r: Tensor, hx: Tensor) -> Tensor:
+    """zr_pre (B,2h,H,W) = [convz ; convr] without bias, hx (B,h+cx,H,W) = cat[h, x] -> cat[sigmoid(r) * h, x]."""
+    zr_pre, hx, bias_r = _nhwc(zr_pre, "gru_reset"), _nhwc(hx, "gru_reset"), _dev(bias_r, "gru_reset")
+    B, two_h, H, W = zr_pre.shape
+    h = two_h // 2
+    out = torch.empty_like(hx, memory_format=torch.channels_last)
+    _count(1)
+    capi.check(_lib.effimvs_gru_reset_f32(zr_pre.data_ptr(), bias_r.data_ptr(), hx.data_ptr(), B * H * W, h, hx.shape[1] - h,
+                                          out.data_ptr(), _stream()))
+    return out
+
+
+@gru_reset.register_fake
+def _(zr_pre, bias_r, hx):
+    return torch.empty_like(hx, memory_format=torch.channels_last)
+
+
+@torch.library.custom_op("effimvs::gru_update", mutates_args=("hx",))
+def gru_update(zr_pre: Tensor, bias_z: Tensor, q_pre: Tensor, bias_q: Tensor, hx: Tensor) -> Tensor:
+    """h' = (1 - z) * h + z * tanh(q_pre + bias_q); updates hx[:, :h] in place (hx must be channels-last) and
+    returns h' as a dense channels-last (B,h,H,W) map."""
+    zr_pre, q_pre = _nhwc(zr_pre, "gru_update"), _nhwc(q_pre, "gru_update")
+    bias_z, bias_q = _dev(bias_z, "gru_update"), _dev(bias_q, "gru_update")
+    if not (hx.is_cuda and hx.dtype == torch.float32 and hx.is_contiguous(memory_format=torch.channels_last)):
+        raise RuntimeError("effimvs::gru_update needs hx as a channels-last fp32 CUDA tensor (it is updated in place)")
+    B, h, H, W = q_pre.shape
+    net = torch.empty_like(q_pre, memory_format=torch.channels_last)
+    _count(1)
+    capi.check(_lib.effimvs_gru_update_f32(zr_pre.data_ptr(), bias_z.data_ptr(), q_pre.data_ptr(), bias_q.data_ptr(), hx.data_ptr(),
+                                           B * H * W, h, hx.shape[1] - h, net.data_ptr(), _stream()))
+    return net
+
+
+@gru_update.register_fake
+def _(zr_pre, bias_z, q_pre, bias_q, hx):
+    return torch.empty_like(q_pre, memory_format=torch.channels_last)
+
+
+@torch.library.custom_op("effimvs::gru_delta", mutates_args=())
+def gru_delta(pre: Optional[Tensor], bias: Optional[Tensor], inv: Tensor, lo_disp: Tensor, hi_disp: Tensor) -> Tuple[Tensor, Tensor]:
+    """inv' = inv + tanh(pre + bias) (pre None: inv' = inv) and depth = 1 / clamp(lo + (hi - lo) * inv', 1e-4); all (B,1,H,W)."""
+    inv, lo_disp, hi_disp = _dev(inv, "gru_delta"), _dev(lo_disp, "gru_delta"), _dev(hi_disp, "gru_delta")
+    B, _, H, W = inv.shape
+    if pre is not None:
+        pre, bias = _dev(pre, "gru_delta"), _dev(bias, "gru_delta")
+        inv_out = torch.empty_like(inv)
+    else:
+        inv_out = inv
+    depth = torch.empty_like(inv)
+    _count(1)
+    capi.check(_lib.effimvs_gru_delta_f32(_opt(pre), _opt(bias), inv.data_ptr(), lo_disp.data_ptr(), hi_disp.data_ptr(), B, H * W,
+                                          inv_out.data_ptr() if pre is not None else None, depth.data_ptr(), _stream()))
+    return (inv_out if pre is not None else inv.clone()), depth
+
+
+@gru_delta.register_fake
+def _(pre, bias, inv, lo_disp, hi_disp):
+    return torch.empty_like(inv), torch.empty_like(inv)
+
+
+@torch.library.custom_op("effimvs::convex_upsample", mutates_args=())
+def convex_upsample(mask_pre: Tensor, mask_bias: Optional[Tensor], mask_scale: float, inv: Tensor, lo_disp: Tensor,
+                    hi_disp: Tensor, ratio: int) -> Tuple[Tensor, Tensor]:
+    """upsample_depth on mask = mask_scale * (mask_pre + mask_bias): (B,9*ratio^2,H,W), inv (B,1,H,W)
+    -> up (B,ratio*H,ratio*W) and disp_to_depth(up)."""
+    mask_pre, inv = _nhwc(mask_pre, "convex_upsample"), _dev(inv, "convex_upsample")
+    lo_disp, hi_disp = _dev(lo_disp, "convex_upsample"), _dev(hi_disp, "convex_upsample")
+    mask_bias = _dev(mask_bias, "convex_upsample") if mask_bias is not None else None
+    B, _, H, W = inv.shape
+    up = torch.empty(B, ratio * H, ratio * W, device=inv.device, dtype=torch.float32)
+    depth = torch.empty_like(up)
+    _count(1)
+    capi.check(_lib.effimvs_convex_upsample_f32(mask_pre.data_ptr(), _opt(mask_bias), mask_scale, inv.data_ptr(), lo_disp.data_ptr(),
+                                                hi_disp.data_ptr(), B, H, W, ratio, up.data_ptr(), depth.data_ptr(), _stream()))
+    return up, depth
+
+
+@convex_upsample.register_fake
+def _(mask_pre, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
+    B, _, H, W = inv.shape
+    return inv.new_empty(B, ratio * H, ratio * W), inv.new_empty(B, ratio * H, ratio * W)

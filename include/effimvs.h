@@ -196,6 +196,35 @@ int effimvs_fusion_filter_f32(const float* ref_depth, const float* srcs_depth, c
                               int relative, uint8_t* final_mask, float* depth_avg, float* points,
                               uint8_t* masks_out, void* stream);
 
+/* ---- per-pixel glue of the ConvGRU update block and convex upsampling --------
+ * The 2-D convolutions stay cuDNN on the upstream side; these entry points replace the elementwise
+ * chains between them.  Multi-channel maps are channels-last (B,H,W,C). */
+
+/* ConvGRU.forward, reset half (models/update.py:41-45).  zr_pre (n_pix, 2h) = [convz ; convr] outputs
+ * WITHOUT bias, hx (n_pix, h + cx) = cat[h, x]  ->  rhx (n_pix, h + cx) = cat[sigmoid(r_pre + bias_r) * h, x]. */
+int effimvs_gru_reset_f32(const float* zr_pre, const float* bias_r, const float* hx, long long n_pix, int h, int cx,
+                          float* rhx, void* stream);
+
+/* ConvGRU.forward, update half (models/update.py:43, 45-48).  q_pre (n_pix, h) = convq output without bias.
+ * h' = (1 - z) * h + z * tanh(q_pre + bias_q), z = sigmoid(z_pre + bias_z); written in place into hx[:, :h]
+ * and densely to net_out (n_pix, h). */
+int effimvs_gru_update_f32(const float* zr_pre, const float* bias_z, const float* q_pre, const float* bias_q, float* hx,
+                           long long n_pix, int h, int cx, float* net_out, void* stream);
+
+/* DepthHead tail + BasicUpdateBlock step + disp_to_depth (models/update.py:27, 121-125;
+ * models/Effi_MVS_plus.py:138-148).  pre (B,HW) = depth_head.conv2 output without bias (NULL: no step),
+ * bias (1), inv (B,HW), lo_disp / hi_disp (B)  ->  inv_out = inv + tanh(pre + bias) (optional),
+ * depth_out = 1 / clamp(lo + (hi - lo) * inv_out, 1e-4). */
+int effimvs_gru_delta_f32(const float* pre, const float* bias, const float* inv, const float* lo_disp, const float* hi_disp,
+                          int B, int HW, float* inv_out, float* depth_out, void* stream);
+
+/* upsample_depth (models/Effi_MVS_plus.py:167-178) on mask = mask_scale * (mask_pre + mask_bias) (models/update.py:128),
+ * mask_pre (B,H,W,9*ratio^2) channels-last conv output without bias, inv (B,H,W)
+ *   -> up_out (B,ratio*H,ratio*W) (optional) and depth_out = disp_to_depth(up) (optional).  ratio = 2. */
+int effimvs_convex_upsample_f32(const float* mask_pre, const float* mask_bias, float mask_scale, const float* inv,
+                                const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio, float* up_out,
+                                float* depth_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -481,3 +481,80 @@ def test_vis_filter_dynamic_dropin_golden(tag):
                                             rel_diff_base=g["rel_diff_base"], thres_view=g["thres_view"])
     assert torch.equal(masks, g["masks"].bool())          # same reproj_xyd in -> identical masks
     assert torch.equal(mask, g["masks"].bool()[:, :, -1:])
+
+
+# ---- update-block glue kernels ------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,H,W", [(16, 37, 53), (32, 24, 40), (48, 19, 25)])
+def test_update_glue_kernels_vs_torch(h, H, W):
+    """each glue kernel against the torch elementwise chain it replaces (upstream models/update.py:41-48, 27,
+    121-125; Effi_MVS_plus.py:138-148, 167-178), same device, fp32"""
+    from effimvs_b200 import ops, net
+    gen = torch.Generator(device=DEV).manual_seed(h)
+    B = 2
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)   # noqa: E731
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=gen)      # noqa: E731
+    zr_pre, q_pre, hv, x = cl(rnd(B, 2 * h, H, W) * 2), cl(rnd(B, h, H, W) * 2), cl(torch.tanh(rnd(B, h, H, W))), cl(torch.relu(rnd(B, h, H, W)))
+    bz, br, bq = rnd(h), rnd(h), rnd(h)
+    hx = cl(torch.cat([hv, x], dim=1))
+    z = torch.sigmoid(zr_pre[:, :h] + bz.reshape(1, -1, 1, 1))
+    r = torch.sigmoid(zr_pre[:, h:] + br.reshape(1, -1, 1, 1))
+    assert float((ops.gru_reset(zr_pre, br, hx) - torch.cat([r * hv, x], dim=1)).abs().max()) <= 2e-7
+    want = (1 - z) * hv + z * torch.tanh(q_pre + bq.reshape(1, -1, 1, 1))
+    got = ops.gru_update(zr_pre, bz, q_pre, bq, hx)
+    assert float((got - want).abs().max()) <= 2e-7        # tanhf / expf: same libdevice functions, at most an ulp of the sum
+    assert torch.equal(hx[:, :h], got) and torch.equal(hx[:, h:], x)
+    # inverse-depth step + disp_to_depth
+    lo, hi = torch.tensor([1 / 935.0, 1 / 1000.0], device=DEV), torch.tensor([1 / 425.0, 1 / 400.0], device=DEV)
+    inv, pre, b1 = torch.rand(B, 1, H, W, device=DEV, generator=gen), rnd(B, 1, H, W), rnd(1)
+    to_depth = lambda v: 1.0 / (lo.reshape(B, 1, 1, 1) + (hi - lo).reshape(B, 1, 1, 1) * v).clamp(min=1e-4)   # noqa: E731
+    inv2, dep2 = ops.gru_delta(pre, b1, inv, lo, hi)
+    want_inv = inv + torch.tanh(pre + b1)
+    assert float((inv2 - want_inv).abs().max()) <= 2e-7
+    assert rel_max(dep2, to_depth(inv2)) <= 2e-7
+    inv0, dep0 = ops.gru_delta(None, None, inv, lo, hi)
+    assert torch.equal(inv0, inv) and rel_max(dep0, to_depth(inv)) <= 2e-7
+    # convex upsampling
+    mask_pre, mb = cl(rnd(B, 36, H, W) * 3), rnd(36)
+    up, dup = ops.convex_upsample(mask_pre, mb, 0.25, inv, lo, hi, 2)
+    want_up = net.convex_upsample(inv, 0.25 * (mask_pre + mb.reshape(1, -1, 1, 1)), 2)
+    assert float((up - want_up).abs().max()) <= 1e-6
+    assert rel_max(dup, to_depth(up.unsqueeze(1)).squeeze(1)) <= 2e-7
+
+
+@pytest.mark.gpu
+def test_update_block_fused_golden(hp):
+    """UpdateBlock.forward_fused (cuDNN convolutions + glue kernels) against upstream's BasicUpdateBlock,
+    upsample_depth and disp_to_depth (tests/golden/update_block.npz)"""
+    from test_net_host import load_update_block, _update_cost_fn
+    g = golden("update_block", DEV)
+    blk = load_update_block(g, DEV)
+    B = g["inv0"].shape[0]
+    lo, hi = (1.0 / g["dmax"]).reshape(B), (1.0 / g["dmin"]).reshape(B)
+    with torch.no_grad():
+        n, invs, deps, up, dup = blk.forward_fused(hp, g["net0"], _update_cost_fn, g["inv0"], g["context"], 3, lo, hi)
+    assert rel_max(n, g["net"]) < 1e-4
+    for i in range(3):
+        assert float((invs[i] - g["inv{}".format(i + 1)]).abs().max()) < 1e-4
+        assert rel_max(deps[i], g["depth{}".format(i + 1)]) < 1e-4
+    assert float((up - g["up"]).abs().max()) < 1e-4 and rel_max(dup, g["depth_up"]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_update_block_fused_equals_plain_at_dtu_stage3(hp):
+    """full DTU stage-3 size (800x592, hidden 16): fused and plain paths agree on the same device"""
+    from test_net_host import _update_cost_fn
+    from effimvs_b200 import net
+    torch.manual_seed(3)
+    blk = net.UpdateBlock(16, 6, 2, 4).to(DEV).eval()
+    B, H, W = 1, 592, 800
+    n0, ctx = torch.tanh(torch.randn(B, 16, H, W, device=DEV)), torch.relu(torch.randn(B, 4, H, W, device=DEV))
+    inv0 = torch.rand(B, 1, H, W, device=DEV)
+    lo, hi = torch.tensor([1 / 935.0], device=DEV), torch.tensor([1 / 425.0], device=DEV)
+    to_depth = lambda v: 1.0 / (lo.reshape(B, 1, 1, 1) + (hi - lo).reshape(B, 1, 1, 1) * v).clamp(min=1e-4)   # noqa: E731
+    with torch.no_grad():
+        n, invs, deps, up, dup = blk.forward_fused(hp, n0, _update_cost_fn, inv0, ctx, 3, lo, hi)
+        n_p, mask_p, invs_p = blk(n0, _update_cost_fn, inv0, ctx, 3, to_depth)
+        up_p = net.convex_upsample(invs_p[-1], mask_p, 2)
+    assert rel_max(n, n_p) < 1e-4 and float((invs[-1] - invs_p[-1]).abs().max()) < 1e-4
+    assert float((up - up_p).abs().max()) < 1e-4 and rel_max(dup, to_depth(up_p.unsqueeze(1)).squeeze(1)) < 1e-4

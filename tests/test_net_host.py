@@ -48,3 +48,33 @@ def test_fused_topdown_cache_follows_weight_updates():
         want = f(x)[2]
     assert float((b - want).abs().max()) <= 2e-5 * float(want.abs().max())
     assert float((a - want).abs().max()) > 1e-3
+
+
+def _update_cost_fn(depth):
+    """the analytic cost function tests/golden/make_golden_update.py used in place of the volume lookup"""
+    k = torch.arange(1, 7, dtype=depth.dtype, device=depth.device).reshape(1, 6, 1, 1)
+    return torch.sin(depth * (k * 0.01)) * 0.5
+
+
+def load_update_block(g, device="cpu"):
+    blk = net.UpdateBlock(16, 6, 2, 4).eval()
+    blk.load_state_dict({k[3:].replace("__", "."): v for k, v in g.items() if k.startswith("w__")}, strict=True)
+    return blk.to(device)
+
+
+def test_update_block_matches_upstream_golden():
+    """net.UpdateBlock / convex_upsample / to_depth (the stock-PyTorch host side) replay upstream's
+    BasicUpdateBlock, upsample_depth and disp_to_depth bit for bit on CPU."""
+    from util import golden
+    g = golden("update_block")
+    blk = load_update_block(g)
+    lo, hi = 1.0 / g["dmax"], 1.0 / g["dmin"]
+    to_depth = lambda inv: 1.0 / (lo + (hi - lo) * inv).clamp(min=1e-4)   # noqa: E731
+    with torch.no_grad():
+        n, mask, invs = blk(g["net0"], _update_cost_fn, g["inv0"], g["context"], 3, to_depth)
+        up = net.convex_upsample(invs[-1], mask, 2)
+    assert torch.equal(n, g["net"]) and torch.equal(mask, g["mask"]) and torch.equal(up, g["up"])
+    for i in range(3):
+        assert torch.equal(invs[i], g["inv{}".format(i + 1)])
+        assert torch.equal(to_depth(invs[i]), g["depth{}".format(i + 1)])
+    assert torch.equal(to_depth(up.unsqueeze(1)).squeeze(1), g["depth_up"])
