@@ -187,18 +187,25 @@ __device__ __forceinline__ Reproj reproject(const Cam& ref, const Cam& src, cons
     return r;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ srcs_depth, const float* __restrict__ conf,
               const float* __restrict__ ref_cam, const float* __restrict__ srcs_cam, const float* __restrict__ inv_cams,
               int v, int h, int w, int hc, int wc, float dist_base, float rel_diff_base, int thres_view,
               float prob_threshold, int relative, float* __restrict__ reproj_xyd, uint8_t* __restrict__ final_mask,
               float* __restrict__ depth_avg, float* __restrict__ points, uint8_t* __restrict__ masks_out) {
     __shared__ Cam cams[MAXV + 1];
+    __shared__ float thr_xy[MAXV], thr_d[MAXV];   // the ladder k / dist_base, k / rel_diff_base (fusion.py:172-176), once per block
     const int n = blockIdx.y;
+    const int K = v - thres_view + 1;
     if (threadIdx.x <= v) {
         const float* cam = threadIdx.x == 0 ? ref_cam + (size_t)n * 32 : srcs_cam + ((size_t)n * v + threadIdx.x - 1) * 32;
         const float* inv = inv_cams ? inv_cams + ((size_t)n * (v + 1) + threadIdx.x) * 32 : nullptr;
         load_cam(cams[threadIdx.x], cam, inv);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + MAXV) {
+        const int k = threadIdx.x - 32;
+        const float kk = (float)(thres_view + k);
+        thr_xy[k] = k < K ? __fdiv_rn(kk, dist_base) : 0.0f;
+        thr_d[k] = k < K ? __fdiv_rn(kk, rel_diff_base) : 0.0f;
     }
     __syncthreads();
     const int hw = h * w;
@@ -212,10 +219,9 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
     float ref_world[4];
     img_to_world(cams[0], cx, cy, dref, ref_world);
 
-    const int K = v - thres_view + 1;
-    int votes[MAXV];
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k) votes[k] = 0;
+    // The ladder thresholds grow with k, so a view passes rungs K-c .. K-1 where c = min(#rungs its pixel
+    // error passes, #rungs its depth error passes).  hist packs the per-view c values: 17 bins of 5 bits.
+    unsigned long long hist_lo = 0ull, hist_hi = 0ull;   // bins 0..11 | bins 12..16
     float sum_d = 0.0f;
     int n_last = 0;
     for (int s = 0; s < v; ++s) {
@@ -229,22 +235,28 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
         float e_xy = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
         float e_d = fabsf(__fsub_rn(dref, r.d));
         if (relative) e_d = __fdiv_rn(e_d, dref);
+        int c_xy = 0, c_d = 0;
 #pragma unroll
         for (int k = 0; k < MAXV; ++k) {
-            if (k < K) {
-                float kk = (float)(thres_view + k);
-                bool m = (e_xy < __fdiv_rn(kk, dist_base)) && (e_d < __fdiv_rn(kk, rel_diff_base));
-                votes[k] += m ? 1 : 0;
-                if (masks_out) masks_out[(((size_t)n * v + s) * K + k) * hw + pix] = m ? 1 : 0;
-                if (k == K - 1 && m) { sum_d = __fadd_rn(sum_d, r.d); n_last += 1; }
-            }
+            c_xy += (k < K && e_xy < thr_xy[k]) ? 1 : 0;
+            c_d += (k < K && e_d < thr_d[k]) ? 1 : 0;
         }
+        const int c = min(c_xy, c_d);
+        if (c < 12) hist_lo += 1ull << (5 * c);
+        else hist_hi += 1ull << (5 * (c - 12));
+        if (masks_out)
+            for (int k = 0; k < K; ++k) masks_out[(((size_t)n * v + s) * K + k) * hw + pix] = (k >= K - c) ? 1 : 0;
+        if (c >= 1) { sum_d = __fadd_rn(sum_d, r.d); n_last += 1; }
     }
     if (!final_mask) return;
+    // votes[k] = #views with c >= K - k; geo = any k with votes[k] >= thres_view + k
     bool geo = false;
-#pragma unroll
-    for (int k = 0; k < MAXV; ++k)
-        if (k < K) geo = geo || (votes[k] >= thres_view + k);
+    int votes = 0;
+    for (int k = 0; k < K; ++k) {
+        const int bin = K - k;   // views whose c equals K - k start passing at rung k
+        votes += bin < 12 ? (int)((hist_lo >> (5 * bin)) & 31ull) : (int)((hist_hi >> (5 * (bin - 12))) & 31ull);
+        geo = geo || (votes >= thres_view + k);
+    }
     // nearest resize of the confidence map: src index = floor(dst * in / out)  (F.interpolate 'nearest')
     int sy = (int)floorf((float)yi * ((float)hc / (float)h)), sx = (int)floorf((float)xi * ((float)wc / (float)w));
     sy = sy < hc - 1 ? sy : hc - 1; sx = sx < wc - 1 ? sx : wc - 1;
