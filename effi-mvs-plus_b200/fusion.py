@@ -48,3 +48,49 @@ def filter_view(ref_depth, ref_conf, srcs_depth, ref_cam, srcs_cam, dist_base, r
     if want_masks:
         out["masks"] = masks.bool()
     return out
+
+
+# ---- the DTU pipeline's filter (test_dtu_dypcd.py:164-350) ---------------------------
+DTU_FIRST_RUNG, DTU_END_RUNG = 1, 11          # s, e (test_dtu_dypcd.py:33-34)
+DTU_DIST_BASE, DTU_DIFF_BASE = 1 / 2, 0.25    # :36-37
+
+
+def dtu_camera_pack(K_ref, E_ref, Ks_src, Es_src):
+    """The float32 matrices of reproject_with_depth / filter_depth, formed on the host with the same NumPy
+    calls upstream uses (np.linalg.inv and np.matmul on float32 arrays, test_dtu_dypcd.py:172-176, 192-196,
+    330-333): (34 + 50 v,) float32 in the layout effimvs_dtu_filter_f32 documents."""
+    import numpy as np
+    f32 = lambda a: np.asarray(a.cpu() if torch.is_tensor(a) else a, dtype=np.float32)   # noqa: E731
+    K_ref, E_ref = f32(K_ref), f32(E_ref)
+    parts = [np.linalg.inv(K_ref).reshape(-1), K_ref.reshape(-1), np.linalg.inv(E_ref).reshape(-1)]
+    for K_src, E_src in zip(Ks_src, Es_src):
+        K_src, E_src = f32(K_src), f32(E_src)
+        parts += [np.matmul(E_src, np.linalg.inv(E_ref)).reshape(-1), K_src.reshape(-1), np.linalg.inv(K_src).reshape(-1),
+                  np.matmul(E_ref, np.linalg.inv(E_src)).reshape(-1)]
+    return torch.from_numpy(np.concatenate(parts).astype(np.float32))
+
+
+def dtu_filter_view(ref_depth, confidence, srcs_depth, K_ref, E_ref, Ks_src, Es_src, conf_thres: float = 0.5,
+                    want_masks: bool = False, first_rung: int = DTU_FIRST_RUNG, end_rung: int = DTU_END_RUNG,
+                    dist_base: float = DTU_DIST_BASE, diff_base: float = DTU_DIFF_BASE):
+    """One reference view of upstream's DTU ``filter_depth`` (test_dtu_dypcd.py:236-337) in a single kernel.
+
+    ref_depth (h,w), srcs_depth (v,h,w) CUDA fp32; confidence (hc,wc) CUDA fp32, resized to (h,w) bilinearly with
+    half-pixel centres like cv2.resize (:258) when the sizes differ; cameras as host arrays (3x3 / 4x4).
+    -> dict(final, geo (h,w) bool, depth_avg (h,w), points (3,h,w)[, masks (v,K,h,w) bool, reproj_depth (v,h,w)])."""
+    import math
+    import numpy as np
+    h, w = ref_depth.shape[-2:]
+    if tuple(confidence.shape[-2:]) != (h, w):
+        confidence = torch.nn.functional.interpolate(confidence.reshape(1, 1, *confidence.shape[-2:]), size=(h, w), mode="bilinear",
+                                                     align_corners=False).reshape(h, w)
+    rungs = range(first_rung, end_rung)
+    thr_dist = [i * dist_base for i in rungs]
+    thr_diff = [float(np.float32(math.log(max(i, 1.05), 10) * diff_base)) for i in rungs]
+    mats = dtu_camera_pack(K_ref, E_ref, Ks_src, Es_src).to(ref_depth.device)
+    final, geo, avg, pts, masks, rep = ops.dtu_filter(ref_depth.reshape(h, w), srcs_depth.reshape(-1, h, w), confidence.reshape(h, w), mats,
+                                                      thr_dist, thr_diff, first_rung, end_rung, float(conf_thres), 0.75, bool(want_masks))
+    out = {"final": final.bool(), "geo": geo.bool(), "depth_avg": avg, "points": pts}
+    if want_masks:
+        out["masks"], out["reproj_depth"] = masks.bool(), rep
+    return out

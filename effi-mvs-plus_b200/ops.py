@@ -530,3 +530,42 @@ def convex_upsample(mask_pre: Tensor, mask_bias: Optional[Tensor], mask_scale: f
 def _(mask_pre, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
     B, _, H, W = inv.shape
     return inv.new_empty(B, ratio * H, ratio * W), inv.new_empty(B, ratio * H, ratio * W)
+
+
+# -------------------------------------------------------------------------------------------
+# DTU geometric filter (csrc/dtu_filter.cu)
+@torch.library.custom_op("effimvs::dtu_filter", mutates_args=())
+def dtu_filter(ref_depth: Tensor, srcs_depth: Tensor, conf: Tensor, mats: Tensor, thr_dist: List[float], thr_diff: List[float],
+               first_rung: int, full_count: int, conf_thres: float, conf_keep: float, want_masks: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """-> final (h,w) u8, geo (h,w) u8, depth_avg (h,w), points (3,h,w), masks (v,K,h,w) u8, reproj_depth (v,h,w)
+    (the last two empty unless want_masks)."""
+    import ctypes
+    ref_depth, srcs_depth, conf, mats = (_dev(ref_depth, "dtu_filter"), _dev(srcs_depth, "dtu_filter"), _dev(conf, "dtu_filter"),
+                                         _dev(mats, "dtu_filter"))
+    v, h, w = srcs_depth.shape
+    K = len(thr_dist)
+    dev = ref_depth.device
+    final = torch.empty(h, w, device=dev, dtype=torch.uint8)
+    geo = torch.empty(h, w, device=dev, dtype=torch.uint8)
+    avg = torch.empty(h, w, device=dev, dtype=torch.float32)
+    pts = torch.empty(3, h, w, device=dev, dtype=torch.float32)
+    masks = torch.empty((v, K, h, w) if want_masks else (0,), device=dev, dtype=torch.uint8)
+    rep = torch.empty((v, h, w) if want_masks else (0,), device=dev, dtype=torch.float32)
+    td = (ctypes.c_double * K)(*thr_dist)
+    tf = (ctypes.c_float * K)(*thr_diff)
+    _count(1)
+    capi.check(_lib.effimvs_dtu_filter_f32(ref_depth.data_ptr(), srcs_depth.data_ptr(), conf.data_ptr(), mats.data_ptr(), td, tf, K,
+                                           first_rung, full_count, conf_thres, conf_keep, v, h, w, final.data_ptr(), geo.data_ptr(),
+                                           avg.data_ptr(), pts.data_ptr(), masks.data_ptr() if want_masks else None,
+                                           rep.data_ptr() if want_masks else None, _stream()))
+    return final, geo, avg, pts, masks, rep
+
+
+@dtu_filter.register_fake
+def _(ref_depth, srcs_depth, conf, mats, thr_dist, thr_diff, first_rung, full_count, conf_thres, conf_keep, want_masks):
+    v, h, w = srcs_depth.shape
+    K = len(thr_dist)
+    u8 = torch.uint8
+    return (ref_depth.new_empty(h, w, dtype=u8), ref_depth.new_empty(h, w, dtype=u8), ref_depth.new_empty(h, w),
+            ref_depth.new_empty(3, h, w), ref_depth.new_empty((v, K, h, w) if want_masks else (0,), dtype=u8),
+            ref_depth.new_empty((v, h, w) if want_masks else (0,)))

@@ -225,6 +225,25 @@ int effimvs_convex_upsample_f32(const float* mask_pre, const float* mask_bias, f
                                 const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio, float* up_out,
                                 float* depth_out, void* stream);
 
+/* ---- the DTU pipeline's NumPy / cv2.remap geometric filter ------------------------
+ * reproject_with_depth + check_geometric_consistency + the aggregation of filter_depth
+ * (test_dtu_dypcd.py:164-233, 261-309, 320-337) for one reference view in one kernel.
+ *   ref_depth (h,w), srcs_depth (v,h,w), conf (h,w) (already resized to the depth map, :258), fp32
+ *   mats: device array of 34 + 50*v floats, the float32 matrices exactly as upstream forms them:
+ *         [inv(K_ref) 3x3][K_ref 3x3][inv(E_ref) 4x4] then per source view
+ *         [E_src @ inv(E_ref) 4x4][K_src 3x3][inv(K_src) 3x3][E_ref @ inv(E_src) 4x4]
+ *   thr_dist_host / thr_diff_host: HOST arrays of n_rungs thresholds, i * dist_base (float64) and
+ *         log10(max(i, 1.05)) * diff_base (float32), i = first_rung .. first_rung + n_rungs - 1 (:226-228)
+ *   full_count: upstream's dy_range of :303 (a pixel also passes if that many views pass the last rung)
+ *   conf_thres: args.conf (:261);  conf_keep: 0.75, above which the reference depth is kept (:300)
+ *   -> final_mask (h,w) u8, geo_mask (h,w) u8 (optional), depth_avg (h,w), points (3,h,w) world coordinates,
+ *      masks_out (v,n_rungs,h,w) u8 (optional), reproj_depth_out (v,h,w) zeroed outside the last rung (optional) */
+int effimvs_dtu_filter_f32(const float* ref_depth, const float* srcs_depth, const float* conf, const float* mats,
+                           const double* thr_dist_host, const float* thr_diff_host, int n_rungs, int first_rung,
+                           int full_count, float conf_thres, float conf_keep, int v, int h, int w,
+                           uint8_t* final_mask, uint8_t* geo_mask, float* depth_avg, float* points, uint8_t* masks_out,
+                           float* reproj_depth_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

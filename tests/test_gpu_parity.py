@@ -6,6 +6,8 @@ Tolerances (BASELINE.json north_star): fp32 cost volumes max|d| <= 1e-4 * max|re
 |d depth| <= 1e-3 * (depth_max - depth_min) on >= 99.9 % of pixels; fusion masks identical except
 within 1e-5 (relative) of a threshold.
 """
+import os
+
 import pytest
 import torch
 
@@ -558,3 +560,59 @@ def test_update_block_fused_equals_plain_at_dtu_stage3(hp):
         up_p = net.convex_upsample(invs_p[-1], mask_p, 2)
     assert rel_max(n, n_p) < 1e-4 and float((invs[-1] - invs_p[-1]).abs().max()) < 1e-4
     assert float((up - up_p).abs().max()) < 1e-4 and rel_max(dup, to_depth(up_p.unsqueeze(1)).squeeze(1)) < 1e-4
+
+
+# ---- DTU geometric filter -------------------------------------------------------
+def _dtu_filter_compare(out, want_final, want_geo, want_avg, want_pts, dist_band, diff_band):
+    """masks identical except where a rung is decided within the band (float64 rounding of the matrix
+    products); averaged depth / points equal wherever the masks agree"""
+    import numpy as np
+    final, geo = out["final"].cpu().numpy(), out["geo"].cpu().numpy()
+    bad_geo = float((geo != want_geo).mean())
+    bad_final = float((final != want_final).mean())
+    assert bad_geo <= dist_band and bad_final <= dist_band, (bad_geo, bad_final)
+    same = geo == want_geo
+    avg = out["depth_avg"].cpu().numpy()
+    close = np.abs(avg - want_avg) <= 1e-6 * np.maximum(np.abs(want_avg), 1.0)
+    assert float((close | ~same).mean()) >= 1.0 - diff_band
+    pts = out["points"].cpu().numpy()
+    ok = (np.abs(pts - want_pts).max(axis=0) <= 1e-3) | ~close
+    assert float(ok.mean()) == 1.0
+
+
+@pytest.mark.gpu
+def test_dtu_filter_golden():
+    """effimvs_dtu_filter_f32 against upstream's own functions + real cv2.remap (tests/golden/dtu_filter.npz)"""
+    import numpy as np
+    from effimvs_b200 import fusion
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dtu_filter.npz"))
+    d, K, E = z["depths"], z["K"], z["E"]
+    v = d.shape[0] - 1
+    dev_d = torch.from_numpy(d).to(DEV)
+    out = fusion.dtu_filter_view(dev_d[0], torch.from_numpy(z["confidence"]).to(DEV), dev_d[1:], K, E[0], [K] * v, list(E[1:]),
+                                 float(z["conf_thres"]), want_masks=True)
+    masks = out["masks"].cpu().numpy()
+    assert float((masks != z["masks"]).mean()) <= 1e-5           # a rung decided within ~1e-12 of its threshold
+    rep = out["reproj_depth"].cpu().numpy()
+    agree = (masks[:, -1] == z["masks"][:, -1])
+    assert float(((np.abs(rep - z["reproj_depth"]) <= 1e-6 * np.maximum(z["reproj_depth"], 1.0)) | ~agree).mean()) == 1.0
+    _dtu_filter_compare(out, z["final_mask"], z["geo_mask"], z["depth_avg"], z["points"], 1e-5, 1e-5)
+
+
+@pytest.mark.gpu
+def test_dtu_filter_vs_oracle_dtu_size():
+    """a 1600x1184 reference view with 10 source views against the NumPy oracle (no cv2 needed on the GPU box)"""
+    from effimvs_b200 import fusion, synthetic
+    from oracle import dtu_filter as o
+    h, w, v = 1184, 1600, 10
+    E, K = synthetic.camera_ring(v + 1, w, h)
+    depths = synthetic.render_plane_scene(E, K, w, h, noise=0.05, seed=2)
+    depths[2, 100:300, 200:500] += 3.0
+    conf = torch.rand(h // 2, w // 2, generator=torch.Generator().manual_seed(0))
+    conf_full = torch.nn.functional.interpolate(conf[None, None], size=(h, w), mode="bilinear", align_corners=False)[0, 0]
+    K32, E32 = K.numpy().astype("float32"), E.numpy().astype("float32")
+    want = o.filter_view(depths[0].numpy(), conf_full.numpy(), depths[1:].numpy(), K32, E32[0], [K32] * v, list(E32[1:]), 0.5)
+    out = fusion.dtu_filter_view(depths[0].to(DEV), conf.to(DEV), depths[1:].to(DEV), K32, E32[0], [K32] * v, list(E32[1:]), 0.5)
+    assert 0.05 < want["final"].mean() < 0.95
+    # the resized confidence is compared with a threshold too: allow pixels whose confidence sits within 1e-6 of 0.5 / 0.75
+    _dtu_filter_compare(out, want["final"], want["geo"], want["depth_avg"], want["points"], 2e-5, 2e-5)

@@ -2,6 +2,8 @@
 tests/golden/make_golden.py produced by running upstream itself (the parity pin),
 plus the explicit ATen restatements (grid_sample, conv3d, conv_transpose3d) against
 the ATen calls they restate."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -139,3 +141,35 @@ def test_restatements_through_hotpath():
     finally:
         ohp.ATEN = True
     assert rel_max(b["volume"], a["volume"]) < 1e-5 and rel_max(b["reg_volume"], a["reg_volume"]) < 1e-4
+
+
+# ---- DTU geometric filter -----------------------------------------------------
+def test_remap_restatement_equals_cv2():
+    """oracle.dtu_filter.remap_bilinear against cv2.remap itself (OpenCV is the absent third-party dependency of
+    this row; it is present in the build container, skipped where it is not)"""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from oracle import dtu_filter as o
+    g = np.random.default_rng(0)
+    src = g.random((37, 53)).astype(np.float32) * 900
+    mx = (g.random((64, 80)) * 60 - 4).astype(np.float32)
+    my = (g.random((64, 80)) * 45 - 4).astype(np.float32)
+    mx[0, :8] = [0.0, 52.0, 51.984375, -1.0, -0.015625, 52.5, 1e9, -1e9]      # borders, exact grid points, far outside
+    my[0, :8] = [0.0, 36.0, 35.984375, -1.0, 36.5, 10.015625, 3.0, 3.0]
+    want = cv2.remap(src, mx, my, interpolation=cv2.INTER_LINEAR)
+    got = o.remap_bilinear(src, mx, my)
+    assert np.array_equal(got, want)
+
+
+def test_dtu_filter_matches_upstream():
+    import numpy as np
+    from oracle import dtu_filter as o
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dtu_filter.npz"))
+    d, K, E = z["depths"], z["K"], z["E"]
+    v = d.shape[0] - 1
+    out = o.filter_view(d[0], z["confidence"], d[1:], K, E[0], [K] * v, list(E[1:]), float(z["conf_thres"]))
+    assert np.array_equal(out["masks"], z["masks"])
+    assert np.array_equal(out["reproj_depth"], z["reproj_depth"])
+    assert np.array_equal(out["final"], z["final_mask"]) and np.array_equal(out["geo"], z["geo_mask"])
+    assert np.array_equal(out["depth_avg"], z["depth_avg"])
+    assert np.allclose(out["points"], z["points"], rtol=0, atol=1e-3)
