@@ -413,7 +413,15 @@ class EffiMVSPlus(nn.Module):
         return [[p.reshape(B, V, *p.shape[1:])[:, v] for v in range(V)] for p in pyr]
 
     def forward(self, imgs, proj_matrices, depth_values):
+        return self.forward_from_features(self.encode(imgs), imgs[:, 0], proj_matrices, depth_values)
+
+    def forward_from_features(self, feats, ref_img, proj_matrices, depth_values):
+        """The cascade on already encoded views (per-scene feature cache -- upstream
+        re-encodes every image for each reference view that lists it as a source, Effi_MVS_plus.py:432-435).
+        feats: per stage a list of V maps (B,C,h,w), the reference view first (what ``encode`` returns);
+        ref_img (B,3,H,W) feeds the context network."""
         hp = self.hotpath
+        imgs = ref_img
         B = imgs.shape[0]
         disp_min = depth_values[:, 0].reshape(B, 1, 1, 1)
         disp_max = depth_values[:, -1].reshape(B, 1, 1, 1)
@@ -425,8 +433,6 @@ class EffiMVSPlus(nn.Module):
         def to_depth(inv):                      # disp_to_depth, Effi_MVS_plus.py:138-148
             return 1.0 / (lo_disp + (hi_disp - lo_disp) * inv).clamp(min=1e-4)
 
-        feats = self.encode(imgs)
-        ref_img = imgs[:, 0]
         ctx_pyr = self.cnet_depth(ref_img.contiguous(memory_format=torch.channels_last) if ref_img.is_cuda else ref_img)
 
         preds = []

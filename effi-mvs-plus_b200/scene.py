@@ -10,8 +10,13 @@ import torch
 import torch.distributed as dist
 
 
-def shard_views(n_views: int, rank: int, world: int) -> List[int]:
-    """Reference views owned by `rank`: rank, rank+world, ..."""
+def shard_views(n_views: int, rank: int, world: int, mode: str = "round_robin") -> List[int]:
+    """Reference views owned by `rank`.  "round_robin": rank, rank+world, ... (even load for any n_views);
+    "block": a contiguous run of slots_per_rank views -- neighbouring reference views share their source
+    images, so a rank that caches encoded features (section 8(f) row 1) encodes each image at most once."""
+    if mode == "block":
+        per = slots_per_rank(n_views, world)
+        return list(range(rank * per, min(n_views, (rank + 1) * per)))
     return list(range(rank, n_views, world))
 
 
@@ -19,28 +24,32 @@ def slots_per_rank(n_views: int, world: int) -> int:
     return (n_views + world - 1) // world
 
 
-def gather_depths(local: Dict[int, torch.Tensor], n_views: int, rank: int, world: int, h: int, w: int, device) -> torch.Tensor:
+def gather_depths(local: Dict[int, torch.Tensor], n_views: int, rank: int, world: int, h: int, w: int, device,
+                  mode: str = "round_robin") -> torch.Tensor:
     """All-gather of the per-rank depth maps into one (n_views,h,w) tensor on every rank.
 
     Each rank contributes a (slots,h,w) block (zero padded when n_views % world != 0); with the
-    round-robin sharding view i lives in slot i // world of rank i % world."""
+    round-robin sharding view i lives in slot i // world of rank i % world, with block sharding in
+    slot i % slots of rank i // slots."""
     slots = slots_per_rank(n_views, world)
     mine = torch.zeros(slots, h, w, device=device, dtype=torch.float32)
     for i, d in local.items():
-        mine[i // world] = d
+        mine[i % slots if mode == "block" else i // world] = d
     if world == 1 or not (dist.is_available() and dist.is_initialized()):
         full = mine.unsqueeze(0)
     else:
         flat = torch.empty(world * slots, h, w, device=device, dtype=torch.float32)   # rank-major concatenation
         dist.all_gather_into_tensor(flat, mine)
         full = flat.reshape(world, slots, h, w)
+    if mode == "block":   # (world, slots) -> view index = rank * slots + slot
+        return full.reshape(world * slots, h, w)[:n_views].contiguous()
     # (world, slots) -> view index = slot * world + rank
     return full.permute(1, 0, 2, 3).reshape(slots * world, h, w)[:n_views].contiguous()
 
 
 @torch.no_grad()
 def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Sequence[int]], rank: int = 0, world: int = 1,
-              device="cuda", fuse_pairs: Sequence[Sequence[int]] = None, timings: dict = None):
+              device="cuda", fuse_pairs: Sequence[Sequence[int]] = None, timings: dict = None, sharding: str = "round_robin"):
     """infer(ref_view, src_views) -> (depth (h,w), conf (hc,wc)) on `device`;
     fuse(ref_view, ref_depth (1,1,h,w), conf (1,hc,wc), src_views, src_depths (1,v,1,h,w)) -> dict with
     'final' (1,1,h,w) bool and 'points' (1,3,h,w).
@@ -48,7 +57,7 @@ def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Seq
     views whose depth maps the consistency filter of view i reads (upstream: 4 and up to 10).
     Returns {ref_view: (points (k,3), depth (h,w))} for the views this rank owns."""
     fuse_pairs = pairs if fuse_pairs is None else fuse_pairs
-    mine = shard_views(n_views, rank, world)
+    mine = shard_views(n_views, rank, world, sharding)
     depths, confs = {}, {}
     for i in mine:
         d, c = infer(i, list(pairs[i]))
@@ -60,7 +69,7 @@ def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Seq
     if timings is not None and torch.cuda.is_available() and str(device).startswith("cuda"):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
-    all_depths = gather_depths(depths, n_views, rank, world, h, w, device)
+    all_depths = gather_depths(depths, n_views, rank, world, h, w, device, sharding)
     if ev:
         ev[1].record()
     out = {}
@@ -78,15 +87,29 @@ def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Seq
 
 
 def cuda_scene_callables(model, imgs: torch.Tensor, cams: Dict[str, torch.Tensor], depth_values: torch.Tensor,
-                         dist_base: float, rel_diff_base: float, thres_view: int, prob_threshold: float):
+                         dist_base: float, rel_diff_base: float, thres_view: int, prob_threshold: float,
+                         feature_cache: bool = False):
     """infer / fuse callables for `run_scene` on the CUDA path.
-    imgs (Nv,3,H,W) on the device; cams {"stage1".."stage4": (Nv,2,4,4)}; depth_values (Dv)."""
+    imgs (Nv,3,H,W) on the device; cams {"stage1".."stage4": (Nv,2,4,4)}; depth_values (Dv).
+    feature_cache: encode every image once per rank and reuse its feature pyramid for each reference view
+    that lists it as a source (section 8(f) row 1; eval-mode results are those of re-encoding it)."""
     from . import fusion
+    cache: Dict[int, list] = {}
+
+    def encoded(j):
+        if j not in cache:
+            cache[j] = [stage[0] for stage in model.encode(imgs[j].reshape(1, 1, *imgs.shape[1:]))]
+        return cache[j]
 
     def infer(i, srcs):
         idx = [i] + list(srcs)
-        out = model(imgs[idx].unsqueeze(0), {k: v[idx].unsqueeze(0) for k, v in cams.items() if k != "stage4"},
-                    depth_values.unsqueeze(0))
+        stage_cams = {k: v[idx].unsqueeze(0) for k, v in cams.items() if k != "stage4"}
+        if feature_cache:
+            per_view = [encoded(j) for j in idx]
+            feats = [[pv[s] for pv in per_view] for s in range(3)]
+            out = model.forward_from_features(feats, imgs[i].unsqueeze(0), stage_cams, depth_values.unsqueeze(0))
+        else:
+            out = model(imgs[idx].unsqueeze(0), stage_cams, depth_values.unsqueeze(0))
         return out["depth"][-1][0], out["photometric_confidence"][0]
 
     def fuse(i, ref_depth, conf, srcs, src_depths):

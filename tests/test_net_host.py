@@ -78,3 +78,23 @@ def test_update_block_matches_upstream_golden():
         assert torch.equal(invs[i], g["inv{}".format(i + 1)])
         assert torch.equal(to_depth(invs[i]), g["depth{}".format(i + 1)])
     assert torch.equal(to_depth(up.unsqueeze(1)).squeeze(1), g["depth_up"])
+
+
+def test_feature_cache_equals_reencoding():
+    """forward_from_features on per-image encodings equals forward() on the stacked views"""
+    import types
+    from effimvs_b200 import synthetic
+    from oracle import hotpath as ohp
+    from util import load_dtu_weights
+    m = net.EffiMVSPlus(types.SimpleNamespace(ndepths="8,4,4", GRUiters="1,1,1", CostNum=3), hotpath=ohp.OracleHotPath())
+    load_dtu_weights(m)
+    m.eval()
+    s = synthetic.make_sample("plumbing", seed=3, width=96, height=64, views=3)
+    with torch.no_grad():
+        want = m(s["imgs"], s["proj_matrices"], s["depth_values"])
+        per_view = [[st[0] for st in m.encode(s["imgs"][:, v:v + 1])] for v in range(3)]
+        feats = [[pv[k] for pv in per_view] for k in range(3)]
+        got = m.forward_from_features(feats, s["imgs"][:, 0], s["proj_matrices"], s["depth_values"])
+    for a, b in zip(want["depth"], got["depth"]):
+        assert float((a - b).abs().max()) <= 1e-2      # mm at ~600 mm: batch-1 vs batch-3 convolution rounding
+    assert float((want["photometric_confidence"] - got["photometric_confidence"]).abs().max()) <= 1e-5

@@ -24,7 +24,7 @@ def _inputs():
     return depths, cams, pairs
 
 
-def _run(rank, world):
+def _run(rank, world, sharding="round_robin"):
     from oracle import fusion as ofu
     depths, cams, pairs = _inputs()
 
@@ -33,30 +33,34 @@ def _run(rank, world):
 
     def fuse(i, ref_depth, conf, srcs, src_depths):
         return ofu.fuse_view(ref_depth, conf, src_depths, cams[:, i], cams[:, srcs], 1, 0.5, 2, 0.3)
-    return scene.run_scene(infer, fuse, N_VIEWS, pairs, rank, world, device="cpu")
+    return scene.run_scene(infer, fuse, N_VIEWS, pairs, rank, world, device="cpu", sharding=sharding)
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, sharding="round_robin"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        res = _run(rank, world)
+        res = _run(rank, world, sharding)
         torch.save({k: (p, d) for k, (p, d) in res.items()}, os.path.join(out_dir, "rank{}.pt".format(rank)))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one(tmp_path):
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("sharding", ["round_robin", "block"])
+def test_two_ranks_equal_one(tmp_path, sharding):
     single = _run(0, 1)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), sharding), nprocs=2, join=True)
     merged = {}
     for r in range(2):
         part = torch.load(os.path.join(str(tmp_path), "rank{}.pt".format(r)))
-        assert sorted(part) == scene.shard_views(N_VIEWS, r, 2)
+        assert sorted(part) == scene.shard_views(N_VIEWS, r, 2, sharding)
         merged.update(part)
     assert sorted(merged) == list(range(N_VIEWS))
     for i in range(N_VIEWS):
@@ -74,4 +78,21 @@ def test_gather_layout_roundtrip():
                 blk[i // world] = float(i)
             blocks.append(blk)
         full = torch.stack(blocks).permute(1, 0, 2, 3).reshape(slots * world, 2, 2)[:n]
+        assert [int(full[i, 0, 0]) for i in range(n)] == list(range(n))
+
+
+def test_block_gather_layout_roundtrip():
+    for n, world in ((7, 2), (49, 8), (5, 4), (3, 1)):
+        local_all = {}
+        for r in range(world):
+            local_all[r] = {i: torch.full((2, 2), float(i)) for i in scene.shard_views(n, r, world, "block")}
+        assert sorted(i for d in local_all.values() for i in d) == list(range(n))
+        slots = scene.slots_per_rank(n, world)
+        blocks = []
+        for r in range(world):
+            blk = torch.zeros(slots, 2, 2)
+            for i, d in local_all[r].items():
+                blk[i % slots] = d
+            blocks.append(blk)
+        full = torch.stack(blocks).reshape(world * slots, 2, 2)[:n]
         assert [int(full[i, 0, 0]) for i in range(n)] == list(range(n))
