@@ -196,9 +196,9 @@ class TimedHotPath:
 
 def ncu_traffic(tag):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel whose label contains `tag`,
-    from the committed `ncu --set full` summary (profiles/r1_kernels_ncu_full.json); None if absent."""
+    from the committed `ncu --set full` summary (profiles/r1_warp_tile_ncu.json); None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_kernels_ncu_full.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_warp_tile_ncu.json")) as f:
             for k in json.load(f):
                 if tag in k["label"] and "warp_corr" in k["label"]:
                     def mb(v):

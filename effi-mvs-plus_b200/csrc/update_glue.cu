@@ -204,3 +204,106 @@ extern "C" int effimvs_convex_upsample_f32(const float* mask_pre, const float* m
                                                                      depth_out);
     return check_launch("convex_upsample_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------
+// ProjectionInput head (upstream models/update.py:88-91): the two input-side convolutions of the cost
+// encoder, relu(convc1(cost)) (1x1, CD -> h) and relu(convd1(inv)) (7x7 pad 3, 1 -> h), written side by
+// side into one channels-last (B,H,W,2h) map -- the input of the (block-diagonal) second layer, so the
+// concatenation upstream performs later (update.py:92) never happens.  With 6 and 1 input channels these
+// layers are far too thin for cuDNN's implicit GEMMs; here a thread owns one pixel, the 7x7 window comes
+// from a shared-memory tile and the weights are broadcast 128-bit shared loads, 16 output channels at a time.
+// ------------------------------------------------------------------------------------------------
+namespace effimvs {
+namespace {
+
+constexpr int EH_TX = 32, EH_TY = 8, EH_R = 3;
+
+__global__ void __launch_bounds__(EH_TX * EH_TY)
+encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restrict__ inv, const float* __restrict__ wc1,
+                    const float* __restrict__ bc1, const float* __restrict__ wd1, const float* __restrict__ bd1, int h, int H, int W,
+                    float* __restrict__ out) {
+    extern __shared__ __align__(16) float esm[];
+    float* s_wd = esm;                       // [49][h]   tap-major, channels contiguous
+    float* s_wc = s_wd + 49 * h;             // [CD][h]
+    float* s_b = s_wc + CD * h;              // [2h]      convc1 bias, convd1 bias
+    float* s_inv = s_b + 2 * h;              // [EH_TY + 6][EH_TX + 6]
+    constexpr int SW = EH_TX + 2 * EH_R, SH = EH_TY + 2 * EH_R;
+    const int tid = threadIdx.y * EH_TX + threadIdx.x, nt = EH_TX * EH_TY;
+    const int b = blockIdx.z;
+    for (int i = tid; i < 49 * h; i += nt) s_wd[i] = wd1[(i % h) * 49 + i / h];
+    for (int i = tid; i < CD * h; i += nt) s_wc[i] = wc1[(i % h) * CD + i / h];
+    for (int i = tid; i < 2 * h; i += nt) s_b[i] = i < h ? bc1[i] : bd1[i - h];
+    const int x0 = blockIdx.x * EH_TX - EH_R, y0 = blockIdx.y * EH_TY - EH_R;
+    const float* ib = inv + (size_t)b * H * W;
+    for (int i = tid; i < SW * SH; i += nt) {
+        const int yy = y0 + i / SW, xx = x0 + i % SW;
+        s_inv[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ib + (size_t)yy * W + xx) : 0.0f;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * EH_TX + threadIdx.x, y = blockIdx.y * EH_TY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float4* o = reinterpret_cast<float4*>(out + (((size_t)b * H + y) * W + x) * (2 * h));
+    // relu(convc1(cost) + b): 1x1
+    float cv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) cv[c] = c < CD ? __ldg(cost + (((size_t)b * CD + c) * H + y) * W + x) : 0.0f;
+    for (int ch = 0; ch < h; ch += 16) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = s_b[ch + j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c < CD) {
+                const float4* wp = reinterpret_cast<const float4*>(s_wc + c * h + ch);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = wp[q];
+                    acc[4 * q] = fmaf(cv[c], wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(cv[c], wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(cv[c], wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(cv[c], wv.w, acc[4 * q + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            o[(ch >> 2) + q] = make_float4(fmaxf(acc[4 * q], 0.0f), fmaxf(acc[4 * q + 1], 0.0f), fmaxf(acc[4 * q + 2], 0.0f), fmaxf(acc[4 * q + 3], 0.0f));
+    }
+    // relu(convd1(inv) + b): 7x7, zero padding 3
+    const float* win = s_inv + threadIdx.y * SW + threadIdx.x;
+    for (int ch = 0; ch < h; ch += 16) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = s_b[h + ch + j];
+#pragma unroll
+        for (int ty = 0; ty < 7; ++ty) {
+#pragma unroll
+            for (int tx = 0; tx < 7; ++tx) {
+                const float v = win[ty * SW + tx];
+                const float4* wp = reinterpret_cast<const float4*>(s_wd + (ty * 7 + tx) * h + ch);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 wv = wp[q];
+                    acc[4 * q] = fmaf(v, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            o[((h + ch) >> 2) + q] = make_float4(fmaxf(acc[4 * q], 0.0f), fmaxf(acc[4 * q + 1], 0.0f), fmaxf(acc[4 * q + 2], 0.0f), fmaxf(acc[4 * q + 3], 0.0f));
+    }
+}
+
+}  // namespace
+}  // namespace effimvs
+
+extern "C" int effimvs_encoder_head_f32(const float* cost, const float* inv, const float* wc1, const float* bc1, const float* wd1,
+                                        const float* bd1, int B, int CD, int h, int H, int W, float* out, void* stream) {
+    EFFI_REQUIRE(cost && inv && wc1 && bc1 && wd1 && bd1 && out, EFFIMVS_EINVAL, "encoder_head: null pointer");
+    EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "encoder_head: bad sizes");
+    EFFI_REQUIRE(CD >= 1 && CD <= 8 && h >= 16 && h % 16 == 0 && h <= 128, EFFIMVS_EUNSUPPORTED,
+                 "encoder_head: cost channels %d must be in [1,8], hidden %d a multiple of 16 up to 128", CD, h);
+    dim3 block(effimvs::EH_TX, effimvs::EH_TY), grid(effimvs::ceil_div(W, effimvs::EH_TX), effimvs::ceil_div(H, effimvs::EH_TY), B);
+    const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX + 6) * (effimvs::EH_TY + 6)) * sizeof(float);
+    effimvs::encoder_head_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    return effimvs::check_launch("encoder_head_kernel");
+}

@@ -176,6 +176,7 @@ class CudaHotPath:
     gru_update = staticmethod(ops.gru_update)
     gru_delta = staticmethod(ops.gru_delta)
     convex_upsample = staticmethod(ops.convex_upsample)
+    encoder_head = staticmethod(ops.encoder_head)
 
     # -- a11 / a12 --------------------------------------------------------------------------------
     def softmax_regress_conf(self, prob_pre, hyp):

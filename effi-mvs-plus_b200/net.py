@@ -303,7 +303,8 @@ class UpdateBlock(nn.Module):
     # ---- inference on CUDA: cuDNN convolutions + the glue kernels of the hot-path table ----------------
     def _fused_weights(self):
         g, e = self.depth_gru, self.encoder
-        ts = (g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias, e.convd.bias, e.convc.weight, e.convc.bias)
+        ts = (g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias, e.convd.bias, e.convc.weight, e.convc.bias,
+              e.convc2.weight, e.convc2.bias, e.convd2.weight, e.convd2.bias)
         stamp = tuple((id(t), t._version, t.device) for t in ts)
         if self._fused is None or self._fused[0] != stamp:
             cl = lambda w: w.detach().contiguous(memory_format=torch.channels_last)   # noqa: E731
@@ -312,7 +313,12 @@ class UpdateBlock(nn.Module):
             # convc(cat[m + b_d, context]) = Wc[:, :hm] m + (Wc[:, hm:] context + b_c + Wc[:, :hm] b_d): the second
             # term does not change over the GRU iterations
             bias_c = e.convc.bias.detach() + wc[:, :hm, 0, 0] @ e.convd.bias.detach()
+            h = self.hidden
+            w_cd2 = wc.new_zeros(2 * h, 2 * h, 3, 3)     # block-diagonal second encoder layer: [convc2 0; 0 convd2]
+            w_cd2[:h, :h] = e.convc2.weight.detach()
+            w_cd2[h:, h:] = e.convd2.weight.detach()
             self._fused = (stamp, {
+                "w_cd2": cl(w_cd2), "b_cd2": torch.cat([e.convc2.bias.detach(), e.convd2.bias.detach()]).contiguous(),
                 "wzr": cl(torch.cat([g.convz.weight, g.convr.weight], dim=0)),      # one convolution for both gates
                 "wc_m": cl(wc[:, :hm]), "wc_ctx": cl(wc[:, hm:]), "bias_c": bias_c.contiguous()})
         return self._fused[1]
@@ -330,9 +336,9 @@ class UpdateBlock(nn.Module):
         inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
         inv_seq, depth_seq = [], []
         for _ in range(iters):
-            c = _conv_relu_mod(e.convc2, _conv_relu_mod(e.convc1, cost_fn(depth)))
-            d = _conv_relu_mod(e.convd2, _conv_relu_mod(e.convd1, inv))
-            m = F.conv2d(torch.cat([c, d], dim=1), e.convd.weight, None, padding=1)
+            c1d1 = glue.encoder_head(cost_fn(depth), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
+            cd = torch.cudnn_convolution_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1), (1, 1), 1)
+            m = F.conv2d(cd, e.convd.weight, None, padding=1)
             hx[:, h:] = torch.cudnn_convolution_add_relu(m, w["wc_m"], ctx_term, 1.0, None, (1, 1), (0, 0), (1, 1), 1)
             zr_pre = F.conv2d(hx, w["wzr"], None, padding=1)
             rhx = glue.gru_reset(zr_pre, g.convr.bias, hx)

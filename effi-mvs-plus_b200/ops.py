@@ -532,6 +532,26 @@ def _(mask_pre, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
     return inv.new_empty(B, ratio * H, ratio * W), inv.new_empty(B, ratio * H, ratio * W)
 
 
+@torch.library.custom_op("effimvs::encoder_head", mutates_args=())
+def encoder_head(cost: Tensor, inv: Tensor, wc1: Tensor, bc1: Tensor, wd1: Tensor, bd1: Tensor) -> Tensor:
+    """cat[relu(convc1(cost)), relu(convd1(inv))] as one channels-last (B,2h,H,W) map (models/update.py:88-91)."""
+    cost, inv = _dev(cost, "encoder_head"), _dev(inv, "encoder_head")
+    wc1, bc1, wd1, bd1 = _dev(wc1, "encoder_head"), _dev(bc1, "encoder_head"), _dev(wd1, "encoder_head"), _dev(bd1, "encoder_head")
+    B, CD, H, W = cost.shape
+    h = wc1.shape[0]
+    out = torch.empty(B, 2 * h, H, W, device=cost.device, dtype=torch.float32, memory_format=torch.channels_last)
+    _count(1)
+    capi.check(_lib.effimvs_encoder_head_f32(cost.data_ptr(), inv.data_ptr(), wc1.data_ptr(), bc1.data_ptr(), wd1.data_ptr(), bd1.data_ptr(),
+                                             B, CD, h, H, W, out.data_ptr(), _stream()))
+    return out
+
+
+@encoder_head.register_fake
+def _(cost, inv, wc1, bc1, wd1, bd1):
+    B, _, H, W = cost.shape
+    return cost.new_empty(B, 2 * wc1.shape[0], H, W, memory_format=torch.channels_last)
+
+
 # -------------------------------------------------------------------------------------------
 # SURVEY section 8(f) row 2: DTU geometric filter (csrc/dtu_filter.cu)
 @torch.library.custom_op("effimvs::dtu_filter", mutates_args=())

@@ -225,6 +225,12 @@ int effimvs_convex_upsample_f32(const float* mask_pre, const float* mask_bias, f
                                 const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio, float* up_out,
                                 float* depth_out, void* stream);
 
+/* ProjectionInput head (models/update.py:88-91): relu(convc1(cost)) (1x1) and relu(convd1(inv)) (7x7, pad 3).
+ * cost (B,CD,H,W) planar (what effimvs_dynamic_cost_f32 writes), inv (B,1,H,W), wc1 (h,CD,1,1), wd1 (h,1,7,7)
+ *   -> out (B,H,W,2h) channels-last = cat[relu(convc1), relu(convd1)]: the input of the second encoder layer. */
+int effimvs_encoder_head_f32(const float* cost, const float* inv, const float* wc1, const float* bc1, const float* wd1,
+                             const float* bd1, int B, int CD, int h, int H, int W, float* out, void* stream);
+
 /* ---- the DTU pipeline's NumPy / cv2.remap geometric filter ------------------------
  * reproject_with_depth + check_geometric_consistency + the aggregation of filter_depth
  * (test_dtu_dypcd.py:164-233, 261-309, 320-337) for one reference view in one kernel.

@@ -616,3 +616,20 @@ def test_dtu_filter_vs_oracle_dtu_size():
     assert 0.05 < want["final"].mean() < 0.95
     # the resized confidence is compared with a threshold too: allow pixels whose confidence sits within 1e-6 of 0.5 / 0.75
     _dtu_filter_compare(out, want["final"], want["geo"], want["depth_avg"], want["points"], 2e-5, 2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,H,W", [(16, 37, 53), (32, 24, 70), (48, 19, 25)])
+def test_encoder_head_vs_torch(h, H, W):
+    """effimvs_encoder_head_f32 against relu(conv2d) of upstream's ProjectionInput head (models/update.py:88-91)"""
+    import torch.nn.functional as F
+    from effimvs_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(h)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=gen)      # noqa: E731
+    B, CD = 2, 6
+    cost, inv = rnd(B, CD, H, W), torch.rand(B, 1, H, W, device=DEV, generator=gen)
+    wc1, bc1, wd1, bd1 = rnd(h, CD, 1, 1) * 0.3, rnd(h), rnd(h, 1, 7, 7) * 0.2, rnd(h)
+    got = ops.encoder_head(cost, inv, wc1, bc1, wd1, bd1)
+    want = torch.cat([F.relu(F.conv2d(cost, wc1, bc1)), F.relu(F.conv2d(inv, wd1, bd1, padding=3))], dim=1)
+    assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert rel_max(got, want) < 1e-5
