@@ -19,6 +19,8 @@ What is replaced:
     CostRegNet_2_sample_FPN3D_Fast.forward models/module.py:453
     cost_up_small.forward                  models/module.py:509
     depth_regression                       models/module.py:518          (module global)
+    BasicUpdateBlock.forward               models/update.py:114          (CUDA table only; section 8(f) row 3)
+    upsample_depth                         models/Effi_MVS_plus.py:167   (module global; CUDA table only)
 
 The table defaults to ``CudaHotPath``; tests inject the oracle's table to check the adapters
 against unpatched upstream on the CPU.
@@ -170,6 +172,39 @@ def make_cost_up_forward(hotpath=None):
     return forward
 
 
+def make_update_block_forward(hotpath=None):
+    hp = _table(hotpath)
+
+    def forward(self, net, depth_cost_func, inv_depth, context, seq_len=4, scale_inv_depth=None):
+        """Drop-in for BasicUpdateBlock.forward (models/update.py:114-141), SURVEY section 8(f) row 3: the 2-D
+        convolutions stay cuDNN, the elementwise chains between them run in the glue kernels.
+        Returns (net, mask_list, inv_depth_list) like upstream: mask_list[-1] = 0.25 * mask(net)."""
+        from .net import update_block_forward_fused
+        kw = getattr(scale_inv_depth, "keywords", None) or {}
+        if "min_depth" not in kw or "max_depth" not in kw:
+            raise NotImplementedError("scale_inv_depth must be upstream's partial(disp_to_depth, min_depth=, max_depth=) (Effi_MVS_plus.py:423)")
+        B = inv_depth.shape[0]
+        lo, hi = (1 / kw["max_depth"]).reshape(-1).expand(B), (1 / kw["min_depth"]).reshape(-1).expand(B)
+        net, inv_seq, _, _, _, mask_pre = update_block_forward_fused(
+            self, hp, net, lambda depth, it: depth_cost_func(depth, iter=it), inv_depth, context, seq_len,
+            lo.contiguous(), hi.contiguous())
+        masks = list(inv_seq)
+        if self.UpMask:
+            masks[-1] = 0.25 * (mask_pre + self.mask[2].bias.reshape(1, -1, 1, 1))
+        return net, masks, inv_seq
+    return forward
+
+
+def make_upsample_depth(hotpath=None):
+    hp = _table(hotpath)
+
+    def upsample_depth(depth, mask, ratio=8):
+        """Drop-in for upsample_depth (models/Effi_MVS_plus.py:167-178): (N,1,H,W), (N,9*ratio^2,H,W) -> (N,ratio*H,ratio*W)."""
+        one = torch.ones(depth.shape[0], device=depth.device, dtype=torch.float32)
+        return hp.convex_upsample(mask, None, 1.0, depth, one, one, ratio)[0]
+    return upsample_depth
+
+
 def patch(model, hotpath=None, upstream_module: str = "models.Effi_MVS_plus"):
     """Swap the hot-path call sites of an upstream ``Effi_MVS_plus`` instance in place.
 
@@ -195,6 +230,11 @@ def patch(model, hotpath=None, upstream_module: str = "models.Effi_MVS_plus"):
     mod = sys.modules.get(upstream_module)
     if mod is not None:
         swap(mod, "pro_bilinear_sampler", make_pro_bilinear_sampler(hp))
+    if getattr(hp, "fused_update", False):     # section 8(f) row 3 (CUDA table only)
+        for blk in model.update_block:
+            swap(blk, "forward", types.MethodType(make_update_block_forward(hp), blk))
+        if mod is not None and all(int(r) == 2 for r in getattr(model, "feat_ratio", [2])):
+            swap(mod, "upsample_depth", make_upsample_depth(hp))
 
     def restore():
         for obj, name, had, old in reversed(undo):

@@ -287,8 +287,6 @@ class UpdateBlock(nn.Module):
         self.depth_head = DeltaHead(hidden)
         self.mask = nn.Sequential(nn.Conv2d(hidden, hidden * 2, 3, padding=1), nn.ReLU(inplace=True),
                                   nn.Conv2d(hidden * 2, ratio * ratio * 9, 1))
-        self.hidden, self.context_dim, self.ratio = hidden, context_dim, ratio
-        self._fused = None
 
     def forward(self, net, cost_fn, inv_depth, context, iters, to_depth):
         inv_seq = []
@@ -300,57 +298,68 @@ class UpdateBlock(nn.Module):
             inv_seq.append(inv_depth)
         return net, 0.25 * self.mask[2](_conv_relu_mod(self.mask[0], net)), inv_seq
 
-    # ---- inference on CUDA: cuDNN convolutions + the glue kernels of the hot-path table ----------------
-    def _fused_weights(self):
-        g, e = self.depth_gru, self.encoder
-        ts = (g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias, e.convd.bias, e.convc.weight, e.convc.bias,
-              e.convc2.weight, e.convc2.bias, e.convd2.weight, e.convd2.bias)
-        stamp = tuple((id(t), t._version, t.device) for t in ts)
-        if self._fused is None or self._fused[0] != stamp:
-            cl = lambda w: w.detach().contiguous(memory_format=torch.channels_last)   # noqa: E731
-            hm = self.hidden - self.context_dim
-            wc = e.convc.weight.detach()
-            # convc(cat[m + b_d, context]) = Wc[:, :hm] m + (Wc[:, hm:] context + b_c + Wc[:, :hm] b_d): the second
-            # term does not change over the GRU iterations
-            bias_c = e.convc.bias.detach() + wc[:, :hm, 0, 0] @ e.convd.bias.detach()
-            h = self.hidden
-            w_cd2 = wc.new_zeros(2 * h, 2 * h, 3, 3)     # block-diagonal second encoder layer: [convc2 0; 0 convd2]
-            w_cd2[:h, :h] = e.convc2.weight.detach()
-            w_cd2[h:, h:] = e.convd2.weight.detach()
-            self._fused = (stamp, {
-                "w_cd2": cl(w_cd2), "b_cd2": torch.cat([e.convc2.bias.detach(), e.convd2.bias.detach()]).contiguous(),
-                "wzr": cl(torch.cat([g.convz.weight, g.convr.weight], dim=0)),      # one convolution for both gates
-                "wc_m": cl(wc[:, :hm]), "wc_ctx": cl(wc[:, hm:]), "bias_c": bias_c.contiguous()})
-        return self._fused[1]
-
     def forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp):
-        """Same arithmetic as forward() + convex_upsample() + to_depth(), with the elementwise chains between
-        the convolutions replaced by glue.gru_reset / gru_update / gru_delta / convex_upsample.
-        Returns (net, inv_seq, depth_seq, inv_up (B,rH,rW), depth_up (B,rH,rW))."""
-        w = self._fused_weights()
-        g, e, hd = self.depth_gru, self.encoder, self.depth_head
-        B, h, H, W = net.shape
-        hx = torch.empty(B, 2 * h, H, W, device=net.device, dtype=net.dtype, memory_format=torch.channels_last)
-        hx[:, :h] = net
-        ctx_term = F.conv2d(context, w["wc_ctx"], w["bias_c"])
-        inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
-        inv_seq, depth_seq = [], []
-        for _ in range(iters):
-            c1d1 = glue.encoder_head(cost_fn(depth), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
-            cd = torch.cudnn_convolution_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1), (1, 1), 1)
-            m = F.conv2d(cd, e.convd.weight, None, padding=1)
-            hx[:, h:] = torch.cudnn_convolution_add_relu(m, w["wc_m"], ctx_term, 1.0, None, (1, 1), (0, 0), (1, 1), 1)
-            zr_pre = F.conv2d(hx, w["wzr"], None, padding=1)
-            rhx = glue.gru_reset(zr_pre, g.convr.bias, hx)
-            q_pre = F.conv2d(rhx, g.convq.weight, None, padding=1)
-            net = glue.gru_update(zr_pre, g.convz.bias, q_pre, g.convq.bias, hx)
-            pre = F.conv2d(_conv_relu_mod(hd.conv1, net), hd.conv2.weight, None, padding=1)
-            inv, depth = glue.gru_delta(pre, hd.conv2.bias, inv, lo_disp, hi_disp)
-            inv_seq.append(inv)
-            depth_seq.append(depth)
-        mask_pre = F.conv2d(_conv_relu_mod(self.mask[0], net), self.mask[2].weight, None)
-        up, depth_up = glue.convex_upsample(mask_pre, self.mask[2].bias, 0.25, inv, lo_disp, hi_disp, self.ratio)
-        return net, inv_seq, depth_seq, up, depth_up
+        return update_block_forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp)
+
+
+# ---- inference on CUDA: cuDNN convolutions + the glue kernels of the hot-path table ------------------
+# Written against the attribute names of upstream's BasicUpdateBlock (encoder.convc1 ... mask[2]), which
+# UpdateBlock shares, so that dropin.patch() can run an upstream instance through the same code.
+def _fused_update_weights(block):
+    g, e = block.depth_gru, block.encoder
+    ts = (g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias, e.convd.bias, e.convc.weight, e.convc.bias,
+          e.convc2.weight, e.convc2.bias, e.convd2.weight, e.convd2.bias)
+    stamp = tuple((id(t), t._version, t.device) for t in ts)
+    hit = getattr(block, "_effimvs_fused", None)
+    if hit is None or hit[0] != stamp:
+        cl = lambda w: w.detach().contiguous(memory_format=torch.channels_last)   # noqa: E731
+        h = g.convz.out_channels
+        hm = e.convd.out_channels                       # hidden - context_dim
+        wc = e.convc.weight.detach()
+        # convc(cat[m + b_d, context]) = Wc[:, :hm] m + (Wc[:, hm:] context + b_c + Wc[:, :hm] b_d): the second
+        # term does not change over the GRU iterations
+        bias_c = e.convc.bias.detach() + wc[:, :hm, 0, 0] @ e.convd.bias.detach()
+        w_cd2 = wc.new_zeros(2 * h, 2 * h, 3, 3)        # block-diagonal second encoder layer: [convc2 0; 0 convd2]
+        w_cd2[:h, :h] = e.convc2.weight.detach()
+        w_cd2[h:, h:] = e.convd2.weight.detach()
+        hit = (stamp, {
+            "w_cd2": cl(w_cd2), "b_cd2": torch.cat([e.convc2.bias.detach(), e.convd2.bias.detach()]).contiguous(),
+            "wzr": cl(torch.cat([g.convz.weight, g.convr.weight], dim=0)),      # one convolution for both gates
+            "wc_m": cl(wc[:, :hm]), "wc_ctx": cl(wc[:, hm:]), "bias_c": bias_c.contiguous()})
+        object.__setattr__(block, "_effimvs_fused", hit)
+    return hit[1]
+
+
+def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp):
+    """Same arithmetic as BasicUpdateBlock.forward (models/update.py:114-141) + upsample_depth + disp_to_depth
+    (Effi_MVS_plus.py:138-178), with the elementwise chains between the convolutions replaced by
+    glue.encoder_head / gru_reset / gru_update / gru_delta / convex_upsample.  cost_fn(depth, iteration).
+    Returns (net, inv_seq, depth_seq, inv_up (B,rH,rW), depth_up (B,rH,rW), mask_pre (B,9rr,H,W) without bias)."""
+    w = _fused_update_weights(block)
+    g, e, hd = block.depth_gru, block.encoder, block.depth_head
+    ratio = int(round((block.mask[2].out_channels / 9) ** 0.5))
+    B, h, H, W = net.shape
+    hx = torch.empty(B, 2 * h, H, W, device=net.device, dtype=net.dtype, memory_format=torch.channels_last)
+    hx[:, :h] = net
+    ctx_term = F.conv2d(context, w["wc_ctx"], w["bias_c"])
+    inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
+    inv_seq, depth_seq = [], []
+    for it in range(iters):
+        c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
+        cd = torch.cudnn_convolution_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1), (1, 1), 1)
+        m = F.conv2d(cd, e.convd.weight, None, padding=1)
+        hx[:, h:] = torch.cudnn_convolution_add_relu(m, w["wc_m"], ctx_term, 1.0, None, (1, 1), (0, 0), (1, 1), 1)
+        zr_pre = F.conv2d(hx, w["wzr"], None, padding=1)
+        rhx = glue.gru_reset(zr_pre, g.convr.bias, hx)
+        q_pre = F.conv2d(rhx, g.convq.weight, None, padding=1)
+        net = glue.gru_update(zr_pre, g.convz.bias, q_pre, g.convq.bias, hx)
+        pre = F.conv2d(_conv_relu_mod(hd.conv1, net), hd.conv2.weight, None, padding=1)
+        inv, depth = glue.gru_delta(pre, hd.conv2.bias, inv, lo_disp, hi_disp)
+        inv_seq.append(inv)
+        depth_seq.append(depth)
+    mask_pre = F.conv2d(_conv_relu_mod(block.mask[0], net), block.mask[2].weight, None)
+    up, depth_up = glue.convex_upsample(mask_pre, block.mask[2].bias, 0.25, inv, lo_disp, hi_disp, ratio)
+    return net, inv_seq, depth_seq, up, depth_up, mask_pre
 
 
 def convex_upsample(x, mask, ratio):
@@ -479,12 +488,12 @@ class EffiMVSPlus(nn.Module):
             inv0 = (1.0 / cur_depth - 1.0 / depth_far) / ((1.0 / depth_near - 1.0 / depth_far) + 1e-10)
             interval = unit * self.RATIOS[s]
 
-            def cost_fn(depth, _raw=raw_vol, _reg=reg_vol, _iv=interval, _n=vol_near, _f=vol_far):
+            def cost_fn(depth, _it=0, _raw=raw_vol, _reg=reg_vol, _iv=interval, _n=vol_near, _f=vol_far):
                 return hp.dynamic_cost(depth, _raw, _reg, _iv, _n, _f, self.cost_num)
 
             glue = hp if (getattr(hp, "fused_update", False) and imgs.is_cuda and not torch.is_grad_enabled()) else None
             if glue is not None:
-                _, _, depth_seq, _, depth_up = self.update_block[s].forward_fused(
+                _, _, depth_seq, _, depth_up, _ = self.update_block[s].forward_fused(
                     glue, hidden, cost_fn, inv0, context, self.iters[s], lo_disp.reshape(B), hi_disp.reshape(B))
                 preds.extend(d.squeeze(1) for d in depth_seq)
                 preds.append(depth_up)

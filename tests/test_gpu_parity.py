@@ -534,7 +534,7 @@ def test_update_block_fused_golden(hp):
     B = g["inv0"].shape[0]
     lo, hi = (1.0 / g["dmax"]).reshape(B), (1.0 / g["dmin"]).reshape(B)
     with torch.no_grad():
-        n, invs, deps, up, dup = blk.forward_fused(hp, g["net0"], _update_cost_fn, g["inv0"], g["context"], 3, lo, hi)
+        n, invs, deps, up, dup, _ = blk.forward_fused(hp, g["net0"], _update_cost_fn, g["inv0"], g["context"], 3, lo, hi)
     assert rel_max(n, g["net"]) < 1e-4
     for i in range(3):
         assert float((invs[i] - g["inv{}".format(i + 1)]).abs().max()) < 1e-4
@@ -555,7 +555,7 @@ def test_update_block_fused_equals_plain_at_dtu_stage3(hp):
     lo, hi = torch.tensor([1 / 935.0], device=DEV), torch.tensor([1 / 425.0], device=DEV)
     to_depth = lambda v: 1.0 / (lo.reshape(B, 1, 1, 1) + (hi - lo).reshape(B, 1, 1, 1) * v).clamp(min=1e-4)   # noqa: E731
     with torch.no_grad():
-        n, invs, deps, up, dup = blk.forward_fused(hp, n0, _update_cost_fn, inv0, ctx, 3, lo, hi)
+        n, invs, deps, up, dup, _ = blk.forward_fused(hp, n0, _update_cost_fn, inv0, ctx, 3, lo, hi)
         n_p, mask_p, invs_p = blk(n0, _update_cost_fn, inv0, ctx, 3, to_depth)
         up_p = net.convex_upsample(invs_p[-1], mask_p, 2)
     assert rel_max(n, n_p) < 1e-4 and float((invs[-1] - invs_p[-1]).abs().max()) < 1e-4
@@ -633,3 +633,28 @@ def test_encoder_head_vs_torch(h, H, W):
     want = torch.cat([F.relu(F.conv2d(cost, wc1, bc1)), F.relu(F.conv2d(inv, wd1, bd1, padding=3))], dim=1)
     assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
     assert rel_max(got, want) < 1e-5
+
+
+@pytest.mark.gpu
+def test_update_block_dropin_golden(hp):
+    """dropin.make_update_block_forward / make_upsample_depth called the way upstream's Effi_MVS_plus.forward calls
+    BasicUpdateBlock.forward and upsample_depth (Effi_MVS_plus.py:552-564), against the upstream golden fixture"""
+    import types
+    from functools import partial
+    from effimvs_b200 import dropin
+    from test_net_host import load_update_block, _update_cost_fn
+    g = golden("update_block", DEV)
+    blk = load_update_block(g, DEV)
+    blk.UpMask = True
+
+    def disp_to_depth(disp, min_depth, max_depth):       # the signature dropin reads the range from
+        raise AssertionError("the drop-in converts in-kernel")
+    scale = partial(disp_to_depth, min_depth=g["dmin"], max_depth=g["dmax"])
+    fwd = types.MethodType(dropin.make_update_block_forward(hp), blk)
+    net_out, masks, invs = fwd(g["net0"], lambda depth, iter=0: _update_cost_fn(depth), g["inv0"], g["context"], seq_len=3,
+                               scale_inv_depth=scale)
+    assert rel_max(net_out, g["net"]) < 1e-4 and rel_max(masks[-1], g["mask"]) < 1e-4
+    for i in range(3):
+        assert float((invs[i] - g["inv{}".format(i + 1)]).abs().max()) < 1e-4
+    up = dropin.make_upsample_depth(hp)(invs[-1], masks[-1], ratio=2)
+    assert float((up - g["up"]).abs().max()) < 1e-4

@@ -50,7 +50,7 @@ def test_fused_topdown_cache_follows_weight_updates():
     assert float((a - want).abs().max()) > 1e-3
 
 
-def _update_cost_fn(depth):
+def _update_cost_fn(depth, _iteration=0):
     """the analytic cost function tests/golden/make_golden_update.py used in place of the volume lookup"""
     k = torch.arange(1, 7, dtype=depth.dtype, device=depth.device).reshape(1, 6, 1, 1)
     return torch.sin(depth * (k * 0.01)) * 0.5
