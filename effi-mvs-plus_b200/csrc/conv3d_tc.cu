@@ -49,10 +49,11 @@ namespace {
 constexpr int TILE_M = 128;
 constexpr int SEG_VOX = 136;  // 128 + 2 (x halo) + 1 (dummy chunk) rounded up to a multiple of 8
 constexpr int SEG_BYTES = SEG_VOX * 16;
-constexpr int MAX_SEGS = 72;
-constexpr int MAX_OPS = 112;
+constexpr int MAX_SEGS = 96;
+constexpr int MAX_OPS = 160;
 constexpr int MAX_BLOCKS = 56;   // packed weight blocks (one K chunk pair each)
-constexpr int MAX_PHASES = 2;
+constexpr int MAX_PHASES = 8;
+constexpr int ZSWEEP_R = 4;     // output planes per unit of the z-sweep programs
 
 enum { L_REG = 0, L_SPLIT = 1 };
 
@@ -111,12 +112,14 @@ struct ConvProgram {
     // columns starting at lo_col0; the epilogue adds the partial sums.  n_lo_part == 0: x_lo products go into
     // the first N columns of the x_hi block (multi-class layers, whose classes already interleave).
     int n_hi_part, n_lo_part, lo_col0;
+    int cls_z;                    // 1: the accumulator classes are consecutive output planes (z-sweep), output z = grid z * up_z + class
+    int b_lbo_rows;               // rows between the two K chunks of a packed weight block (b_rows, or 3 * b_rows when stacked)
     int debug;                    // EFFIMVS_TC_DEBUG bits (profiling only): 1 no MMA, 2 no operand copies, 4 no epilogue body, 8 no stores
     Phase ph[MAX_PHASES];
     Seg segs[MAX_SEGS];
     Op ops[MAX_OPS];
 };
-struct PackTable { int n_blocks, N, rows, cout, cin, transposed; Block blk[MAX_BLOCKS]; };
+struct PackTable { int n_blocks, N, rows, cout, cin, transposed; int stack, brows; Block blk[MAX_BLOCKS]; };   // stack 3: rows = [a=2 ; a=1 ; a=0] blocks of brows rows, tap = a*9 + Block tap
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -256,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
     uint8_t* slab = smem + P.w_smem_bytes;            // n_stages slabs of slab_bytes
     const int S = P.n_stages;
     {
-        const uint32_t a_base = smem_u32(slab), w_base = smem_u32(wsm), b_lbo = (uint32_t)P.b_rows * 16u;
+        const uint32_t a_base = smem_u32(slab), w_base = smem_u32(wsm), b_lbo = (uint32_t)P.b_lbo_rows * 16u;
         for (int p = 0; p < P.n_phases; ++p) {
             const Phase ph = P.ph[p];
             for (int i = ph.op_begin + tid; i < ph.op_end; i += CTA_THREADS) {
@@ -384,7 +387,8 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                     for (int cls = 0; cls < 8; ++cls) {
                         if (cls < P.n_classes) {
                             int pz = 0, py = 0, px = 0;
-                            if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
+                            if (P.cls_z) pz = cls;
+                            else if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
                             else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
                             const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
                             rhi[cls] = __ldg(res + act_index(RL, b, g, oz, oy, ox));
@@ -396,7 +400,8 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                 for (int cls = 0; cls < 8; ++cls) {
                     if (cls >= P.n_classes) break;
                     int pz = 0, py = 0, px = 0;
-                    if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
+                    if (P.cls_z) pz = cls;
+                    else if (P.n_classes == 8) { pz = cls >> 2; py = (cls >> 1) & 1; px = cls & 1; }
                     else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
                     const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
                     float v[8];
@@ -470,11 +475,13 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
 __global__ void pack_weights_kernel(const __grid_constant__ PackTable T, const float* __restrict__ w, __nv_bfloat16* __restrict__ dst) {
     const int total = T.n_blocks * 2 * T.rows * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int kk = i & 7, row = (i >> 3) % T.rows, j = (i / (8 * T.rows)) & 1, blk = i / (16 * T.rows);
+        const int kk = i & 7, row_all = (i >> 3) % T.rows, j = (i / (8 * T.rows)) & 1, blk = i / (16 * T.rows);
+        const int row = T.stack > 1 ? row_all % T.brows : row_all;
         const bool lo = row >= T.N;
         const int n = lo ? row - T.N : row;
         const Block c = T.blk[blk];
-        const int tap = j ? c.tap1 : c.tap0, cb = j ? c.cb1 : c.cb0;
+        const int tap_bc = j ? c.tap1 : c.tap0, cb = j ? c.cb1 : c.cb0;
+        const int tap = (T.stack > 1 && tap_bc >= 0) ? (T.stack - 1 - row_all / T.brows) * 9 + tap_bc : tap_bc;
         float v = 0.0f;
         if (tap >= 0 && n < T.cout) {
             const int ci = cb + kk;
@@ -492,11 +499,13 @@ __global__ void pack_weights_multi_kernel(const __grid_constant__ PackJobs J) {
     __nv_bfloat16* __restrict__ dst = J.dst[blockIdx.y];
     const int total = T.n_blocks * 2 * T.rows * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int kk = i & 7, row = (i >> 3) % T.rows, j = (i / (8 * T.rows)) & 1, blk = i / (16 * T.rows);
+        const int kk = i & 7, row_all = (i >> 3) % T.rows, j = (i / (8 * T.rows)) & 1, blk = i / (16 * T.rows);
+        const int row = T.stack > 1 ? row_all % T.brows : row_all;
         const bool lo = row >= T.N;
         const int n = lo ? row - T.N : row;
         const Block c = T.blk[blk];
-        const int tap = j ? c.tap1 : c.tap0, cb = j ? c.cb1 : c.cb0;
+        const int tap_bc = j ? c.tap1 : c.tap0, cb = j ? c.cb1 : c.cb0;
+        const int tap = (T.stack > 1 && tap_bc >= 0) ? (T.stack - 1 - row_all / T.brows) * 9 + tap_bc : tap_bc;
         float v = 0.0f;
         if (tap >= 0 && n < T.cout) {
             const int ci = cb + kk;
@@ -656,6 +665,7 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
     if (n_phases > MAX_PHASES) return false;
     P.n_phases = n_phases;
     P.b_rows = T.rows = hilo ? 2 * P.N : P.N;
+    P.b_lbo_rows = P.b_rows; P.cls_z = 0; T.stack = 1; T.brows = T.rows;
     int n_seg = 0, n_op = 0, n_blk = 0;
     {
         int want = 1;   // measured: no gain (the MMAs of a CTA are serialised by operand-fetch latency, not by the accumulator)
@@ -772,7 +782,10 @@ void init_program(ConvProgram& P, PackTable& T, int Cin, int Cout, int n_classes
 }
 
 // stride-1 convolution, input REGULAR on the output grid
+bool build_conv_s1_zsweep(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLayout& IL, int relu, bool hilo);
+
 bool build_conv_s1(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLayout& IL, int relu) {
+    if (build_conv_s1_zsweep(P, T, Cin, Cout, IL, relu, IL.lo_off != 0)) return true;
     init_program(P, T, Cin, Cout, 1, IL.D, IL.H, IL.W, IL, relu, 0);
     std::vector<PlaneSeg> pseg;
     for (int a = 0; a < 3; ++a)
@@ -783,6 +796,105 @@ bool build_conv_s1(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLay
         for (int b = 0; b < 3; ++b)
             for (int c = 0; c < 3; ++c) terms.push_back(Term{a * 3 + b, c * 16, a * 9 + b * 3 + c, 0});
     return assemble(P, T, terms, pseg, Cin / 8, IL.vs, (long long)IL.lo_off * IL.vs, IL.lo_off != 0);
+}
+
+// Stride-1 convolution as a z-sweep: a unit is one 128-position tile in ZSWEEP_R consecutive output planes, whose
+// accumulators sit side by side in TMEM.  A load phase stages ONE input plane (its three y rows per channel plane
+// and hi/lo half); every staged row then feeds the up-to-three output planes it contributes to with a single MMA
+// against the stacked weight block [w(a=2) ; w(a=1) ; w(a=0)] -- N = 3 * b_rows instead of three N = b_rows
+// MMAs, i.e. one A-operand fetch (the binding cost of these layers, ~32 clk for 8-16 clk of math) serves three
+// taps, and each input row is staged (R+2)/R times per output plane instead of three times.
+// The x_lo operand is multiplied with the full [w_hi ; w_lo] block too (the extra x_lo * w_lo term is 2^-16 of
+// 2^-16 and only makes the product more exact), so hi and lo MMAs share shape, weights and accumulator columns.
+bool build_conv_s1_zsweep(ConvProgram& P, PackTable& T, int Cin, int Cout, const ActLayout& IL, int relu, bool hilo) {
+    const int R = ZSWEEP_R, NP = Cin / 8, halves = hilo ? 2 : 1;
+    if (IL.D % R != 0 || (NP != 1 && NP != 2) || getenv("EFFIMVS_TC_NO_ZSWEEP")) return false;
+    init_program(P, T, Cin, Cout, R, IL.D / R, IL.H, IL.W, IL, relu, 0);
+    P.up_z = R; P.cls_z = 1;
+    P.zstride = (long long)R * IL.zstride;          // the tile enumeration advances by R planes
+    P.b_rows = hilo ? 2 * P.N : P.N;
+    P.b_lbo_rows = 3 * P.b_rows;
+    P.n_hi_part = 1; P.n_lo_part = 0; P.lo_col0 = 0;
+    T.rows = 3 * P.b_rows; T.stack = 3; T.brows = P.b_rows;
+    const long long plane_stride = IL.vs, lo_plane_off = (long long)IL.lo_off * IL.vs;
+    const uint32_t blk_bytes = 2u * (uint32_t)T.rows * 16u;
+    const uint32_t lo_smem = (uint32_t)(NP * 3 * SEG_BYTES);
+    // weight blocks: one per K-chunk pair of (b, c) taps -- shared by all phases
+    struct Base { uint32_t a_off, lbo; int blk; };
+    std::vector<Base> bases;
+    int n_blk = 0;
+    if (NP == 1) {   // 8 input channels: pair the nine (b, c) taps in ascending shared-memory address
+        for (int t = 0; t < 9; t += 2) {
+            const int b0 = t / 3, c0 = t % 3;
+            const uint32_t a0 = (uint32_t)(b0 * SEG_BYTES + c0 * 16);
+            if (t + 1 < 9) {
+                const int b1 = (t + 1) / 3, c1 = (t + 1) % 3;
+                const uint32_t a1 = (uint32_t)(b1 * SEG_BYTES + c1 * 16);
+                T.blk[n_blk] = Block{(short)t, 0, (short)(t + 1), 0};
+                bases.push_back(Base{a0, a1 - a0, n_blk++});
+            } else {
+                T.blk[n_blk] = Block{(short)t, 0, -1, 0};                 // zero-weight dummy chunk
+                bases.push_back(Base{a0, 16, n_blk++});
+            }
+        }
+    } else {         // 16 input channels: the two channel planes are the two K chunks
+        for (int t = 0; t < 9; ++t) {
+            const int b = t / 3, c = t % 3;
+            T.blk[n_blk] = Block{(short)t, 0, (short)t, 8};
+            bases.push_back(Base{(uint32_t)(b * SEG_BYTES + c * 16), (uint32_t)(3 * SEG_BYTES), n_blk++});
+        }
+    }
+    T.n_blocks = n_blk;
+    P.n_phases = R + 2;
+    if (P.n_phases > MAX_PHASES) return false;
+    int n_seg = 0, n_op = 0;
+    std::vector<bool> started(R, false);
+    for (int zi = 0; zi < R + 2; ++zi) {             // padded input plane z0 * R + zi
+        Phase& F = P.ph[zi];
+        F.seg_begin = n_seg; F.op_begin = n_op; F.w_off = 0; F.w_bytes = 0;
+        for (int h = 0; h < halves; ++h)
+            for (int pl = 0; pl < NP; ++pl)
+                for (int b = 0; b < 3; ++b) {
+                    if (n_seg >= MAX_SEGS) return false;
+                    Seg& sg = P.segs[n_seg++];
+                    sg.src_off = (long long)pl * plane_stride + (h ? lo_plane_off : 0) + IL.guard + (long long)zi * IL.zstride +
+                                 (long long)(b - 1) * IL.Px - 1;
+                    sg.copy_vox = TILE_M + 3;
+                    sg.slot = (h * NP + pl) * 3 + b;
+                }
+        // output plane o (0..R-1) reads padded input planes o + a: this plane serves a in [a_min, a_max], o = zi - a
+        const int a_max = std::min(2, zi), a_min = std::max(0, zi - R + 1);
+        const int o_first = zi - a_max, o_last = zi - a_min;
+        for (auto& bs : bases)
+            for (int h = 0; h < halves; ++h) {
+                // split into runs of output planes that are all started / all fresh (one accumulate flag per MMA)
+                int o = o_first;
+                while (o <= o_last) {
+                    int e = o;
+                    while (e + 1 <= o_last && started[e + 1] == started[o]) ++e;
+                    if (n_op >= MAX_OPS) return false;
+                    Op& op = P.ops[n_op++];
+                    op.a_off = bs.a_off + (h ? lo_smem : 0u);
+                    op.a_lbo = bs.lbo;
+                    const int a_hi = zi - o;                                  // tap of the first covered output plane
+                    op.b_off = (uint32_t)bs.blk * blk_bytes + (uint32_t)(2 - a_hi) * (uint32_t)P.b_rows * 16u;
+                    op.d_col = (uint16_t)(o * P.b_rows);
+                    op.n8 = (uint8_t)((e - o + 1) * P.b_rows / 8);
+                    op.accum = started[o] ? 1 : 0;
+                    for (int k = o; k <= e; ++k) started[k] = true;
+                    o = e + 1;
+                }
+            }
+        F.seg_end = n_seg; F.op_end = n_op;
+    }
+    P.w_smem_bytes = (int)((size_t)n_blk * blk_bytes);
+    P.slab_bytes = halves * NP * 3 * SEG_BYTES;
+    const size_t budget = 220 * 1024;
+    if ((size_t)P.w_smem_bytes + P.slab_bytes > budget) return false;
+    P.n_stages = ((size_t)P.w_smem_bytes + 2 * (size_t)P.slab_bytes <= budget) ? 2 : 1;
+    P.tile_cols = R * P.b_rows;
+    P.tmem_cols = pow2_cols(2 * P.tile_cols);
+    return P.tmem_cols <= 512 && n_blk <= MAX_BLOCKS;
 }
 
 // stride-(2,2,2) convolution, input PARITY-SPLIT (its sub-volumes live on the output grid)
