@@ -106,12 +106,6 @@ struct ConvProgram {
     int w_smem_bytes;             // packed weights of all phases (resident in shared memory, loaded once per CTA)
     int slab_bytes, n_stages;     // operand slab of one load unit; number of slab stages (1 or 2)
     int tile_cols;                // TMEM columns of one accumulator stage (two stages are allocated)
-    // Partial accumulators (single-class layers): successive MMAs into the SAME TMEM columns are serialised by
-    // the accumulate dependency (~80 clk each at these tiny N, against 8-16 clk of math), so the x_hi products
-    // rotate over n_hi_part column blocks of b_rows columns and the x_lo products over n_lo_part blocks of N
-    // columns starting at lo_col0; the epilogue adds the partial sums.  n_lo_part == 0: x_lo products go into
-    // the first N columns of the x_hi block (multi-class layers, whose classes already interleave).
-    int n_hi_part, n_lo_part, lo_col0;
     int cls_z;                    // 1: the accumulator classes are consecutive output planes (z-sweep), output z = grid z * up_z + class
     int b_lbo_rows;               // rows between the two K chunks of a packed weight block (b_rows, or 3 * b_rows when stacked)
     int debug;                    // EFFIMVS_TC_DEBUG bits (profiling only): 1 no MMA, 2 no operand copies, 4 no epilogue body, 8 no stores
@@ -245,42 +239,10 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2], bar_w;
     __shared__ uint32_t tmem_base_s;
-    // The MMA issuer and the TMA producer are single threads: whatever they compute per instruction is a chain
-    // of dependent-latency stalls nobody hides.  Everything tile-invariant (complete UMMA descriptors for slab
-    // stage 0, instruction descriptors, copy sources / destinations / sizes) is therefore built once per CTA
-    // by all threads; the two loops only load, add the stage / tile offset and issue.
-    __shared__ __align__(8) uint64_t s_adesc[MAX_OPS], s_bdesc[MAX_OPS];
-    __shared__ uint32_t s_opm[MAX_OPS];               // idesc | accumulate flag in bit 0 (idesc bit 0 is unused)
-    __shared__ uint32_t s_dcol[MAX_OPS];
-    __shared__ long long s_seg_src[MAX_SEGS];
-    __shared__ uint32_t s_seg_dst[MAX_SEGS], s_seg_bytes[MAX_SEGS], s_phase_bytes[MAX_PHASES];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* wsm = smem;                              // all phases' weights, resident for the CTA's lifetime
     uint8_t* slab = smem + P.w_smem_bytes;            // n_stages slabs of slab_bytes
     const int S = P.n_stages;
-    {
-        const uint32_t a_base = smem_u32(slab), w_base = smem_u32(wsm), b_lbo = (uint32_t)P.b_lbo_rows * 16u;
-        for (int p = 0; p < P.n_phases; ++p) {
-            const Phase ph = P.ph[p];
-            for (int i = ph.op_begin + tid; i < ph.op_end; i += CTA_THREADS) {
-                const Op op = P.ops[i];
-                s_adesc[i] = umma_desc(a_base + op.a_off, op.a_lbo, 128);
-                s_bdesc[i] = umma_desc(w_base + (uint32_t)ph.w_off + op.b_off, b_lbo, 128);
-                s_opm[i] = umma_idesc(op.n8 * 8) | (op.accum ? 1u : 0u);
-                s_dcol[i] = op.d_col;
-            }
-            for (int i = ph.seg_begin + tid; i < ph.seg_end; i += CTA_THREADS) {
-                s_seg_src[i] = P.segs[i].src_off;
-                s_seg_dst[i] = (uint32_t)P.segs[i].slot * SEG_BYTES;
-                s_seg_bytes[i] = (uint32_t)P.segs[i].copy_vox * 16u;
-            }
-            if (tid == 0) {
-                uint32_t bytes = 0;
-                for (int i = ph.seg_begin; i < ph.seg_end; ++i) bytes += (uint32_t)P.segs[i].copy_vox * 16u;
-                s_phase_bytes[p] = bytes;
-            }
-        }
-    }
 
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)P.tmem_cols) : "memory");
@@ -308,24 +270,17 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                 const long long q0 = (long long)P.gPx + (long long)t * TILE_M;
                 const uint4* base = in + (long long)b * in_batch_stride + (long long)z * P.zstride + q0;
                 for (int p = 0; p < P.n_phases; ++p, ++u) {
-                    const int seg_begin = P.ph[p].seg_begin, seg_end = P.ph[p].seg_end;
+                    const Phase ph = P.ph[p];
                     const uint32_t s = u % S, n = u / S;
                     mbar_wait(&bar_empty[s], (n & 1) ^ 1);          // slab stage free (first use passes)
-                    mbar_expect_tx(&bar_full[s], (P.debug & 2) ? 0u : s_phase_bytes[p]);
+                    uint32_t bytes = 0;
+                    if (!(P.debug & 2))
+                        for (int i = ph.seg_begin; i < ph.seg_end; ++i) bytes += (uint32_t)P.segs[i].copy_vox * 16u;
+                    mbar_expect_tx(&bar_full[s], bytes);
                     uint8_t* dst = slab + (size_t)s * P.slab_bytes;
-                    if (!(P.debug & 2)) {
-                        int i = seg_begin;
-                        for (; i + 4 <= seg_end; i += 4) {          // table loads of four copies in flight before the first issue
-                            const long long o0 = s_seg_src[i], o1 = s_seg_src[i + 1], o2 = s_seg_src[i + 2], o3 = s_seg_src[i + 3];
-                            const uint32_t d0 = s_seg_dst[i], d1 = s_seg_dst[i + 1], d2 = s_seg_dst[i + 2], d3 = s_seg_dst[i + 3];
-                            const uint32_t n0 = s_seg_bytes[i], n1 = s_seg_bytes[i + 1], n2 = s_seg_bytes[i + 2], n3 = s_seg_bytes[i + 3];
-                            bulk_g2s(dst + d0, base + o0, n0, &bar_full[s]);
-                            bulk_g2s(dst + d1, base + o1, n1, &bar_full[s]);
-                            bulk_g2s(dst + d2, base + o2, n2, &bar_full[s]);
-                            bulk_g2s(dst + d3, base + o3, n3, &bar_full[s]);
-                        }
-                        for (; i < seg_end; ++i) bulk_g2s(dst + s_seg_dst[i], base + s_seg_src[i], s_seg_bytes[i], &bar_full[s]);
-                    }
+                    if (!(P.debug & 2))
+                        for (int i = ph.seg_begin; i < ph.seg_end; ++i)
+                            bulk_g2s(dst + (size_t)P.segs[i].slot * SEG_BYTES, base + P.segs[i].src_off, (uint32_t)P.segs[i].copy_vox * 16u, &bar_full[s]);
                 }
             }
         }
@@ -333,6 +288,7 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
     } else if (warp == 5) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
+            const uint32_t w0 = smem_u32(wsm), b_lbo = (uint32_t)P.b_lbo_rows * 16u;
             mbar_wait(&bar_w, 0);
             uint32_t u = 0, k = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
@@ -341,23 +297,16 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                 tc_fence_after();
                 const uint32_t d0 = tmem + acc * (uint32_t)P.tile_cols;
                 for (int p = 0; p < P.n_phases; ++p, ++u) {
-                    const int op_begin = P.ph[p].op_begin, op_end = (P.debug & 1) ? P.ph[p].op_begin : P.ph[p].op_end;
+                    const Phase ph = P.ph[p];
                     const uint32_t s = u % S, n = u / S;
                     mbar_wait(&bar_full[s], n & 1);                  // operands landed
                     tc_fence_after();
-                    const uint64_t stage_add = (uint64_t)((s * (uint32_t)P.slab_bytes) >> 4);   // start-address field of the A descriptor
-                    int i = op_begin;
-                    for (; i + 4 <= op_end; i += 4) {                // four table entries in flight before the first issue
-                        const uint64_t a0 = s_adesc[i], a1 = s_adesc[i + 1], a2 = s_adesc[i + 2], a3 = s_adesc[i + 3];
-                        const uint64_t b0 = s_bdesc[i], b1 = s_bdesc[i + 1], b2 = s_bdesc[i + 2], b3 = s_bdesc[i + 3];
-                        const uint32_t m0 = s_opm[i], m1 = s_opm[i + 1], m2 = s_opm[i + 2], m3 = s_opm[i + 3];
-                        const uint32_t c0 = s_dcol[i], c1 = s_dcol[i + 1], c2 = s_dcol[i + 2], c3 = s_dcol[i + 3];
-                        umma_bf16(d0 + c0, a0 + stage_add, b0, m0 & ~1u, m0 & 1u);
-                        umma_bf16(d0 + c1, a1 + stage_add, b1, m1 & ~1u, m1 & 1u);
-                        umma_bf16(d0 + c2, a2 + stage_add, b2, m2 & ~1u, m2 & 1u);
-                        umma_bf16(d0 + c3, a3 + stage_add, b3, m3 & ~1u, m3 & 1u);
+                    const uint32_t a0 = smem_u32(slab + (size_t)s * P.slab_bytes), b0 = w0 + (uint32_t)ph.w_off;
+                    for (int i = ph.op_begin; i < ph.op_end && !(P.debug & 1); ++i) {
+                        const Op op = P.ops[i];
+                        umma_bf16(d0 + op.d_col, umma_desc(a0 + op.a_off, op.a_lbo, 128), umma_desc(b0 + op.b_off, b_lbo, 128),
+                                  umma_idesc(op.n8 * 8), op.accum);
                     }
-                    for (; i < op_end; ++i) umma_bf16(d0 + s_dcol[i], s_adesc[i] + stage_add, s_bdesc[i], s_opm[i] & ~1u, s_opm[i] & 1u);
                     umma_commit(&bar_empty[s]);                      // slab stage reusable once these MMAs retire
                 }
                 umma_commit(&bar_tfull[acc]);                        // accumulator complete
@@ -409,23 +358,6 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                     if (P.b_rows != P.N) {   // hi/lo mode: columns [N, 2N) hold x_hi * w_lo
                         float w2[8];
                         tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + P.N + g * 8), w2);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] += w2[j];
-                    }
-                    for (int hp = 1; hp < P.n_hi_part; ++hp) {   // partial accumulators (single-class layers)
-                        float w2[8];
-                        tmem_ld8(lane_base + (uint32_t)(hp * P.b_rows + g * 8), w2);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] += w2[j];
-                        if (P.b_rows != P.N) {
-                            tmem_ld8(lane_base + (uint32_t)(hp * P.b_rows + P.N + g * 8), w2);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] += w2[j];
-                        }
-                    }
-                    for (int lp = 0; lp < P.n_lo_part; ++lp) {
-                        float w2[8];
-                        tmem_ld8(lane_base + (uint32_t)(P.lo_col0 + lp * P.N + g * 8), w2);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] += w2[j];
                     }
@@ -667,17 +599,7 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
     P.b_rows = T.rows = hilo ? 2 * P.N : P.N;
     P.b_lbo_rows = P.b_rows; P.cls_z = 0; T.stack = 1; T.brows = T.rows;
     int n_seg = 0, n_op = 0, n_blk = 0;
-    {
-        int want = 1;   // measured: no gain (the MMAs of a CTA are serialised by operand-fetch latency, not by the accumulator)
-        if (const char* e = getenv("EFFIMVS_TC_PARTS")) want = atoi(e);
-        P.n_hi_part = (P.n_classes == 1 && want > 1) ? want : 1;
-        P.n_lo_part = (P.n_classes == 1 && want > 1 && hilo) ? want : 0;
-        while (P.n_hi_part > 1 && 2 * (P.n_hi_part * P.b_rows + P.n_lo_part * P.N) > 512) { P.n_hi_part /= 2; P.n_lo_part /= 2; }
-        if (P.n_hi_part <= 1) { P.n_hi_part = 1; P.n_lo_part = 0; }
-        P.lo_col0 = P.n_hi_part * P.b_rows * P.n_classes;
-    }
-    std::vector<bool> started(P.n_classes * P.n_hi_part, false), started_lo(std::max(1, P.n_lo_part), false);
-    int hi_ctr = 0, lo_ctr = 0;
+    std::vector<bool> started(P.n_classes, false);
     size_t max_slab = 0;
     struct Base { uint32_t a_off, lbo; int cls; Block blk; };
     for (int ph = 0; ph < n_phases; ++ph) {
@@ -724,24 +646,14 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
             if (n_blk + 1 > MAX_BLOCKS || n_op + halves > MAX_OPS) return false;
             const uint32_t b_off = (uint32_t)(n_blk - blk_begin) * blk_bytes;
             T.blk[n_blk++] = bs.blk;
-            const int hp = hi_ctr++ % P.n_hi_part;
-            auto push = [&](uint32_t a_off, int n, bool lo_block) {
+            auto push = [&](uint32_t a_off, int n) {
                 Op& op = P.ops[n_op++];
-                op.a_off = a_off; op.a_lbo = bs.lbo; op.b_off = b_off; op.n8 = (uint8_t)(n / 8);
-                if (lo_block) {
-                    const int lp = lo_ctr++ % P.n_lo_part;
-                    op.d_col = (uint16_t)(P.lo_col0 + lp * P.N);
-                    op.accum = started_lo[lp] ? 1 : 0;
-                    started_lo[lp] = true;
-                } else {
-                    const int slot = bs.cls * P.n_hi_part + hp;
-                    op.d_col = (uint16_t)(hp * P.b_rows * P.n_classes + bs.cls * P.b_rows);
-                    op.accum = started[slot] ? 1 : 0;
-                    started[slot] = true;
-                }
+                op.a_off = a_off; op.a_lbo = bs.lbo; op.b_off = b_off;
+                op.d_col = (uint16_t)(bs.cls * P.b_rows); op.accum = started[bs.cls] ? 1 : 0; op.n8 = (uint8_t)(n / 8);
+                started[bs.cls] = true;
             };
-            push(bs.a_off, P.b_rows, false);                               // x_hi * [w_hi ; w_lo]  (or x * w)
-            if (hilo) push(bs.a_off + lo_smem, P.N, P.n_lo_part > 0);      // x_lo * w_hi
+            push(bs.a_off, P.b_rows);                      // x_hi * [w_hi ; w_lo]  (or x * w)
+            if (hilo) push(bs.a_off + lo_smem, P.N);        // x_lo * w_hi, into the first N columns
         }
         F.seg_end = n_seg; F.op_end = n_op;
         F.w_off = (int)((size_t)blk_begin * blk_bytes); F.w_bytes = (int)((size_t)(n_blk - blk_begin) * blk_bytes);
@@ -760,8 +672,7 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
     if (P.n_stages == 2 && (size_t)P.w_smem_bytes + 2 * (size_t)P.slab_bytes > two_cta &&
         (size_t)P.w_smem_bytes + (size_t)P.slab_bytes <= two_cta)
         P.n_stages = 1;
-    if (const char* e = getenv("EFFIMVS_TC_STAGES")) { if (atoi(e) == 1) P.n_stages = 1; }
-    P.tile_cols = P.n_hi_part * P.b_rows * P.n_classes + P.n_lo_part * P.N;
+    P.tile_cols = P.b_rows * P.n_classes;
     P.tmem_cols = pow2_cols(2 * P.tile_cols);
     if (P.tmem_cols > 512) return false;
     return true;
@@ -814,7 +725,6 @@ bool build_conv_s1_zsweep(ConvProgram& P, PackTable& T, int Cin, int Cout, const
     P.zstride = (long long)R * IL.zstride;          // the tile enumeration advances by R planes
     P.b_rows = hilo ? 2 * P.N : P.N;
     P.b_lbo_rows = 3 * P.b_rows;
-    P.n_hi_part = 1; P.n_lo_part = 0; P.lo_col0 = 0;
     T.rows = 3 * P.b_rows; T.stack = 3; T.brows = P.b_rows;
     const long long plane_stride = IL.vs, lo_plane_off = (long long)IL.lo_off * IL.vs;
     const uint32_t blk_bytes = 2u * (uint32_t)T.rows * 16u;
