@@ -216,7 +216,7 @@ extern "C" int effimvs_convex_upsample_f32(const float* mask_pre, const float* m
 namespace effimvs {
 namespace {
 
-constexpr int EH_TX = 32, EH_TY = 8, EH_R = 3;
+constexpr int EH_TX = 32, EH_TY = 8, EH_R = 3, EH_PX = 2;   // a thread owns EH_PX horizontally adjacent pixels: weights loaded once for both
 
 __global__ void __launch_bounds__(EH_TX * EH_TY)
 encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restrict__ inv, const float* __restrict__ wc1,
@@ -226,31 +226,38 @@ encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restr
     float* s_wd = esm;                       // [49][h]   tap-major, channels contiguous
     float* s_wc = s_wd + 49 * h;             // [CD][h]
     float* s_b = s_wc + CD * h;              // [2h]      convc1 bias, convd1 bias
-    float* s_inv = s_b + 2 * h;              // [EH_TY + 6][EH_TX + 6]
-    constexpr int SW = EH_TX + 2 * EH_R, SH = EH_TY + 2 * EH_R;
+    float* s_inv = s_b + 2 * h;              // [EH_TY + 6][EH_TX * EH_PX + 6]
+    constexpr int TWP = EH_TX * EH_PX, SW = TWP + 2 * EH_R, SH = EH_TY + 2 * EH_R;
     const int tid = threadIdx.y * EH_TX + threadIdx.x, nt = EH_TX * EH_TY;
     const int b = blockIdx.z;
     for (int i = tid; i < 49 * h; i += nt) s_wd[i] = wd1[(i % h) * 49 + i / h];
     for (int i = tid; i < CD * h; i += nt) s_wc[i] = wc1[(i % h) * CD + i / h];
     for (int i = tid; i < 2 * h; i += nt) s_b[i] = i < h ? bc1[i] : bd1[i - h];
-    const int x0 = blockIdx.x * EH_TX - EH_R, y0 = blockIdx.y * EH_TY - EH_R;
+    const int x0 = blockIdx.x * TWP - EH_R, y0 = blockIdx.y * EH_TY - EH_R;
     const float* ib = inv + (size_t)b * H * W;
     for (int i = tid; i < SW * SH; i += nt) {
         const int yy = y0 + i / SW, xx = x0 + i % SW;
         s_inv[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ib + (size_t)yy * W + xx) : 0.0f;
     }
     __syncthreads();
-    const int x = blockIdx.x * EH_TX + threadIdx.x, y = blockIdx.y * EH_TY + threadIdx.y;
+    const int x = blockIdx.x * TWP + threadIdx.x * EH_PX, y = blockIdx.y * EH_TY + threadIdx.y;
     if (x >= W || y >= H) return;
-    float4* o = reinterpret_cast<float4*>(out + (((size_t)b * H + y) * W + x) * (2 * h));
+    const bool has[EH_PX] = {true, x + 1 < W};
+    float4* o[EH_PX];
+#pragma unroll
+    for (int p = 0; p < EH_PX; ++p) o[p] = reinterpret_cast<float4*>(out + (((size_t)b * H + y) * W + (has[p] ? x + p : x)) * (2 * h));
     // relu(convc1(cost) + b): 1x1
-    float cv[8];
+    float cv[EH_PX][8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) cv[c] = c < CD ? __ldg(cost + (((size_t)b * CD + c) * H + y) * W + x) : 0.0f;
+    for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cv[p][c] = (c < CD && has[p]) ? __ldg(cost + (((size_t)b * CD + c) * H + y) * W + x + p) : 0.0f;
     for (int ch = 0; ch < h; ch += 16) {
-        float acc[16];
+        float acc[EH_PX][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = s_b[ch + j];
+        for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[p][j] = s_b[ch + j];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             if (c < CD) {
@@ -258,38 +265,56 @@ encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restr
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 wv = wp[q];
-                    acc[4 * q] = fmaf(cv[c], wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(cv[c], wv.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(cv[c], wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(cv[c], wv.w, acc[4 * q + 3]);
+#pragma unroll
+                    for (int p = 0; p < EH_PX; ++p) {
+                        acc[p][4 * q] = fmaf(cv[p][c], wv.x, acc[p][4 * q]); acc[p][4 * q + 1] = fmaf(cv[p][c], wv.y, acc[p][4 * q + 1]);
+                        acc[p][4 * q + 2] = fmaf(cv[p][c], wv.z, acc[p][4 * q + 2]); acc[p][4 * q + 3] = fmaf(cv[p][c], wv.w, acc[p][4 * q + 3]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            o[(ch >> 2) + q] = make_float4(fmaxf(acc[4 * q], 0.0f), fmaxf(acc[4 * q + 1], 0.0f), fmaxf(acc[4 * q + 2], 0.0f), fmaxf(acc[4 * q + 3], 0.0f));
-    }
-    // relu(convd1(inv) + b): 7x7, zero padding 3
-    const float* win = s_inv + threadIdx.y * SW + threadIdx.x;
-    for (int ch = 0; ch < h; ch += 16) {
-        float acc[16];
+        for (int p = 0; p < EH_PX; ++p)
+            if (has[p])
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = s_b[h + ch + j];
+                for (int q = 0; q < 4; ++q)
+                    o[p][(ch >> 2) + q] = make_float4(fmaxf(acc[p][4 * q], 0.0f), fmaxf(acc[p][4 * q + 1], 0.0f), fmaxf(acc[p][4 * q + 2], 0.0f),
+                                                      fmaxf(acc[p][4 * q + 3], 0.0f));
+    }
+    // relu(convd1(inv) + b): 7x7, zero padding 3; the two pixels of a thread share a row of 8 window values
+    const float* win = s_inv + threadIdx.y * SW + threadIdx.x * EH_PX;
+    for (int ch = 0; ch < h; ch += 16) {
+        float acc[EH_PX][16];
+#pragma unroll
+        for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[p][j] = s_b[h + ch + j];
 #pragma unroll
         for (int ty = 0; ty < 7; ++ty) {
+            float v[7 + EH_PX - 1];
+#pragma unroll
+            for (int i = 0; i < 7 + EH_PX - 1; ++i) v[i] = win[ty * SW + i];
 #pragma unroll
             for (int tx = 0; tx < 7; ++tx) {
-                const float v = win[ty * SW + tx];
                 const float4* wp = reinterpret_cast<const float4*>(s_wd + (ty * 7 + tx) * h + ch);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 wv = wp[q];
-                    acc[4 * q] = fmaf(v, wv.x, acc[4 * q]); acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+#pragma unroll
+                    for (int p = 0; p < EH_PX; ++p) {
+                        acc[p][4 * q] = fmaf(v[tx + p], wv.x, acc[p][4 * q]); acc[p][4 * q + 1] = fmaf(v[tx + p], wv.y, acc[p][4 * q + 1]);
+                        acc[p][4 * q + 2] = fmaf(v[tx + p], wv.z, acc[p][4 * q + 2]); acc[p][4 * q + 3] = fmaf(v[tx + p], wv.w, acc[p][4 * q + 3]);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            o[((h + ch) >> 2) + q] = make_float4(fmaxf(acc[4 * q], 0.0f), fmaxf(acc[4 * q + 1], 0.0f), fmaxf(acc[4 * q + 2], 0.0f), fmaxf(acc[4 * q + 3], 0.0f));
+        for (int p = 0; p < EH_PX; ++p)
+            if (has[p])
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    o[p][((h + ch) >> 2) + q] = make_float4(fmaxf(acc[p][4 * q], 0.0f), fmaxf(acc[p][4 * q + 1], 0.0f), fmaxf(acc[p][4 * q + 2], 0.0f),
+                                                            fmaxf(acc[p][4 * q + 3], 0.0f));
     }
 }
 
@@ -302,8 +327,73 @@ extern "C" int effimvs_encoder_head_f32(const float* cost, const float* inv, con
     EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "encoder_head: bad sizes");
     EFFI_REQUIRE(CD >= 1 && CD <= 8 && h >= 16 && h % 16 == 0 && h <= 128, EFFIMVS_EUNSUPPORTED,
                  "encoder_head: cost channels %d must be in [1,8], hidden %d a multiple of 16 up to 128", CD, h);
-    dim3 block(effimvs::EH_TX, effimvs::EH_TY), grid(effimvs::ceil_div(W, effimvs::EH_TX), effimvs::ceil_div(H, effimvs::EH_TY), B);
-    const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX + 6) * (effimvs::EH_TY + 6)) * sizeof(float);
+    dim3 block(effimvs::EH_TX, effimvs::EH_TY), grid(effimvs::ceil_div(W, effimvs::EH_TX * effimvs::EH_PX), effimvs::ceil_div(H, effimvs::EH_TY), B);
+    const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX * effimvs::EH_PX + 6) * (effimvs::EH_TY + 6)) * sizeof(float);
     effimvs::encoder_head_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
     return effimvs::check_launch("encoder_head_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// ProjectionInput tail (upstream models/update.py:93-95): relu(convc(cat[cor_dfm, context])), a 1x1
+// convolution.  Its context half (+ both biases) does not change over the GRU iterations and arrives as
+// ctx_term; the rest is a tiny per-pixel GEMM (hm x h, hm = h - context channels) whose result is written
+// straight into the x half of the GRU's input map hx = cat[h, x] (no separate output + copy).
+// ------------------------------------------------------------------------------------------------
+namespace effimvs {
+namespace {
+
+template <int HM4>   // input channels / 4
+__global__ void __launch_bounds__(256)
+encoder_tail_kernel(const float4* __restrict__ m, const float* __restrict__ w, const float4* __restrict__ ctx_term, long long n_pix,
+                    int h, float4* __restrict__ hx) {
+    extern __shared__ __align__(16) float tsm[];   // [hm][h]: input-major so that 4 outputs are one 128-bit broadcast load
+    constexpr int HM = HM4 * 4;
+    for (int i = threadIdx.x; i < HM * h; i += blockDim.x) tsm[i] = w[(i % h) * HM + i / h];
+    __syncthreads();
+    const int h4 = h >> 2;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
+        float mv[HM];
+#pragma unroll
+        for (int q = 0; q < HM4; ++q) {
+            const float4 v = __ldg(m + p * HM4 + q);
+            mv[4 * q] = v.x; mv[4 * q + 1] = v.y; mv[4 * q + 2] = v.z; mv[4 * q + 3] = v.w;
+        }
+        for (int c4 = 0; c4 < h4; ++c4) {
+            float4 acc = __ldg(ctx_term + p * h4 + c4);
+#pragma unroll
+            for (int k = 0; k < HM; ++k) {
+                const float4 wv = *reinterpret_cast<const float4*>(tsm + k * h + c4 * 4);
+                acc.x = fmaf(mv[k], wv.x, acc.x); acc.y = fmaf(mv[k], wv.y, acc.y);
+                acc.z = fmaf(mv[k], wv.z, acc.z); acc.w = fmaf(mv[k], wv.w, acc.w);
+            }
+            hx[p * (2 * h4) + h4 + c4] = make_float4(fmaxf(acc.x, 0.0f), fmaxf(acc.y, 0.0f), fmaxf(acc.z, 0.0f), fmaxf(acc.w, 0.0f));
+        }
+    }
+}
+
+}  // namespace
+}  // namespace effimvs
+
+extern "C" int effimvs_encoder_tail_f32(const float* m, const float* w, const float* ctx_term, long long n_pix, int hm, int h,
+                                        float* hx, void* stream) {
+    using namespace effimvs;
+    EFFI_REQUIRE(m && w && ctx_term && hx, EFFIMVS_EINVAL, "encoder_tail: null pointer");
+    EFFI_REQUIRE(n_pix > 0 && h >= 4 && h % 4 == 0 && h <= 128, EFFIMVS_EINVAL, "encoder_tail: h=%d must be a multiple of 4 up to 128", h);
+    const long long blocks = (n_pix + 255) / 256;
+    const int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+    const size_t smem = (size_t)hm * h * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define EFFI_TAIL_CASE(Q)                                                                                        \
+    case Q * 4:                                                                                                  \
+        encoder_tail_kernel<Q><<<grid, 256, smem, st>>>((const float4*)m, w, (const float4*)ctx_term, n_pix, h, (float4*)hx); \
+        break;
+    switch (hm) {
+        EFFI_TAIL_CASE(2) EFFI_TAIL_CASE(3) EFFI_TAIL_CASE(4) EFFI_TAIL_CASE(5) EFFI_TAIL_CASE(6) EFFI_TAIL_CASE(7) EFFI_TAIL_CASE(8)
+        EFFI_TAIL_CASE(9) EFFI_TAIL_CASE(10) EFFI_TAIL_CASE(11) EFFI_TAIL_CASE(12)
+        default:
+            set_error("encoder_tail: input channels %d must be a multiple of 4 in [8,48]", hm);
+            return EFFIMVS_EUNSUPPORTED;
+    }
+#undef EFFI_TAIL_CASE
+    return check_launch("encoder_tail_kernel");
 }

@@ -177,6 +177,7 @@ class CudaHotPath:
     gru_delta = staticmethod(ops.gru_delta)
     convex_upsample = staticmethod(ops.convex_upsample)
     encoder_head = staticmethod(ops.encoder_head)
+    encoder_tail = staticmethod(ops.encoder_tail)
 
     # -- a11 / a12 --------------------------------------------------------------------------------
     def softmax_regress_conf(self, prob_pre, hyp):

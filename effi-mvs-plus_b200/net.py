@@ -348,7 +348,7 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
         c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
         cd = torch.cudnn_convolution_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1), (1, 1), 1)
         m = F.conv2d(cd, e.convd.weight, None, padding=1)
-        hx[:, h:] = torch.cudnn_convolution_add_relu(m, w["wc_m"], ctx_term, 1.0, None, (1, 1), (0, 0), (1, 1), 1)
+        glue.encoder_tail(m, w["wc_m"], ctx_term, hx)      # hx[:, h:] = relu(conv1x1(m) + ctx_term)
         zr_pre = F.conv2d(hx, w["wzr"], None, padding=1)
         rhx = glue.gru_reset(zr_pre, g.convr.bias, hx)
         q_pre = F.conv2d(rhx, g.convq.weight, None, padding=1)

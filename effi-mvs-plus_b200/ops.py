@@ -552,6 +552,20 @@ def _(cost, inv, wc1, bc1, wd1, bd1):
     return cost.new_empty(B, 2 * wc1.shape[0], H, W, memory_format=torch.channels_last)
 
 
+@torch.library.custom_op("effimvs::encoder_tail", mutates_args=("hx",))
+def encoder_tail(m: Tensor, w: Tensor, ctx_term: Tensor, hx: Tensor) -> None:
+    """hx[:, h:] = relu(conv1x1(m, w) + ctx_term) in place; m (B,hm,H,W), ctx_term (B,h,H,W), hx (B,2h,H,W) channels-last."""
+    m, ctx_term, w = _nhwc(m, "encoder_tail"), _nhwc(ctx_term, "encoder_tail"), _dev(w, "encoder_tail")
+    if not (hx.is_cuda and hx.dtype == torch.float32 and hx.is_contiguous(memory_format=torch.channels_last)):
+        raise RuntimeError("effimvs::encoder_tail needs hx as a channels-last fp32 CUDA tensor (it is updated in place)")
+    B, hm, H, W = m.shape
+    h = ctx_term.shape[1]
+    if hx.shape[1] != 2 * h or w.shape[0] != h or w.shape[1] != hm:
+        raise ValueError("encoder_tail: shapes do not match")
+    _count(1)
+    capi.check(_lib.effimvs_encoder_tail_f32(m.data_ptr(), w.data_ptr(), ctx_term.data_ptr(), B * H * W, hm, h, hx.data_ptr(), _stream()))
+
+
 # -------------------------------------------------------------------------------------------
 # SURVEY section 8(f) row 2: DTU geometric filter (csrc/dtu_filter.cu)
 @torch.library.custom_op("effimvs::dtu_filter", mutates_args=())

@@ -231,6 +231,12 @@ int effimvs_convex_upsample_f32(const float* mask_pre, const float* mask_bias, f
 int effimvs_encoder_head_f32(const float* cost, const float* inv, const float* wc1, const float* bc1, const float* wd1,
                              const float* bd1, int B, int CD, int h, int H, int W, float* out, void* stream);
 
+/* ProjectionInput tail (models/update.py:93-95): x = relu(Wc[:, :hm] m + ctx_term), ctx_term (n_pix, h) = the context half of
+ * convc plus both biases (constant over the GRU iterations), m (n_pix, hm) channels-last, w (h, hm) = convc.weight[:, :hm].
+ * The result is written into the x half of hx (n_pix, 2h) = cat[h, x] in place. */
+int effimvs_encoder_tail_f32(const float* m, const float* w, const float* ctx_term, long long n_pix, int hm, int h,
+                             float* hx, void* stream);
+
 /* ---- the DTU pipeline's NumPy / cv2.remap geometric filter ------------------------
  * reproject_with_depth + check_geometric_consistency + the aggregation of filter_depth
  * (test_dtu_dypcd.py:164-233, 261-309, 320-337) for one reference view in one kernel.

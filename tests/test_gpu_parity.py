@@ -658,3 +658,23 @@ def test_update_block_dropin_golden(hp):
         assert float((invs[i] - g["inv{}".format(i + 1)]).abs().max()) < 1e-4
     up = dropin.make_upsample_depth(hp)(invs[-1], masks[-1], ratio=2)
     assert float((up - g["up"]).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,ctx,H,W", [(16, 4, 37, 53), (32, 8, 24, 70), (48, 12, 19, 25)])
+def test_encoder_tail_vs_torch(h, ctx, H, W):
+    """effimvs_encoder_tail_f32 against relu(convc(cat[m + b_d, context])) of upstream's ProjectionInput (models/update.py:93-95)"""
+    import torch.nn.functional as F
+    from effimvs_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(h)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=gen)      # noqa: E731
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)   # noqa: E731
+    B, hm = 2, h - ctx
+    m, context, hprev = cl(rnd(B, hm, H, W)), cl(torch.relu(rnd(B, ctx, H, W))), cl(rnd(B, h, H, W))
+    wc, bc, bd = rnd(h, h, 1, 1) * 0.3, rnd(h), rnd(hm)
+    want = F.relu(F.conv2d(torch.cat([m + bd.reshape(1, -1, 1, 1), context], dim=1), wc, bc))
+    ctx_term = F.conv2d(context, wc[:, hm:], bc + wc[:, :hm, 0, 0] @ bd)
+    hx = cl(torch.cat([hprev, torch.zeros_like(hprev)], dim=1))
+    ops.encoder_tail(m, wc[:, :hm].contiguous(), ctx_term, hx)
+    assert torch.equal(hx[:, :h], hprev)
+    assert rel_max(hx[:, h:], want) < 1e-5

@@ -72,6 +72,13 @@ def main():
                 row = {"W": W, "H": H, "C": C, "D": D, "G": G, "views": V}
                 by = 4.0 * (V * C * H * W + D * H * W + (V - 1) * H * W + G * D * H * W)
                 row.update(ms=ms, algorithmic_MB=by / 1e6, GBs=by / ms / 1e6, frac_of_hbm_peak=by / ms / 1e6 / peak)
+                # the same call on channels-last maps (what the channels_last FPN of this repo emits): tiled TMA kernel
+                fcl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+                ms_cl, got_cl = timed(lambda: ops.warp_corr_agg(fcl[0], fcl[1:], proj, hyp, capi.HYP_TENSOR, None, wts, D, G, False)[0],
+                                      flush, 3)
+                row.update(nhwc_ms=ms_cl, nhwc_GBs=by / ms_cl / 1e6, nhwc_frac_of_hbm_peak=by / ms_cl / 1e6 / peak,
+                           nhwc_vs_nchw_rel_diff=float((got_cl - got).abs().max() / got.abs().max()))
+                del fcl, got_cl
                 # eager PyTorch reference on the same device; skip the sizes whose materialised warped volumes are huge
                 if 4.0 * C * D * H * W < 3e9:
                     def ref():
