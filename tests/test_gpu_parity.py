@@ -678,3 +678,53 @@ def test_encoder_tail_vs_torch(h, ctx, H, W):
     ops.encoder_tail(m, wc[:, :hm].contiguous(), ctx_term, hx)
     assert torch.equal(hx[:, :h], hprev)
     assert rel_max(hx[:, h:], want) < 1e-5
+
+
+# ---- size-independent properties at BASELINE's full stage sizes (no oracle needed at these sizes) -----------
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,D,H,W,G", [(8, 8, 592, 800, 1), (16, 8, 296, 400, 1), (32, 48, 148, 200, 1), (8, 16, 592, 800, 8)])
+def test_warp_corr_agg_properties_at_dtu_stage_sizes(hp, C, D, H, W, G):
+    """DTU stage shapes: (a) channels-last (tiled TMA kernel) and planar (gather kernel) agree; (b) the similarity is
+    linear in the reference features (exactly, for a power-of-two factor); (c) a source view with the reference camera
+    samples pixel centres, so every plane holds mean_c(ref * src) whatever the hypothesis; (d) with equal features and
+    weights the weighted aggregation of identical views is the single-view similarity."""
+    from effimvs_b200 import synthetic
+    feats, cams, hyp, wts = synthetic.microbench_inputs(C, D, H, W, views=5, seed=C + D, device=DEV)
+    cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    planar = hp.warp_corr_agg(feats, cams, hyp, wts, G)
+    tiled = hp.warp_corr_agg(cl, cams, hyp, wts, G)
+    assert rel_max(tiled, planar) < 1e-5                                                     # (a)
+    doubled = hp.warp_corr_agg([cl[0] * 2.0] + cl[1:], cams, hyp, wts, G)
+    assert torch.equal(doubled, tiled * 2.0)                                                 # (b)
+    same_cam = cams[:, :1].repeat(1, 5, 1, 1, 1)
+    for fs in (feats, cl):
+        ident = hp.warp_corr_agg(fs, same_cam, hyp, None, G)                                 # (c)
+        want = sum((fs[0] * fs[v]).reshape(1, G, C // G, H, W).mean(2) for v in range(1, 5)) / 4
+        # upstream's coordinate chain ((x*d + t) / (z*d + t), normalise, un-normalise) lands within ~1e-4 px of the centre at
+        # x ~ 800, i.e. a 1e-4 blend with the neighbouring pixel
+        assert rel_max(ident, want.unsqueeze(2).expand(-1, -1, D, -1, -1)) < 1e-3
+    rep = [cl[0]] + [cl[1]] * 4
+    one = hp.warp_corr_agg(rep[:2], cams[:, :2], hyp, wts[:, :1], G)
+    four = hp.warp_corr_agg(rep, cams[:, [0, 1, 1, 1, 1]], hyp, wts[:, :1].repeat(1, 4, 1, 1), G)
+    w = wts[:, :1].unsqueeze(1)
+    assert rel_max(four * (4 * w + 1e-6), one * (w + 1e-6) * 4) < 1e-5                        # (d)
+
+
+@pytest.mark.gpu
+def test_stage1_views_properties_at_dtu_size(hp):
+    """stage-1 shape (C=32, D=48, 200x148): tiled and planar per-view similarities / entropies agree; the entropy of a
+    view whose similarities do not depend on the plane is log(D) (reference camera as source)"""
+    import math
+    from effimvs_b200 import capi, ops, synthetic
+    C, D, H, W = 32, 48, 148, 200
+    feats, cams, hyp, _ = synthetic.microbench_inputs(C, D, H, W, views=5, seed=1, device=DEV)
+    feats = [f * 0.3 for f in feats]
+    cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    planes = hyp[:, :, 0, 0].contiguous()
+    proj = hp.relative_projection(cams)
+    s_p, e_p = ops.warp_corr_views(feats[0], feats[1:], proj, planes, capi.HYP_PLANES, D)
+    s_t, e_t = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
+    assert rel_max(s_t, s_p) < 1e-5 and float((e_t - e_p).abs().max()) < 1e-4
+    proj_id = hp.relative_projection(cams[:, :1].repeat(1, 5, 1, 1, 1))
+    _, e_id = ops.warp_corr_views(cl[0], cl[1:], proj_id, planes, capi.HYP_PLANES, D)
+    assert float((e_id - math.log(D)).abs().max()) < 1e-3
