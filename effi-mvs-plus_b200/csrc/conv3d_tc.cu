@@ -920,6 +920,139 @@ int run_cin1(const float* x, const float* w, const float* bias, int B, int D, in
     return check_launch("conv_cin1_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// 8 -> 1 channel layers (the `prob` convolution of the regularization FPN, the last transposed convolution of
+// cost_up_small) on CUDA cores.  With one output channel an MMA tile would spend 15 of its 16 accumulator
+// columns on padding (these layers took as long as their 8 -> 8 neighbours on the tensor pipe); as a dot
+// product of 216 terms per voxel they are a few hundred FMAs per thread.  Inputs are read from the padded c8
+// layout (halos are the zero padding, so no bounds checks), hi + lo halves are summed back to fp32 and the
+// weights stay fp32 in shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_voxel_f32(const uint4* __restrict__ hi, long long lo_delta, long long idx, float (&v)[8]) {
+    unpack_bf16x8(__ldg(hi + idx), v);
+    if (lo_delta) {
+        float l[8];
+        unpack_bf16x8(__ldg(hi + idx + lo_delta), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += l[j];
+    }
+}
+
+constexpr int COUT1_X = 4;   // consecutive outputs of a row per thread (the convolution form)
+
+// conv 8 -> 1, k3 p1 s1: w (1,8,3,3,3) fp32, out (B,1,D,H,W) fp32
+__global__ void __launch_bounds__(128)
+conv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float* __restrict__ w, const float* __restrict__ bias, int relu,
+                  float* __restrict__ out) {
+    __shared__ __align__(16) float sw[27 * 8];
+    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];   // [tap][ci]
+    __syncthreads();
+    const int b = blockIdx.y, D = IL.D, H = IL.H, W = IL.W;
+    const int Wq = (W + COUT1_X - 1) / COUT1_X;
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= (size_t)D * H * Wq) return;
+    const int x0 = (int)(o % Wq) * COUT1_X, y = (int)((o / Wq) % H), z = (int)(o / ((size_t)Wq * H));
+    const long long lo_delta = (long long)IL.lo_off * IL.vs;
+    const long long base = (long long)b * IL.batch_stride + IL.guard;   // plane 0 (hi) of batch item b
+    float acc[COUT1_X];
+#pragma unroll
+    for (int i = 0; i < COUT1_X; ++i) acc[i] = bias ? __ldg(bias) : 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb) {
+            // padded coordinates: input voxel (z + a - 1, y + bb - 1, x + c - 1) sits at (z + a, y + bb, x + c)
+            const long long row = base + (long long)(z + a) * IL.zstride + (long long)(y + bb) * IL.Px + x0;
+            float v[COUT1_X + 2][8];
+#pragma unroll
+            for (int j = 0; j < COUT1_X + 2; ++j) {
+                if (x0 + j <= W + 1) load_voxel_f32(in, lo_delta, row + j, v[j]);   // padded x up to W + 1
+                else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) v[j][c] = 0.0f;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 w0 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8 + 4);
+#pragma unroll
+                for (int i = 0; i < COUT1_X; ++i) {
+                    const float (&u)[8] = v[i + c];
+                    float t = acc[i];
+                    t = fmaf(u[0], w0.x, t); t = fmaf(u[1], w0.y, t); t = fmaf(u[2], w0.z, t); t = fmaf(u[3], w0.w, t);
+                    t = fmaf(u[4], w1.x, t); t = fmaf(u[5], w1.y, t); t = fmaf(u[6], w1.z, t); t = fmaf(u[7], w1.w, t);
+                    acc[i] = t;
+                }
+            }
+        }
+    float* op = out + (((size_t)b * D + z) * H + y) * W + x0;
+#pragma unroll
+    for (int i = 0; i < COUT1_X; ++i)
+        if (x0 + i < W) op[i] = relu ? fmaxf(acc[i], 0.0f) : acc[i];
+}
+
+// transposed conv 8 -> 1, k3, stride (1,2,2), padding 1, output_padding (0,1,1): w (8,1,3,3,3) fp32,
+// out (B,1,D,2H,2W) fp32.  A thread owns one input position and writes its 2x2 output parities:
+// out[z, 2y+py, 2x+px] = sum over a and the taps b, c of that parity (b = 1 <-> input y; b = 0 <-> y + 1; b = 2 <-> y)
+__global__ void __launch_bounds__(128)
+deconv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float* __restrict__ w, const float* __restrict__ bias, int relu,
+                    float* __restrict__ out) {
+    __shared__ __align__(16) float sw[27 * 8];
+    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];   // w[ci][0][tap] -> [tap][ci]
+    __syncthreads();
+    const int b = blockIdx.y, D = IL.D, H = IL.H, W = IL.W;
+    const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= (size_t)D * H * W) return;
+    const int x = (int)(o % W), y = (int)((o / W) % H), z = (int)(o / ((size_t)W * H));
+    const long long lo_delta = (long long)IL.lo_off * IL.vs;
+    const long long base = (long long)b * IL.batch_stride + IL.guard;
+    const float b0 = bias ? __ldg(bias) : 0.0f;
+    float acc[2][2] = {{b0, b0}, {b0, b0}};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        // out z = in z - 1 + a  ->  input plane z + 1 - a, padded index z + 2 - a
+        const long long plane = base + (long long)(z + 2 - a) * IL.zstride;
+        float v[2][2][8];   // input (y + dy, x + dx)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) load_voxel_f32(in, lo_delta, plane + (long long)(y + 1 + dy) * IL.Px + (x + 1 + dx), v[dy][dx]);
+#pragma unroll
+        for (int bb = 0; bb < 3; ++bb)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int py = bb != 1, dy = bb == 0, px = c != 1, dx = c == 0;
+                const float4 w0 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8);
+                const float4 w1 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8 + 4);
+                const float (&u)[8] = v[dy][dx];
+                float t = acc[py][px];
+                t = fmaf(u[0], w0.x, t); t = fmaf(u[1], w0.y, t); t = fmaf(u[2], w0.z, t); t = fmaf(u[3], w0.w, t);
+                t = fmaf(u[4], w1.x, t); t = fmaf(u[5], w1.y, t); t = fmaf(u[6], w1.z, t); t = fmaf(u[7], w1.w, t);
+                acc[py][px] = t;
+            }
+    }
+    const int Ho = 2 * H, Wo = 2 * W;
+#pragma unroll
+    for (int py = 0; py < 2; ++py) {
+        float2 r = make_float2(acc[py][0], acc[py][1]);
+        if (relu) { r.x = fmaxf(r.x, 0.0f); r.y = fmaxf(r.y, 0.0f); }
+        *reinterpret_cast<float2*>(out + (((size_t)b * D + z) * Ho + 2 * y + py) * Wo + 2 * x) = r;
+    }
+}
+
+int run_cout1(bool deconv, int B, const void* in, const ActLayout& IL, const float* w, const float* bias, int relu, float* out,
+              cudaStream_t st) {
+    if (deconv) {
+        const size_t work = (size_t)IL.D * IL.H * IL.W;
+        deconv_cout1_kernel<<<dim3((unsigned)((work + 127) / 128), B), 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+        return check_launch("deconv_cout1_kernel");
+    }
+    const size_t work = (size_t)IL.D * IL.H * ((IL.W + COUT1_X - 1) / COUT1_X);
+    conv_cout1_kernel<<<dim3((unsigned)((work + 127) / 128), B), 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+    return check_launch("conv_cout1_kernel");
+}
+
 struct Carver {
     char* base; size_t off, cap;
     void* take(size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; }
@@ -982,6 +1115,8 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
     if ((rc = run_tile_kernel(P[4], B, c4, L4, wp[4], biases[5], L5, c5, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[5], B, c5, L5, wp[5], biases[6], L6, c6, &L3, c3, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[6], B, c6, L6, wp[6], biases[7], L7, c7, &L1, c1, nullptr, st))) return rc;
+    // measured: the z-sweep tensor-core program (0.49 ms for the net) beats the CUDA-core form (0.52 ms) for this stride-1 layer
+    if (getenv("EFFIMVS_CUDA_CORE_PROB")) return run_cout1(false, B, c7, L7, weights[8], nullptr, 0, prob_out, st);
     return run_tile_kernel(P[7], B, c7, L7, wp[7], nullptr, L7, nullptr, nullptr, nullptr, prob_out, st);  // fp32 out, logical dims of L7
 }
 
@@ -1024,6 +1159,7 @@ int cost_up_bf16(const float* x, const float* prev, const float* const* weights,
     if ((rc = run_cin1(prev, weights[1], biases[1], B, D, H2, W2, 1, Lcat, 1, cat, st))) return rc;
     if ((rc = run_tile_kernel(P1, B, cat, Lcat, wp1, biases[2], L1, c1, nullptr, nullptr, nullptr, st))) return rc;
     ActLayout LO = make_layout(L_REG, 8, D, H, W, false);  // fp32 output indexed with the logical (full-resolution) dims
+    if (!getenv("EFFIMVS_TC_COUT1")) return run_cout1(true, B, c1, L1, weights[3], biases[3], 1, out, st);        // 8 -> 1: CUDA cores
     return run_tile_kernel(P2, B, c1, L1, wp2, biases[3], LO, nullptr, nullptr, nullptr, out, st);
 }
 
