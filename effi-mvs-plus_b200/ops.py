@@ -549,7 +549,7 @@ def encoder_head(cost: Tensor, inv: Tensor, wc1: Tensor, bc1: Tensor, wd1: Tenso
 @encoder_head.register_fake
 def _(cost, inv, wc1, bc1, wd1, bd1):
     B, _, H, W = cost.shape
-    return cost.new_empty(B, 2 * wc1.shape[0], H, W, memory_format=torch.channels_last)
+    return torch.empty((B, 2 * wc1.shape[0], H, W), device=cost.device, dtype=cost.dtype, memory_format=torch.channels_last)
 
 
 @torch.library.custom_op("effimvs::encoder_tail", mutates_args=("hx",))

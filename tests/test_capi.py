@@ -47,6 +47,18 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16X3) > lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16)
     with pytest.raises(capi.EffiMVSError):
         capi.check(capi.EWORKSPACE)
+    # section 8(f) entry points
+    assert lib.effimvs_gru_reset_f32(one, one, one, 10, 18, 16, one, None) == capi.EINVAL and "multiples of 4" in capi.last_error()
+    assert lib.effimvs_gru_update_f32(one, one, None, one, one, 10, 16, 16, one, None) == capi.EINVAL
+    assert lib.effimvs_gru_delta_f32(one, None, one, one, one, 1, 16, one, one, None) == capi.EINVAL        # pre without bias
+    assert lib.effimvs_convex_upsample_f32(one, None, 0.25, one, one, one, 1, 4, 4, 8, one, one, None) == capi.EUNSUPPORTED
+    assert "ratio=8" in capi.last_error()
+    assert lib.effimvs_encoder_head_f32(one, one, one, one, one, one, 1, 6, 20, 4, 4, one, None) == capi.EUNSUPPORTED   # hidden not a multiple of 16
+    assert lib.effimvs_encoder_tail_f32(one, one, one, 10, 10, 16, one, None) == capi.EUNSUPPORTED                      # hm not a multiple of 4
+    td, tf = (ctypes.c_double * 2)(1.0, 0.5), (ctypes.c_float * 2)(0.1, 0.2)
+    assert lib.effimvs_dtu_filter_f32(one, one, one, one, td, tf, 2, 1, 11, 0.5, 0.75, 3, 8, 8, one, None, one, one, None, None, None) == capi.EUNSUPPORTED
+    assert "non-decreasing" in capi.last_error()
+    assert lib.effimvs_dtu_filter_f32(one, one, one, one, td, tf, 2, 1, 11, 0.5, 0.75, 40, 8, 8, one, None, one, one, None, None, None) == capi.EINVAL
 
 
 def test_cpu_tensors_are_rejected_not_emulated():
@@ -58,6 +70,12 @@ def test_cpu_tensors_are_rejected_not_emulated():
 
 def test_fake_implementations_give_shapes_without_a_device():
     with torch.device("meta"):
+        zr, hx = torch.empty(2, 32, 6, 8), torch.empty(2, 32, 6, 8)
+        assert torch.ops.effimvs.gru_reset(zr, torch.empty(16), hx).shape == (2, 32, 6, 8)
+        assert torch.ops.effimvs.encoder_head(torch.empty(2, 6, 6, 8), torch.empty(2, 1, 6, 8), torch.empty(16, 6, 1, 1), torch.empty(16),
+                                              torch.empty(16, 1, 7, 7), torch.empty(16)).shape == (2, 32, 6, 8)
+        up, dep = torch.ops.effimvs.convex_upsample(torch.empty(2, 36, 6, 8), None, 0.25, torch.empty(2, 1, 6, 8), torch.empty(2), torch.empty(2), 2)
+        assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
         ref = torch.empty(2, 16, 24, 32)
         sim, hyp = torch.ops.effimvs.warp_corr_agg(ref, [ref, ref], torch.empty(2, 2, 12), torch.empty(2, 1, 24, 32), 2,
                                                    torch.empty(2), None, 8, 1, True)

@@ -728,3 +728,27 @@ def test_stage1_views_properties_at_dtu_size(hp):
     proj_id = hp.relative_projection(cams[:, :1].repeat(1, 5, 1, 1, 1))
     _, e_id = ops.warp_corr_views(cl[0], cl[1:], proj_id, planes, capi.HYP_PLANES, D)
     assert float((e_id - math.log(D)).abs().max()) < 1e-3
+
+
+@pytest.mark.gpu
+def test_scene_runner_feature_cache_on_device(hp):
+    """run_scene with the CUDA callables on a small 6-view scene: depth maps and fused point counts with the
+    per-scene feature cache + block sharding equal those of re-encoding every view"""
+    from effimvs_b200 import scene, synthetic
+    N, W, H = 6, 160, 128
+    model = dtu_model(hp, DEV, ndepths="8,4,4")
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(N, 3, H, W, generator=g).to(DEV)
+    E, K = synthetic.camera_arc(N, W, H)
+    cams = {k: v[0].to(DEV) for k, v in synthetic.stage_cameras(E, K, 1).items()}
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384, device=DEV)
+    pairs = [[(i + d) % N for d in (1, 2, N - 1, N - 2)] for i in range(N)]
+    runs = {}
+    for cache in (False, True):
+        infer, fuse = scene.cuda_scene_callables(model, imgs, cams, dv, 2.0, 6.0, 2, 0.3, feature_cache=cache)
+        runs[cache] = scene.run_scene(infer, fuse, N, pairs, 0, 1, DEV, sharding="block" if cache else "round_robin")
+    for i in range(N):
+        d0, d1 = runs[False][i][1], runs[True][i][1]
+        assert frac_within(d1, d0, 1e-3 * DEPTH_RANGE) >= 0.999
+        n0, n1 = runs[False][i][0].shape[0], runs[True][i][0].shape[0]
+        assert abs(n0 - n1) <= 0.02 * H * W
