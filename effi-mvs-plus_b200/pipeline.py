@@ -6,7 +6,7 @@ whole cascade (possible because the hot path has no host synchronisation), and o
 
     host -> device copy of sample k+1   (copy stream)
     forward of sample k                 (compute stream, one graph replay)
-    device -> host read of depth k      (compute stream, after the replay)
+    device -> host read of depth k      (read-back stream, overlapping the forward of sample k+1)
 
 so that the PCIe transfer of the 113 MB of images per sample hides behind the previous sample's
 compute.  Upstream's drivers do the same steps strictly one after the other
@@ -27,6 +27,7 @@ class _Slot:
         self.host_depth = None      # pinned host outputs
         self.host_conf = None
         self.copied = torch.cuda.Event()
+        self.computed = torch.cuda.Event()
         self.done = torch.cuda.Event()
         self.busy = False
 
@@ -39,6 +40,7 @@ class DepthMapPipeline:
         self.device = next(model.parameters()).device
         self.compute = torch.cuda.Stream(self.device)
         self.copy = torch.cuda.Stream(self.device)
+        self.readback = torch.cuda.Stream(self.device)
         self.slots: List[_Slot] = []
         self.graphed = use_graph
         self.before_replay = before_replay      # optional callable enqueued on the compute stream before each forward
@@ -94,6 +96,7 @@ class DepthMapPipeline:
             s.copied.record(self.copy)
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(s.copied)
+            self.compute.wait_event(s.done)     # the slot's previous outputs have left the device (no-op the first time)
             if self.before_replay is not None:
                 self.before_replay()
             if s.graph is not None:
@@ -101,9 +104,15 @@ class DepthMapPipeline:
             else:
                 out = self.model(s.inputs["imgs"], s.inputs["proj_matrices"], s.inputs["depth_values"])
                 s.out = (out["depth"][-1], out["photometric_confidence"])
+            s.computed.record(self.compute)
+        with torch.cuda.stream(self.readback):  # device -> host on its own stream: the next sample's forward starts at once
+            self.readback.wait_event(s.computed)
+            if s.graph is None:
+                for t in s.out:
+                    t.record_stream(self.readback)   # eager outputs come from the caching allocator
             s.host_depth.copy_(s.out[0], non_blocking=True)
             s.host_conf.copy_(s.out[1], non_blocking=True)
-            s.done.record(self.compute)
+            s.done.record(self.readback)
         s.busy = True
         self._n += 1
         return i
