@@ -282,6 +282,14 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
         out["warp_corr_agg_stage{}".format(s + 1)] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6,
                                                       "feature_layout": "NHWC" if not f[0].is_contiguous() else "NCHW",
                                                       "inputs": "current depth and view weights recorded from the bench forward"}
+        # the same launch on the depth of a smooth rendered surface (what a converged scene looks like: neighbouring
+        # lanes sample neighbouring source pixels, no shared-memory bank-conflict replays)
+        from effimvs_b200 import synthetic as _syn
+        Es, Ks = _syn.camera_ring(V, W, H)
+        smooth = _syn.render_plane_scene(Es[:1], Ks, W, H, noise=0.0)[0].to(dev).reshape(1, 1, H, W).repeat(B, 1, 1, 1)
+        ms = timed(lambda: ops.warp_corr_agg(f[0], f[1:], proj, smooth, capi.HYP_LOCAL, iv, wts, D, 1, True))
+        out["warp_corr_agg_stage{}_smooth_depth".format(s + 1)] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6,
+                                                                   "inputs": "current depth = rendered smooth surface (synthetic.render_plane_scene)"}
         noise = torch.full((B, 1, H, W), 680.0, device=dev) + 40 * torch.rand(B, 1, H, W, device=dev)
         ms = timed(lambda: ops.warp_corr_agg(f[0], f[1:], proj, noise, capi.HYP_LOCAL, iv, wts, D, 1, True))
         out["warp_corr_agg_stage{}_noise_depth".format(s + 1)] = {"ms": ms, "bytes": by, "gbs": by / ms / 1e6,

@@ -86,15 +86,82 @@ def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Seq
     return out
 
 
+class GraphedViewRunner:
+    """Depth inference of one reference view from cached feature pyramids as two CUDA graphs: `encode` (one image
+    through the FPN) and `forward` (the cascade on static feature / camera buffers).  The hot path has no host
+    synchronisation, so both capture; per view the host only issues a handful of device-to-device copies and
+    one replay instead of ~320 launches (section 8(f) row 1 + SURVEY section 8(e) "CUDA-graph the forward")."""
+
+    def __init__(self, model, imgs: torch.Tensor, cams: Dict[str, torch.Tensor], depth_values: torch.Tensor, n_src: int):
+        self.model, self.imgs, self.cams = model, imgs, cams
+        self.stages = [k for k in ("stage1", "stage2", "stage3") if k in cams]
+        V = n_src + 1
+        dev = imgs.device
+        self.cache: Dict[int, list] = {}
+        self.stream = torch.cuda.Stream(dev)
+        self.img_in = imgs[:1].reshape(1, 1, *imgs.shape[1:]).clone()
+        self.ref_in = imgs[:1].clone()
+        self.cam_in = {k: cams[k][:V].unsqueeze(0).clone() for k in self.stages}
+        self.dv = depth_values.reshape(1, -1).clone()
+        with torch.no_grad():
+            torch.cuda.synchronize(dev)
+            with torch.cuda.stream(self.stream):
+                for _ in range(2):                                        # warm-up: cuDNN autotune, lazy init, workspace sizes
+                    enc = [st[0] for st in model.encode(self.img_in)]
+                self.feat_in = [[torch.empty_like(e) for _ in range(V)] for e in enc]
+                for row, e in zip(self.feat_in, enc):
+                    for t in row:
+                        t.copy_(e)
+                for _ in range(2):
+                    model.forward_from_features(self.feat_in, self.ref_in, self.cam_in, self.dv)
+            self.stream.synchronize()
+            self.g_enc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_enc, stream=self.stream):
+                self.enc_out = [st[0] for st in model.encode(self.img_in)]
+            self.g_fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_fwd, stream=self.stream):
+                out = model.forward_from_features(self.feat_in, self.ref_in, self.cam_in, self.dv)
+            self.out = (out["depth"][-1], out["photometric_confidence"])
+
+    @torch.no_grad()
+    def encoded(self, j: int):
+        if j not in self.cache:
+            self.img_in.copy_(self.imgs[j].reshape(self.img_in.shape))
+            self.g_enc.replay()
+            self.cache[j] = [e.clone() for e in self.enc_out]
+        return self.cache[j]
+
+    @torch.no_grad()
+    def infer(self, i: int, srcs: Sequence[int]):
+        idx = [i] + list(srcs)
+        if len(idx) != len(self.feat_in[0]):
+            raise ValueError("GraphedViewRunner was captured for {} source views, got {}".format(len(self.feat_in[0]) - 1, len(srcs)))
+        with torch.cuda.stream(self.stream):
+            for v, j in enumerate(idx):
+                for s, e in enumerate(self.encoded(j)):
+                    self.feat_in[s][v].copy_(e)
+            self.ref_in.copy_(self.imgs[i:i + 1])
+            sel = torch.as_tensor(idx, device=self.imgs.device)
+            for k in self.stages:
+                self.cam_in[k].copy_(self.cams[k].index_select(0, sel).unsqueeze(0))
+            self.g_fwd.replay()
+            depth, conf = self.out[0][0].clone(), self.out[1][0].clone()
+        torch.cuda.current_stream().wait_stream(self.stream)
+        return depth, conf
+
+
 def cuda_scene_callables(model, imgs: torch.Tensor, cams: Dict[str, torch.Tensor], depth_values: torch.Tensor,
                          dist_base: float, rel_diff_base: float, thres_view: int, prob_threshold: float,
-                         feature_cache: bool = False):
+                         feature_cache: bool = False, graphed_src_views: int = 0):
     """infer / fuse callables for `run_scene` on the CUDA path.
     imgs (Nv,3,H,W) on the device; cams {"stage1".."stage4": (Nv,2,4,4)}; depth_values (Dv).
     feature_cache: encode every image once per rank and reuse its feature pyramid for each reference view
-    that lists it as a source (section 8(f) row 1; eval-mode results are those of re-encoding it)."""
+    that lists it as a source (section 8(f) row 1; eval-mode results are those of re-encoding it).
+    graphed_src_views > 0: run encode / cascade as CUDA graphs captured for that many source views (implies the
+    feature cache)."""
     from . import fusion
     cache: Dict[int, list] = {}
+    runner = GraphedViewRunner(model, imgs, cams, depth_values, graphed_src_views) if graphed_src_views > 0 else None
 
     def encoded(j):
         if j not in cache:
@@ -102,6 +169,8 @@ def cuda_scene_callables(model, imgs: torch.Tensor, cams: Dict[str, torch.Tensor
         return cache[j]
 
     def infer(i, srcs):
+        if runner is not None:
+            return runner.infer(i, srcs)
         idx = [i] + list(srcs)
         stage_cams = {k: v[idx].unsqueeze(0) for k, v in cams.items() if k != "stage4"}
         if feature_cache:

@@ -733,7 +733,8 @@ def test_stage1_views_properties_at_dtu_size(hp):
 @pytest.mark.gpu
 def test_scene_runner_feature_cache_on_device(hp):
     """run_scene with the CUDA callables on a small 6-view scene: depth maps and fused point counts with the
-    per-scene feature cache + block sharding equal those of re-encoding every view"""
+    per-scene feature cache + block sharding, eager and as CUDA graphs, equal those of re-encoding every view
+    """
     from effimvs_b200 import scene, synthetic
     N, W, H = 6, 160, 128
     model = dtu_model(hp, DEV, ndepths="8,4,4")
@@ -744,11 +745,13 @@ def test_scene_runner_feature_cache_on_device(hp):
     dv = torch.linspace(1 / 935.0, 1 / 425.0, 384, device=DEV)
     pairs = [[(i + d) % N for d in (1, 2, N - 1, N - 2)] for i in range(N)]
     runs = {}
-    for cache in (False, True):
-        infer, fuse = scene.cuda_scene_callables(model, imgs, cams, dv, 2.0, 6.0, 2, 0.3, feature_cache=cache)
-        runs[cache] = scene.run_scene(infer, fuse, N, pairs, 0, 1, DEV, sharding="block" if cache else "round_robin")
+    for mode in ("plain", "cache", "graph"):
+        infer, fuse = scene.cuda_scene_callables(model, imgs, cams, dv, 2.0, 6.0, 2, 0.3, feature_cache=mode != "plain",
+                                                 graphed_src_views=4 if mode == "graph" else 0)
+        runs[mode] = scene.run_scene(infer, fuse, N, pairs, 0, 1, DEV, sharding="round_robin" if mode == "plain" else "block")
     for i in range(N):
-        d0, d1 = runs[False][i][1], runs[True][i][1]
-        assert frac_within(d1, d0, 1e-3 * DEPTH_RANGE) >= 0.999
-        n0, n1 = runs[False][i][0].shape[0], runs[True][i][0].shape[0]
-        assert abs(n0 - n1) <= 0.02 * H * W
+        for mode in ("cache", "graph"):
+            d0, d1 = runs["plain"][i][1], runs[mode][i][1]
+            assert frac_within(d1, d0, 1e-3 * DEPTH_RANGE) >= 0.999, mode
+            n0, n1 = runs["plain"][i][0].shape[0], runs[mode][i][0].shape[0]
+            assert abs(n0 - n1) <= 0.02 * H * W, mode

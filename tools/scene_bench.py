@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--height", type=int, default=1184)
     ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--feature-cache", action="store_true", help="encode each image once per rank (block sharding)")
+    ap.add_argument("--graph", action="store_true", help="feature cache + encode / cascade replayed as CUDA graphs")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     dev = torch.device("cuda", local)
@@ -51,7 +52,9 @@ def main():
     dv = torch.linspace(1 / 935.0, 1 / 425.0, 384, device=dev)
     nb = lambda i, n: [j for d in range(1, n // 2 + 1) for j in ((i - d) % N, (i + d) % N)]      # noqa: E731
     pairs, fpairs = [nb(i, 4) for i in range(N)], [nb(i, 10) for i in range(N)]
-    infer, fuse = scene.cuda_scene_callables(model, imgs, cams, dv, 2.0, 6.0, 2, 0.3, feature_cache=a.feature_cache)
+    a.feature_cache = a.feature_cache or a.graph
+    infer, fuse = scene.cuda_scene_callables(model, imgs, cams, dv, 2.0, 6.0, 2, 0.3, feature_cache=a.feature_cache,
+                                             graphed_src_views=4 if a.graph else 0)
     sharding = "block" if a.feature_cache else "round_robin"
     with torch.no_grad():
         infer(rank % N, pairs[rank % N])            # warm-up (cuDNN autotune, lazy init)
@@ -72,8 +75,8 @@ def main():
     if rank == 0:
         print(json.dumps({"scene_views": N, "n_gpus": world, "shape": [W, H], "seconds": float(dt), "depth_maps_per_sec_incl_fusion": N / float(dt),
                           "all_gather_ms_rank0": tm.get("all_gather_ms"), "fusion_ms_rank0": tm.get("fusion_ms"),
-                          "fused_points": int(pts), "precision": a.precision, "feature_cache": a.feature_cache, "sharding": sharding,
-                          "note": "eager forward per view (no CUDA graph), 4 source views for depth, 10 for fusion"}), flush=True)
+                          "fused_points": int(pts), "precision": a.precision, "feature_cache": a.feature_cache, "cuda_graphs": a.graph, "sharding": sharding,
+                          "note": "4 source views for depth, 10 for fusion"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
