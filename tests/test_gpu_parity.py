@@ -88,6 +88,10 @@ def test_warp_corr_agg_per_pixel_hypotheses_and_edge_cases(hp, ohp):
     ok = torch.isfinite(want)
     assert ok.float().mean() > 0.99
     assert rel_max(got[ok], want[ok]) < 1e-4
+    # the same through the tiled (TMA-staged) kernel: channels-last maps, batch of 2, staged and gathered samples mixed
+    got_cl = hp.warp_corr_agg([f.contiguous(memory_format=torch.channels_last) for f in feats], cams, hyp, wts, 2)
+    assert torch.isfinite(got_cl).all()
+    assert rel_max(got_cl[ok], want[ok]) < 1e-4
 
 
 def test_local_volume_golden_and_oracle(hp, ohp):
