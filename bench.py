@@ -31,6 +31,12 @@ import torch.distributed as dist  # noqa: E402
 METRIC = "depth_maps_per_sec_1600x1184_5view"
 UNIT = "depth maps/s"
 WORKLOAD = "configs[2]: DTU eval shape 1600x1184, 5 views, full cross-scale cascade with dynamic cost volume (ndepths 48,8,8; GRU 3,3,3)"
+# non-default --shape runs are labelled as what they are (the driver's contract run uses the default DTU shape)
+LABELS = {"dtu": (METRIC, WORKLOAD),
+          "tanks": ("depth_maps_per_sec_1920x1056_7view",
+                    "configs[3]: Tanks & Temples shape 1920x1056, 7 views, full cross-scale cascade (ndepths 96,8,8; GRU 3,3,3)"),
+          "plumbing": ("depth_maps_per_sec_640x512_5view",
+                       "configs[0]: plumbing shape 640x512, 5 views, full cross-scale cascade (ndepths 48,8,8; GRU 3,3,3)")}
 
 
 def parse():
@@ -161,9 +167,10 @@ def run_reference(a, rank, world):
     value = done_k / total
     sample = "{} of {} requested steps, each one full {} depth map on {} host threads ({} warm-up; {:.0f} s cap)".format(
         done_k, a.steps, a.shape, cores, done_w, a.cpu_budget_s)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done_k,
+    metric, workload = LABELS[a.shape]
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done_k,
             "warmup": done_w, "ms_per_step": 1e3 * total / done_k, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": data, "config": {"workload": WORKLOAD, "device": "cpu"},
+            "vs_baseline": None, "dtype": "f32", "data": data, "config": {"workload": workload, "device": "cpu"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     OUT.emit(json.dumps(line))
@@ -450,12 +457,13 @@ def run_ours(a, rank, world, local_rank):
         return
     value = world * a.steps / (ms_dev / 1e3)
     e2e = world * a.steps / (ms_e2e / 1e3)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+    metric, workload = LABELS[a.shape]
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"f32": "f32", "bf16": "bf16 MMA, f32 accumulate (3-D regularization) / f32 (warp, lookup, regression)",
                       "bf16x3": "hi+lo bf16 MMA x3, f32 accumulate (3-D regularization, fp32-grade) / f32 (warp, lookup, regression)"}[a.precision],
             "data": data,
-            "config": {"workload": WORKLOAD, "shape": a.shape, "views": int(stat["imgs"].shape[1]), "ndepths": ndepths,
+            "config": {"workload": workload, "shape": a.shape, "views": int(stat["imgs"].shape[1]), "ndepths": ndepths,
                        "sharding": "one reference view per rank per step, no collective", "cuda_graph": graph is not None,
                        "l2": "256 MiB memset between steps (inside the timed region)",
                        "stock_pytorch": "FPN, ConvGRU, convex upsampling: cuDNN, TF32 allowed (torch default, as upstream)"},
