@@ -34,6 +34,13 @@
 // empty arrive comes from tcgen05.commit) and so is the TMEM accumulator (tmem_full / tmem_empty),
 // so the loads of tile k+2, the MMAs of tile k+1 and the epilogue of tile k overlap; the packed
 // weights are loaded once per CTA.
+//
+// Stride-1 layers with 8 or 16 input channels run as a z-sweep instead (build_conv_s1_zsweep): a unit is one
+// tile in 4 consecutive output planes, a load phase stages one input plane, and every staged row is multiplied
+// once against the stacked weights of the three z-taps (N = 3 x b_rows) -- a third of the MMAs and of the
+// staging.  What limits all of these layers is the ~80 clk a CTA waits per MMA of this shape (operand-fetch
+// latency; tools/tc_debug.py), which is why two resident CTAs are preferred over double buffering.
+// The 8 -> 1 transposed convolution at the end of cost_up_small runs on CUDA cores (deconv_cout1_kernel).
 #include <cuda_bf16.h>
 
 #include <algorithm>
