@@ -364,11 +364,11 @@ def run_ours(a, rank, world, local_rank):
 
     graph = None
     with torch.no_grad():
+        for _ in range(2):       # the first forward also prepares the persistent regularization workspaces
+            out = forward()
         ops.LAUNCHES = 0
         out = forward()
         launches_per_step = ops.LAUNCHES
-        for _ in range(2):
-            out = forward()
         torch.cuda.synchronize()
         if not a.no_graph:
             try:

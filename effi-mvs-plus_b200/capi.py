@@ -15,6 +15,7 @@ HYP_TENSOR, HYP_PLANES, HYP_LOCAL = 0, 1, 2
 RANGE_SCALAR, RANGE_PIXEL = 0, 1
 FEA_NCHW, FEA_NHWC = 0, 1
 PREC_F32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+WS_PREPARE, WS_RUN = 1, 2
 MAX_SRC_VIEWS = 16
 
 
@@ -54,6 +55,8 @@ SIGNATURES = {
     "effimvs_costreg_fpn3d": (_i, [_p, _pp, _pp, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "effimvs_cost_up_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "effimvs_cost_up_small": (_i, [_p, _p, _pp, _pp, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "effimvs_costreg_fpn3d_ex": (_i, [_p, _pp, _pp, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
+    "effimvs_cost_up_small_ex": (_i, [_p, _p, _pp, _pp, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p]),
     "effimvs_gru_reset_f32": (_i, [_p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_gru_update_f32": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_gru_delta_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),

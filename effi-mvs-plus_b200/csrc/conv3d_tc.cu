@@ -1083,7 +1083,7 @@ size_t costreg_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo) {
 }
 
 int costreg_bf16(const float* x, const float* const* weights, const float* const* biases, int B, int D, int H, int W, bool hilo,
-                 void* ws, size_t ws_bytes, float* prob_out, cudaStream_t st) {
+                 int phases, void* ws, size_t ws_bytes, float* prob_out, cudaStream_t st) {
     EFFI_REQUIRE(D % 4 == 0 && H % 4 == 0 && W % 4 == 0, EFFIMVS_EUNSUPPORTED, "costreg bf16: D, H, W must be multiples of 4");
     EFFI_REQUIRE(D <= 65535 && B <= 65535, EFFIMVS_EUNSUPPORTED, "costreg bf16: D or B too large");
     const int D2 = D / 2, H2 = H / 2, W2 = W / 2, D4 = D / 4, H4 = H / 4, W4 = W / 4;
@@ -1100,7 +1100,8 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
     EFFI_REQUIRE(cv.off <= ws_bytes, EFFIMVS_EWORKSPACE, "costreg bf16: workspace %zu < %zu", ws_bytes, cv.off);
     (void)act_bytes;
     int rc;
-    {   // halos and guards must read as zero
+    const bool prepare = (phases & EFFIMVS_WS_PREPARE) != 0, run = (phases & EFFIMVS_WS_RUN) != 0;
+    if (prepare) {   // halos and guards must read as zero (the layers only ever store to interior positions)
         void* bufs[8] = {c0, c7, c1, c2, c6, c3, c4, c5};
         ActLayout lays[8] = {L0, L7, L1, L2, L6, L3, L4, L5};
         if ((rc = run_zero_halo(8, bufs, lays, B, st))) return rc;
@@ -1115,7 +1116,8 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
     EFFI_REQUIRE(ok, EFFIMVS_EUNSUPPORTED, "costreg bf16: program does not fit");
     for (int i = 0; i < 8; ++i)
         EFFI_REQUIRE(program_weight_bytes(T[i]) <= W_SLOT, EFFIMVS_EUNSUPPORTED, "costreg bf16: packed weights of layer %d too large", i + 1);
-    if ((rc = run_pack_multi(8, T, weights + 1, wp, st))) return rc;
+    if (prepare && (rc = run_pack_multi(8, T, weights + 1, wp, st))) return rc;
+    if (!run) return EFFIMVS_OK;
     if ((rc = run_cin1(x, weights[0], biases[0], B, D, H, W, 1, L0, 0, c0, st))) return rc;
     if ((rc = run_tile_kernel(P[0], B, c0, L0, wp[0], biases[1], L1, c1, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[1], B, c1, L1, wp[1], biases[2], L2, c2, nullptr, nullptr, nullptr, st))) return rc;
@@ -1138,7 +1140,7 @@ size_t cost_up_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo) {
 }
 
 int cost_up_bf16(const float* x, const float* prev, const float* const* weights, const float* const* biases, int B, int D, int H,
-                 int W, bool hilo, void* ws, size_t ws_bytes, float* out, cudaStream_t st) {
+                 int W, bool hilo, int phases, void* ws, size_t ws_bytes, float* out, cudaStream_t st) {
     EFFI_REQUIRE(D <= 65535 && B <= 65535, EFFIMVS_EUNSUPPORTED, "cost_up bf16: D or B too large");
     const int H2 = H / 2, W2 = W / 2;
     ActLayout Lcat = make_layout(L_REG, 16, D, H2, W2, hilo), L1 = make_layout(L_REG, 8, D, H2, W2, hilo);
@@ -1149,7 +1151,8 @@ int cost_up_bf16(const float* x, const float* prev, const float* const* weights,
     EFFI_REQUIRE(cv.off <= ws_bytes, EFFIMVS_EWORKSPACE, "cost_up bf16: workspace %zu < %zu", ws_bytes, cv.off);
     (void)act_bytes;
     int rc;
-    {
+    const bool prepare = (phases & EFFIMVS_WS_PREPARE) != 0, run = (phases & EFFIMVS_WS_RUN) != 0;
+    if (prepare) {
         void* bufs[2] = {cat, c1};
         ActLayout lays[2] = {Lcat, L1};
         if ((rc = run_zero_halo(2, bufs, lays, B, st))) return rc;
@@ -1159,10 +1162,11 @@ int cost_up_bf16(const float* x, const float* prev, const float* const* weights,
     PackTable &T1 = T12[0], &T2 = T12[1];
     bool ok = build_conv_s1(P1, T1, 16, 8, Lcat, 1) && build_deconv(P2, T2, 8, 1, L1, 1, 1);
     EFFI_REQUIRE(ok, EFFIMVS_EUNSUPPORTED, "cost_up bf16: program does not fit");
-    {
+    if (prepare) {
         void* dsts[2] = {wp1, wp2};
         if ((rc = run_pack_multi(2, T12, weights + 2, dsts, st))) return rc;
     }
+    if (!run) return EFFIMVS_OK;
     // in a hi/lo layout the concatenated tensor has planes [conv0 hi, conv_cost hi, conv0 lo, conv_cost lo]
     if ((rc = run_cin1(x, weights[0], biases[0], B, D, H, W, 2, Lcat, 0, cat, st))) return rc;
     if ((rc = run_cin1(prev, weights[1], biases[1], B, D, H2, W2, 1, Lcat, 1, cat, st))) return rc;

@@ -15,10 +15,10 @@ int conv3d_f32(const float* x, const float* weight, const float* bias, const flo
 // bf16 tcgen05 implementations (conv3d_tc.cu)
 size_t costreg_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo);
 int costreg_bf16(const float* x, const float* const* weights, const float* const* biases, int B, int D, int H, int W,
-                 bool hilo, void* ws, size_t ws_bytes, float* prob_out, cudaStream_t st);
+                 bool hilo, int phases, void* ws, size_t ws_bytes, float* prob_out, cudaStream_t st);
 size_t cost_up_bf16_workspace_bytes(int B, int D, int H, int W, bool hilo);
 int cost_up_bf16(const float* x, const float* prev, const float* const* weights, const float* const* biases, int B,
-                 int D, int H, int W, bool hilo, void* ws, size_t ws_bytes, float* out, cudaStream_t st);
+                 int D, int H, int W, bool hilo, int phases, void* ws, size_t ws_bytes, float* out, cudaStream_t st);
 
 namespace {
 size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
@@ -39,7 +39,16 @@ extern "C" size_t effimvs_costreg_workspace_bytes(int B, int D, int H, int W, in
 extern "C" int effimvs_costreg_fpn3d(const float* x, const float* const* weights, const float* const* biases,
                                      int B, int D, int H, int W, int precision, void* workspace, size_t workspace_bytes,
                                      float* prob_out, void* stream) {
-    EFFI_REQUIRE(x && weights && biases && prob_out && workspace, EFFIMVS_EINVAL, "costreg_fpn3d: null pointer");
+    return effimvs_costreg_fpn3d_ex(x, weights, biases, B, D, H, W, precision, EFFIMVS_WS_PREPARE | EFFIMVS_WS_RUN, workspace,
+                                    workspace_bytes, prob_out, stream);
+}
+
+extern "C" int effimvs_costreg_fpn3d_ex(const float* x, const float* const* weights, const float* const* biases,
+                                        int B, int D, int H, int W, int precision, int phases, void* workspace,
+                                        size_t workspace_bytes, float* prob_out, void* stream) {
+    EFFI_REQUIRE(phases > 0 && !(phases & ~(EFFIMVS_WS_PREPARE | EFFIMVS_WS_RUN)), EFFIMVS_EINVAL, "costreg_fpn3d: phases=%d", phases);
+    const bool run = (phases & EFFIMVS_WS_RUN) != 0;
+    EFFI_REQUIRE(weights && biases && workspace && (!run || (x && prob_out)), EFFIMVS_EINVAL, "costreg_fpn3d: null pointer");
     EFFI_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, EFFIMVS_EINVAL, "costreg_fpn3d: bad sizes");
     EFFI_REQUIRE(D % 4 == 0 && H % 4 == 0 && W % 4 == 0, EFFIMVS_EUNSUPPORTED,
                  "costreg_fpn3d: D,H,W = %d,%d,%d must be multiples of 4 (two stride-2 levels)", D, H, W);
@@ -48,8 +57,9 @@ extern "C" int effimvs_costreg_fpn3d(const float* x, const float* const* weights
     EFFI_REQUIRE(workspace_bytes >= need, EFFIMVS_EWORKSPACE, "costreg_fpn3d: workspace %zu < %zu bytes", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == EFFIMVS_PREC_BF16 || precision == EFFIMVS_PREC_BF16X3)
-        return costreg_bf16(x, weights, biases, B, D, H, W, precision == EFFIMVS_PREC_BF16X3, workspace, workspace_bytes, prob_out, st);
+        return costreg_bf16(x, weights, biases, B, D, H, W, precision == EFFIMVS_PREC_BF16X3, phases, workspace, workspace_bytes, prob_out, st);
     EFFI_REQUIRE(precision == EFFIMVS_PREC_F32, EFFIMVS_EINVAL, "costreg_fpn3d: precision=%d", precision);
+    if (!run) return EFFIMVS_OK;   // nothing to prepare for the fp32 layers
 
     size_t v = (size_t)B * D * H * W;
     char* p = (char*)workspace;
@@ -84,7 +94,16 @@ extern "C" size_t effimvs_cost_up_workspace_bytes(int B, int D, int H, int W, in
 extern "C" int effimvs_cost_up_small(const float* x, const float* prev, const float* const* weights,
                                      const float* const* biases, int B, int D, int H, int W, int precision,
                                      void* workspace, size_t workspace_bytes, float* out, void* stream) {
-    EFFI_REQUIRE(x && prev && weights && biases && out && workspace, EFFIMVS_EINVAL, "cost_up_small: null pointer");
+    return effimvs_cost_up_small_ex(x, prev, weights, biases, B, D, H, W, precision, EFFIMVS_WS_PREPARE | EFFIMVS_WS_RUN, workspace,
+                                    workspace_bytes, out, stream);
+}
+
+extern "C" int effimvs_cost_up_small_ex(const float* x, const float* prev, const float* const* weights,
+                                        const float* const* biases, int B, int D, int H, int W, int precision, int phases,
+                                        void* workspace, size_t workspace_bytes, float* out, void* stream) {
+    EFFI_REQUIRE(phases > 0 && !(phases & ~(EFFIMVS_WS_PREPARE | EFFIMVS_WS_RUN)), EFFIMVS_EINVAL, "cost_up_small: phases=%d", phases);
+    const bool run = (phases & EFFIMVS_WS_RUN) != 0;
+    EFFI_REQUIRE(weights && biases && workspace && (!run || (x && prev && out)), EFFIMVS_EINVAL, "cost_up_small: null pointer");
     EFFI_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, EFFIMVS_EINVAL, "cost_up_small: bad sizes");
     EFFI_REQUIRE(H % 2 == 0 && W % 2 == 0, EFFIMVS_EUNSUPPORTED, "cost_up_small: H,W = %d,%d must be even", H, W);
     for (int i = 0; i < 4; ++i)
@@ -93,8 +112,9 @@ extern "C" int effimvs_cost_up_small(const float* x, const float* prev, const fl
     EFFI_REQUIRE(workspace_bytes >= need, EFFIMVS_EWORKSPACE, "cost_up_small: workspace %zu < %zu bytes", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == EFFIMVS_PREC_BF16 || precision == EFFIMVS_PREC_BF16X3)
-        return cost_up_bf16(x, prev, weights, biases, B, D, H, W, precision == EFFIMVS_PREC_BF16X3, workspace, workspace_bytes, out, st);
+        return cost_up_bf16(x, prev, weights, biases, B, D, H, W, precision == EFFIMVS_PREC_BF16X3, phases, workspace, workspace_bytes, out, st);
     EFFI_REQUIRE(precision == EFFIMVS_PREC_F32, EFFIMVS_EINVAL, "cost_up_small: precision=%d", precision);
+    if (!run) return EFFIMVS_OK;
 
     const int H2 = H / 2, W2 = W / 2;
     size_t v = (size_t)B * D * H2 * W2;

@@ -440,10 +440,14 @@ class EffiMVSPlus(nn.Module):
         B = imgs.shape[0]
         disp_min = depth_values[:, 0].reshape(B, 1, 1, 1)
         disp_max = depth_values[:, -1].reshape(B, 1, 1, 1)
-        depth_far, depth_near = 1.0 / disp_min, 1.0 / disp_max
+        # x.reciprocal() is what torch evaluates for 1.0 / x (followed by a multiplication by 1.0): same bits, one
+        # launch instead of two.  Everything that depends on depth_values only is formed once, here.
+        depth_far, depth_near = disp_min.reciprocal(), disp_max.reciprocal()
         unit = (disp_max - disp_min) / depth_values.size(1)
+        intervals = [unit * r for r in self.RATIOS]
 
-        lo_disp, hi_disp = 1.0 / depth_far, 1.0 / depth_near   # double reciprocal, as upstream rounds it
+        lo_disp, hi_disp = depth_far.reciprocal(), depth_near.reciprocal()   # double reciprocal, as upstream rounds it
+        inv_span = (hi_disp - lo_disp) + 1e-10                    # depth_to_disp's denominator, Effi_MVS_plus.py:151-164
 
         def to_depth(inv):                      # disp_to_depth, Effi_MVS_plus.py:138-148
             return 1.0 / (lo_disp + (hi_disp - lo_disp) * inv).clamp(min=1e-4)
@@ -464,7 +468,7 @@ class EffiMVSPlus(nn.Module):
                 D = self.ndepths[0]
                 k = torch.arange(D, device=imgs.device, dtype=imgs.dtype).reshape(1, D)
                 inv_s = disp_min.reshape(B, 1) + k * ((disp_max - disp_min).reshape(B, 1) / (D - 1))
-                hyp = (1.0 / inv_s).reshape(B, D, 1, 1).expand(B, D, H, W)   # plane sweep: stride-0 view
+                hyp = inv_s.reciprocal().reshape(B, D, 1, 1).expand(B, D, H, W)   # plane sweep: stride-0 view
                 out = hp.stage1(f, cams, hyp, self.PixelwiseNet, self.cost_regularization, self.G)
                 conf = F.interpolate(out["photometric_confidence"].unsqueeze(1), [H * 4, W * 4], mode="nearest").squeeze(1)
                 view_w = out["view_weights"]
@@ -476,17 +480,29 @@ class EffiMVSPlus(nn.Module):
                 cur_depth = preds[-1].unsqueeze(1).detach()
                 view_w = F.interpolate(view_w, scale_factor=2, mode="nearest")
                 D = self.ndepths[s]
-                loc, hyp = hp.local_volume(cur_depth, f, cams, unit * self.RATIOS[s], view_w, D, self.G)
+                loc, hyp = hp.local_volume(cur_depth, f, cams, intervals[s], view_w, D, self.G)
                 hyp_low = hyp[:, :, ::2, ::2]                 # nearest x1/2 (Effi_MVS_plus.py:514)
                 loc5 = loc.reshape(B, self.G, D, H, W)
+                # the two cross-scale branches (regularized / raw volume) are independent: the raw one runs on a side
+                # stream when the table offers one (a parallel branch of the CUDA graph under capture)
+                side = hp.side_stream(loc.device) if hasattr(hp, "side_stream") else None
+                if side is not None:
+                    main = torch.cuda.current_stream(loc.device)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        raw_prev = hp.volume_lookup(raw_vol, hyp_low, vol_near, vol_far)
+                        raw_vol = hp.cross_scale(self.CSP_C[s - 1], loc5, raw_prev.unsqueeze(1)).squeeze(1)
                 reg_prev = hp.volume_lookup(reg_vol, hyp_low, vol_near, vol_far)
-                raw_prev = hp.volume_lookup(raw_vol, hyp_low, vol_near, vol_far)
                 reg_vol = hp.cross_scale(self.CSP_R[s - 1], loc5, reg_prev.unsqueeze(1)).squeeze(1)
-                raw_vol = hp.cross_scale(self.CSP_C[s - 1], loc5, raw_prev.unsqueeze(1)).squeeze(1)
+                if side is not None:
+                    main.wait_stream(side)
+                else:
+                    raw_prev = hp.volume_lookup(raw_vol, hyp_low, vol_near, vol_far)
+                    raw_vol = hp.cross_scale(self.CSP_C[s - 1], loc5, raw_prev.unsqueeze(1)).squeeze(1)
                 vol_far, vol_near = hyp[:, 0:1], hyp[:, -1:]
 
-            inv0 = (1.0 / cur_depth - 1.0 / depth_far) / ((1.0 / depth_near - 1.0 / depth_far) + 1e-10)
-            interval = unit * self.RATIOS[s]
+            inv0 = (cur_depth.reciprocal() - lo_disp) / inv_span
+            interval = intervals[s]
 
             def cost_fn(depth, _it=0, _raw=raw_vol, _reg=reg_vol, _iv=interval, _n=vol_near, _f=vol_far):
                 return hp.dynamic_cost(depth, _raw, _reg, _iv, _n, _f, self.cost_num)

@@ -383,6 +383,89 @@ def _(x, prev, weights, biases, precision):
     return x.new_empty(x.shape)
 
 
+# ---- the same two networks against a caller-kept workspace (effimvs_*_ex: PREPARE once per weights and shape, then RUN) ----
+def costreg_workspace_bytes(B: int, D: int, H: int, W: int, precision: int) -> int:
+    return int(_lib.effimvs_costreg_workspace_bytes(B, D, H, W, precision))
+
+
+def cost_up_workspace_bytes(B: int, D: int, H: int, W: int, precision: int) -> int:
+    return int(_lib.effimvs_cost_up_workspace_bytes(B, D, H, W, precision))
+
+
+def _wsbuf(ws: Tensor, what: str) -> Tensor:
+    if not ws.is_cuda or ws.dtype != torch.uint8 or not ws.is_contiguous():
+        raise RuntimeError("effimvs::{}: the workspace must be a contiguous CUDA uint8 tensor".format(what))
+    return ws
+
+
+def _reg_args(weights, biases, nw, nb, what):
+    weights = [_dev(w, what) for w in weights]
+    biases = [_dev(b, what) for b in biases]
+    if len(weights) != nw or len(biases) != nb:
+        raise ValueError("{} wants {} weights and {} biases".format(what, nw, nb))
+    return capi.ptr_array([w.data_ptr() for w in weights]), capi.ptr_array([b.data_ptr() for b in biases])
+
+
+@torch.library.custom_op("effimvs::costreg_prepare", mutates_args=("ws",))
+def costreg_prepare(weights: List[Tensor], biases: List[Tensor], B: int, D: int, H: int, W: int, precision: int, ws: Tensor) -> None:
+    (wa, k1), (ba, k2) = _reg_args(weights, biases, 9, 8, "costreg_prepare")
+    ws = _wsbuf(ws, "costreg_prepare")
+    _count(0 if precision == capi.PREC_F32 else 2)
+    capi.check(_lib.effimvs_costreg_fpn3d_ex(None, wa, ba, B, D, H, W, precision, capi.WS_PREPARE, ws.data_ptr(), ws.numel(),
+                                             None, _stream()))
+    del k1, k2
+
+
+@torch.library.custom_op("effimvs::costreg_run", mutates_args=("ws",))
+def costreg_run(x: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int, ws: Tensor) -> Tensor:
+    """costreg_fpn3d on a workspace prepared by costreg_prepare for these weights and this shape."""
+    x, ws = _dev(x, "costreg_run"), _wsbuf(ws, "costreg_run")
+    (wa, k1), (ba, k2) = _reg_args(weights, biases, 9, 8, "costreg_run")
+    B, _, D, H, W = x.shape
+    out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
+    _count(9)
+    capi.check(_lib.effimvs_costreg_fpn3d_ex(x.data_ptr(), wa, ba, B, D, H, W, precision, capi.WS_RUN, ws.data_ptr(), ws.numel(),
+                                             out.data_ptr(), _stream()))
+    del k1, k2
+    return out
+
+
+@costreg_run.register_fake
+def _(x, weights, biases, precision, ws):
+    return x.new_empty(x.shape)
+
+
+@torch.library.custom_op("effimvs::cost_up_prepare", mutates_args=("ws",))
+def cost_up_prepare(weights: List[Tensor], biases: List[Tensor], B: int, D: int, H: int, W: int, precision: int, ws: Tensor) -> None:
+    (wa, k1), (ba, k2) = _reg_args(weights, biases, 4, 4, "cost_up_prepare")
+    ws = _wsbuf(ws, "cost_up_prepare")
+    _count(0 if precision == capi.PREC_F32 else 2)
+    capi.check(_lib.effimvs_cost_up_small_ex(None, None, wa, ba, B, D, H, W, precision, capi.WS_PREPARE, ws.data_ptr(), ws.numel(),
+                                             None, _stream()))
+    del k1, k2
+
+
+@torch.library.custom_op("effimvs::cost_up_run", mutates_args=("ws",))
+def cost_up_run(x: Tensor, prev: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int, ws: Tensor) -> Tensor:
+    """cost_up_small on a workspace prepared by cost_up_prepare for these weights and this shape."""
+    x, prev, ws = _dev(x, "cost_up_run"), _dev(prev, "cost_up_run"), _wsbuf(ws, "cost_up_run")
+    (wa, k1), (ba, k2) = _reg_args(weights, biases, 4, 4, "cost_up_run")
+    B, _, D, H, W = x.shape
+    if tuple(prev.shape) != (B, 1, D, H // 2, W // 2):
+        raise ValueError("cost_up_run: prev {} does not match x {}".format(tuple(prev.shape), tuple(x.shape)))
+    out = torch.empty(B, 1, D, H, W, device=x.device, dtype=torch.float32)
+    _count(4)
+    capi.check(_lib.effimvs_cost_up_small_ex(x.data_ptr(), prev.data_ptr(), wa, ba, B, D, H, W, precision, capi.WS_RUN, ws.data_ptr(),
+                                             ws.numel(), out.data_ptr(), _stream()))
+    del k1, k2
+    return out
+
+
+@cost_up_run.register_fake
+def _(x, prev, weights, biases, precision, ws):
+    return x.new_empty(x.shape)
+
+
 # -------------------------------------------------------------------------------------------
 @torch.library.custom_op("effimvs::fusion_reproject", mutates_args=())
 def fusion_reproject(ref_depth: Tensor, srcs_depth: Tensor, ref_cam: Tensor, srcs_cam: Tensor,

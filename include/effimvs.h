@@ -168,6 +168,23 @@ int effimvs_cost_up_small(const float* x, const float* prev, const float* const*
                           const float* const* biases, int B, int D, int H, int W, int precision,
                           void* workspace, size_t workspace_bytes, float* out, void* stream);
 
+/* The two net-level calls above, split into phases for callers that keep one workspace per network
+ * instance and shape (the tensor-core precisions; EFFIMVS_PREC_F32 has no preparation and ignores phases):
+ *   EFFIMVS_WS_PREPARE  clear the halos / guards of the padded activation volumes and pack the weights
+ *                       (hi / lo bf16 blocks) into the workspace -- depends on the weights and the shape only;
+ *   EFFIMVS_WS_RUN      the layers.  The workspace must have been prepared by this entry point with the same
+ *                       weights, shape and precision, and not written by anything else since (the layers never
+ *                       store to halo positions, so a prepared workspace stays prepared across runs).
+ * phases = PREPARE | RUN is the plain call.  x / prev / outputs may be NULL for a PREPARE-only call. */
+#define EFFIMVS_WS_PREPARE 1
+#define EFFIMVS_WS_RUN 2
+int effimvs_costreg_fpn3d_ex(const float* x, const float* const* weights, const float* const* biases,
+                             int B, int D, int H, int W, int precision, int phases, void* workspace,
+                             size_t workspace_bytes, float* prob_out, void* stream);
+int effimvs_cost_up_small_ex(const float* x, const float* prev, const float* const* weights,
+                             const float* const* biases, int B, int D, int H, int W, int precision, int phases,
+                             void* workspace, size_t workspace_bytes, float* out, void* stream);
+
 /* a13: get_reproj_dynamic (misc/fusion.py:117-154).
  *   ref_depth (n,1,h,w), srcs_depth (n,v,1,h,w), ref_cam (n,2,4,4), srcs_cam (n,v,2,4,4)
  *   -> reproj_xyd (n,v,3,h,w).  Camera inverses are taken in-kernel (fp32 adjugate/LU as

@@ -45,6 +45,14 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_costreg_fpn3d(one, arr, arr, 1, 6, 8, 8, 0, one, 1 << 30, one, None) == capi.EUNSUPPORTED   # D not a multiple of 4
     assert lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_F32) > 0
     assert lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16X3) > lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16)
+    # phased forms: unknown phase bits, RUN without data pointers, PREPARE-only accepts NULL data pointers up to the workspace check
+    assert lib.effimvs_costreg_fpn3d_ex(one, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, 4, one, 1 << 30, one, None) == capi.EINVAL
+    assert "phases" in capi.last_error()
+    assert lib.effimvs_costreg_fpn3d_ex(None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_RUN, one, 1 << 30, None, None) == capi.EINVAL
+    assert lib.effimvs_costreg_fpn3d_ex(None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_PREPARE, one, 16, None, None) == capi.EWORKSPACE
+    assert lib.effimvs_cost_up_small_ex(None, None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_PREPARE, one, 16, None, None) == capi.EWORKSPACE
+    assert lib.effimvs_cost_up_small_ex(None, None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, 0, one, 16, None, None) == capi.EINVAL
+    assert lib.effimvs_cost_up_small_ex(None, None, arr, arr, 1, 8, 8, 8, capi.PREC_F32, capi.WS_PREPARE, one, 1 << 30, None, None) == capi.OK
     with pytest.raises(capi.EffiMVSError):
         capi.check(capi.EWORKSPACE)
     # section 8(f) entry points
@@ -80,5 +88,8 @@ def test_fake_implementations_give_shapes_without_a_device():
         sim, hyp = torch.ops.effimvs.warp_corr_agg(ref, [ref, ref], torch.empty(2, 2, 12), torch.empty(2, 1, 24, 32), 2,
                                                    torch.empty(2), None, 8, 1, True)
         assert sim.shape == (2, 1, 8, 24, 32) and hyp.shape == (2, 8, 24, 32)
+        ws = torch.empty(64, dtype=torch.uint8)
+        assert torch.ops.effimvs.costreg_run(torch.empty(1, 1, 8, 8, 8), [ref] * 9, [ref] * 8, 2, ws).shape == (1, 1, 8, 8, 8)
+        assert torch.ops.effimvs.cost_up_run(torch.empty(1, 1, 8, 8, 8), torch.empty(1, 1, 8, 4, 4), [ref] * 4, [ref] * 4, 2, ws).shape == (1, 1, 8, 8, 8)
         out = torch.ops.effimvs.conv3d_bf16(torch.empty(1, 16, 4, 6, 8), torch.empty(16, 8, 3, 3, 3), None, None, 2, True, True, 2)
         assert out.shape == (1, 8, 8, 12, 16)

@@ -394,6 +394,39 @@ def test_regnets_tensor_core_vs_fp32(prec, tol):
     assert rel_max(hb.cross_scale(csp, xs, prev), hf.cross_scale(csp, xs, prev)) < tol
 
 
+def test_regnets_persistent_workspace_equals_plain_call():
+    """effimvs_*_ex phases: a workspace prepared once serves repeated runs (bit-identical to the plain
+    PREPARE | RUN call, also after other shapes were run in between and with a dirty output buffer), and a
+    change of the weights re-prepares it."""
+    from effimvs_b200 import hotpath
+    g = golden("regnets", DEV)
+    keep, plain = hotpath.CudaHotPath("bf16x3"), hotpath.CudaHotPath("bf16x3", persistent_workspaces=False)
+    assert keep.persistent_workspaces and not plain.persistent_workspaces
+    reg, csp = regnet(g, DEV), cspnet(g, DEV)
+    gen = torch.Generator().manual_seed(3)
+    x2 = torch.randn(1, 1, 48, 36, 52, generator=gen).to(DEV)
+    xs2, prev2 = torch.randn(2, 1, 8, 40, 56, generator=gen).to(DEV), torch.randn(2, 1, 8, 20, 28, generator=gen).to(DEV)
+    want = [plain.cost_regularization(reg, g["x"]), plain.cost_regularization(reg, x2),
+            plain.cross_scale(csp, g["xs"], g["prev"]), plain.cross_scale(csp, xs2, prev2)]
+    for _ in range(3):      # runs 2 and 3 reuse the prepared workspaces; shapes interleaved
+        got = [keep.cost_regularization(reg, g["x"]), keep.cost_regularization(reg, x2),
+               keep.cross_scale(csp, g["xs"], g["prev"]), keep.cross_scale(csp, xs2, prev2)]
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    assert len(keep._workspaces._store) == 4
+    # different activations through the same prepared workspace: nothing of the previous run leaks (halos stay clean)
+    x3 = torch.randn(1, 1, 48, 36, 52, generator=gen).to(DEV) * 50
+    assert torch.equal(keep.cost_regularization(reg, x3), plain.cost_regularization(reg, x3))
+    assert torch.equal(keep.cost_regularization(reg, x2), want[1])
+    # new weights (in-place update bumps the version -> new fold -> new stamp -> PREPARE again)
+    with torch.no_grad():
+        reg.conv1.conv.weight.mul_(1.25)
+        csp.conv1.conv.weight.mul_(0.75)
+    assert torch.equal(keep.cost_regularization(reg, x2), plain.cost_regularization(reg, x2))
+    assert not torch.equal(keep.cost_regularization(reg, x2), want[1])
+    assert torch.equal(keep.cross_scale(csp, xs2, prev2), plain.cross_scale(csp, xs2, prev2))
+
+
 def test_model_forward_tensor_core_tanks_shape():
     """7 views, 96 stage-1 planes through the tcgen05 (bf16x3) regularization against the fp32 CUDA-core nets."""
     from effimvs_b200 import hotpath, synthetic
@@ -686,7 +719,8 @@ def test_encoder_tail_vs_torch(h, ctx, H, W):
 
 # ---- size-independent properties at BASELINE's full stage sizes (no oracle needed at these sizes) -----------
 @pytest.mark.gpu
-@pytest.mark.parametrize("C,D,H,W,G", [(8, 8, 592, 800, 1), (16, 8, 296, 400, 1), (32, 48, 148, 200, 1), (8, 16, 592, 800, 8)])
+@pytest.mark.parametrize("C,D,H,W,G", [(8, 8, 592, 800, 1), (16, 8, 296, 400, 1), (32, 48, 148, 200, 1), (8, 16, 592, 800, 8),
+                                       (32, 8, 296, 400, 8), (16, 16, 592, 800, 4)])
 def test_warp_corr_agg_properties_at_dtu_stage_sizes(hp, C, D, H, W, G):
     """DTU stage shapes: (a) channels-last (tiled TMA kernel) and planar (gather kernel) agree; (b) the similarity is
     linear in the reference features (exactly, for a power-of-two factor); (c) a source view with the reference camera

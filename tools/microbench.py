@@ -42,6 +42,8 @@ def timed(fn, flush, reps, warm=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of WxH:C:D points, e.g. 800x592:32:8,1600x1184:32:16")
+    ap.add_argument("--no-ref", action="store_true", help="skip the eager PyTorch composition")
     a = ap.parse_args()
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -57,39 +59,42 @@ def main():
     grid = [(C, D) for C in (8, 16, 32) for D in (8, 16, 32, 48)]
     if a.quick:
         sizes, grid = [(200, 148), (800, 592)], [(8, 8), (32, 48)]
+    points = [(W, H, C, D) for (W, H) in sizes for (C, D) in grid]
+    if a.only:
+        points = [(int(wh.split("x")[0]), int(wh.split("x")[1]), int(c), int(d))
+                  for wh, c, d in (p.split(":") for p in a.only.split(","))]
     rows = []
     G, V = 8, 5
     with torch.no_grad():
-        for (W, H) in sizes:
-            for (C, D) in grid:
-                out_bytes = 4.0 * G * D * H * W
-                if out_bytes > 6e9:
-                    continue
-                feats, cams, hyp, wts = synthetic.microbench_inputs(C, D, H, W, views=V, seed=C + D, device=dev)
-                proj = hp.relative_projection(cams)          # 4x4 algebra once, outside the timed kernel
-                ms, got = timed(lambda: ops.warp_corr_agg(feats[0], feats[1:], proj, hyp, capi.HYP_TENSOR, None, wts, D, G, False)[0],
-                                flush, 3)
-                row = {"W": W, "H": H, "C": C, "D": D, "G": G, "views": V}
-                by = 4.0 * (V * C * H * W + D * H * W + (V - 1) * H * W + G * D * H * W)
-                row.update(ms=ms, algorithmic_MB=by / 1e6, GBs=by / ms / 1e6, frac_of_hbm_peak=by / ms / 1e6 / peak)
-                # the same call on channels-last maps (what the channels_last FPN of this repo emits): tiled TMA kernel
-                fcl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
-                ms_cl, got_cl = timed(lambda: ops.warp_corr_agg(fcl[0], fcl[1:], proj, hyp, capi.HYP_TENSOR, None, wts, D, G, False)[0],
-                                      flush, 3)
-                row.update(nhwc_ms=ms_cl, nhwc_GBs=by / ms_cl / 1e6, nhwc_frac_of_hbm_peak=by / ms_cl / 1e6 / peak,
-                           nhwc_vs_nchw_rel_diff=float((got_cl - got).abs().max() / got.abs().max()))
-                del fcl, got_cl
-                # eager PyTorch reference on the same device; skip the sizes whose materialised warped volumes are huge
-                if 4.0 * C * D * H * W < 3e9:
-                    def ref():
-                        sims = [ohp.view_similarity(feats[0], feats[v], cams[:, 0], cams[:, v], hyp, G) for v in range(1, V)]
-                        return ohp.weighted_aggregate(sims, [wts[:, i:i + 1] for i in range(V - 1)])
-                    rms, want = timed(ref, flush, 1)
-                    row.update(ref_eager_ms=rms, ref_GBs=by / rms / 1e6, speedup_vs_eager=rms / ms,
-                               rel_max_diff=float((got - want).abs().max() / want.abs().max()))
-                    del want
-                rows.append(row)
-                del feats, hyp, wts, got
+        for (W, H, C, D) in points:
+            out_bytes = 4.0 * G * D * H * W
+            if out_bytes > 6e9:
+                continue
+            feats, cams, hyp, wts = synthetic.microbench_inputs(C, D, H, W, views=V, seed=C + D, device=dev)
+            proj = hp.relative_projection(cams)          # 4x4 algebra once, outside the timed kernel
+            ms, got = timed(lambda: ops.warp_corr_agg(feats[0], feats[1:], proj, hyp, capi.HYP_TENSOR, None, wts, D, G, False)[0],
+                            flush, 3)
+            row = {"W": W, "H": H, "C": C, "D": D, "G": G, "views": V}
+            by = 4.0 * (V * C * H * W + D * H * W + (V - 1) * H * W + G * D * H * W)
+            row.update(ms=ms, algorithmic_MB=by / 1e6, GBs=by / ms / 1e6, frac_of_hbm_peak=by / ms / 1e6 / peak)
+            # the same call on channels-last maps (what the channels_last FPN of this repo emits): tiled TMA kernel
+            fcl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+            ms_cl, got_cl = timed(lambda: ops.warp_corr_agg(fcl[0], fcl[1:], proj, hyp, capi.HYP_TENSOR, None, wts, D, G, False)[0],
+                                  flush, 3)
+            row.update(nhwc_ms=ms_cl, nhwc_GBs=by / ms_cl / 1e6, nhwc_frac_of_hbm_peak=by / ms_cl / 1e6 / peak,
+                       nhwc_vs_nchw_rel_diff=float((got_cl - got).abs().max() / got.abs().max()))
+            del fcl, got_cl
+            # eager PyTorch reference on the same device; skip the sizes whose materialised warped volumes are huge
+            if 4.0 * C * D * H * W < 3e9 and not a.no_ref:
+                def ref():
+                    sims = [ohp.view_similarity(feats[0], feats[v], cams[:, 0], cams[:, v], hyp, G) for v in range(1, V)]
+                    return ohp.weighted_aggregate(sims, [wts[:, i:i + 1] for i in range(V - 1)])
+                rms, want = timed(ref, flush, 1)
+                row.update(ref_eager_ms=rms, ref_GBs=by / rms / 1e6, speedup_vs_eager=rms / ms,
+                           rel_max_diff=float((got - want).abs().max() / want.abs().max()))
+                del want
+            rows.append(row)
+            del feats, hyp, wts, got
     print(json.dumps({"config": "BASELINE.json configs[1]", "hbm_peak_GBs": peak, "peak_source": src, "rows": rows}, indent=1))
 
 
