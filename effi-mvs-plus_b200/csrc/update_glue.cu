@@ -193,6 +193,101 @@ extern "C" int effimvs_gru_delta_f32(const float* pre, const float* bias, const 
     return check_launch("gru_delta_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// DepthHead.conv2 (hidden -> 1, 3x3, zero padding; upstream models/update.py:19-27) fused with the step above:
+// a one-channel convolution is 9 * h multiply-adds per pixel -- a stream over the hidden map, not a GEMM (one
+// output channel would leave 15 of 16 accumulator columns of an MMA tile idle, and cuDNN pays an NHWC -> NCHW
+// conversion kernel for the single-channel result).  Four lanes share a pixel column (lane q owns channel quads
+// q, q+4, ...), a thread sweeps DH_ROWS output rows so that each input row is loaded once for the three rows it
+// contributes to, the four partial sums are reduced with two shuffles and lane q finishes row q:
+// inv' = inv + tanh(conv + bias), depth = disp_to_depth(inv').
+// ------------------------------------------------------------------------------------------------
+namespace effimvs {
+namespace {
+
+constexpr int DH_ROWS = 4, DH_COLS = 64;   // output tile of a 256-thread block: 64 columns x 4 rows
+
+template <int J>   // hidden channels / 16
+__global__ void __launch_bounds__(256)
+delta_head_kernel(const float4* __restrict__ t, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ inv,
+                  const float* __restrict__ lo, const float* __restrict__ hi, int H, int W, float* __restrict__ inv_out,
+                  float* __restrict__ depth_out) {
+    constexpr int h = 16 * J, h4 = 4 * J;
+    __shared__ float4 s_w[9 * h4];                       // [tap][channel quad]
+    float* s_wf = reinterpret_cast<float*>(s_w);
+    for (int i = threadIdx.x; i < 9 * h; i += blockDim.x) s_wf[i] = w[(i % h) * 9 + i / h];   // weight (1, h, 3, 3)
+    __syncthreads();
+    const int q = threadIdx.x & 3;
+    const int px = blockIdx.x * DH_COLS + (threadIdx.x >> 2), y0 = blockIdx.y * DH_ROWS, b = blockIdx.z;
+    float acc[DH_ROWS];
+#pragma unroll
+    for (int o = 0; o < DH_ROWS; ++o) acc[o] = 0.0f;
+    if (px < W) {
+#pragma unroll
+        for (int r = -1; r <= DH_ROWS; ++r) {
+            const int yy = y0 + r;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = px + kx - 1;
+                if (xx < 0 || xx >= W) continue;
+                const float4* base = t + (((size_t)b * H + yy) * W + xx) * h4 + q;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const float4 v = __ldg(base + 4 * j);
+#pragma unroll
+                    for (int o = 0; o < DH_ROWS; ++o) {
+                        const int ky = r - o + 1;
+                        if (ky < 0 || ky > 2) continue;
+                        const float4 wv = s_w[(ky * 3 + kx) * h4 + 4 * j + q];
+                        acc[o] = fmaf(v.x, wv.x, acc[o]); acc[o] = fmaf(v.y, wv.y, acc[o]);
+                        acc[o] = fmaf(v.z, wv.z, acc[o]); acc[o] = fmaf(v.w, wv.w, acc[o]);
+                    }
+                }
+            }
+        }
+    }
+    float mine = 0.0f;
+#pragma unroll
+    for (int o = 0; o < DH_ROWS; ++o) {
+        float a = acc[o];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        if (o == q) mine = a;
+    }
+    const int y = y0 + q;
+    if (px >= W || y >= H) return;
+    const size_t o = ((size_t)b * H + y) * W + px;
+    const float v = __fadd_rn(__ldg(inv + o), tanhf(__fadd_rn(mine, __ldg(bias))));
+    inv_out[o] = v;
+    depth_out[o] = to_depth(v, __ldg(lo + b), __ldg(hi + b));
+}
+
+}  // namespace
+}  // namespace effimvs
+
+extern "C" int effimvs_delta_head_f32(const float* t, const float* weight, const float* bias, const float* inv, const float* lo_disp,
+                                      const float* hi_disp, int B, int h, int H, int W, float* inv_out, float* depth_out, void* stream) {
+    using namespace effimvs;
+    EFFI_REQUIRE(t && weight && bias && inv && lo_disp && hi_disp && inv_out && depth_out, EFFIMVS_EINVAL, "delta_head: null pointer");
+    EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "delta_head: bad sizes");
+    dim3 grid(ceil_div(W, DH_COLS), ceil_div(H, DH_ROWS), B);
+    EFFI_REQUIRE(grid.y <= 65535, EFFIMVS_EUNSUPPORTED, "delta_head: H=%d too large", H);
+    cudaStream_t st = (cudaStream_t)stream;
+#define EFFI_DH_CASE(JJ)                                                                                                     \
+    case 16 * JJ:                                                                                                            \
+        delta_head_kernel<JJ><<<grid, 256, 0, st>>>((const float4*)t, weight, bias, inv, lo_disp, hi_disp, H, W, inv_out, depth_out); \
+        break;
+    switch (h) {
+        EFFI_DH_CASE(1) EFFI_DH_CASE(2) EFFI_DH_CASE(3) EFFI_DH_CASE(4) EFFI_DH_CASE(6) EFFI_DH_CASE(8)
+        default:
+            set_error("delta_head: hidden channels %d not in {16,32,48,64,96,128}", h);
+            return EFFIMVS_EUNSUPPORTED;
+    }
+#undef EFFI_DH_CASE
+    return check_launch("delta_head_kernel");
+}
+
 extern "C" int effimvs_convex_upsample_f32(const float* mask_pre, const float* mask_bias, float mask_scale, const float* inv,
                                            const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio, float* up_out,
                                            float* depth_out, void* stream) {

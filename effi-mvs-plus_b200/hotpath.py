@@ -236,6 +236,7 @@ class CudaHotPath:
     gru_reset = staticmethod(ops.gru_reset)
     gru_update = staticmethod(ops.gru_update)
     gru_delta = staticmethod(ops.gru_delta)
+    delta_head = staticmethod(ops.delta_head)
     convex_upsample = staticmethod(ops.convex_upsample)
     encoder_head = staticmethod(ops.encoder_head)
     encoder_tail = staticmethod(ops.encoder_tail)

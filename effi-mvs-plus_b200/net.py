@@ -344,6 +344,8 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
     ctx_term = F.conv2d(context, w["wc_ctx"], w["bias_c"])
     inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
     inv_seq, depth_seq = [], []
+    head_fused = (hasattr(glue, "delta_head") and h % 16 == 0 and h <= 128 and tuple(hd.conv2.weight.shape) == (1, h, 3, 3)
+                  and os.environ.get("EFFIMVS_DELTA_HEAD", "1") != "0")
     for it in range(iters):
         c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
         cd = torch.cudnn_convolution_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1), (1, 1), 1)
@@ -353,8 +355,11 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
         rhx = glue.gru_reset(zr_pre, g.convr.bias, hx)
         q_pre = F.conv2d(rhx, g.convq.weight, None, padding=1)
         net = glue.gru_update(zr_pre, g.convz.bias, q_pre, g.convq.bias, hx)
-        pre = F.conv2d(_conv_relu_mod(hd.conv1, net), hd.conv2.weight, None, padding=1)
-        inv, depth = glue.gru_delta(pre, hd.conv2.bias, inv, lo_disp, hi_disp)
+        if head_fused:     # depth_head.conv2 (h -> 1) + tanh + step + disp_to_depth: one streaming kernel
+            inv, depth = glue.delta_head(_conv_relu_mod(hd.conv1, net), hd.conv2.weight, hd.conv2.bias, inv, lo_disp, hi_disp)
+        else:
+            pre = F.conv2d(_conv_relu_mod(hd.conv1, net), hd.conv2.weight, None, padding=1)
+            inv, depth = glue.gru_delta(pre, hd.conv2.bias, inv, lo_disp, hi_disp)
         inv_seq.append(inv)
         depth_seq.append(depth)
     mask_pre = F.conv2d(_conv_relu_mod(block.mask[0], net), block.mask[2].weight, None)

@@ -592,6 +592,27 @@ def _(pre, bias, inv, lo_disp, hi_disp):
     return torch.empty_like(inv), torch.empty_like(inv)
 
 
+@torch.library.custom_op("effimvs::delta_head", mutates_args=())
+def delta_head(t: Tensor, weight: Tensor, bias: Tensor, inv: Tensor, lo_disp: Tensor, hi_disp: Tensor) -> Tuple[Tensor, Tensor]:
+    """t (B,h,H,W) = relu(depth_head.conv1(net)), weight (1,h,3,3), bias (1): inv' = inv + tanh(conv3x3(t) + bias) and
+    depth = 1 / clamp(lo + (hi - lo) * inv', 1e-4), both (B,1,H,W) -- depth_head.conv2 and gru_delta in one pass."""
+    t, weight, bias = _nhwc(t, "delta_head"), _dev(weight, "delta_head"), _dev(bias, "delta_head")
+    inv, lo_disp, hi_disp = _dev(inv, "delta_head"), _dev(lo_disp, "delta_head"), _dev(hi_disp, "delta_head")
+    B, h, H, W = t.shape
+    if tuple(weight.shape) != (1, h, 3, 3) or inv.numel() != B * H * W:
+        raise ValueError("delta_head: weight {} / inv {} do not match t {}".format(tuple(weight.shape), tuple(inv.shape), tuple(t.shape)))
+    inv_out, depth = torch.empty_like(inv), torch.empty_like(inv)
+    _count(1)
+    capi.check(_lib.effimvs_delta_head_f32(t.data_ptr(), weight.data_ptr(), bias.data_ptr(), inv.data_ptr(), lo_disp.data_ptr(),
+                                           hi_disp.data_ptr(), B, h, H, W, inv_out.data_ptr(), depth.data_ptr(), _stream()))
+    return inv_out, depth
+
+
+@delta_head.register_fake
+def _(t, weight, bias, inv, lo_disp, hi_disp):
+    return torch.empty_like(inv), torch.empty_like(inv)
+
+
 @torch.library.custom_op("effimvs::convex_upsample", mutates_args=())
 def convex_upsample(mask_pre: Tensor, mask_bias: Optional[Tensor], mask_scale: float, inv: Tensor, lo_disp: Tensor,
                     hi_disp: Tensor, ratio: int) -> Tuple[Tensor, Tensor]:

@@ -235,6 +235,13 @@ int effimvs_gru_update_f32(const float* zr_pre, const float* bias_z, const float
 int effimvs_gru_delta_f32(const float* pre, const float* bias, const float* inv, const float* lo_disp, const float* hi_disp,
                           int B, int HW, float* inv_out, float* depth_out, void* stream);
 
+/* DepthHead.conv2 + the step above in one pass (models/update.py:19-27, 121-125; models/Effi_MVS_plus.py:138-148):
+ * t (B,H,W,h) channels-last = relu(depth_head.conv1(net)), weight (1,h,3,3), bias (1), inv (B,H,W), lo_disp / hi_disp (B)
+ *   -> inv_out = inv + tanh(conv3x3(t, weight; zero padding 1) + bias), depth_out = disp_to_depth(inv_out).
+ * h in {16,32,48,64,96,128}. */
+int effimvs_delta_head_f32(const float* t, const float* weight, const float* bias, const float* inv, const float* lo_disp,
+                           const float* hi_disp, int B, int h, int H, int W, float* inv_out, float* depth_out, void* stream);
+
 /* upsample_depth (models/Effi_MVS_plus.py:167-178) on mask = mask_scale * (mask_pre + mask_bias) (models/update.py:128),
  * mask_pre (B,H,W,9*ratio^2) channels-last conv output without bias, inv (B,H,W)
  *   -> up_out (B,ratio*H,ratio*W) (optional) and depth_out = disp_to_depth(up) (optional).  ratio = 2. */

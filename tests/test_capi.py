@@ -59,6 +59,9 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_gru_reset_f32(one, one, one, 10, 18, 16, one, None) == capi.EINVAL and "multiples of 4" in capi.last_error()
     assert lib.effimvs_gru_update_f32(one, one, None, one, one, 10, 16, 16, one, None) == capi.EINVAL
     assert lib.effimvs_gru_delta_f32(one, None, one, one, one, 1, 16, one, one, None) == capi.EINVAL        # pre without bias
+    assert lib.effimvs_delta_head_f32(one, one, one, one, one, one, 1, 24, 8, 8, one, one, None) == capi.EUNSUPPORTED
+    assert "hidden channels 24" in capi.last_error()
+    assert lib.effimvs_delta_head_f32(one, one, None, one, one, one, 1, 16, 8, 8, one, one, None) == capi.EINVAL
     assert lib.effimvs_convex_upsample_f32(one, None, 0.25, one, one, one, 1, 4, 4, 8, one, one, None) == capi.EUNSUPPORTED
     assert "ratio=8" in capi.last_error()
     assert lib.effimvs_encoder_head_f32(one, one, one, one, one, one, 1, 6, 20, 4, 4, one, None) == capi.EUNSUPPORTED   # hidden not a multiple of 16
@@ -82,6 +85,9 @@ def test_fake_implementations_give_shapes_without_a_device():
         assert torch.ops.effimvs.gru_reset(zr, torch.empty(16), hx).shape == (2, 32, 6, 8)
         assert torch.ops.effimvs.encoder_head(torch.empty(2, 6, 6, 8), torch.empty(2, 1, 6, 8), torch.empty(16, 6, 1, 1), torch.empty(16),
                                               torch.empty(16, 1, 7, 7), torch.empty(16)).shape == (2, 32, 6, 8)
+        iv, dp = torch.ops.effimvs.delta_head(torch.empty(2, 16, 6, 8), torch.empty(1, 16, 3, 3), torch.empty(1), torch.empty(2, 1, 6, 8),
+                                              torch.empty(2), torch.empty(2))
+        assert iv.shape == (2, 1, 6, 8) and dp.shape == (2, 1, 6, 8)
         up, dep = torch.ops.effimvs.convex_upsample(torch.empty(2, 36, 6, 8), None, 0.25, torch.empty(2, 1, 6, 8), torch.empty(2), torch.empty(2), 2)
         assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
         ref = torch.empty(2, 16, 24, 32)

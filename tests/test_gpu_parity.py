@@ -524,6 +524,31 @@ def test_vis_filter_dynamic_dropin_golden(tag):
 
 # ---- update-block glue kernels ------------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.parametrize("h,B,H,W", [(16, 2, 37, 70), (32, 1, 24, 129), (48, 2, 19, 25), (16, 1, 3, 2), (64, 1, 9, 66)])
+def test_delta_head_vs_torch(h, B, H, W):
+    """DepthHead.conv2 + tanh + inverse-depth step + disp_to_depth in one kernel against the torch chain
+    (upstream models/update.py:19-27, 121-125; Effi_MVS_plus.py:138-148): zero padding at every border, tile edges
+    (64-column x 4-row blocks), planar and channels-last inputs."""
+    import torch.nn.functional as F
+    from effimvs_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(h + W)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=gen)      # noqa: E731
+    t, w, bias = torch.relu(rnd(B, h, H, W)), rnd(1, h, 3, 3) * 0.1, rnd(1) * 0.1
+    inv = torch.rand(B, 1, H, W, device=DEV, generator=gen)
+    lo, hi = torch.full((B,), 1 / 935.0, device=DEV), torch.full((B,), 1 / 425.0, device=DEV)
+    hi[-1] = 1 / 300.0
+    want_inv = inv + torch.tanh(F.conv2d(t, w, bias, padding=1))
+    want_depth = 1.0 / (lo.reshape(B, 1, 1, 1) + (hi - lo).reshape(B, 1, 1, 1) * want_inv).clamp(min=1e-4)
+    for tt in (t, t.contiguous(memory_format=torch.channels_last)):
+        got_inv, got_depth = ops.delta_head(tt, w, bias, inv, lo, hi)
+        assert got_inv.shape == inv.shape and got_depth.shape == inv.shape
+        assert float((got_inv - want_inv).abs().max()) < 2e-5
+        assert rel_max(got_depth, want_depth) < 2e-5
+    with pytest.raises(Exception):
+        ops.delta_head(torch.relu(rnd(1, 24, 8, 8)), rnd(1, 24, 3, 3), bias, torch.rand(1, 1, 8, 8, device=DEV), lo[:1], hi[:1])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("h,H,W", [(16, 37, 53), (32, 24, 40), (48, 19, 25)])
 def test_update_glue_kernels_vs_torch(h, H, W):
     """each glue kernel against the torch elementwise chain it replaces (upstream models/update.py:41-48, 27,
