@@ -62,8 +62,11 @@ SIGNATURES = {
     "effimvs_gru_delta_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "effimvs_delta_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_convex_upsample_f32": (_i, [_p, _p, _f, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "effimvs_convex_upsample_conv_f32": (_i, [_p, _i, _p, _p, _f, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_encoder_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "effimvs_encoder_tail_f32": (_i, [_p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
+    "effimvs_encoder_tail_ctx_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, C.c_longlong, _i, _i, _p, _p]),
+    "effimvs_gru_init_f32": (_i, [_p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_dtu_filter_f32": (_i, [_p, _p, _p, _p, C.POINTER(C.c_double), C.POINTER(C.c_float), _i, _i, _i, _f, _f, _i, _i, _i,
                                     _p, _p, _p, _p, _p, _p, _p]),
     "effimvs_fusion_reproject_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),

@@ -94,14 +94,19 @@ gru_delta_kernel(const float* __restrict__ pre, const float* __restrict__ bias, 
 
 // upsample_depth with ratio R (2): mask (B,H,W,9*R*R) = scale * (mask_pre + bias), channel = (k*R + ry)*R + rx;
 // softmax over the 9 neighbours k, weighted sum of the zero-padded 3x3 neighbourhood of inv.
-template <int R>
+// CONV: mask_pre is not given; the kernel forms it from t (B,H,W,K) = relu(mask[0](net)) and mask[2].weight (CH, K) -- a
+// per-pixel K x CH product against weights held in shared memory -- so the CH-channel mask map is never written or read.
+template <int R, bool CONV>
 __global__ void __launch_bounds__(128)
-convex_upsample_kernel(const float* __restrict__ mask_pre, const float* __restrict__ mask_bias, float scale, const float* __restrict__ inv,
-                       const float* __restrict__ lo, const float* __restrict__ hi, int H, int W, float* __restrict__ up_out,
-                       float* __restrict__ depth_out) {
+convex_upsample_kernel(const float* __restrict__ mask_pre, const float* __restrict__ mask_w, int K, const float* __restrict__ mask_bias,
+                       float scale, const float* __restrict__ inv, const float* __restrict__ lo, const float* __restrict__ hi, int H, int W,
+                       float* __restrict__ up_out, float* __restrict__ depth_out) {
     constexpr int CH = 9 * R * R;
     __shared__ float sb[CH];
+    extern __shared__ __align__(16) float s_mw[];        // CONV: [K][CH]
     for (int i = threadIdx.x; i < CH; i += blockDim.x) sb[i] = mask_bias ? mask_bias[i] : 0.0f;
+    if (CONV)
+        for (int i = threadIdx.x; i < K * CH; i += blockDim.x) s_mw[i] = mask_w[(i % CH) * K + i / CH];
     __syncthreads();
     const int b = blockIdx.y;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,12 +120,32 @@ convex_upsample_kernel(const float* __restrict__ mask_pre, const float* __restri
         const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
         nb[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ib + (size_t)yy * W + xx) : 0.0f;
     }
-    const float4* mp = reinterpret_cast<const float4*>(mask_pre + ((size_t)b * H * W + pix) * CH);
     float m[CH];
+    if (CONV) {
+        const float4* tp = reinterpret_cast<const float4*>(mask_pre + ((size_t)b * H * W + pix) * K);
 #pragma unroll
-    for (int q = 0; q < CH / 4; ++q) {
-        const float4 v = __ldg(mp + q);
-        m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+        for (int c = 0; c < CH; ++c) m[c] = 0.0f;
+        for (int k4 = 0; k4 < (K >> 2); ++k4) {
+            const float4 v = __ldg(tp + k4);
+            const float tv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4* wr = reinterpret_cast<const float4*>(s_mw + (4 * k4 + j) * CH);
+#pragma unroll
+                for (int q = 0; q < CH / 4; ++q) {
+                    const float4 wv = wr[q];
+                    m[4 * q] = fmaf(tv[j], wv.x, m[4 * q]); m[4 * q + 1] = fmaf(tv[j], wv.y, m[4 * q + 1]);
+                    m[4 * q + 2] = fmaf(tv[j], wv.z, m[4 * q + 2]); m[4 * q + 3] = fmaf(tv[j], wv.w, m[4 * q + 3]);
+                }
+            }
+        }
+    } else {
+        const float4* mp = reinterpret_cast<const float4*>(mask_pre + ((size_t)b * H * W + pix) * CH);
+#pragma unroll
+        for (int q = 0; q < CH / 4; ++q) {
+            const float4 v = __ldg(mp + q);
+            m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+        }
     }
 #pragma unroll
     for (int c = 0; c < CH; ++c) m[c] = __fmul_rn(scale, __fadd_rn(m[c], sb[c]));
@@ -295,8 +320,22 @@ extern "C" int effimvs_convex_upsample_f32(const float* mask_pre, const float* m
     EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "convex_upsample: bad sizes");
     EFFI_REQUIRE(ratio == 2, EFFIMVS_EUNSUPPORTED, "convex_upsample: ratio=%d (only 2, the value upstream uses, is built)", ratio);
     dim3 grid(ceil_div(H * W, 128), B);
-    convex_upsample_kernel<2><<<grid, 128, 0, (cudaStream_t)stream>>>(mask_pre, mask_bias, mask_scale, inv, lo_disp, hi_disp, H, W, up_out,
-                                                                     depth_out);
+    convex_upsample_kernel<2, false><<<grid, 128, 0, (cudaStream_t)stream>>>(mask_pre, nullptr, 0, mask_bias, mask_scale, inv, lo_disp, hi_disp,
+                                                                            H, W, up_out, depth_out);
+    return check_launch("convex_upsample_kernel");
+}
+
+extern "C" int effimvs_convex_upsample_conv_f32(const float* t, int K, const float* mask_w, const float* mask_bias, float mask_scale,
+                                                const float* inv, const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio,
+                                                float* up_out, float* depth_out, void* stream) {
+    EFFI_REQUIRE(t && mask_w && inv && lo_disp && hi_disp && (up_out || depth_out), EFFIMVS_EINVAL, "convex_upsample_conv: null pointer");
+    EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "convex_upsample_conv: bad sizes");
+    EFFI_REQUIRE(ratio == 2, EFFIMVS_EUNSUPPORTED, "convex_upsample_conv: ratio=%d (only 2, the value upstream uses, is built)", ratio);
+    EFFI_REQUIRE(K >= 4 && K % 4 == 0 && K <= 256, EFFIMVS_EUNSUPPORTED, "convex_upsample_conv: K=%d must be a multiple of 4 up to 256", K);
+    dim3 grid(ceil_div(H * W, 128), B);
+    const size_t smem = (size_t)K * 36 * sizeof(float);
+    convex_upsample_kernel<2, true><<<grid, 128, smem, (cudaStream_t)stream>>>(t, mask_w, K, mask_bias, mask_scale, inv, lo_disp, hi_disp, H, W,
+                                                                              up_out, depth_out);
     return check_launch("convex_upsample_kernel");
 }
 
@@ -468,6 +507,121 @@ encoder_tail_kernel(const float4* __restrict__ m, const float* __restrict__ w, c
 
 }  // namespace
 }  // namespace effimvs
+
+// ------------------------------------------------------------------------------------------------
+// The same tail with the context half computed in the kernel: x = relu(Wm m + Wctx act(context) + bias).
+// The context map has 4 / 8 / 12 channels, so reading it (instead of a precomputed h-channel ctx_term) is
+// less traffic than the term it replaces, and the 1x1 convolution + bias-add launches that formed the term
+// once per stage disappear.  ``ctx`` is read at a pixel stride of ctx_stride floats (a channel range of the
+// context network's output map), optionally through relu (models/Effi_MVS_plus.py:466).
+// gru_init: hx[:, :h] = tanh(ctx_map[:, :h]) -- the hidden state the GRU starts from (Effi_MVS_plus.py:465).
+// ------------------------------------------------------------------------------------------------
+namespace effimvs {
+namespace {
+
+template <int HM4>
+__global__ void __launch_bounds__(256)
+encoder_tail_ctx_kernel(const float4* __restrict__ m, const float* __restrict__ w_m, const float* __restrict__ ctx, int ctx_stride, int cx,
+                        int ctx_relu, const float* __restrict__ w_ctx, const float* __restrict__ bias, long long n_pix, int h,
+                        float4* __restrict__ hx) {
+    extern __shared__ __align__(16) float tsm[];   // [hm][h] | [cx][h] | [h]
+    constexpr int HM = HM4 * 4;
+    float* tcx = tsm + HM * h;
+    float* tb = tcx + cx * h;
+    for (int i = threadIdx.x; i < HM * h; i += blockDim.x) tsm[i] = w_m[(i % h) * HM + i / h];
+    for (int i = threadIdx.x; i < cx * h; i += blockDim.x) tcx[i] = w_ctx[(i % h) * cx + i / h];
+    for (int i = threadIdx.x; i < h; i += blockDim.x) tb[i] = bias[i];
+    __syncthreads();
+    const int h4 = h >> 2;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
+        float mv[HM], cv[12];
+#pragma unroll
+        for (int q = 0; q < HM4; ++q) {
+            const float4 v = __ldg(m + p * HM4 + q);
+            mv[4 * q] = v.x; mv[4 * q + 1] = v.y; mv[4 * q + 2] = v.z; mv[4 * q + 3] = v.w;
+        }
+        const float4* cp = reinterpret_cast<const float4*>(ctx + p * ctx_stride);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (4 * q < cx) v = __ldg(cp + q);
+            if (ctx_relu) { v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f); }
+            cv[4 * q] = v.x; cv[4 * q + 1] = v.y; cv[4 * q + 2] = v.z; cv[4 * q + 3] = v.w;
+        }
+        for (int c4 = 0; c4 < h4; ++c4) {
+            float4 acc = *reinterpret_cast<const float4*>(tb + c4 * 4);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                if (k < cx) {
+                    const float4 wv = *reinterpret_cast<const float4*>(tcx + k * h + c4 * 4);
+                    acc.x = fmaf(cv[k], wv.x, acc.x); acc.y = fmaf(cv[k], wv.y, acc.y);
+                    acc.z = fmaf(cv[k], wv.z, acc.z); acc.w = fmaf(cv[k], wv.w, acc.w);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < HM; ++k) {
+                const float4 wv = *reinterpret_cast<const float4*>(tsm + k * h + c4 * 4);
+                acc.x = fmaf(mv[k], wv.x, acc.x); acc.y = fmaf(mv[k], wv.y, acc.y);
+                acc.z = fmaf(mv[k], wv.z, acc.z); acc.w = fmaf(mv[k], wv.w, acc.w);
+            }
+            hx[p * (2 * h4) + h4 + c4] = make_float4(fmaxf(acc.x, 0.0f), fmaxf(acc.y, 0.0f), fmaxf(acc.z, 0.0f), fmaxf(acc.w, 0.0f));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gru_init_kernel(const float4* __restrict__ ctx_map, long long n_pix, int h4, int ct4, float4* __restrict__ hx) {
+    const long long total = n_pix * h4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / h4;
+        const int c4 = (int)(i - p * h4);
+        const float4 v = __ldg(ctx_map + p * ct4 + c4);
+        hx[p * (2 * h4) + c4] = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+    }
+}
+
+}  // namespace
+}  // namespace effimvs
+
+extern "C" int effimvs_gru_init_f32(const float* ctx_map, long long n_pix, int h, int cx, float* hx, void* stream) {
+    using namespace effimvs;
+    EFFI_REQUIRE(ctx_map && hx, EFFIMVS_EINVAL, "gru_init: null pointer");
+    EFFI_REQUIRE(n_pix > 0 && h >= 4 && h % 4 == 0 && cx >= 0 && cx % 4 == 0, EFFIMVS_EINVAL,
+                 "gru_init: h=%d, cx=%d must be multiples of 4", h, cx);
+    const long long blocks = (n_pix * (h / 4) + 255) / 256;
+    const int grid = (int)(blocks < (long long)kNumSMs * 16 ? blocks : (long long)kNumSMs * 16);
+    gru_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)ctx_map, n_pix, h / 4, (h + cx) / 4, (float4*)hx);
+    return check_launch("gru_init_kernel");
+}
+
+extern "C" int effimvs_encoder_tail_ctx_f32(const float* m, const float* w_m, const float* ctx, int ctx_stride, int cx, int ctx_relu,
+                                            const float* w_ctx, const float* bias, long long n_pix, int hm, int h, float* hx,
+                                            void* stream) {
+    using namespace effimvs;
+    EFFI_REQUIRE(m && w_m && ctx && w_ctx && bias && hx, EFFIMVS_EINVAL, "encoder_tail_ctx: null pointer");
+    EFFI_REQUIRE(n_pix > 0 && h >= 4 && h % 4 == 0 && h <= 128, EFFIMVS_EINVAL, "encoder_tail_ctx: h=%d must be a multiple of 4 up to 128", h);
+    EFFI_REQUIRE(cx >= 4 && cx <= 12 && cx % 4 == 0 && ctx_stride >= cx && ctx_stride % 4 == 0, EFFIMVS_EUNSUPPORTED,
+                 "encoder_tail_ctx: context channels %d must be 4, 8 or 12 (pixel stride %d a multiple of 4)", cx, ctx_stride);
+    EFFI_REQUIRE((reinterpret_cast<uintptr_t>(ctx) & 15) == 0, EFFIMVS_EINVAL, "encoder_tail_ctx: ctx must be 16-byte aligned");
+    const long long blocks = (n_pix + 255) / 256;
+    const int grid = (int)(blocks < (long long)kNumSMs * 8 ? blocks : (long long)kNumSMs * 8);
+    const size_t smem = (size_t)(hm * h + cx * h + h) * sizeof(float);
+    cudaStream_t st = (cudaStream_t)stream;
+#define EFFI_TAILC_CASE(Q)                                                                                                        \
+    case Q * 4:                                                                                                                   \
+        encoder_tail_ctx_kernel<Q><<<grid, 256, smem, st>>>((const float4*)m, w_m, ctx, ctx_stride, cx, ctx_relu, w_ctx, bias, n_pix, h, \
+                                                            (float4*)hx);                                                        \
+        break;
+    switch (hm) {
+        EFFI_TAILC_CASE(2) EFFI_TAILC_CASE(3) EFFI_TAILC_CASE(4) EFFI_TAILC_CASE(5) EFFI_TAILC_CASE(6) EFFI_TAILC_CASE(7) EFFI_TAILC_CASE(8)
+        EFFI_TAILC_CASE(9) EFFI_TAILC_CASE(10) EFFI_TAILC_CASE(11) EFFI_TAILC_CASE(12)
+        default:
+            set_error("encoder_tail_ctx: input channels %d must be a multiple of 4 in [8,48]", hm);
+            return EFFIMVS_EUNSUPPORTED;
+    }
+#undef EFFI_TAILC_CASE
+    return check_launch("encoder_tail_ctx_kernel");
+}
 
 extern "C" int effimvs_encoder_tail_f32(const float* m, const float* w, const float* ctx_term, long long n_pix, int hm, int h,
                                         float* hx, void* stream) {

@@ -238,8 +238,11 @@ class CudaHotPath:
     gru_delta = staticmethod(ops.gru_delta)
     delta_head = staticmethod(ops.delta_head)
     convex_upsample = staticmethod(ops.convex_upsample)
+    convex_upsample_conv = staticmethod(ops.convex_upsample_conv)
     encoder_head = staticmethod(ops.encoder_head)
     encoder_tail = staticmethod(ops.encoder_tail)
+    encoder_tail_ctx = staticmethod(ops.encoder_tail_ctx)
+    gru_init = staticmethod(ops.gru_init)
 
     # -- a11 / a12 --------------------------------------------------------------------------------
     def softmax_regress_conf(self, prob_pre, hyp):

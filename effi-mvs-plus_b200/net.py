@@ -298,8 +298,8 @@ class UpdateBlock(nn.Module):
             inv_seq.append(inv_depth)
         return net, 0.25 * self.mask[2](_conv_relu_mod(self.mask[0], net)), inv_seq
 
-    def forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp):
-        return update_block_forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp)
+    def forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map=None, want_mask=True):
+        return update_block_forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map, want_mask)
 
 
 # ---- inference on CUDA: cuDNN convolutions + the glue kernels of the hot-path table ------------------
@@ -330,18 +330,36 @@ def _fused_update_weights(block):
     return hit[1]
 
 
-def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp):
+def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map=None, want_mask=True):
     """Same arithmetic as BasicUpdateBlock.forward (models/update.py:114-141) + upsample_depth + disp_to_depth
     (Effi_MVS_plus.py:138-178), with the elementwise chains between the convolutions replaced by
     glue.encoder_head / gru_reset / gru_update / gru_delta / convex_upsample.  cost_fn(depth, iteration).
-    Returns (net, inv_seq, depth_seq, inv_up (B,rH,rW), depth_up (B,rH,rW), mask_pre (B,9rr,H,W) without bias)."""
+    ctx_map (B,h+cx,H,W): the context network's raw output map; when given, net = tanh(ctx_map[:, :h]) and
+    context = relu(ctx_map[:, h:]) (Effi_MVS_plus.py:464-466) are formed inside the glue kernels and the net / context
+    arguments are ignored.
+    Returns (net, inv_seq, depth_seq, inv_up (B,rH,rW), depth_up (B,rH,rW), mask_pre (B,9rr,H,W) without bias; None
+    unless want_mask)."""
     w = _fused_update_weights(block)
     g, e, hd = block.depth_gru, block.encoder, block.depth_head
     ratio = int(round((block.mask[2].out_channels / 9) ** 0.5))
-    B, h, H, W = net.shape
-    hx = torch.empty(B, 2 * h, H, W, device=net.device, dtype=net.dtype, memory_format=torch.channels_last)
-    hx[:, :h] = net
-    ctx_term = F.conv2d(context, w["wc_ctx"], w["bias_c"])
+    h = g.convz.out_channels
+    cx = e.convc.in_channels - e.convd.out_channels                  # context channels
+    tail_ctx = hasattr(glue, "encoder_tail_ctx") and cx in (4, 8, 12) and os.environ.get("EFFIMVS_TAIL_CTX", "1") != "0"
+    if ctx_map is not None and tail_ctx and hasattr(glue, "gru_init") and ctx_map.shape[1] == h + cx and h % 4 == 0:
+        hx = glue.gru_init(ctx_map, h)                               # hx[:, :h] = tanh(hidden half)
+        net = hx[:, :h]
+        ctx_src, ctx_off, ctx_relu = ctx_map, h, True
+    else:
+        if ctx_map is not None:
+            hidden, context = torch.split(ctx_map, [h, ctx_map.shape[1] - h], dim=1)
+            net, context = torch.tanh(hidden), torch.relu(context)
+        B, _, H, W = net.shape
+        hx = torch.empty(B, 2 * h, H, W, device=net.device, dtype=net.dtype, memory_format=torch.channels_last)
+        hx[:, :h] = net
+        ctx_src = context.contiguous(memory_format=torch.channels_last) if (tail_ctx and context.is_cuda) else context
+        ctx_off, ctx_relu = 0, False
+    if not tail_ctx:
+        ctx_term = F.conv2d(context, w["wc_ctx"], w["bias_c"])
     inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
     inv_seq, depth_seq = [], []
     head_fused = (hasattr(glue, "delta_head") and h % 16 == 0 and h <= 128 and tuple(hd.conv2.weight.shape) == (1, h, 3, 3)
@@ -350,7 +368,10 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
         c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
         cd = torch.cudnn_convolution_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1), (1, 1), 1)
         m = F.conv2d(cd, e.convd.weight, None, padding=1)
-        glue.encoder_tail(m, w["wc_m"], ctx_term, hx)      # hx[:, h:] = relu(conv1x1(m) + ctx_term)
+        if tail_ctx:       # hx[:, h:] = relu(Wm m + Wctx context + bias): the context term is formed in the kernel
+            glue.encoder_tail_ctx(m, w["wc_m"], ctx_src, ctx_off, cx, ctx_relu, w["wc_ctx"], w["bias_c"], hx)
+        else:
+            glue.encoder_tail(m, w["wc_m"], ctx_term, hx)      # hx[:, h:] = relu(conv1x1(m) + ctx_term)
         zr_pre = F.conv2d(hx, w["wzr"], None, padding=1)
         rhx = glue.gru_reset(zr_pre, g.convr.bias, hx)
         q_pre = F.conv2d(rhx, g.convq.weight, None, padding=1)
@@ -362,7 +383,15 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
             inv, depth = glue.gru_delta(pre, hd.conv2.bias, inv, lo_disp, hi_disp)
         inv_seq.append(inv)
         depth_seq.append(depth)
-    mask_pre = F.conv2d(_conv_relu_mod(block.mask[0], net), block.mask[2].weight, None)
+    m0 = _conv_relu_mod(block.mask[0], net)
+    if (not want_mask and hasattr(glue, "convex_upsample_conv") and tuple(block.mask[2].kernel_size) == (1, 1) and m0.shape[1] % 4 == 0
+            and os.environ.get("EFFIMVS_UPSAMPLE_CONV", "0") == "1"):
+        # mask[2] (1x1) folded into the upsampling kernel: the 9 r^2-channel mask map is never materialised.  Opt-in:
+        # measured on B200 the thread-per-pixel K x 36 product is shared-memory bound (one broadcast LDS.128 per four
+        # FMAs) and the fused kernel loses 0.06 ms per DTU depth map against cuDNN's 1x1 convolution + the plain kernel.
+        up, depth_up = glue.convex_upsample_conv(m0, block.mask[2].weight, block.mask[2].bias, 0.25, inv, lo_disp, hi_disp, ratio)
+        return net, inv_seq, depth_seq, up, depth_up, None
+    mask_pre = F.conv2d(m0, block.mask[2].weight, None)
     up, depth_up = glue.convex_upsample(mask_pre, block.mask[2].bias, 0.25, inv, lo_disp, hi_disp, ratio)
     return net, inv_seq, depth_seq, up, depth_up, mask_pre
 
@@ -466,8 +495,10 @@ class EffiMVSPlus(nn.Module):
         for s in range(3):
             f = feats[s]
             cams = proj_matrices["stage{}".format(s + 1)]
-            hidden, context = torch.split(ctx_pyr[s], [self.HIDDEN[s], self.CONTEXT[s]], dim=1)
-            hidden, context = torch.tanh(hidden), torch.relu(context)
+            glue = hp if (getattr(hp, "fused_update", False) and imgs.is_cuda and not torch.is_grad_enabled()) else None
+            if glue is None:
+                hidden, context = torch.split(ctx_pyr[s], [self.HIDDEN[s], self.CONTEXT[s]], dim=1)
+                hidden, context = torch.tanh(hidden), torch.relu(context)
             H, W = f[0].shape[2:]
             if s == 0:
                 D = self.ndepths[0]
@@ -512,10 +543,9 @@ class EffiMVSPlus(nn.Module):
             def cost_fn(depth, _it=0, _raw=raw_vol, _reg=reg_vol, _iv=interval, _n=vol_near, _f=vol_far):
                 return hp.dynamic_cost(depth, _raw, _reg, _iv, _n, _f, self.cost_num)
 
-            glue = hp if (getattr(hp, "fused_update", False) and imgs.is_cuda and not torch.is_grad_enabled()) else None
-            if glue is not None:
+            if glue is not None:     # tanh / relu of the context map happen inside the glue kernels
                 _, _, depth_seq, _, depth_up, _ = self.update_block[s].forward_fused(
-                    glue, hidden, cost_fn, inv0, context, self.iters[s], lo_disp.reshape(B), hi_disp.reshape(B))
+                    glue, None, cost_fn, inv0, None, self.iters[s], lo_disp.reshape(B), hi_disp.reshape(B), ctx_pyr[s], False)
                 preds.extend(d.squeeze(1) for d in depth_seq)
                 preds.append(depth_up)
                 continue

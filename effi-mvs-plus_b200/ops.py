@@ -636,6 +636,32 @@ def _(mask_pre, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
     return inv.new_empty(B, ratio * H, ratio * W), inv.new_empty(B, ratio * H, ratio * W)
 
 
+@torch.library.custom_op("effimvs::convex_upsample_conv", mutates_args=())
+def convex_upsample_conv(t: Tensor, mask_w: Tensor, mask_bias: Optional[Tensor], mask_scale: float, inv: Tensor, lo_disp: Tensor,
+                         hi_disp: Tensor, ratio: int) -> Tuple[Tensor, Tensor]:
+    """convex_upsample with mask = mask_scale * (conv1x1(t, mask_w) + mask_bias) formed in the kernel: t (B,K,H,W) =
+    relu(mask[0](net)), mask_w (9*ratio^2, K, 1, 1)."""
+    t, mask_w, inv = _nhwc(t, "convex_upsample_conv"), _dev(mask_w, "convex_upsample_conv"), _dev(inv, "convex_upsample_conv")
+    lo_disp, hi_disp = _dev(lo_disp, "convex_upsample_conv"), _dev(hi_disp, "convex_upsample_conv")
+    mask_bias = _dev(mask_bias, "convex_upsample_conv") if mask_bias is not None else None
+    B, K, H, W = t.shape
+    if mask_w.numel() != 9 * ratio * ratio * K or inv.numel() != B * H * W:
+        raise ValueError("convex_upsample_conv: shapes do not match")
+    up = torch.empty(B, ratio * H, ratio * W, device=inv.device, dtype=torch.float32)
+    depth = torch.empty_like(up)
+    _count(1)
+    capi.check(_lib.effimvs_convex_upsample_conv_f32(t.data_ptr(), K, mask_w.data_ptr(), _opt(mask_bias), mask_scale, inv.data_ptr(),
+                                                     lo_disp.data_ptr(), hi_disp.data_ptr(), B, H, W, ratio, up.data_ptr(),
+                                                     depth.data_ptr(), _stream()))
+    return up, depth
+
+
+@convex_upsample_conv.register_fake
+def _(t, mask_w, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
+    B, _, H, W = inv.shape
+    return inv.new_empty(B, ratio * H, ratio * W), inv.new_empty(B, ratio * H, ratio * W)
+
+
 @torch.library.custom_op("effimvs::encoder_head", mutates_args=())
 def encoder_head(cost: Tensor, inv: Tensor, wc1: Tensor, bc1: Tensor, wd1: Tensor, bd1: Tensor) -> Tensor:
     """cat[relu(convc1(cost)), relu(convd1(inv))] as one channels-last (B,2h,H,W) map (models/update.py:88-91)."""
@@ -668,6 +694,46 @@ def encoder_tail(m: Tensor, w: Tensor, ctx_term: Tensor, hx: Tensor) -> None:
         raise ValueError("encoder_tail: shapes do not match")
     _count(1)
     capi.check(_lib.effimvs_encoder_tail_f32(m.data_ptr(), w.data_ptr(), ctx_term.data_ptr(), B * H * W, hm, h, hx.data_ptr(), _stream()))
+
+
+@torch.library.custom_op("effimvs::encoder_tail_ctx", mutates_args=("hx",))
+def encoder_tail_ctx(m: Tensor, w_m: Tensor, ctx: Tensor, ctx_offset: int, cx: int, ctx_relu: bool, w_ctx: Tensor, bias: Tensor,
+                     hx: Tensor) -> None:
+    """hx[:, h:] = relu(conv1x1(m, w_m) + conv1x1(act(ctx[:, ctx_offset:ctx_offset+cx]), w_ctx) + bias) in place;
+    m (B,hm,H,W), ctx (B,*,H,W), hx (B,2h,H,W) channels-last; act = relu if ctx_relu else identity."""
+    m, ctx = _nhwc(m, "encoder_tail_ctx"), _nhwc(ctx, "encoder_tail_ctx")
+    w_m, w_ctx, bias = _dev(w_m, "encoder_tail_ctx"), _dev(w_ctx, "encoder_tail_ctx"), _dev(bias, "encoder_tail_ctx")
+    if not (hx.is_cuda and hx.dtype == torch.float32 and hx.is_contiguous(memory_format=torch.channels_last)):
+        raise RuntimeError("effimvs::encoder_tail_ctx needs hx as a channels-last fp32 CUDA tensor (it is updated in place)")
+    B, hm, H, W = m.shape
+    h = w_m.shape[0]
+    ct = ctx.shape[1]
+    if (hx.shape[1] != 2 * h or w_m.numel() != h * hm or w_ctx.numel() != h * cx or bias.numel() != h or ctx_offset < 0
+            or ctx_offset + cx > ct or ctx_offset % 4 or tuple(ctx.shape[2:]) != (H, W)):
+        raise ValueError("encoder_tail_ctx: shapes do not match")
+    _count(1)
+    capi.check(_lib.effimvs_encoder_tail_ctx_f32(m.data_ptr(), w_m.data_ptr(), ctx.data_ptr() + 4 * ctx_offset, ct, cx, int(ctx_relu),
+                                                 w_ctx.data_ptr(), bias.data_ptr(), B * H * W, hm, h, hx.data_ptr(), _stream()))
+
+
+@torch.library.custom_op("effimvs::gru_init", mutates_args=())
+def gru_init(ctx_map: Tensor, h: int) -> Tensor:
+    """ctx_map (B,h+cx,H,W) -> hx (B,2h,H,W) channels-last with hx[:, :h] = tanh(ctx_map[:, :h]) (the x half is left for
+    encoder_tail to fill)."""
+    ctx_map = _nhwc(ctx_map, "gru_init")
+    B, ct, H, W = ctx_map.shape
+    if h <= 0 or h % 4 or ct < h or (ct - h) % 4:
+        raise ValueError("gru_init: hidden {} / map channels {} must be multiples of 4".format(h, ct))
+    hx = torch.empty(B, 2 * h, H, W, device=ctx_map.device, dtype=torch.float32, memory_format=torch.channels_last)
+    _count(1)
+    capi.check(_lib.effimvs_gru_init_f32(ctx_map.data_ptr(), B * H * W, h, ct - h, hx.data_ptr(), _stream()))
+    return hx
+
+
+@gru_init.register_fake
+def _(ctx_map, h):
+    B, _, H, W = ctx_map.shape
+    return torch.empty((B, 2 * h, H, W), device=ctx_map.device, dtype=ctx_map.dtype, memory_format=torch.channels_last)
 
 
 # -------------------------------------------------------------------------------------------

@@ -249,6 +249,13 @@ int effimvs_convex_upsample_f32(const float* mask_pre, const float* mask_bias, f
                                 const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio, float* up_out,
                                 float* depth_out, void* stream);
 
+/* The same with the mask head's last layer folded in (models/update.py:109-112, 128): t (B,H,W,K) channels-last =
+ * relu(mask[0](net)), mask_w (9*ratio^2, K) = mask[2].weight (1x1), mask = mask_scale * (mask_w t + mask_bias) is formed per
+ * pixel in the kernel and never stored.  K a multiple of 4 up to 256. */
+int effimvs_convex_upsample_conv_f32(const float* t, int K, const float* mask_w, const float* mask_bias, float mask_scale,
+                                     const float* inv, const float* lo_disp, const float* hi_disp, int B, int H, int W, int ratio,
+                                     float* up_out, float* depth_out, void* stream);
+
 /* ProjectionInput head (models/update.py:88-91): relu(convc1(cost)) (1x1) and relu(convd1(inv)) (7x7, pad 3).
  * cost (B,CD,H,W) planar (what effimvs_dynamic_cost_f32 writes), inv (B,1,H,W), wc1 (h,CD,1,1), wd1 (h,1,7,7)
  *   -> out (B,H,W,2h) channels-last = cat[relu(convc1), relu(convd1)]: the input of the second encoder layer. */
@@ -260,6 +267,17 @@ int effimvs_encoder_head_f32(const float* cost, const float* inv, const float* w
  * The result is written into the x half of hx (n_pix, 2h) = cat[h, x] in place. */
 int effimvs_encoder_tail_f32(const float* m, const float* w, const float* ctx_term, long long n_pix, int hm, int h,
                              float* hx, void* stream);
+
+/* The same tail with the context half formed in the kernel: x = relu(w_m m + w_ctx act(ctx) + bias), w_ctx (h, cx) =
+ * convc.weight[:, hm:], bias (h) = convc.bias + convc.weight[:, :hm] convd.bias.  ctx points at the first context channel
+ * of a channels-last map and is read at a pixel stride of ctx_stride floats (cx in {4,8,12}); ctx_relu != 0 applies the
+ * relu of models/Effi_MVS_plus.py:466 on the fly. */
+int effimvs_encoder_tail_ctx_f32(const float* m, const float* w_m, const float* ctx, int ctx_stride, int cx, int ctx_relu,
+                                 const float* w_ctx, const float* bias, long long n_pix, int hm, int h, float* hx, void* stream);
+
+/* GRU start state (models/Effi_MVS_plus.py:464-465): hx[:, :h] = tanh(ctx_map[:, :h]) for ctx_map (n_pix, h + cx) channels-last,
+ * hx (n_pix, 2h) = cat[h, x]. */
+int effimvs_gru_init_f32(const float* ctx_map, long long n_pix, int h, int cx, float* hx, void* stream);
 
 /* ---- the DTU pipeline's NumPy / cv2.remap geometric filter ------------------------
  * reproject_with_depth + check_geometric_consistency + the aggregation of filter_depth

@@ -39,17 +39,18 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_volume_lookup_f32(one, one, one, one, 0, 3, 1, 8, 3, 4, 4, one, None) == capi.EINVAL
     assert "sample_stride" in capi.last_error()
     arr, keep = capi.ptr_array([16] * 4)
+    arr9, keep9 = capi.ptr_array([16] * 9)
     assert lib.effimvs_warp_corr_agg_f32(one, arr, 4, one, one, 0, None, None, 1, 12, 8, 8, 4, 1, 0, one, None, None) == capi.EUNSUPPORTED
     assert "C=12" in capi.last_error()
     assert lib.effimvs_warp_corr_agg_f32(one, arr, 4, one, one, 0, None, None, 1, 8, 8, 8, 4, 3, 0, one, None, None) == capi.EINVAL
-    assert lib.effimvs_costreg_fpn3d(one, arr, arr, 1, 6, 8, 8, 0, one, 1 << 30, one, None) == capi.EUNSUPPORTED   # D not a multiple of 4
+    assert lib.effimvs_costreg_fpn3d(one, arr9, arr9, 1, 6, 8, 8, 0, one, 1 << 30, one, None) == capi.EUNSUPPORTED   # D not a multiple of 4
     assert lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_F32) > 0
     assert lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16X3) > lib.effimvs_costreg_workspace_bytes(1, 48, 148, 200, capi.PREC_BF16)
     # phased forms: unknown phase bits, RUN without data pointers, PREPARE-only accepts NULL data pointers up to the workspace check
-    assert lib.effimvs_costreg_fpn3d_ex(one, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, 4, one, 1 << 30, one, None) == capi.EINVAL
+    assert lib.effimvs_costreg_fpn3d_ex(one, arr9, arr9, 1, 8, 8, 8, capi.PREC_BF16X3, 4, one, 1 << 30, one, None) == capi.EINVAL
     assert "phases" in capi.last_error()
-    assert lib.effimvs_costreg_fpn3d_ex(None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_RUN, one, 1 << 30, None, None) == capi.EINVAL
-    assert lib.effimvs_costreg_fpn3d_ex(None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_PREPARE, one, 16, None, None) == capi.EWORKSPACE
+    assert lib.effimvs_costreg_fpn3d_ex(None, arr9, arr9, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_RUN, one, 1 << 30, None, None) == capi.EINVAL
+    assert lib.effimvs_costreg_fpn3d_ex(None, arr9, arr9, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_PREPARE, one, 16, None, None) == capi.EWORKSPACE
     assert lib.effimvs_cost_up_small_ex(None, None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, capi.WS_PREPARE, one, 16, None, None) == capi.EWORKSPACE
     assert lib.effimvs_cost_up_small_ex(None, None, arr, arr, 1, 8, 8, 8, capi.PREC_BF16X3, 0, one, 16, None, None) == capi.EINVAL
     assert lib.effimvs_cost_up_small_ex(None, None, arr, arr, 1, 8, 8, 8, capi.PREC_F32, capi.WS_PREPARE, one, 1 << 30, None, None) == capi.OK
@@ -64,8 +65,13 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_delta_head_f32(one, one, None, one, one, one, 1, 16, 8, 8, one, one, None) == capi.EINVAL
     assert lib.effimvs_convex_upsample_f32(one, None, 0.25, one, one, one, 1, 4, 4, 8, one, one, None) == capi.EUNSUPPORTED
     assert "ratio=8" in capi.last_error()
+    assert lib.effimvs_convex_upsample_conv_f32(one, 30, one, None, 0.25, one, one, one, 1, 4, 4, 2, one, one, None) == capi.EUNSUPPORTED
+    assert "K=30" in capi.last_error()
     assert lib.effimvs_encoder_head_f32(one, one, one, one, one, one, 1, 6, 20, 4, 4, one, None) == capi.EUNSUPPORTED   # hidden not a multiple of 16
     assert lib.effimvs_encoder_tail_f32(one, one, one, 10, 10, 16, one, None) == capi.EUNSUPPORTED                      # hm not a multiple of 4
+    assert lib.effimvs_encoder_tail_ctx_f32(one, one, one, 20, 5, 1, one, one, 10, 12, 16, one, None) == capi.EUNSUPPORTED           # cx = 5
+    assert lib.effimvs_encoder_tail_ctx_f32(one, one, ctypes.c_void_p(20), 20, 4, 1, one, one, 10, 12, 16, one, None) == capi.EINVAL  # misaligned ctx
+    assert lib.effimvs_gru_init_f32(one, 10, 18, 4, one, None) == capi.EINVAL
     td, tf = (ctypes.c_double * 2)(1.0, 0.5), (ctypes.c_float * 2)(0.1, 0.2)
     assert lib.effimvs_dtu_filter_f32(one, one, one, one, td, tf, 2, 1, 11, 0.5, 0.75, 3, 8, 8, one, None, one, one, None, None, None) == capi.EUNSUPPORTED
     assert "non-decreasing" in capi.last_error()
@@ -88,6 +94,10 @@ def test_fake_implementations_give_shapes_without_a_device():
         iv, dp = torch.ops.effimvs.delta_head(torch.empty(2, 16, 6, 8), torch.empty(1, 16, 3, 3), torch.empty(1), torch.empty(2, 1, 6, 8),
                                               torch.empty(2), torch.empty(2))
         assert iv.shape == (2, 1, 6, 8) and dp.shape == (2, 1, 6, 8)
+        up, dep = torch.ops.effimvs.convex_upsample_conv(torch.empty(2, 32, 6, 8), torch.empty(36, 32, 1, 1), None, 0.25, torch.empty(2, 1, 6, 8),
+                                                         torch.empty(2), torch.empty(2), 2)
+        assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
+        assert torch.ops.effimvs.gru_init(torch.empty(2, 20, 6, 8), 16).shape == (2, 32, 6, 8)
         up, dep = torch.ops.effimvs.convex_upsample(torch.empty(2, 36, 6, 8), None, 0.25, torch.empty(2, 1, 6, 8), torch.empty(2), torch.empty(2), 2)
         assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
         ref = torch.empty(2, 16, 24, 32)

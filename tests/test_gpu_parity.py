@@ -524,6 +524,36 @@ def test_vis_filter_dynamic_dropin_golden(tag):
 
 # ---- update-block glue kernels ------------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.parametrize("h,cx,H,W", [(16, 4, 37, 53), (32, 8, 24, 40), (48, 12, 19, 25)])
+def test_gru_init_and_encoder_tail_ctx_vs_torch(h, cx, H, W):
+    """gru_init (tanh of the hidden half of the context map into hx) and the encoder tail with the context term
+    formed in the kernel (relu on the fly, channel range of the map) against the torch chain
+    (models/Effi_MVS_plus.py:464-466, models/update.py:93-95)."""
+    import torch.nn.functional as F
+    from effimvs_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(h)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=gen)      # noqa: E731
+    B, hm = 2, h - cx
+    ctx_map = rnd(B, h + cx, H, W).contiguous(memory_format=torch.channels_last)
+    hx = ops.gru_init(ctx_map, h)
+    assert hx.shape == (B, 2 * h, H, W) and hx.is_contiguous(memory_format=torch.channels_last)
+    assert float((hx[:, :h] - torch.tanh(ctx_map[:, :h])).abs().max()) < 1e-6
+    m, w_m, w_ctx, bias = rnd(B, hm, H, W), rnd(h, hm, 1, 1) * 0.2, rnd(h, cx, 1, 1) * 0.2, rnd(h) * 0.1
+    context = torch.relu(ctx_map[:, h:])
+    want = torch.relu(F.conv2d(m, w_m) + F.conv2d(context, w_ctx, bias))
+    keep = hx[:, :h].clone()
+    ops.encoder_tail_ctx(m, w_m, ctx_map, h, cx, True, w_ctx, bias, hx)           # channel range of the map, relu in the kernel
+    assert rel_max(hx[:, h:], want) < 1e-5 and torch.equal(hx[:, :h], keep)
+    hx2 = torch.zeros_like(hx)
+    ops.encoder_tail_ctx(m, w_m, context.contiguous(), 0, cx, False, w_ctx, bias, hx2)   # an already activated planar context tensor
+    assert rel_max(hx2[:, h:], want) < 1e-5
+    ctx_term = F.conv2d(context, w_ctx, bias)
+    hx3 = torch.zeros_like(hx)
+    ops.encoder_tail(m, w_m, ctx_term, hx3)                                        # the precomputed-term form agrees
+    assert rel_max(hx3[:, h:], hx2[:, h:]) < 1e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("h,B,H,W", [(16, 2, 37, 70), (32, 1, 24, 129), (48, 2, 19, 25), (16, 1, 3, 2), (64, 1, 9, 66)])
 def test_delta_head_vs_torch(h, B, H, W):
     """DepthHead.conv2 + tanh + inverse-depth step + disp_to_depth in one kernel against the torch chain
@@ -584,6 +614,14 @@ def test_update_glue_kernels_vs_torch(h, H, W):
     want_up = net.convex_upsample(inv, 0.25 * (mask_pre + mb.reshape(1, -1, 1, 1)), 2)
     assert float((up - want_up).abs().max()) <= 1e-6
     assert rel_max(dup, to_depth(up.unsqueeze(1)).squeeze(1)) <= 2e-7
+    # the same with the mask head's 1x1 convolution folded into the kernel
+    import torch.nn.functional as F
+    t, mw = torch.relu(rnd(B, 2 * h, H, W)), rnd(36, 2 * h, 1, 1) * 0.3
+    for tt in (t, cl(t)):
+        up2, dup2 = ops.convex_upsample_conv(tt, mw, mb, 0.25, inv, lo, hi, 2)
+        want2 = net.convex_upsample(inv, 0.25 * (F.conv2d(t, mw) + mb.reshape(1, -1, 1, 1)), 2)
+        assert float((up2 - want2).abs().max()) <= 2e-6
+        assert rel_max(dup2, to_depth(up2.unsqueeze(1)).squeeze(1)) <= 2e-7
 
 
 @pytest.mark.gpu
