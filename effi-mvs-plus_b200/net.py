@@ -308,7 +308,7 @@ class UpdateBlock(nn.Module):
 def _fused_update_weights(block):
     g, e = block.depth_gru, block.encoder
     ts = (g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias, e.convd.bias, e.convc.weight, e.convc.bias,
-          e.convc2.weight, e.convc2.bias, e.convd2.weight, e.convd2.bias)
+          e.convc2.weight, e.convc2.bias, e.convd2.weight, e.convd2.bias, block.depth_head.conv2.weight)
     stamp = tuple((id(t), t._version, t.device) for t in ts)
     hit = getattr(block, "_effimvs_fused", None)
     if hit is None or hit[0] != stamp:
@@ -325,7 +325,9 @@ def _fused_update_weights(block):
         hit = (stamp, {
             "w_cd2": cl(w_cd2), "b_cd2": torch.cat([e.convc2.bias.detach(), e.convd2.bias.detach()]).contiguous(),
             "wzr": cl(torch.cat([g.convz.weight, g.convr.weight], dim=0)),      # one convolution for both gates
-            "wc_m": cl(wc[:, :hm]), "wc_ctx": cl(wc[:, hm:]), "bias_c": bias_c.contiguous()})
+            "wc_m": cl(wc[:, :hm]), "wc_ctx": cl(wc[:, hm:]), "bias_c": bias_c.contiguous(),
+            # (1, h, 3, 3) in its planar order for delta_head: a channels-last module would otherwise be re-laid out per call
+            "w_d2": block.depth_head.conv2.weight.detach().contiguous()})
         object.__setattr__(block, "_effimvs_fused", hit)
     return hit[1]
 
@@ -377,7 +379,7 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
         q_pre = F.conv2d(rhx, g.convq.weight, None, padding=1)
         net = glue.gru_update(zr_pre, g.convz.bias, q_pre, g.convq.bias, hx)
         if head_fused:     # depth_head.conv2 (h -> 1) + tanh + step + disp_to_depth: one streaming kernel
-            inv, depth = glue.delta_head(_conv_relu_mod(hd.conv1, net), hd.conv2.weight, hd.conv2.bias, inv, lo_disp, hi_disp)
+            inv, depth = glue.delta_head(_conv_relu_mod(hd.conv1, net), w["w_d2"], hd.conv2.bias, inv, lo_disp, hi_disp)
         else:
             pre = F.conv2d(_conv_relu_mod(hd.conv1, net), hd.conv2.weight, None, padding=1)
             inv, depth = glue.gru_delta(pre, hd.conv2.bias, inv, lo_disp, hi_disp)
