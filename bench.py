@@ -203,7 +203,16 @@ class TimedHotPath:
 
 def ncu_traffic(tag):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel whose label contains `tag`,
-    from the committed `ncu --set full` summary (profiles/r1_warp_tile_ncu.json); None if absent."""
+    from the committed `ncu --set full` summaries (profiles/r1b_forward_kernels_ncu_full.json, else
+    profiles/r1_warp_tile_ncu.json); None if absent."""
+    try:    # latest capture first: the kernel inside the bench forward (profiles/r1b_forward_kernels_ncu_full.json)
+        with open(os.path.join(ROOT, "profiles", "r1b_forward_kernels_ncu_full.json")) as f:
+            want = {"stage3": "warp_corr_tile_kernel<8", "stage2": "warp_corr_tile_kernel<16"}.get(tag)
+            for k in json.load(f)["launches"]:
+                if want and want in k["kernel"]:
+                    return (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6
+    except (OSError, KeyError, ValueError, TypeError):
+        pass
     try:
         with open(os.path.join(ROOT, "profiles", "r1_warp_tile_ncu.json")) as f:
             for k in json.load(f):
