@@ -171,6 +171,17 @@ __device__ __forceinline__ float sample_depth(const float* __restrict__ img, int
 
 struct Reproj { float x, y, d; };
 
+// Number of ladder rungs k in [0, K) with e < thr[k], thr[k] = fl((tv + k) / base) (fusion.py:172-176).  The
+// thresholds are non-decreasing in k, so the rungs passed are exactly k >= idx with idx the first rung passed:
+// idx is estimated from e * base - tv and settled with the same comparisons upstream makes (typically one or two
+// instead of all K).  NaN passes no rung, like the comparison chain it replaces.
+__device__ __forceinline__ int ladder_count(float e, const float* __restrict__ thr, int K, float base, float tv) {
+    int idx = (int)fminf(fmaxf(floorf(fmaf(e, base, -tv)) + 1.0f, 0.0f), (float)K);
+    while (idx > 0 && e < thr[idx - 1]) --idx;
+    while (idx < K && !(e < thr[idx])) ++idx;
+    return K - idx;
+}
+
 __device__ __forceinline__ Reproj reproject(const Cam& ref, const Cam& src, const float ref_world[4],
                                             const float* __restrict__ src_depth, int h, int w,
                                             float inv_half_w, float inv_half_h) {
@@ -235,13 +246,8 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
         float e_xy = sqrtf(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)));
         float e_d = fabsf(__fsub_rn(dref, r.d));
         if (relative) e_d = __fdiv_rn(e_d, dref);
-        int c_xy = 0, c_d = 0;
-#pragma unroll
-        for (int k = 0; k < MAXV; ++k) {
-            c_xy += (k < K && e_xy < thr_xy[k]) ? 1 : 0;
-            c_d += (k < K && e_d < thr_d[k]) ? 1 : 0;
-        }
-        const int c = min(c_xy, c_d);
+        const int c = min(ladder_count(e_xy, thr_xy, K, dist_base, (float)thres_view),
+                          ladder_count(e_d, thr_d, K, rel_diff_base, (float)thres_view));
         if (c < 12) hist_lo += 1ull << (5 * c);
         else hist_hi += 1ull << (5 * (c - 12));
         if (masks_out)
