@@ -13,6 +13,8 @@
 // Multi-channel maps are channels-last (B,H,W,C), what cuDNN's NHWC convolutions emit; the arithmetic
 // repeats torch's elementwise kernels operation by operation (no contraction across torch ops):
 // sigmoid = 1 / (1 + exp(-x)), tanh = tanhf, reciprocal = 1 / x, bias added first as cuDNN's epilogue does.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace effimvs {
@@ -350,8 +352,11 @@ extern "C" int effimvs_convex_upsample_conv_f32(const float* t, int K, const flo
 namespace effimvs {
 namespace {
 
-constexpr int EH_TX = 32, EH_TY = 8, EH_R = 3, EH_PX = 2;   // a thread owns EH_PX horizontally adjacent pixels: weights loaded once for both
+constexpr int EH_TX = 32, EH_R = 3, EH_PX = 2;   // a thread owns EH_PX horizontally adjacent pixels: weights loaded once for both
 
+// EH_TY: rows of a block's tile.  4 by default: 64 x 8 tiles leave SMs idle on the small stages (200 x 148 is 76 such tiles)
+// and at two 256-thread blocks per SM (126 registers) the tail wave of the large one costs more than the extra halo reads.
+template <int EH_TY>
 __global__ void __launch_bounds__(EH_TX * EH_TY)
 encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restrict__ inv, const float* __restrict__ wc1,
                     const float* __restrict__ bc1, const float* __restrict__ wd1, const float* __restrict__ bd1, int h, int H, int W,
@@ -461,9 +466,15 @@ extern "C" int effimvs_encoder_head_f32(const float* cost, const float* inv, con
     EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "encoder_head: bad sizes");
     EFFI_REQUIRE(CD >= 1 && CD <= 8 && h >= 16 && h % 16 == 0 && h <= 128, EFFIMVS_EUNSUPPORTED,
                  "encoder_head: cost channels %d must be in [1,8], hidden %d a multiple of 16 up to 128", CD, h);
-    dim3 block(effimvs::EH_TX, effimvs::EH_TY), grid(effimvs::ceil_div(W, effimvs::EH_TX * effimvs::EH_PX), effimvs::ceil_div(H, effimvs::EH_TY), B);
-    const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX * effimvs::EH_PX + 6) * (effimvs::EH_TY + 6)) * sizeof(float);
-    effimvs::encoder_head_kernel<<<grid, block, smem, (cudaStream_t)stream>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    const int tiles_x = effimvs::ceil_div(W, effimvs::EH_TX * effimvs::EH_PX);
+    static const int force_ty = [] { const char* e = getenv("EFFIMVS_EH_TY"); return e ? atoi(e) : 0; }();   // tuning switch: 4 or 8
+    const int ty = force_ty == 8 ? 8 : 4;   // measured per DTU depth map (9 launches): 64 x 4 tiles 6.65 ms, 64 x 8 tiles 6.70 ms
+    dim3 block(effimvs::EH_TX, ty), grid(tiles_x, effimvs::ceil_div(H, ty), B);
+    const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX * effimvs::EH_PX + 6) * (ty + 6)) * sizeof(float);
+    if (ty == 4)
+        effimvs::encoder_head_kernel<4><<<grid, block, smem, (cudaStream_t)stream>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else
+        effimvs::encoder_head_kernel<8><<<grid, block, smem, (cudaStream_t)stream>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
     return effimvs::check_launch("encoder_head_kernel");
 }
 
