@@ -368,7 +368,7 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
                   and os.environ.get("EFFIMVS_DELTA_HEAD", "1") != "0")
     for it in range(iters):
         c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
-        cd = torch.cudnn_convolution_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1), (1, 1), 1)
+        cd = conv_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1))
         m = F.conv2d(cd, e.convd.weight, None, padding=1)
         if tail_ctx:       # hx[:, h:] = relu(Wm m + Wctx context + bias): the context term is formed in the kernel
             glue.encoder_tail_ctx(m, w["wc_m"], ctx_src, ctx_off, cx, ctx_relu, w["wc_ctx"], w["bias_c"], hx)

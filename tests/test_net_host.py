@@ -80,6 +80,38 @@ def test_update_block_matches_upstream_golden():
     assert torch.equal(to_depth(up.unsqueeze(1)).squeeze(1), g["depth_up"])
 
 
+@pytest.mark.parametrize("use_ctx_map", [False, True])
+@pytest.mark.parametrize("want_mask", [False, True])
+def test_fused_update_wiring_equals_plain_block(use_ctx_map, want_mask, monkeypatch):
+    """net.update_block_forward_fused (merged gate convolution, block-diagonal encoder layer, context term inside the
+    tail kernel, delta head, optional mask fold) wired to a plain-torch glue table equals UpdateBlock.forward +
+    convex_upsample + disp_to_depth -- every host-side code path, on CPU."""
+    from util import TorchGlue, golden
+    g = golden("update_block")
+    blk = load_update_block(g)
+    torch.manual_seed(5)
+    B, _, H, W = g["inv0"].shape
+    ctx_map = torch.randn(B, 20, H, W)
+    net0, context = torch.tanh(ctx_map[:, :16]), torch.relu(ctx_map[:, 16:])
+    lo, hi = (1.0 / g["dmax"]).reshape(B), (1.0 / g["dmin"]).reshape(B)
+    to_depth = lambda inv: 1.0 / (lo.reshape(B, 1, 1, 1) + (hi - lo).reshape(B, 1, 1, 1) * inv).clamp(min=1e-4)   # noqa: E731
+    monkeypatch.setenv("EFFIMVS_UPSAMPLE_CONV", "1")       # exercise the folded mask head when no mask is wanted
+    with torch.no_grad():
+        n_w, mask_w, invs_w = blk(net0, _update_cost_fn, g["inv0"], context, 3, to_depth)
+        up_w = net.convex_upsample(invs_w[-1], mask_w, 2)
+        args = (None, _update_cost_fn, g["inv0"], None, 3, lo, hi, ctx_map) if use_ctx_map else \
+               (net0, _update_cost_fn, g["inv0"], context, 3, lo, hi, None)
+        n, invs, deps, up, dup, mask_pre = blk.forward_fused(TorchGlue, *args, want_mask=want_mask)
+    close = lambda a, b: float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))   # noqa: E731
+    assert close(n, n_w) and close(up, up_w) and close(dup, to_depth(up_w.unsqueeze(1)).squeeze(1))
+    for i in range(3):
+        assert close(invs[i], invs_w[i]) and close(deps[i], to_depth(invs_w[i]))
+    if want_mask:
+        assert close(0.25 * (mask_pre + blk.mask[2].bias.detach().reshape(1, -1, 1, 1)), mask_w)
+    else:
+        assert mask_pre is None
+
+
 def test_feature_cache_equals_reencoding():
     """forward_from_features on per-image encodings equals forward() on the stacked views"""
     import types
@@ -98,3 +130,20 @@ def test_feature_cache_equals_reencoding():
     for a, b in zip(want["depth"], got["depth"]):
         assert float((a - b).abs().max()) <= 1e-2      # mm at ~600 mm: batch-1 vs batch-3 convolution rounding
     assert float((want["photometric_confidence"] - got["photometric_confidence"]).abs().max()) <= 1e-5
+
+
+def test_workspace_cache_keeps_one_buffer_per_key_and_evicts_least_recently_used():
+    """hotpath._WorkspaceCache: the persistent regularization workspaces (one per network, shape, precision, device)"""
+    from effimvs_b200 import hotpath
+    c = hotpath._WorkspaceCache(cap=3)
+    a = c.get(("costreg", 1), 1000, "cpu")
+    assert a["ws"].numel() >= 1000 and a["ws"].dtype == torch.uint8 and a["stamp"] is None
+    a["stamp"] = "prepared"
+    assert c.get(("costreg", 1), 1000, "cpu") is a                   # same key: same buffer, stamp kept
+    assert c.get(("costreg", 1), 5000, "cpu") is not a               # a larger request replaces it (unprepared)
+    assert c.get(("costreg", 1), 5000, "cpu")["stamp"] is None
+    for k in (2, 3):
+        c.get(("cost_up", k), 10, "cpu")
+    c.get(("costreg", 1), 10, "cpu")                                 # touch -> most recently used
+    c.get(("cost_up", 4), 10, "cpu")                                 # evicts ("cost_up", 2)
+    assert set(c._store) == {("costreg", 1), ("cost_up", 3), ("cost_up", 4)}

@@ -4,6 +4,7 @@ import types
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 import effimvs_b200  # noqa: F401
 from effimvs_b200 import net
@@ -61,3 +62,70 @@ def load_dtu_weights(m):
 def rel_max(a, b):
     """max|a-b| / max|b|  -- the north_star's cost-volume metric (SURVEY.md section 7 'hard parts')."""
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+class TorchGlue:
+    """Plain-torch stand-in for the update-block glue entries of the hot-path table (CudaHotPath.gru_init ...
+    convex_upsample_conv): test infrastructure for the host-side wiring of net.update_block_forward_fused on CPU."""
+
+    @staticmethod
+    def _to_depth(inv, lo, hi):
+        lo, hi = lo.reshape(-1, 1, 1, 1), hi.reshape(-1, 1, 1, 1)
+        return 1.0 / (lo + (hi - lo) * inv).clamp(min=1e-4)
+
+    @staticmethod
+    def gru_init(ctx_map, h):
+        B, _, H, W = ctx_map.shape
+        hx = torch.full((B, 2 * h, H, W), float("nan"))
+        hx[:, :h] = torch.tanh(ctx_map[:, :h])
+        return hx
+
+    @staticmethod
+    def encoder_head(cost, inv, wc1, bc1, wd1, bd1):
+        return torch.cat([torch.relu(F.conv2d(cost, wc1, bc1)), torch.relu(F.conv2d(inv, wd1, bd1, padding=3))], dim=1)
+
+    @staticmethod
+    def encoder_tail(m, w, ctx_term, hx):
+        h = ctx_term.shape[1]
+        hx[:, h:] = torch.relu(F.conv2d(m, w) + ctx_term)
+
+    @staticmethod
+    def encoder_tail_ctx(m, w_m, ctx, ctx_offset, cx, ctx_relu, w_ctx, bias, hx):
+        h = w_m.shape[0]
+        c = ctx[:, ctx_offset:ctx_offset + cx]
+        c = torch.relu(c) if ctx_relu else c
+        hx[:, h:] = torch.relu(F.conv2d(m, w_m) + F.conv2d(c, w_ctx, bias))
+
+    @staticmethod
+    def gru_reset(zr_pre, bias_r, hx):
+        h = zr_pre.shape[1] // 2
+        out = hx.clone()
+        out[:, :h] = torch.sigmoid(zr_pre[:, h:] + bias_r.reshape(1, -1, 1, 1)) * hx[:, :h]
+        return out
+
+    @staticmethod
+    def gru_update(zr_pre, bias_z, q_pre, bias_q, hx):
+        h = q_pre.shape[1]
+        z = torch.sigmoid(zr_pre[:, :h] + bias_z.reshape(1, -1, 1, 1))
+        net_new = (1 - z) * hx[:, :h] + z * torch.tanh(q_pre + bias_q.reshape(1, -1, 1, 1))
+        hx[:, :h] = net_new
+        return net_new.clone()
+
+    @classmethod
+    def gru_delta(cls, pre, bias, inv, lo, hi):
+        new = inv.clone() if pre is None else inv + torch.tanh(pre + bias.reshape(1, -1, 1, 1))
+        return new, cls._to_depth(new, lo, hi)
+
+    @classmethod
+    def delta_head(cls, t, weight, bias, inv, lo, hi):
+        new = inv + torch.tanh(F.conv2d(t, weight, bias, padding=1))
+        return new, cls._to_depth(new, lo, hi)
+
+    @classmethod
+    def convex_upsample(cls, mask_pre, mask_bias, scale, inv, lo, hi, ratio):
+        up = net.convex_upsample(inv, scale * (mask_pre + mask_bias.reshape(1, -1, 1, 1)), ratio)
+        return up, cls._to_depth(up.unsqueeze(1), lo, hi).squeeze(1)
+
+    @classmethod
+    def convex_upsample_conv(cls, t, mask_w, mask_bias, scale, inv, lo, hi, ratio):
+        return cls.convex_upsample(F.conv2d(t, mask_w), mask_bias, scale, inv, lo, hi, ratio)
