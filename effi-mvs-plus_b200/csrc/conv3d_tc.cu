@@ -115,6 +115,8 @@ struct ConvProgram {
     int tile_cols;                // TMEM columns of one accumulator stage (two stages are allocated)
     int cls_z;                    // 1: the accumulator classes are consecutive output planes (z-sweep), output z = grid z * up_z + class
     int b_lbo_rows;               // rows between the two K chunks of a packed weight block (b_rows, or 3 * b_rows when stacked)
+    int out_f32_pair;             // output (8 channels, hi/lo layout geometry) stored as raw fp32: channels 0-3 in the "hi" voxel, 4-7 in the "lo" voxel
+                                  // (16 bytes each) -- for a consumer on CUDA cores (deconv_cout1_kernel), which then needs no hi + lo unpacking
     int debug;                    // EFFIMVS_TC_DEBUG bits (profiling only): 1 no MMA, 2 no operand copies, 4 no epilogue body, 8 no stores
     Phase ph[MAX_PHASES];
     Seg segs[MAX_SEGS];
@@ -394,6 +396,11 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] += r[j];
                         }
+                    }
+                    if (P.out_f32_pair) {
+                        out[act_index(OL, b, g, oz, oy, ox)] = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                        out[act_index(OL, b, g + OL.lo_off, oz, oy, ox)] = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                        continue;
                     }
                     if (!(P.debug & 8)) store_voxel(out, OL, b, g, oz, oy, ox, v);
                 }
@@ -937,7 +944,15 @@ int run_cin1(const float* x, const float* w, const float* bias, int B, int D, in
 // layout (halos are the zero padding, so no bounds checks), hi + lo halves are summed back to fp32 and the
 // weights stay fp32 in shared memory.
 // ------------------------------------------------------------------------------------------------
+// RAW: the two 16-byte voxels hold fp32 channels 0-3 / 4-7 (ConvProgram::out_f32_pair) instead of bf16 hi / lo halves
+template <bool RAW = false>
 __device__ __forceinline__ void load_voxel_f32(const uint4* __restrict__ hi, long long lo_delta, long long idx, float (&v)[8]) {
+    if (RAW) {
+        const uint4 a = __ldg(hi + idx), c = __ldg(hi + idx + lo_delta);
+        v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+        v[4] = __uint_as_float(c.x); v[5] = __uint_as_float(c.y); v[6] = __uint_as_float(c.z); v[7] = __uint_as_float(c.w);
+        return;
+    }
     unpack_bf16x8(__ldg(hi + idx), v);
     if (lo_delta) {
         float l[8];
@@ -1004,6 +1019,7 @@ conv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float*
 // transposed conv 8 -> 1, k3, stride (1,2,2), padding 1, output_padding (0,1,1): w (8,1,3,3,3) fp32,
 // out (B,1,D,2H,2W) fp32.  A thread owns one input position and writes its 2x2 output parities:
 // out[z, 2y+py, 2x+px] = sum over a and the taps b, c of that parity (b = 1 <-> input y; b = 0 <-> y + 1; b = 2 <-> y)
+template <bool RAW>
 __global__ void __launch_bounds__(128)
 deconv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float* __restrict__ w, const float* __restrict__ bias, int relu,
                     float* __restrict__ out) {
@@ -1026,7 +1042,7 @@ deconv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const floa
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) load_voxel_f32(in, lo_delta, plane + (long long)(y + 1 + dy) * IL.Px + (x + 1 + dx), v[dy][dx]);
+            for (int dx = 0; dx < 2; ++dx) load_voxel_f32<RAW>(in, lo_delta, plane + (long long)(y + 1 + dy) * IL.Px + (x + 1 + dx), v[dy][dx]);
 #pragma unroll
         for (int bb = 0; bb < 3; ++bb)
 #pragma unroll
@@ -1051,10 +1067,12 @@ deconv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const floa
 }
 
 int run_cout1(bool deconv, int B, const void* in, const ActLayout& IL, const float* w, const float* bias, int relu, float* out,
-              cudaStream_t st) {
+              cudaStream_t st, bool raw_f32 = false) {
     if (deconv) {
         const size_t work = (size_t)IL.D * IL.H * IL.W;
-        deconv_cout1_kernel<<<dim3((unsigned)((work + 127) / 128), B), 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+        const dim3 grid((unsigned)((work + 127) / 128), B);
+        if (raw_f32) deconv_cout1_kernel<true><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+        else deconv_cout1_kernel<false><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
         return check_launch("deconv_cout1_kernel");
     }
     const size_t work = (size_t)IL.D * IL.H * ((IL.W + COUT1_X - 1) / COUT1_X);
@@ -1170,9 +1188,14 @@ int cost_up_bf16(const float* x, const float* prev, const float* const* weights,
     // in a hi/lo layout the concatenated tensor has planes [conv0 hi, conv_cost hi, conv0 lo, conv_cost lo]
     if ((rc = run_cin1(x, weights[0], biases[0], B, D, H, W, 2, Lcat, 0, cat, st))) return rc;
     if ((rc = run_cin1(prev, weights[1], biases[1], B, D, H2, W2, 1, Lcat, 1, cat, st))) return rc;
+    // conv1's only consumer is the CUDA-core 8 -> 1 layer: in a hi/lo layout (two 16-byte voxels per position) it gets the
+    // eight fp32 values as they are instead of bf16 hi + lo halves (same bytes, exact, no unpacking on the other side)
+    const bool tc_cout1 = getenv("EFFIMVS_TC_COUT1") != nullptr;
+    const bool raw = hilo && !tc_cout1 && !getenv("EFFIMVS_NO_RAW_F32");
+    P1.out_f32_pair = raw ? 1 : 0;
     if ((rc = run_tile_kernel(P1, B, cat, Lcat, wp1, biases[2], L1, c1, nullptr, nullptr, nullptr, st))) return rc;
     ActLayout LO = make_layout(L_REG, 8, D, H, W, false);  // fp32 output indexed with the logical (full-resolution) dims
-    if (!getenv("EFFIMVS_TC_COUT1")) return run_cout1(true, B, c1, L1, weights[3], biases[3], 1, out, st);        // 8 -> 1: CUDA cores
+    if (!tc_cout1) return run_cout1(true, B, c1, L1, weights[3], biases[3], 1, out, st, raw);        // 8 -> 1: CUDA cores
     return run_tile_kernel(P2, B, c1, L1, wp2, biases[3], LO, nullptr, nullptr, nullptr, out, st);
 }
 
