@@ -965,6 +965,7 @@ __device__ __forceinline__ void load_voxel_f32(const uint4* __restrict__ hi, lon
 constexpr int COUT1_X = 4;   // consecutive outputs of a row per thread (the convolution form)
 
 // conv 8 -> 1, k3 p1 s1: w (1,8,3,3,3) fp32, out (B,1,D,H,W) fp32
+template <bool RAW>
 __global__ void __launch_bounds__(128)
 conv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float* __restrict__ w, const float* __restrict__ bias, int relu,
                   float* __restrict__ out) {
@@ -990,7 +991,7 @@ conv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float*
             float v[COUT1_X + 2][8];
 #pragma unroll
             for (int j = 0; j < COUT1_X + 2; ++j) {
-                if (x0 + j <= W + 1) load_voxel_f32(in, lo_delta, row + j, v[j]);   // padded x up to W + 1
+                if (x0 + j <= W + 1) load_voxel_f32<RAW>(in, lo_delta, row + j, v[j]);   // padded x up to W + 1
                 else {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) v[j][c] = 0.0f;
@@ -1076,7 +1077,9 @@ int run_cout1(bool deconv, int B, const void* in, const ActLayout& IL, const flo
         return check_launch("deconv_cout1_kernel");
     }
     const size_t work = (size_t)IL.D * IL.H * ((IL.W + COUT1_X - 1) / COUT1_X);
-    conv_cout1_kernel<<<dim3((unsigned)((work + 127) / 128), B), 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+    const dim3 grid((unsigned)((work + 127) / 128), B);
+    if (raw_f32) conv_cout1_kernel<true><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+    else conv_cout1_kernel<false><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
     return check_launch("conv_cout1_kernel");
 }
 
@@ -1143,8 +1146,15 @@ int costreg_bf16(const float* x, const float* const* weights, const float* const
     if ((rc = run_tile_kernel(P[3], B, c3, L3, wp[3], biases[4], L4, c4, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[4], B, c4, L4, wp[4], biases[5], L5, c5, nullptr, nullptr, nullptr, st))) return rc;
     if ((rc = run_tile_kernel(P[5], B, c5, L5, wp[5], biases[6], L6, c6, &L3, c3, nullptr, st))) return rc;
+    // conv7's only consumer is the 8 -> 1 prob layer.  EFFIMVS_PROB_PATH=raw: conv7 stores its eight fp32 channels as they are
+    // (two 16-byte voxels of the hi/lo geometry) and prob runs on CUDA cores without unpacking; default: prob as a z-sweep
+    // tensor-core program on hi/lo bf16 (see the measurements in DESIGN.md)
+    const char* prob_path = getenv("EFFIMVS_PROB_PATH");
+    const bool raw_prob = hilo && prob_path && !strcmp(prob_path, "raw");
+    P[6].out_f32_pair = raw_prob ? 1 : 0;
     if ((rc = run_tile_kernel(P[6], B, c6, L6, wp[6], biases[7], L7, c7, &L1, c1, nullptr, st))) return rc;
-    // measured: the z-sweep tensor-core program (0.49 ms for the net) beats the CUDA-core form (0.52 ms) for this stride-1 layer
+    if (raw_prob) return run_cout1(false, B, c7, L7, weights[8], nullptr, 0, prob_out, st, true);
+    // measured: the z-sweep tensor-core program (0.49 ms for the net) beats the CUDA-core form on hi/lo input (0.52 ms) for this stride-1 layer
     if (getenv("EFFIMVS_CUDA_CORE_PROB")) return run_cout1(false, B, c7, L7, weights[8], nullptr, 0, prob_out, st);
     return run_tile_kernel(P[7], B, c7, L7, wp[7], nullptr, L7, nullptr, nullptr, nullptr, prob_out, st);  // fp32 out, logical dims of L7
 }
