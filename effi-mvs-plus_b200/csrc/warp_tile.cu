@@ -496,6 +496,38 @@ softmax_entropy_kernel(const float* __restrict__ sims, int D, int HW, float* __r
     entropy_out[(size_t)blockIdx.y * HW + pix] = ent;
 }
 
+// The same with the D similarities of a pixel held in registers (D <= DMAX, unrolled): one read of the volume instead
+// of three and each exponential evaluated once; operations and their order are those of the kernel above.
+template <int DMAX>
+__global__ void __launch_bounds__(256)
+softmax_entropy_reg_kernel(const float* __restrict__ sims, int D, int HW, float* __restrict__ entropy_out) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= HW) return;
+    const float* mine = sims + (size_t)blockIdx.y * D * HW + pix;
+    float e[DMAX];
+    float m = -INFINITY;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d) {
+        e[d] = d < D ? __ldg(mine + (size_t)d * HW) : -INFINITY;
+        m = fmaxf(m, e[d]);
+    }
+    float z = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+        if (d < D) {
+            e[d] = expf(e[d] - m);
+            z += e[d];
+        }
+    float ent = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DMAX; ++d)
+        if (d < D) {
+            const float p = __fdiv_rn(e[d], z);
+            ent -= p * logf(p + 1e-7f);
+        }
+    entropy_out[(size_t)blockIdx.y * HW + pix] = ent;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -578,7 +610,10 @@ int launch_views(const float* ref, const SrcPtrs& srcs, int n_src, const float* 
     cudaFuncSetAttribute(warp_views_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     warp_views_tile_kernel<C><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
     if ((rc = check_launch("warp_views_tile_kernel"))) return rc;
-    softmax_entropy_kernel<<<dim3(ceil_div(H * W, 256), B * n_src), 256, 0, st>>>(sims_out, D, H * W, entropy_out);
+    const dim3 egrid(ceil_div(H * W, 256), B * n_src);
+    if (D <= 48) softmax_entropy_reg_kernel<48><<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);
+    else if (D <= 96) softmax_entropy_reg_kernel<96><<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);
+    else softmax_entropy_kernel<<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);
     return check_launch("softmax_entropy_kernel");
 }
 
