@@ -107,5 +107,10 @@ def test_fake_implementations_give_shapes_without_a_device():
         ws = torch.empty(64, dtype=torch.uint8)
         assert torch.ops.effimvs.costreg_run(torch.empty(1, 1, 8, 8, 8), [ref] * 9, [ref] * 8, 2, ws).shape == (1, 1, 8, 8, 8)
         assert torch.ops.effimvs.cost_up_run(torch.empty(1, 1, 8, 8, 8), torch.empty(1, 1, 8, 4, 4), [ref] * 4, [ref] * 4, 2, ws).shape == (1, 1, 8, 8, 8)
+        # ops without outputs (in-place on a caller-kept buffer) trace as no-ops
+        assert torch.ops.effimvs.costreg_prepare([ref] * 9, [ref] * 8, 1, 8, 8, 8, 2, ws) is None
+        assert torch.ops.effimvs.cost_up_prepare([ref] * 4, [ref] * 4, 1, 8, 8, 8, 2, ws) is None
+        assert torch.ops.effimvs.encoder_tail_ctx(torch.empty(1, 12, 4, 4), torch.empty(16, 12, 1, 1), torch.empty(1, 20, 4, 4), 16, 4, True,
+                                                  torch.empty(16, 4, 1, 1), torch.empty(16), torch.empty(1, 32, 4, 4)) is None
         out = torch.ops.effimvs.conv3d_bf16(torch.empty(1, 16, 4, 6, 8), torch.empty(16, 8, 3, 3, 3), None, None, 2, True, True, 2)
         assert out.shape == (1, 8, 8, 12, 16)
