@@ -114,3 +114,32 @@ def test_fake_implementations_give_shapes_without_a_device():
                                                   torch.empty(16, 4, 1, 1), torch.empty(16), torch.empty(1, 32, 4, 4)) is None
         out = torch.ops.effimvs.conv3d_bf16(torch.empty(1, 16, 4, 6, 8), torch.empty(16, 8, 3, 3, 3), None, None, 2, True, True, 2)
         assert out.shape == (1, 8, 8, 12, 16)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/effimvs.h compiles as C99 (no C++ or torch types in the boundary) and a C program linked against
+    libeffimvs.so reaches the library: version, and an argument error reported through effimvs_last_error()."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "effimvs.h"\n'
+        "int main(void) {\n"
+        "    if (effimvs_version() < 100) return 1;\n"
+        "    int rc = effimvs_weighted_agg_f32(NULL, NULL, 1, 1, 1, 1, 1, NULL, NULL);\n"
+        "    if (rc != EFFIMVS_EINVAL) return 2;\n"
+        '    if (!strstr(effimvs_last_error(), "null pointer")) return 3;\n'
+        "    size_t n = effimvs_costreg_workspace_bytes(1, 48, 148, 200, EFFIMVS_PREC_BF16X3);\n"
+        "    rc = effimvs_costreg_fpn3d_ex(NULL, NULL, NULL, 1, 48, 148, 200, EFFIMVS_PREC_BF16X3, EFFIMVS_WS_PREPARE, NULL, n, NULL, NULL);\n"
+        "    if (rc != EFFIMVS_EINVAL) return 4;\n"
+        '    printf("%zu\\n", n);\n'
+        "    return 0;\n}\n")
+    exe = tmp_path / "probe"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-leffimvs", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True)
+    assert int(out.stdout.strip()) > 100 << 20      # the DTU-shape bf16x3 workspace is a few hundred MB
