@@ -143,3 +143,15 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
                     "-L", libdir, "-leffimvs", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True)
     assert int(out.stdout.strip()) > 100 << 20      # the DTU-shape bf16x3 workspace is a few hundred MB
+
+
+def test_documents_name_only_declared_entry_points():
+    """every effimvs_* function that INTEGRATION.md, DESIGN.md or README.md mentions is declared in include/effimvs.h"""
+    declared = set(declared_functions())
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        text = open(os.path.join(ROOT, doc)).read()
+        for name in set(re.findall(r"\b(effimvs_[a-z0-9_]*[a-z0-9])\b", text)):
+            if name in ("effimvs_b200",) or name.startswith("effimvs_b200"):
+                continue
+            # shorthand like `effimvs_*_ex` / `effimvs_*_workspace_bytes` is written with a star and never matches; `_conv_f32` style suffixes neither
+            assert name in declared or any(d.startswith(name) for d in declared), "{} names {} which the header does not declare".format(doc, name)
