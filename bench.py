@@ -76,6 +76,47 @@ def build_model(hotpath, device, ndepths):
     return model, data
 
 
+def reference_model(device, ndepths):
+    """The reference arm's model: UNMODIFIED upstream (oracle/_ref byte copy, kind "reference") when it is staged,
+    else the oracle port inside this repo's host cascade (kind "port").  -> (model, kind, description)"""
+    from oracle import upstream
+    wfile = os.path.join(ROOT, "tests", "golden", "dtu_weights.pt")
+    if upstream.available():
+        sd = torch.load(wfile, map_location="cpu") if os.path.exists(wfile) else None
+        torch.manual_seed(0)
+        with _silenced():
+            model = upstream.build_model(sd, ndepths, device)
+        return model, "reference", "unmodified upstream Effi_MVS_plus.forward (oracle/_ref byte copy), eager PyTorch"
+    from oracle import hotpath as ohp
+    model, _ = build_model(ohp.OracleHotPath(), device, ndepths)
+    return model, "port", "oracle port of the hot path inside this repo's host cascade, eager PyTorch"
+
+
+class _silenced:
+    """upstream's constructor prints its configuration; keep it off the bench's stdout / stderr"""
+
+    def __enter__(self):
+        import contextlib
+        import io
+        self.cm = contextlib.redirect_stdout(io.StringIO())
+        return self.cm.__enter__()
+
+    def __exit__(self, *a):
+        return self.cm.__exit__(*a)
+
+
+def config_keys(a, views, ndepths):
+    """the `config` object BOTH arms print, value for value (the driver compares them to tell that the two arms ran
+    the same workload); what differs between the arms is stated per arm inside it, run facts go to `run`"""
+    _, workload = LABELS[a.shape]
+    return {"workload": workload, "shape": a.shape, "views": views, "ndepths": ndepths,
+            "l2": "impl ours: 256 MiB memset between steps, inside the timed region; impl reference: CPU arm, inputs in host memory",
+            "sharding": "impl ours: one reference view per rank per step, no collective; impl reference: ONE CPU process on the "
+                        "box's host cores whatever --gpus says",
+            "stock_pytorch": "FPN, ConvGRU convolutions: cuDNN, TF32 allowed (torch default, as upstream) in impl ours; "
+                             "impl reference: unmodified upstream, eager PyTorch fp32 on the CPU"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -131,15 +172,17 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(a, rank, world):
-    """Oracle port of the upstream path on the host cores (kind 'port'); rank 0 only."""
+    """The reference's own implementation of the path on the box's host cores: unmodified upstream from oracle/_ref
+    (kind 'reference'; the oracle port, kind 'port', only if the byte copy is not staged); rank 0 only -- at N > 1
+    this is still ONE CPU box, not N of them."""
     if rank != 0:
         return
     import effimvs_b200  # noqa: F401
     from effimvs_b200 import synthetic
-    from oracle import hotpath as ohp
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model, data = build_model(ohp.OracleHotPath(), "cpu", synthetic.SHAPES[a.shape]["ndepths"])
+    ndepths = synthetic.SHAPES[a.shape]["ndepths"]
+    model, kind, what = reference_model("cpu", ndepths)
     s = synthetic.make_sample(a.shape, seed=0)
     times = []
     t_begin = time.perf_counter()
@@ -165,14 +208,17 @@ def run_reference(a, rank, world):
     done_k = len(times)
     total = sum(times)
     value = done_k / total
-    sample = "{} of {} requested steps, each one full {} depth map on {} host threads ({} warm-up; {:.0f} s cap)".format(
-        done_k, a.steps, a.shape, cores, done_w, a.cpu_budget_s)
-    metric, workload = LABELS[a.shape]
+    sample = "{} of {} requested steps, each one full {} depth map on {} host threads ({} warm-up; {:.0f} s cap); {}".format(
+        done_k, a.steps, a.shape, cores, done_w, a.cpu_budget_s, what)
+    metric, _ = LABELS[a.shape]
+    data = "synthetic images/cameras (seeded); weights = upstream model_dtu.ckpt values (tests/golden/dtu_weights.pt)"
+    cfg = config_keys(a, int(s["imgs"].shape[1]), ndepths)
     line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": done_k,
             "warmup": done_w, "ms_per_step": 1e3 * total / done_k, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": data, "config": {"workload": workload, "device": "cpu"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "vs_baseline": None, "dtype": "f32", "data": data, "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "run": {"device": "cpu", "cores": cores, "processes": 1}}
     OUT.emit(json.dumps(line))
 
 
@@ -459,39 +505,39 @@ def run_ours(a, rank, world, local_rank):
         if rank == 0:
             roof, roof_reg, kern = kernel_rooflines(hp, model, stat, hbm_peak, tf_peak, peak_src)
 
-    cpu = None
+    cpu = eager = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        eager = gpu_eager_baseline(a, ndepths, stat, dev)
         cpu = cpu_baseline(a, ndepths)
     if rank != 0:
         return
     value = world * a.steps / (ms_dev / 1e3)
     e2e = world * a.steps / (ms_e2e / 1e3)
-    metric, workload = LABELS[a.shape]
+    metric, _ = LABELS[a.shape]
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"f32": "f32", "bf16": "bf16 MMA, f32 accumulate (3-D regularization) / f32 (warp, lookup, regression)",
                       "bf16x3": "hi+lo bf16 MMA x3, f32 accumulate (3-D regularization, fp32-grade) / f32 (warp, lookup, regression)"}[a.precision],
             "data": data,
-            "config": {"workload": workload, "shape": a.shape, "views": int(stat["imgs"].shape[1]), "ndepths": ndepths,
-                       "sharding": "one reference view per rank per step, no collective", "cuda_graph": graph is not None,
-                       "l2": "256 MiB memset between steps (inside the timed region)",
-                       "stock_pytorch": "FPN, ConvGRU, convex upsampling: cuDNN, TF32 allowed (torch default, as upstream)"},
+            "config": config_keys(a, int(stat["imgs"].shape[1]), ndepths),
+            "run": {"device": "cuda", "cuda_graph": graph is not None, "processes": world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps,
                     "api": "effimvs_b200.pipeline.DepthMapPipeline.submit/result: pinned host -> device copy of step k+1 overlapped with the forward of step k"},
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clk.summary(), "roofline": roof, "roofline_regularization": roof_reg, "kernels": kern}
     if cpu:
         line["cpu_baseline"] = cpu
+    if eager:
+        line["gpu_eager_baseline"] = eager
     OUT.emit(json.dumps(line))
 
 
 def cpu_baseline(a, ndepths):
-    """Oracle port of the same workload on this box's host cores, bounded to a few forwards."""
+    """The reference arm's model on this box's host cores, bounded to a few forwards."""
     from effimvs_b200 import synthetic
-    from oracle import hotpath as ohp
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    model, _ = build_model(ohp.OracleHotPath(), "cpu", ndepths)
+    model, kind, what = reference_model("cpu", ndepths)
     s = synthetic.make_sample(a.shape, seed=0)
     ts = []
     with torch.no_grad():
@@ -503,9 +549,40 @@ def cpu_baseline(a, ndepths):
                 break
     timed = ts[1:] if len(ts) > 1 else ts
     v = len(timed) / sum(timed)
-    return {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "{} full {} depth map(s) after {} warm-up, oracle port (torch CPU kernels) on {} threads".format(
-                len(timed), a.shape, len(ts) - len(timed), cores)}
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "{} full {} depth map(s) after {} warm-up on {} threads; {}".format(
+                len(timed), a.shape, len(ts) - len(timed), cores, what)}
+
+
+def gpu_eager_baseline(a, ndepths, sample, dev, reps=3):
+    """The reference's eager PyTorch forward on the SAME B200: unmodified upstream, device-resident
+    inputs, CUDA events around `reps` forwards after one warm-up, with TF32 off (the parity setting) and with torch's
+    defaults for cuDNN (TF32 allowed for convolutions, as upstream's own test scripts run)."""
+    model, kind, what = reference_model(dev, ndepths)
+    out = {"kind": kind, "what": what, "unit": UNIT, "steps": reps}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        with torch.no_grad():
+            for tag, tf32 in (("tf32_off", False), ("tf32_on", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.benchmark = True          # as test_dtu_dypcd.py:41
+                for _ in range(2):
+                    model(sample["imgs"], sample["proj_matrices"], sample["depth_values"])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    model(sample["imgs"], sample["proj_matrices"], sample["depth_values"])
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                out[tag] = {"ms_per_step": ms, "value": 1e3 / ms}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 class _QuietStdout:

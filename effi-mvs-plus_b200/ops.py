@@ -51,7 +51,35 @@ def _features(ref: Tensor, srcs: List[Tensor], name: str):
 
 
 def _stream() -> int:
+    # inside _on_tensor_device the current device is the tensors' device, so this is THEIR current stream
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_tensor_device(fn):
+    """Run an op body with the CUDA device of its tensor arguments current (so that the launch, the stream handed
+    to the library and the output allocations all belong to that device, whatever torch's current device is), and
+    reject tensors spread over several CUDA devices.  CPU tensors pass through: the body reports them by name."""
+    import functools
+
+    def tensors(args):
+        for a in args:
+            if isinstance(a, Tensor):
+                yield a
+            elif isinstance(a, (list, tuple)):
+                for b in a:
+                    if isinstance(b, Tensor):
+                        yield b
+
+    @functools.wraps(fn)
+    def call(*args, **kw):
+        devs = {t.device for t in tensors(list(args) + list(kw.values())) if t.is_cuda}
+        if len(devs) > 1:
+            raise RuntimeError("effimvs::{} got tensors on several devices: {}".format(fn.__name__, sorted(map(str, devs))))
+        if not devs or next(iter(devs)).index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(next(iter(devs))):
+            return fn(*args, **kw)
+    return call
 
 
 def _opt(t: Optional[Tensor]):
@@ -60,6 +88,7 @@ def _opt(t: Optional[Tensor]):
 
 # -------------------------------------------------------------------------------------------
 @torch.library.custom_op("effimvs::relative_projection", mutates_args=())
+@_on_tensor_device
 def relative_projection(cams: Tensor) -> Tensor:
     cams = _dev(cams, "relative_projection")
     B, V = cams.shape[0], cams.shape[1]
@@ -76,6 +105,7 @@ def _(cams):
 
 # -------------------------------------------------------------------------------------------
 @torch.library.custom_op("effimvs::homo_warp", mutates_args=())
+@_on_tensor_device
 def homo_warp(src_fea: Tensor, proj: Tensor, hyp: Tensor, hyp_mode: int, D: int) -> Tensor:
     src_fea, proj, hyp = _dev(src_fea, "homo_warp"), _dev(proj, "homo_warp"), _dev(hyp, "homo_warp")
     B, Cc, H, W = src_fea.shape
@@ -93,6 +123,7 @@ def _(src_fea, proj, hyp, hyp_mode, D):
 
 
 @torch.library.custom_op("effimvs::depth_range_samples", mutates_args=())
+@_on_tensor_device
 def depth_range_samples(cur: Tensor, interval: Tensor, ndepth: int) -> Tensor:
     cur, interval = _dev(cur, "depth_range_samples"), _dev(interval, "depth_range_samples")
     B, H, W = cur.shape
@@ -109,6 +140,7 @@ def _(cur, interval, ndepth):
 
 
 @torch.library.custom_op("effimvs::fusion_masks", mutates_args=())
+@_on_tensor_device
 def fusion_masks(ref_depth: Tensor, reproj_xyd: Tensor, dist_base: float, rel_diff_base: float, thres_view: int,
                  relative: bool) -> Tensor:
     ref_depth, reproj_xyd = _dev(ref_depth, "fusion_masks"), _dev(reproj_xyd, "fusion_masks")
@@ -129,6 +161,7 @@ def _(ref_depth, reproj_xyd, dist_base, rel_diff_base, thres_view, relative):
 
 # -------------------------------------------------------------------------------------------
 @torch.library.custom_op("effimvs::warp_corr_agg", mutates_args=())
+@_on_tensor_device
 def warp_corr_agg(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hyp_mode: int,
                   interval: Optional[Tensor], weights: Optional[Tensor], D: int, G: int,
                   want_hyp: bool) -> Tuple[Tensor, Tensor]:
@@ -155,6 +188,7 @@ def _(ref, srcs, proj, hyp, hyp_mode, interval, weights, D, G, want_hyp):
 
 
 @torch.library.custom_op("effimvs::warp_corr_views", mutates_args=())
+@_on_tensor_device
 def warp_corr_views(ref: Tensor, srcs: List[Tensor], proj: Tensor, hyp: Tensor, hyp_mode: int, D: int) -> Tuple[Tensor, Tensor]:
     ref, srcs, layout = _features(ref, srcs, "warp_corr_views")
     proj, hyp = _dev(proj, "warp_corr_views"), _dev(hyp, "warp_corr_views")
@@ -177,6 +211,7 @@ def _(ref, srcs, proj, hyp, hyp_mode, D):
 
 
 @torch.library.custom_op("effimvs::weighted_agg", mutates_args=())
+@_on_tensor_device
 def weighted_agg(sims: Tensor, weights: Tensor) -> Tensor:
     sims, weights = _dev(sims, "weighted_agg"), _dev(weights, "weighted_agg")
     B, n, D, H, W = sims.shape
@@ -202,6 +237,7 @@ def _range_mode(dmin: Tensor, B: int, H: int, W: int) -> int:
 
 
 @torch.library.custom_op("effimvs::volume_lookup", mutates_args=())
+@_on_tensor_device
 def volume_lookup(volume: Tensor, depth_sample: Tensor, depth_min: Tensor, depth_max: Tensor, sample_stride: int) -> Tensor:
     volume, depth_sample = _dev(volume, "volume_lookup"), _dev(depth_sample, "volume_lookup")
     depth_min, depth_max = _dev(depth_min, "volume_lookup"), _dev(depth_max, "volume_lookup")
@@ -226,6 +262,7 @@ def _(volume, depth_sample, depth_min, depth_max, sample_stride):
 
 
 @torch.library.custom_op("effimvs::dynamic_cost", mutates_args=())
+@_on_tensor_device
 def dynamic_cost(cur_depth: Tensor, raw: Tensor, reg: Tensor, interval: Tensor, depth_min: Tensor, depth_max: Tensor,
                  ndepth: int) -> Tensor:
     cur_depth, raw, reg = _dev(cur_depth, "dynamic_cost"), _dev(raw, "dynamic_cost"), _dev(reg, "dynamic_cost")
@@ -251,6 +288,7 @@ def _(cur_depth, raw, reg, interval, depth_min, depth_max, ndepth):
 
 
 @torch.library.custom_op("effimvs::softmax_regress_conf", mutates_args=())
+@_on_tensor_device
 def softmax_regress_conf(prob_pre: Tensor, hyp: Tensor, hyp_mode: int) -> Tuple[Tensor, Tensor]:
     prob_pre, hyp = _dev(prob_pre, "softmax_regress_conf"), _dev(hyp, "softmax_regress_conf")
     B, D, H, W = prob_pre.shape
@@ -270,6 +308,7 @@ def _(prob_pre, hyp, hyp_mode):
 
 # -------------------------------------------------------------------------------------------
 @torch.library.custom_op("effimvs::conv3d", mutates_args=())
+@_on_tensor_device
 def conv3d(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], stride: List[int],
            transposed: bool, relu: bool) -> Tensor:
     x, weight = _dev(x, "conv3d"), _dev(weight, "conv3d")
@@ -300,6 +339,7 @@ def _(x, weight, bias, residual, stride, transposed, relu):
 
 
 @torch.library.custom_op("effimvs::conv3d_bf16", mutates_args=())
+@_on_tensor_device
 def conv3d_bf16(x: Tensor, weight: Tensor, bias: Optional[Tensor], residual: Optional[Tensor], sd: int,
                 transposed: bool, relu: bool, precision: int) -> Tensor:
     """One (de)conv layer on the tensor cores (tcgen05), fp32 NCDHW in/out.  Conv: stride sd in all
@@ -332,6 +372,7 @@ def _(x, weight, bias, residual, sd, transposed, relu, precision):
 
 
 @torch.library.custom_op("effimvs::costreg_fpn3d", mutates_args=())
+@_on_tensor_device
 def costreg_fpn3d(x: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int) -> Tensor:
     x = _dev(x, "costreg_fpn3d")
     weights = [_dev(w, "costreg_fpn3d") for w in weights]
@@ -357,6 +398,7 @@ def _(x, weights, biases, precision):
 
 
 @torch.library.custom_op("effimvs::cost_up_small", mutates_args=())
+@_on_tensor_device
 def cost_up_small(x: Tensor, prev: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int) -> Tensor:
     x, prev = _dev(x, "cost_up_small"), _dev(prev, "cost_up_small")
     weights = [_dev(w, "cost_up_small") for w in weights]
@@ -407,6 +449,7 @@ def _reg_args(weights, biases, nw, nb, what):
 
 
 @torch.library.custom_op("effimvs::costreg_prepare", mutates_args=("ws",))
+@_on_tensor_device
 def costreg_prepare(weights: List[Tensor], biases: List[Tensor], B: int, D: int, H: int, W: int, precision: int, ws: Tensor) -> None:
     (wa, k1), (ba, k2) = _reg_args(weights, biases, 9, 8, "costreg_prepare")
     ws = _wsbuf(ws, "costreg_prepare")
@@ -417,6 +460,7 @@ def costreg_prepare(weights: List[Tensor], biases: List[Tensor], B: int, D: int,
 
 
 @torch.library.custom_op("effimvs::costreg_run", mutates_args=("ws",))
+@_on_tensor_device
 def costreg_run(x: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int, ws: Tensor) -> Tensor:
     """costreg_fpn3d on a workspace prepared by costreg_prepare for these weights and this shape."""
     x, ws = _dev(x, "costreg_run"), _wsbuf(ws, "costreg_run")
@@ -436,6 +480,7 @@ def _(x, weights, biases, precision, ws):
 
 
 @torch.library.custom_op("effimvs::cost_up_prepare", mutates_args=("ws",))
+@_on_tensor_device
 def cost_up_prepare(weights: List[Tensor], biases: List[Tensor], B: int, D: int, H: int, W: int, precision: int, ws: Tensor) -> None:
     (wa, k1), (ba, k2) = _reg_args(weights, biases, 4, 4, "cost_up_prepare")
     ws = _wsbuf(ws, "cost_up_prepare")
@@ -446,6 +491,7 @@ def cost_up_prepare(weights: List[Tensor], biases: List[Tensor], B: int, D: int,
 
 
 @torch.library.custom_op("effimvs::cost_up_run", mutates_args=("ws",))
+@_on_tensor_device
 def cost_up_run(x: Tensor, prev: Tensor, weights: List[Tensor], biases: List[Tensor], precision: int, ws: Tensor) -> Tensor:
     """cost_up_small on a workspace prepared by cost_up_prepare for these weights and this shape."""
     x, prev, ws = _dev(x, "cost_up_run"), _dev(prev, "cost_up_run"), _wsbuf(ws, "cost_up_run")
@@ -468,6 +514,7 @@ def _(x, prev, weights, biases, precision, ws):
 
 # -------------------------------------------------------------------------------------------
 @torch.library.custom_op("effimvs::fusion_reproject", mutates_args=())
+@_on_tensor_device
 def fusion_reproject(ref_depth: Tensor, srcs_depth: Tensor, ref_cam: Tensor, srcs_cam: Tensor,
                      inv_cams: Optional[Tensor]) -> Tensor:
     ref_depth, srcs_depth = _dev(ref_depth, "fusion_reproject"), _dev(srcs_depth, "fusion_reproject")
@@ -488,6 +535,7 @@ def _(ref_depth, srcs_depth, ref_cam, srcs_cam, inv_cams):
 
 
 @torch.library.custom_op("effimvs::fusion_filter", mutates_args=())
+@_on_tensor_device
 def fusion_filter(ref_depth: Tensor, srcs_depth: Tensor, conf: Tensor, ref_cam: Tensor, srcs_cam: Tensor,
                   inv_cams: Optional[Tensor], dist_base: float, rel_diff_base: float, thres_view: int,
                   prob_threshold: float, relative: bool, want_masks: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
@@ -532,6 +580,7 @@ def _nhwc(t: Tensor, name: str) -> Tensor:
 
 
 @torch.library.custom_op("effimvs::gru_reset", mutates_args=())
+@_on_tensor_device
 def gru_reset(zr_pre: Tensor, bias_r: Tensor, hx: Tensor) -> Tensor:
     """zr_pre (B,2h,H,W) = [convz ; convr] without bias, hx (B,h+cx,H,W) = cat[h, x] -> cat[sigmoid(r) * h, x]."""
     zr_pre, hx, bias_r = _nhwc(zr_pre, "gru_reset"), _nhwc(hx, "gru_reset"), _dev(bias_r, "gru_reset")
@@ -550,6 +599,7 @@ def _(zr_pre, bias_r, hx):
 
 
 @torch.library.custom_op("effimvs::gru_update", mutates_args=("hx",))
+@_on_tensor_device
 def gru_update(zr_pre: Tensor, bias_z: Tensor, q_pre: Tensor, bias_q: Tensor, hx: Tensor) -> Tensor:
     """h' = (1 - z) * h + z * tanh(q_pre + bias_q); updates hx[:, :h] in place (hx must be channels-last) and
     returns h' as a dense channels-last (B,h,H,W) map."""
@@ -571,6 +621,7 @@ def _(zr_pre, bias_z, q_pre, bias_q, hx):
 
 
 @torch.library.custom_op("effimvs::gru_delta", mutates_args=())
+@_on_tensor_device
 def gru_delta(pre: Optional[Tensor], bias: Optional[Tensor], inv: Tensor, lo_disp: Tensor, hi_disp: Tensor) -> Tuple[Tensor, Tensor]:
     """inv' = inv + tanh(pre + bias) (pre None: inv' = inv) and depth = 1 / clamp(lo + (hi - lo) * inv', 1e-4); all (B,1,H,W)."""
     inv, lo_disp, hi_disp = _dev(inv, "gru_delta"), _dev(lo_disp, "gru_delta"), _dev(hi_disp, "gru_delta")
@@ -593,6 +644,7 @@ def _(pre, bias, inv, lo_disp, hi_disp):
 
 
 @torch.library.custom_op("effimvs::delta_head", mutates_args=())
+@_on_tensor_device
 def delta_head(t: Tensor, weight: Tensor, bias: Tensor, inv: Tensor, lo_disp: Tensor, hi_disp: Tensor) -> Tuple[Tensor, Tensor]:
     """t (B,h,H,W) = relu(depth_head.conv1(net)), weight (1,h,3,3), bias (1): inv' = inv + tanh(conv3x3(t) + bias) and
     depth = 1 / clamp(lo + (hi - lo) * inv', 1e-4), both (B,1,H,W) -- depth_head.conv2 and gru_delta in one pass."""
@@ -614,6 +666,7 @@ def _(t, weight, bias, inv, lo_disp, hi_disp):
 
 
 @torch.library.custom_op("effimvs::convex_upsample", mutates_args=())
+@_on_tensor_device
 def convex_upsample(mask_pre: Tensor, mask_bias: Optional[Tensor], mask_scale: float, inv: Tensor, lo_disp: Tensor,
                     hi_disp: Tensor, ratio: int) -> Tuple[Tensor, Tensor]:
     """upsample_depth on mask = mask_scale * (mask_pre + mask_bias): (B,9*ratio^2,H,W), inv (B,1,H,W)
@@ -637,6 +690,7 @@ def _(mask_pre, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
 
 
 @torch.library.custom_op("effimvs::convex_upsample_conv", mutates_args=())
+@_on_tensor_device
 def convex_upsample_conv(t: Tensor, mask_w: Tensor, mask_bias: Optional[Tensor], mask_scale: float, inv: Tensor, lo_disp: Tensor,
                          hi_disp: Tensor, ratio: int) -> Tuple[Tensor, Tensor]:
     """convex_upsample with mask = mask_scale * (conv1x1(t, mask_w) + mask_bias) formed in the kernel: t (B,K,H,W) =
@@ -663,6 +717,7 @@ def _(t, mask_w, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
 
 
 @torch.library.custom_op("effimvs::encoder_head", mutates_args=())
+@_on_tensor_device
 def encoder_head(cost: Tensor, inv: Tensor, wc1: Tensor, bc1: Tensor, wd1: Tensor, bd1: Tensor) -> Tensor:
     """cat[relu(convc1(cost)), relu(convd1(inv))] as one channels-last (B,2h,H,W) map (models/update.py:88-91)."""
     cost, inv = _dev(cost, "encoder_head"), _dev(inv, "encoder_head")
@@ -683,6 +738,7 @@ def _(cost, inv, wc1, bc1, wd1, bd1):
 
 
 @torch.library.custom_op("effimvs::encoder_tail", mutates_args=("hx",))
+@_on_tensor_device
 def encoder_tail(m: Tensor, w: Tensor, ctx_term: Tensor, hx: Tensor) -> None:
     """hx[:, h:] = relu(conv1x1(m, w) + ctx_term) in place; m (B,hm,H,W), ctx_term (B,h,H,W), hx (B,2h,H,W) channels-last."""
     m, ctx_term, w = _nhwc(m, "encoder_tail"), _nhwc(ctx_term, "encoder_tail"), _dev(w, "encoder_tail")
@@ -697,6 +753,7 @@ def encoder_tail(m: Tensor, w: Tensor, ctx_term: Tensor, hx: Tensor) -> None:
 
 
 @torch.library.custom_op("effimvs::encoder_tail_ctx", mutates_args=("hx",))
+@_on_tensor_device
 def encoder_tail_ctx(m: Tensor, w_m: Tensor, ctx: Tensor, ctx_offset: int, cx: int, ctx_relu: bool, w_ctx: Tensor, bias: Tensor,
                      hx: Tensor) -> None:
     """hx[:, h:] = relu(conv1x1(m, w_m) + conv1x1(act(ctx[:, ctx_offset:ctx_offset+cx]), w_ctx) + bias) in place;
@@ -717,6 +774,7 @@ def encoder_tail_ctx(m: Tensor, w_m: Tensor, ctx: Tensor, ctx_offset: int, cx: i
 
 
 @torch.library.custom_op("effimvs::gru_init", mutates_args=())
+@_on_tensor_device
 def gru_init(ctx_map: Tensor, h: int) -> Tensor:
     """ctx_map (B,h+cx,H,W) -> hx (B,2h,H,W) channels-last with hx[:, :h] = tanh(ctx_map[:, :h]) (the x half is left for
     encoder_tail to fill)."""
@@ -739,6 +797,7 @@ def _(ctx_map, h):
 # -------------------------------------------------------------------------------------------
 # DTU geometric filter (csrc/dtu_filter.cu)
 @torch.library.custom_op("effimvs::dtu_filter", mutates_args=())
+@_on_tensor_device
 def dtu_filter(ref_depth: Tensor, srcs_depth: Tensor, conf: Tensor, mats: Tensor, thr_dist: List[float], thr_diff: List[float],
                first_rung: int, full_count: int, conf_thres: float, conf_keep: float, want_masks: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     """-> final (h,w) u8, geo (h,w) u8, depth_avg (h,w), points (3,h,w), masks (v,K,h,w) u8, reproj_depth (v,h,w)

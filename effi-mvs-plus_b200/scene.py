@@ -10,13 +10,19 @@ import torch
 import torch.distributed as dist
 
 
+def block_start(n_views: int, rank: int, world: int) -> int:
+    """First view of rank's block under balanced block sharding (rank == world gives n_views)."""
+    q, r = divmod(n_views, world)
+    return rank * q + min(rank, r)
+
+
 def shard_views(n_views: int, rank: int, world: int, mode: str = "round_robin") -> List[int]:
-    """Reference views owned by `rank`.  "round_robin": rank, rank+world, ... (even load for any n_views);
-    "block": a contiguous run of slots_per_rank views -- neighbouring reference views share their source
-    images, so a rank that caches encoded features (section 8(f) row 1) encodes each image at most once."""
+    """Reference views owned by `rank`.  "round_robin": rank, rank+world, ... ; "block": a contiguous run --
+    neighbouring reference views share their source images, so a rank that caches encoded features (section 8(f)
+    row 1) encodes each image at most once.  Both are balanced: every rank owns floor(n/world) views and the first
+    n % world ranks one more, so a rank is empty only when n_views < world (49 views on 8 ranks: 7,6,6,6,6,6,6,6)."""
     if mode == "block":
-        per = slots_per_rank(n_views, world)
-        return list(range(rank * per, min(n_views, (rank + 1) * per)))
+        return list(range(block_start(n_views, rank, world), block_start(n_views, rank + 1, world)))
     return list(range(rank, n_views, world))
 
 
@@ -24,27 +30,50 @@ def slots_per_rank(n_views: int, world: int) -> int:
     return (n_views + world - 1) // world
 
 
+def view_slot(i: int, n_views: int, world: int, mode: str = "round_robin"):
+    """(owner rank, slot inside the owner's all-gather block) of reference view i."""
+    if mode != "block":
+        return i % world, i // world
+    q, r = divmod(n_views, world)
+    owner = i // (q + 1) if i < r * (q + 1) else r + (i - r * (q + 1)) // max(q, 1)
+    return owner, i - block_start(n_views, owner, world)
+
+
 def gather_depths(local: Dict[int, torch.Tensor], n_views: int, rank: int, world: int, h: int, w: int, device,
                   mode: str = "round_robin") -> torch.Tensor:
     """All-gather of the per-rank depth maps into one (n_views,h,w) tensor on every rank.
 
-    Each rank contributes a (slots,h,w) block (zero padded when n_views % world != 0); with the
-    round-robin sharding view i lives in slot i // world of rank i % world, with block sharding in
-    slot i % slots of rank i // slots."""
+    Each rank contributes a (slots,h,w) block, zero padded where it owns fewer than `slots` views (a rank that owns
+    none still contributes its zero block: every rank must enter the collective); view i lives at
+    view_slot(i) = (owner, slot) of the rank-major concatenation."""
     slots = slots_per_rank(n_views, world)
     mine = torch.zeros(slots, h, w, device=device, dtype=torch.float32)
     for i, d in local.items():
-        mine[i % slots if mode == "block" else i // world] = d
+        owner, slot = view_slot(i, n_views, world, mode)
+        if owner != rank:
+            raise ValueError("view {} belongs to rank {}, not {} ({} sharding)".format(i, owner, rank, mode))
+        mine[slot] = d
     if world == 1 or not (dist.is_available() and dist.is_initialized()):
-        full = mine.unsqueeze(0)
+        flat = mine
     else:
         flat = torch.empty(world * slots, h, w, device=device, dtype=torch.float32)   # rank-major concatenation
         dist.all_gather_into_tensor(flat, mine)
-        full = flat.reshape(world, slots, h, w)
-    if mode == "block":   # (world, slots) -> view index = rank * slots + slot
-        return full.reshape(world * slots, h, w)[:n_views].contiguous()
-    # (world, slots) -> view index = slot * world + rank
-    return full.permute(1, 0, 2, 3).reshape(slots * world, h, w)[:n_views].contiguous()
+    index = [o * slots + s for o, s in (view_slot(i, n_views, world, mode) for i in range(n_views))]
+    if index == list(range(n_views)):
+        return flat[:n_views]
+    return flat.index_select(0, torch.as_tensor(index, device=flat.device))
+
+
+def agree_on_size(local_hw, n_views: int, world: int, device):
+    """(h, w) of the depth maps on every rank.  Only when n_views < world can a rank own no view and not know the
+    size; then (and only then -- the condition is the same on all ranks) one 2-element MAX all-reduce tells it."""
+    if n_views >= world or world == 1 or not (dist.is_available() and dist.is_initialized()):
+        if local_hw is None:
+            raise ValueError("no depth map on this rank and no peer to learn its size from")
+        return local_hw
+    t = torch.tensor(list(local_hw or (0, 0)), device=device, dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t[0]), int(t[1])
 
 
 @torch.no_grad()
@@ -62,9 +91,8 @@ def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Seq
     for i in mine:
         d, c = infer(i, list(pairs[i]))
         depths[i], confs[i] = d, c
-    if not depths:
-        raise ValueError("rank {} owns no reference view (n_views={} < world={})".format(rank, n_views, world))
-    h, w = next(iter(depths.values())).shape[-2:]
+    # a rank without a view (n_views < world) still enters the collective below with a zero block
+    h, w = agree_on_size(tuple(next(iter(depths.values())).shape[-2:]) if depths else None, n_views, world, device)
     ev = None
     if timings is not None and torch.cuda.is_available() and str(device).startswith("cuda"):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]

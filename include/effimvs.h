@@ -87,7 +87,10 @@ int effimvs_depth_range_samples_f32(const float* cur, const float* interval, int
  *   proj      (B,n_src,12) from effimvs_relative_projection_f32 (or torch)
  *   hyp       see EFFIMVS_HYP_*;  interval (B) inverse-depth step, only for HYP_LOCAL
  *   weights   (B,n_src,H,W) view weights or NULL (plain mean over views)
- *   sim_out   (B,G,D,H,W);  hyp_out (B,D,H,W) depth hypotheses actually used, or NULL */
+ *   sim_out   (B,G,D,H,W);  hyp_out (B,D,H,W) depth hypotheses actually used, or NULL
+ * Alignment: feature pointers need 16 bytes (NCHW: 4).  EFFIMVS_FEA_NHWC maps whose pointers are all 32-byte
+ * aligned take the TMA-staged tile kernels (256-bit loads); 16-byte aligned ones run the gather kernels --
+ * same results, slower. */
 int effimvs_warp_corr_agg_f32(const float* ref_fea, const float* const* src_fea, int n_src,
                               const float* proj, const float* hyp, int hyp_mode, const float* interval,
                               const float* weights, int B, int C, int H, int W, int D, int G, int fea_layout,

@@ -123,7 +123,8 @@ class TorchGlue:
 
     @classmethod
     def convex_upsample(cls, mask_pre, mask_bias, scale, inv, lo, hi, ratio):
-        up = net.convex_upsample(inv, scale * (mask_pre + mask_bias.reshape(1, -1, 1, 1)), ratio)
+        mask = mask_pre if mask_bias is None else mask_pre + mask_bias.reshape(1, -1, 1, 1)
+        up = net.convex_upsample(inv, scale * mask, ratio)
         return up, cls._to_depth(up.unsqueeze(1), lo, hi).squeeze(1)
 
     @classmethod
