@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import collections
 import os
+import weakref
 
 import torch
 
@@ -27,19 +28,27 @@ def fold_bn(block, transposed: bool):
 
 
 class _FoldCache:
-    """Folded weights per module, invalidated when a parameter / buffer is replaced or updated in place."""
+    """Folded weights per module, invalidated when a parameter / buffer is replaced or updated in place.  Keyed by the
+    module object itself through a weak reference: an entry dies with its module, so a recycled id() cannot serve
+    another module's weights."""
 
     def __init__(self):
-        self._store = {}
+        self._store = weakref.WeakKeyDictionary()
 
     def get(self, net, build):
-        key = id(net)
         stamp = tuple((id(t), t._version, t.device) for t in list(net.parameters()) + list(net.buffers()))
-        hit = self._store.get(key)
+        hit = self._store.get(net)
         if hit is None or hit[0] != stamp:
             hit = (stamp, build(net))
-            self._store[key] = hit
+            self._store[net] = hit
         return hit[1]
+
+
+def _inference_only(*tensors):
+    """The effimvs:: ops carry no autograd formula: refuse to drop gradients silently."""
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+        raise RuntimeError("the CUDA hot path is inference only (no autograd formula): run it under torch.no_grad(), "
+                           "or use upstream's PyTorch path for training / test-time adaptation")
 
 
 class _WorkspaceCache:
@@ -53,18 +62,41 @@ class _WorkspaceCache:
         self.cap = cap
 
     def get(self, key, nbytes, device):
+        """A workspace that was handed out while its stream was being captured is baked into a CUDA graph by raw
+        pointer: it is pinned and never evicted or reallocated (the graph owner may replay it at any time)."""
+        capturing = torch.cuda.is_current_stream_capturing() if torch.device(device).type == "cuda" else False
         ent = self._store.get(key)
-        if ent is None or ent["ws"].numel() < nbytes:
-            ent = {"ws": torch.empty(max(nbytes, 256), device=device, dtype=torch.uint8), "stamp": None}
+        if ent is not None and ent["ws"].numel() < nbytes:
+            if ent["pinned"]:
+                raise RuntimeError("a regularization workspace captured in a CUDA graph is too small for this call")
+            ent = None
+        if ent is None:
+            if capturing:
+                raise RuntimeError("regularization workspace requested for the first time during CUDA-graph capture: "
+                                   "run one eager forward of this shape before capturing")
+            ent = {"ws": torch.empty(max(nbytes, 256), device=device, dtype=torch.uint8), "stamp": None, "pinned": False}
             self._store[key] = ent
-            while len(self._store) > self.cap:
-                self._store.popitem(last=False)
+            evictable = [k for k, e in self._store.items() if not e["pinned"] and k != key]
+            while len(self._store) > self.cap and evictable:
+                del self._store[evictable.pop(0)]
+        ent["pinned"] = ent["pinned"] or capturing
         self._store.move_to_end(key)
         return ent
+
+    def drop(self, owner_id):
+        for k in [k for k in self._store if k[1] == owner_id]:
+            del self._store[k]
 
 
 def _is_planes(hyp: torch.Tensor) -> bool:
     return hyp.dim() == 2 or (hyp.dim() == 4 and (hyp.shape[2:] == (1, 1) or (hyp.stride(2) == 0 and hyp.stride(3) == 0)))
+
+
+def _forget(hp_ref, owner_id):
+    hp = hp_ref()
+    if hp is not None:
+        hp._tracked.discard(owner_id)
+        hp._workspaces.drop(owner_id)
 
 
 class CudaHotPath:
@@ -91,6 +123,7 @@ class CudaHotPath:
         self._folds = _FoldCache()
         self._workspaces = _WorkspaceCache()
         self._side_streams = {}
+        self._tracked = set()
 
     def side_stream(self, device):
         """Stream for work that is independent of the caller's current stream (None: run it in line)."""
@@ -126,6 +159,7 @@ class CudaHotPath:
     def stage1(self, features, cams, depth_hyp, pixel_wise_net, reg_net, G):
         if G != 1:
             raise ValueError("stage-1 view weighting requires G == 1 (upstream squeezes the group axis, Effi_MVS_plus.py:43)")
+        _inference_only(*features)
         ref, srcs = features[0], list(features[1:])
         B, _, H, W = ref.shape
         D = depth_hyp.shape[1]
@@ -145,6 +179,7 @@ class CudaHotPath:
 
     # -- a5 ---------------------------------------------------------------------------------------
     def local_volume(self, cur_depth, features, cams, interval, view_weights, ndepth, G):
+        _inference_only(cur_depth, *features)
         ref, srcs = features[0], list(features[1:])
         B, _, H, W = ref.shape
         proj = self.relative_projection(cams)
@@ -206,12 +241,19 @@ class CudaHotPath:
             return [p[0] for p in pairs], [p[1] for p in pairs]
         return self._folds.get(net, build)
 
+    def _track(self, net):
+        """workspaces are keyed by id(net): drop them when the network dies so that a recycled id starts clean"""
+        if id(net) not in self._tracked:
+            self._tracked.add(id(net))
+            weakref.finalize(net, _forget, weakref.ref(self), id(net))
+
     def cost_regularization(self, net, x):
         """x (B,1,D,H,W) -> prob_pre (B,1,D,H,W)   (upstream models/module.py:453-463)."""
         ws, bs = self._reg_weights(net)
         if self.precision == capi.PREC_F32 or not self.persistent_workspaces:
             return ops.costreg_fpn3d(x, ws, bs, self.precision)
         B, _, D, H, W = x.shape
+        self._track(net)
         ent = self._workspaces.get(("costreg", id(net), B, D, H, W, self.precision, x.device),
                                    ops.costreg_workspace_bytes(B, D, H, W, self.precision), x.device)
         if ent["stamp"] is not ws:
@@ -225,6 +267,7 @@ class CudaHotPath:
         if self.precision == capi.PREC_F32 or not self.persistent_workspaces:
             return ops.cost_up_small(cur_volume, prev_resampled, ws, bs, self.precision)
         B, _, D, H, W = cur_volume.shape
+        self._track(net)
         ent = self._workspaces.get(("cost_up", id(net), B, D, H, W, self.precision, cur_volume.device),
                                    ops.cost_up_workspace_bytes(B, D, H, W, self.precision), cur_volume.device)
         if ent["stamp"] is not ws:

@@ -69,7 +69,9 @@ class ConvBNReLU2d(nn.Module):
         return self._fold[1], self._fold[2]
 
     def forward(self, x):
-        if self.training:
+        if self.training or torch.is_grad_enabled():
+            # the fold below is detached: with autograd on (frozen-BN fine-tuning, test-time adaptation) keep the plain
+            # expression so that the convolution's parameters receive gradients, as in upstream
             return F.relu(self.bn(self.conv(x)), inplace=True)
         w, b = self._folded()
         return conv_relu(x, w, b, self.conv.stride, self.conv.padding)
