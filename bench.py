@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--shape", default="dtu", choices=["dtu", "tanks", "plumbing"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the forward in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scene", action="store_true", help="skip the 49-view scene leg (configs[4])")
+    ap.add_argument("--scene-views", type=int, default=49)
     ap.add_argument("--profile-one", action="store_true",
                     help="3 warm eager forwards, then ONE forward between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
@@ -386,6 +388,53 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
     return roof, roof_reg, out
 
 
+def scene_leg(a, model, rank, world, dev):
+    """BASELINE.json configs[4]: depth maps for every view of a synthetic `--scene-views`-view scene at the DTU shape (4
+    source views each), reference views sharded in balanced blocks over the ranks (every image encoded at most once per
+    rank, encode / cascade replayed as CUDA graphs), ONE all-gather of the final depth maps (NCCL over NVLink at N > 1),
+    then the geometric-consistency filter (10 source views) of the views each rank owns.  Returns the `scene49` object."""
+    from effimvs_b200 import scene, synthetic
+    N = a.scene_views
+    cfg = synthetic.SHAPES["dtu"]
+    W, H = cfg["width"], cfg["height"]
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(N, 3, H, W, generator=g).to(dev)
+    E, K = synthetic.camera_arc(N, W, H)
+    cams = {k: v[0].to(dev) for k, v in synthetic.stage_cameras(E, K, 1).items()}
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384, device=dev)
+    nb = lambda i, n: [j for d in range(1, n // 2 + 1) for j in ((i - d) % N, (i + d) % N)]      # noqa: E731
+    pairs, fpairs = [nb(i, 4) for i in range(N)], [nb(i, min(10, (N - 1) // 2 * 2)) for i in range(N)]
+    infer, fuse = scene.cuda_scene_callables(model, imgs, cams, dv, 2.0, 6.0, 2, 0.3, feature_cache=True, graphed_src_views=4)
+    with torch.no_grad():
+        mine = scene.shard_views(N, rank, world, "block")
+        if mine:
+            infer(mine[0], pairs[mine[0]])            # warm-up (graph capture happened in cuda_scene_callables)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tm = {}
+    t0 = time.perf_counter()
+    out = scene.run_scene(infer, fuse, N, pairs, rank, world, dev, fuse_pairs=fpairs, timings=tm, sharding="block")
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    stats = torch.tensor([time.perf_counter() - t0, tm.get("all_gather_ms", 0.0), tm.get("fusion_ms", 0.0)], device=dev)
+    pts = torch.tensor([float(sum(v[0].shape[0] for v in out.values()))], device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pts)
+    secs, ag_ms, fu_ms = (float(x) for x in stats)
+    slots = scene.slots_per_rank(N, world)
+    recv = (world - 1) * slots * H * W * 4                      # bytes every rank receives from its peers
+    return {"views": N, "shape": [W, H], "n_gpus": world, "seconds": secs, "depth_maps_per_sec_incl_fusion": N / secs,
+            "all_gather_ms": ag_ms if world > 1 else None, "all_gather_bytes_received_per_rank": recv if world > 1 else 0,
+            "all_gather_GBs_per_rank": (recv / ag_ms / 1e6) if world > 1 and ag_ms > 0 else None,
+            "fusion_ms_max_rank": fu_ms, "fused_points": int(pts), "sharding": "block (balanced): views per rank " +
+            ",".join(str(len(scene.shard_views(N, r, world, "block"))) for r in range(world)),
+            "note": "4 source views for depth, 10 for fusion; feature cache + CUDA graphs; wall clock around run_scene, max over ranks; "
+                    "all-gather timed with CUDA events (max over ranks)"}
+
+
 def run_ours(a, rank, world, local_rank):
     import effimvs_b200  # noqa: F401
     from effimvs_b200 import hotpath, ops, synthetic
@@ -397,8 +446,15 @@ def run_ours(a, rank, world, local_rank):
     ndepths = synthetic.SHAPES[a.shape]["ndepths"]
     model, data = build_model(hp, dev, ndepths)
     s_host = synthetic.make_sample(a.shape, seed=rank)
-    pin = {"imgs": s_host["imgs"].pin_memory(), "depth_values": s_host["depth_values"].pin_memory(),
-           "proj_matrices": {k: v.pin_memory() for k, v in s_host["proj_matrices"].items() if k != "stage4"}}
+    # 8-bit images, as image files hold them; the fp32 images every leg computes on are u8 / 255 exactly as upstream's
+    # loaders form them (np.float32 / 255., datasets/general_eval.py:83-87)
+    import numpy as np
+    u8 = (s_host["imgs"] * 255.0).round().clamp(0, 255).to(torch.uint8)
+    f32 = torch.from_numpy(u8.numpy().astype(np.float32) / np.float32(255.0))
+    rest = {"depth_values": s_host["depth_values"].pin_memory(),
+            "proj_matrices": {k: v.pin_memory() for k, v in s_host["proj_matrices"].items() if k != "stage4"}}
+    pin = dict(rest, imgs=f32.pin_memory())           # fp32 host images (what upstream's loaders hand over)
+    pin_u8 = dict(rest, imgs=u8.pin_memory())         # 8-bit host images, normalised on the device
     stat = {"imgs": pin["imgs"].to(dev), "depth_values": pin["depth_values"].to(dev),
             "proj_matrices": {k: v.to(dev) for k, v in pin["proj_matrices"].items()}}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -477,34 +533,47 @@ def run_ours(a, rank, world, local_rank):
             from effimvs_b200 import pipeline
             pipe = pipeline.DepthMapPipeline(model, pin, slots=2, use_graph=graph is not None, before_replay=flush.zero_)
 
-            def e2e_run(n):
-                prev = None
-                for _ in range(n):
-                    t = pipe.submit(pin)
-                    if prev is not None:
-                        pipe.result(prev)
-                    prev = t
-                return pipe.result(prev)
+            def e2e_timed(sample):
+                def run(n):
+                    prev = None
+                    for _ in range(n):
+                        t = pipe.submit(sample)
+                        if prev is not None:
+                            pipe.result(prev)
+                        prev = t
+                    return pipe.result(prev)
 
-            e2e_run(max(a.warmup, 3))
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(pipe.copy)                      # the first timed operation is the H2D copy of step 0
-            host_depth, host_conf = e2e_run(a.steps)
-            e1.record(pipe.compute)                   # after the last D2H read
-            barrier()
-            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-            if world > 1:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-            ms_e2e = float(ms)
-        h2d = pin["imgs"].numel() * 4 + pin["depth_values"].numel() * 4 + sum(v.numel() * 4 for v in pin["proj_matrices"].values())
-        d2h = host_depth.numel() * 4 + host_conf.numel() * 4
+                run(max(a.warmup, 3))
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(pipe.copy)                      # the first timed operation is the H2D copy of step 0
+                hd, hc = run(a.steps)
+                e1.record(pipe.compute)                   # after the last D2H read
+                barrier()
+                ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                if world > 1:
+                    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+                return float(ms), hd.numel() * 4 + hc.numel() * 4
+
+            ms_e2e, d2h = e2e_timed(pin_u8)               # headline: 8-bit images over PCIe
+            ms_e2e_f32, _ = e2e_timed(pin)                # the same with fp32 host images (4x the image bytes)
+        h2d, h2d_f32 = pipe.h2d_bytes(pin_u8), pipe.h2d_bytes(pin)
 
         hbm_peak, tf_peak, peak_src = peaks()
         roof = roof_reg = kern = None
         if rank == 0:
             roof, roof_reg, kern = kernel_rooflines(hp, model, stat, hbm_peak, tf_peak, peak_src)
 
+    scene49 = None
+    if not a.no_scene and a.shape == "dtu":
+        del pipe
+        torch.cuda.empty_cache()
+        try:
+            scene49 = scene_leg(a, model, rank, world, dev)
+        except Exception as e:  # noqa: BLE001  (an extra leg must not cost the headline line)
+            scene49 = {"error": "{}: {}".format(type(e).__name__, e)}
+            if world > 1:
+                raise
     cpu = eager = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         eager = gpu_eager_baseline(a, ndepths, stat, dev)
@@ -522,9 +591,14 @@ def run_ours(a, rank, world, local_rank):
             "config": config_keys(a, int(stat["imgs"].shape[1]), ndepths),
             "run": {"device": "cuda", "cuda_graph": graph is not None, "processes": world},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps,
-                    "api": "effimvs_b200.pipeline.DepthMapPipeline.submit/result: pinned host -> device copy of step k+1 overlapped with the forward of step k"},
+                    "api": "effimvs_b200.pipeline.DepthMapPipeline.submit/result with 8-bit host images (divided by 255 on the device, "
+                           "upstream's loader arithmetic): pinned host -> device copy of step k+1 overlapped with the forward of step k"},
+            "e2e_fp32_images": {"value": world * a.steps / (ms_e2e_f32 / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_f32,
+                                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_f32 / a.steps},
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clk.summary(), "roofline": roof, "roofline_regularization": roof_reg, "kernels": kern}
+    if scene49:
+        line["scene49"] = scene49
     if cpu:
         line["cpu_baseline"] = cpu
     if eager:

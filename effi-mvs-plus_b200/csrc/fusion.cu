@@ -18,15 +18,16 @@ namespace {
 
 constexpr int MAXV = EFFIMVS_MAX_SRC_VIEWS;
 
-struct Cam {       // one camera in shared memory
-    float E[16];   // world -> camera
-    float Ei[16];  // inverse(E)
-    float K[9];
-    float Ki[9];
+struct alignas(16) Cam {   // one camera in shared memory; every matrix row is one 128-bit record
+    float4 E[4];           // world -> camera
+    float4 Ei[4];          // inverse(E)
+    float4 K[3];           // rows of the 3x3 intrinsics (w unused)
+    float4 Ki[3];
     // last row exactly (0,0,0,1) / (0,0,1): the homogeneous coordinate is then exactly 1 and
     // x / (1 + 1e-9f) == x bit for bit, so upstream's renormalising divisions can be skipped
     int affE, affEi, affK, affKi;
 };
+struct RefCam { float4 E[4]; float4 K[3]; int affE; };   // what the per-view loop needs of the reference camera: in registers
 
 __device__ bool invert_n(const double* A, double* inv, int n) {
     double M[4][8];
@@ -56,38 +57,55 @@ __device__ bool invert_n(const double* A, double* inv, int n) {
     return true;
 }
 
-// cam: (2,4,4) fp32.  inv: (2,4,4) holding inverse(E), inverse(K) padded, or nullptr -> invert here.
+// cam: (2,4,4) fp32.  inv: (2,4,4) holding inverse(E), inverse(K) padded.  INVERT: inv may be nullptr -> invert here
+// (fp64 Gauss-Jordan with pivoting; its local arrays are why the <true> instantiation has a stack frame -- the torch
+// binding always passes the inverses, from torch's LU or from effimvs_fusion_invert_cameras_f32).
+template <bool INVERT>
 __device__ void load_cam(Cam& c, const float* __restrict__ cam, const float* __restrict__ inv) {
-    for (int i = 0; i < 16; ++i) c.E[i] = cam[i];
+    float E[16], Ei[16], K[9], Ki[9];
+    for (int i = 0; i < 16; ++i) E[i] = cam[i];
     for (int r = 0; r < 3; ++r)
-        for (int k = 0; k < 3; ++k) c.K[r * 3 + k] = cam[16 + r * 4 + k];
-    if (inv) {
-        for (int i = 0; i < 16; ++i) c.Ei[i] = inv[i];
+        for (int k = 0; k < 3; ++k) K[r * 3 + k] = cam[16 + r * 4 + k];
+    if (!INVERT || inv) {
+        for (int i = 0; i < 16; ++i) Ei[i] = inv[i];
         for (int r = 0; r < 3; ++r)
-            for (int k = 0; k < 3; ++k) c.Ki[r * 3 + k] = inv[16 + r * 4 + k];
+            for (int k = 0; k < 3; ++k) Ki[r * 3 + k] = inv[16 + r * 4 + k];
     } else {
         double A[16], I[16];
-        for (int i = 0; i < 16; ++i) A[i] = c.E[i];
+        for (int i = 0; i < 16; ++i) A[i] = E[i];
         bool ok = invert_n(A, I, 4);
-        for (int i = 0; i < 16; ++i) c.Ei[i] = ok ? (float)I[i] : __int_as_float(0x7fc00000);
-        for (int i = 0; i < 9; ++i) A[i] = c.K[i];
+        for (int i = 0; i < 16; ++i) Ei[i] = ok ? (float)I[i] : __int_as_float(0x7fc00000);
+        for (int i = 0; i < 9; ++i) A[i] = K[i];
         ok = invert_n(A, I, 3);
-        for (int i = 0; i < 9; ++i) c.Ki[i] = ok ? (float)I[i] : __int_as_float(0x7fc00000);
+        for (int i = 0; i < 9; ++i) Ki[i] = ok ? (float)I[i] : __int_as_float(0x7fc00000);
     }
-    c.affE = c.E[12] == 0.0f && c.E[13] == 0.0f && c.E[14] == 0.0f && c.E[15] == 1.0f;
-    c.affEi = c.Ei[12] == 0.0f && c.Ei[13] == 0.0f && c.Ei[14] == 0.0f && c.Ei[15] == 1.0f;
-    c.affK = c.K[6] == 0.0f && c.K[7] == 0.0f && c.K[8] == 1.0f;
-    c.affKi = c.Ki[6] == 0.0f && c.Ki[7] == 0.0f && c.Ki[8] == 1.0f;
+    for (int r = 0; r < 4; ++r) {
+        c.E[r] = make_float4(E[r * 4], E[r * 4 + 1], E[r * 4 + 2], E[r * 4 + 3]);
+        c.Ei[r] = make_float4(Ei[r * 4], Ei[r * 4 + 1], Ei[r * 4 + 2], Ei[r * 4 + 3]);
+    }
+    for (int r = 0; r < 3; ++r) {
+        c.K[r] = make_float4(K[r * 3], K[r * 3 + 1], K[r * 3 + 2], 0.0f);
+        c.Ki[r] = make_float4(Ki[r * 3], Ki[r * 3 + 1], Ki[r * 3 + 2], 0.0f);
+    }
+    c.affE = E[12] == 0.0f && E[13] == 0.0f && E[14] == 0.0f && E[15] == 1.0f;
+    c.affEi = Ei[12] == 0.0f && Ei[13] == 0.0f && Ei[14] == 0.0f && Ei[15] == 1.0f;
+    c.affK = K[6] == 0.0f && K[7] == 0.0f && K[8] == 1.0f;
+    c.affKi = Ki[6] == 0.0f && Ki[7] == 0.0f && Ki[8] == 1.0f;
 }
 
-__device__ __forceinline__ void mat3(const float* M, float x, float y, float z, float o[3]) {
+__device__ __forceinline__ void mat3(const float4* M, float x, float y, float z, float o[3]) {
 #pragma unroll
-    for (int r = 0; r < 3; ++r) o[r] = fmaf(M[r * 3 + 2], z, fmaf(M[r * 3 + 1], y, __fmul_rn(M[r * 3], x)));
+    for (int r = 0; r < 3; ++r) {
+        const float4 m = M[r];
+        o[r] = fmaf(m.z, z, fmaf(m.y, y, __fmul_rn(m.x, x)));
+    }
 }
-__device__ __forceinline__ void mat4(const float* M, const float p[4], float o[4]) {
+__device__ __forceinline__ void mat4(const float4* M, const float p[4], float o[4]) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-        o[r] = fmaf(M[r * 4 + 3], p[3], fmaf(M[r * 4 + 2], p[2], fmaf(M[r * 4 + 1], p[1], __fmul_rn(M[r * 4], p[0]))));
+    for (int r = 0; r < 4; ++r) {
+        const float4 m = M[r];
+        o[r] = fmaf(m.w, p[3], fmaf(m.z, p[2], fmaf(m.y, p[1], __fmul_rn(m.x, p[0]))));
+    }
 }
 
 // idx_img2cam + idx_cam2world (fusion.py:23-34): pixel (u,v,1), depth -> homogeneous world point
@@ -116,10 +134,10 @@ __device__ __forceinline__ void img_to_world(const Cam& c, float u, float v, flo
 }
 
 // idx_world2cam (fusion.py:37-40)
-__device__ __forceinline__ void world_to_cam(const Cam& c, const float pw[4], float pc[4]) {
+__device__ __forceinline__ void world_to_cam(const float4* E, int affE, const float pw[4], float pc[4]) {
     float t[4];
-    mat4(c.E, pw, t);
-    if (c.affE && pw[3] == 1.0f) {   // t[3] == 1 exactly
+    mat4(E, pw, t);
+    if (affE && pw[3] == 1.0f) {   // t[3] == 1 exactly
 #pragma unroll
         for (int i = 0; i < 4; ++i) pc[i] = t[i];
     } else {
@@ -130,17 +148,15 @@ __device__ __forceinline__ void world_to_cam(const Cam& c, const float pw[4], fl
 }
 
 // idx_cam2img (fusion.py:43-47)
-__device__ __forceinline__ void cam_to_img(const Cam& c, const float pc[4], float& u, float& v) {
+__device__ __forceinline__ void cam_to_img(const float4* K, const float pc[4], float& u, float& v) {
     float k[3];
     if (pc[3] == 1.0f) {             // (1 + 1e-9f) == 1: the division is the identity
-        mat3(c.K, pc[0], pc[1], pc[2], k);
+        mat3(K, pc[0], pc[1], pc[2], k);
     } else {
         float ww = __fadd_rn(pc[3], 1e-9f);
-        mat3(c.K, __fdiv_rn(pc[0], ww), __fdiv_rn(pc[1], ww), __fdiv_rn(pc[2], ww), k);
+        mat3(K, __fdiv_rn(pc[0], ww), __fdiv_rn(pc[1], ww), __fdiv_rn(pc[2], ww), k);
     }
-    float zz = __fadd_rn(k[2], 1e-9f);
-    u = __fdiv_rn(k[0], zz);
-    v = __fdiv_rn(k[1], zz);
+    div2_rn(k[0], k[1], __fadd_rn(k[2], 1e-9f), u, v);
 }
 
 // bilinear sample, zeros padding, align_corners=True, pixel coordinates (u,v) normalised the way
@@ -182,22 +198,23 @@ __device__ __forceinline__ int ladder_count(float e, const float* __restrict__ t
     return K - idx;
 }
 
-__device__ __forceinline__ Reproj reproject(const Cam& ref, const Cam& src, const float ref_world[4],
+__device__ __forceinline__ Reproj reproject(const RefCam& ref, const Cam& src, const float ref_world[4],
                                             const float* __restrict__ src_depth, int h, int w,
                                             float inv_half_w, float inv_half_h) {
     float pc[4], u, v;
-    world_to_cam(src, ref_world, pc);
-    cam_to_img(src, pc, u, v);
+    world_to_cam(src.E, src.affE, ref_world, pc);
+    cam_to_img(src.K, pc, u, v);
     float ds = sample_depth(src_depth, h, w, u, v, inv_half_w, inv_half_h);
     float pw[4], back[4];
     img_to_world(src, u, v, ds, pw);
-    world_to_cam(ref, pw, back);
+    world_to_cam(ref.E, ref.affE, pw, back);
     Reproj r;
     r.d = back[2];
-    cam_to_img(ref, back, r.x, r.y);
+    cam_to_img(ref.K, back, r.x, r.y);
     return r;
 }
 
+template <bool INVERT>
 __global__ void __launch_bounds__(128, 6)
 fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ srcs_depth, const float* __restrict__ conf,
               const float* __restrict__ ref_cam, const float* __restrict__ srcs_cam, const float* __restrict__ inv_cams,
@@ -211,7 +228,7 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
     if (threadIdx.x <= v) {
         const float* cam = threadIdx.x == 0 ? ref_cam + (size_t)n * 32 : srcs_cam + ((size_t)n * v + threadIdx.x - 1) * 32;
         const float* inv = inv_cams ? inv_cams + ((size_t)n * (v + 1) + threadIdx.x) * 32 : nullptr;
-        load_cam(cams[threadIdx.x], cam, inv);
+        load_cam<INVERT>(cams[threadIdx.x], cam, inv);
     } else if (threadIdx.x >= 32 && threadIdx.x < 32 + MAXV) {
         const int k = threadIdx.x - 32;
         const float kk = (float)(thres_view + k);
@@ -229,6 +246,12 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
     const float dref = __ldg(ref_depth + (size_t)n * hw + pix);
     float ref_world[4];
     img_to_world(cams[0], cx, cy, dref, ref_world);
+    RefCam rc;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rc.E[r] = cams[0].E[r];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) rc.K[r] = cams[0].K[r];
+    rc.affE = cams[0].affE;
 
     // The ladder thresholds grow with k, so a view passes rungs K-c .. K-1 where c = min(#rungs its pixel
     // error passes, #rungs its depth error passes).  hist packs the per-view c values: 17 bins of 5 bits.
@@ -236,7 +259,7 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
     float sum_d = 0.0f;
     int n_last = 0;
     for (int s = 0; s < v; ++s) {
-        Reproj r = reproject(cams[0], cams[s + 1], ref_world, srcs_depth + ((size_t)n * v + s) * hw, h, w, inv_half_w, inv_half_h);
+        Reproj r = reproject(rc, cams[s + 1], ref_world, srcs_depth + ((size_t)n * v + s) * hw, h, w, inv_half_w, inv_half_h);
         if (reproj_xyd) {
             float* o = reproj_xyd + (((size_t)n * v + s) * 3) * hw + pix;
             o[0] = r.x; o[(size_t)hw] = r.y; o[(size_t)2 * hw] = r.d;
@@ -277,6 +300,24 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
     points[((size_t)n * 3 + 2) * hw + pix] = pw[2];
 }
 
+// inverse(E), inverse(K) of the 1 + v cameras of every batch item -> inv (n, 1+v, 2, 4, 4), the layout fusion_kernel reads
+__global__ void invert_cameras_kernel(const float* __restrict__ ref_cam, const float* __restrict__ srcs_cam, int v, float* __restrict__ inv) {
+    const int n = blockIdx.x, i = threadIdx.x;
+    if (i > v) return;
+    const float* cam = i == 0 ? ref_cam + (size_t)n * 32 : srcs_cam + ((size_t)n * v + i - 1) * 32;
+    float* o = inv + ((size_t)n * (v + 1) + i) * 32;
+    double A[16], I[16];
+    for (int k = 0; k < 16; ++k) A[k] = cam[k];
+    bool ok = invert_n(A, I, 4);
+    for (int k = 0; k < 16; ++k) o[k] = ok ? (float)I[k] : __int_as_float(0x7fc00000);
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) A[r * 3 + k] = cam[16 + r * 4 + k];
+    ok = invert_n(A, I, 3);
+    for (int k = 0; k < 16; ++k) o[16 + k] = 0.0f;
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) o[16 + r * 4 + k] = ok ? (float)I[r * 3 + k] : __int_as_float(0x7fc00000);
+}
+
 // vis_filter_dynamic (misc/fusion.py:157-181) on an existing reproj_xyd (n,v,3,h,w) -> masks (n,v,K,h,w)
 __global__ void fusion_masks_kernel(const float* __restrict__ ref_depth, const float* __restrict__ xyd, int v, int h, int w,
                                     float dist_base, float rel_diff_base, int thres_view, int relative, uint8_t* __restrict__ masks) {
@@ -310,8 +351,12 @@ extern "C" int effimvs_fusion_reproject_f32(const float* ref_depth, const float*
     EFFI_REQUIRE(ref_depth && srcs_depth && ref_cam && srcs_cam && reproj_xyd, EFFIMVS_EINVAL, "fusion_reproject: null pointer");
     EFFI_REQUIRE(n > 0 && v >= 1 && v <= MAXV && h > 1 && w > 1, EFFIMVS_EINVAL, "fusion_reproject: bad sizes (v in [1,%d])", MAXV);
     dim3 block(128), grid(ceil_div(h * w, 128), n);
-    fusion_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, nullptr, ref_cam, srcs_cam, inv_cams, v, h, w,
-                                                           1, 1, 1.0f, 1.0f, 1, 0.0f, 0, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
+    if (inv_cams)
+        fusion_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, nullptr, ref_cam, srcs_cam, inv_cams, v, h, w,
+                                                                      1, 1, 1.0f, 1.0f, 1, 0.0f, 0, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
+    else
+        fusion_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, nullptr, ref_cam, srcs_cam, inv_cams, v, h, w,
+                                                                     1, 1, 1.0f, 1.0f, 1, 0.0f, 0, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
     return check_launch("fusion_kernel(reproject)");
 }
 
@@ -328,10 +373,22 @@ extern "C" int effimvs_fusion_filter_f32(const float* ref_depth, const float* sr
     EFFI_REQUIRE(thres_view >= 1 && thres_view <= v, EFFIMVS_EINVAL, "fusion_filter: thres_view=%d outside [1,%d]", thres_view, v);
     EFFI_REQUIRE(dist_base > 0.0f && rel_diff_base > 0.0f, EFFIMVS_EINVAL, "fusion_filter: thresholds must be positive");
     dim3 block(128), grid(ceil_div(h * w, 128), n);
-    fusion_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, v, h, w, hc, wc,
-                                                           dist_base, rel_diff_base, thres_view, prob_threshold, relative,
-                                                           nullptr, final_mask, depth_avg, points, masks_out);
+    if (inv_cams)
+        fusion_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, v, h, w, hc, wc,
+                                                                      dist_base, rel_diff_base, thres_view, prob_threshold, relative,
+                                                                      nullptr, final_mask, depth_avg, points, masks_out);
+    else
+        fusion_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, v, h, w, hc, wc,
+                                                                     dist_base, rel_diff_base, thres_view, prob_threshold, relative,
+                                                                     nullptr, final_mask, depth_avg, points, masks_out);
     return check_launch("fusion_kernel(filter)");
+}
+
+extern "C" int effimvs_fusion_invert_cameras_f32(const float* ref_cam, const float* srcs_cam, int n, int v, float* inv_out, void* stream) {
+    EFFI_REQUIRE(ref_cam && srcs_cam && inv_out, EFFIMVS_EINVAL, "fusion_invert_cameras: null pointer");
+    EFFI_REQUIRE(n > 0 && v >= 1 && v <= MAXV, EFFIMVS_EINVAL, "fusion_invert_cameras: bad sizes (v in [1,%d])", MAXV);
+    invert_cameras_kernel<<<n, 32, 0, (cudaStream_t)stream>>>(ref_cam, srcs_cam, v, inv_out);
+    return check_launch("invert_cameras_kernel");
 }
 
 extern "C" int effimvs_fusion_masks_f32(const float* ref_depth, const float* reproj_xyd, int n, int v, int h, int w,

@@ -205,6 +205,28 @@ __global__ void softmax_regress_conf_kernel(const float* __restrict__ prob_pre, 
     conf_out[(size_t)b * HW + pix] = __fmul_rn(4.0f, __fmul_rn(conf, 0.25f));
 }
 
+// uint8 image -> fp32 in [0,1], the arithmetic of upstream's loaders (datasets/general_eval.py:83-87 read_img:
+// np.array(img, dtype=np.float32) / 255.): an IEEE division, 16 pixels-channels per thread
+__global__ void __launch_bounds__(256)
+images_u8_kernel(const uint8_t* __restrict__ in, size_t n, float* __restrict__ out) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i + 16 <= n && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 o;
+            o.x = __fdiv_rn((float)(w[q] & 255u), 255.0f);
+            o.y = __fdiv_rn((float)((w[q] >> 8) & 255u), 255.0f);
+            o.z = __fdiv_rn((float)((w[q] >> 16) & 255u), 255.0f);
+            o.w = __fdiv_rn((float)(w[q] >> 24), 255.0f);
+            reinterpret_cast<float4*>(out + i)[q] = o;
+        }
+    } else {
+        for (size_t k = i; k < n && k < i + 16; ++k) out[k] = __fdiv_rn((float)in[k], 255.0f);
+    }
+}
+
 }  // namespace
 }  // namespace effimvs
 
@@ -262,4 +284,12 @@ extern "C" int effimvs_depth_range_samples_f32(const float* cur, const float* in
     dim3 block(128), grid(ceil_div(H * W, 128), B);
     range_samples_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(cur, interval, ndepth, H * W, samples_out);
     return check_launch("range_samples_kernel");
+}
+
+extern "C" int effimvs_images_u8_to_f32(const unsigned char* images, long long n, float* out, void* stream) {
+    EFFI_REQUIRE(images && out, EFFIMVS_EINVAL, "images_u8_to_f32: null pointer");
+    EFFI_REQUIRE(n > 0, EFFIMVS_EINVAL, "images_u8_to_f32: n=%lld", n);
+    const long long threads = (n + 15) / 16;
+    images_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images, (size_t)n, out);
+    return check_launch("images_u8_kernel");
 }

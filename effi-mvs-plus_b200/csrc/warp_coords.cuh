@@ -40,8 +40,8 @@ __device__ __forceinline__ void sample_coords(const Ray& r, float depth, int H, 
     float py = __fadd_rn(__fmul_rn(r.ry, depth), r.ty);
     float pz = __fadd_rn(__fmul_rn(r.rz, depth), r.tz);
     if (pz == 0.0f) pz = __fadd_rn(pz, 1e-8f);
-    float u = __fdiv_rn(px, pz);
-    float v = __fdiv_rn(py, pz);
+    float u, v;
+    div2_rn(px, py, pz, u, v);     // = px / pz, py / pz rounded to nearest, one shared reciprocal
     float gx = __fsub_rn(__fmul_rn(u, inv_half_w), 1.0f);
     float gy = __fsub_rn(__fmul_rn(v, inv_half_h), 1.0f);
     ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));

@@ -346,6 +346,158 @@ __device__ __forceinline__ void run_round(TileShared& sh, const uint8_t* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Segment form.  The D planes of one (pixel, source view) sample ONE epipolar segment, and in the cascade's
+// local volumes (and in a stage-1 plane group) neighbouring planes are a fraction of a source pixel apart: the
+// D x 4 bilinear taps keep hitting the same few source pixels.  Bilinear interpolation commutes with the channel
+// dot product,
+//     sim(p, d) = sum_taps w_t <ref_p, src_{q_t}> / C,
+// so a thread first forms g(q) = <ref_p, src_q> ONCE for every source pixel q of the segment's footprint (the
+// bounding box of its cells: FX x FY pixels, a handful), parks the scalars in a thread-private strip of shared
+// memory (slot-major, so bank = lane whatever the slot: conflict free), and then every plane costs four 4-byte
+// reads and three blends instead of 4 x C channel reads and a C-wide interpolation: ~3x fewer instructions and
+// ~F / (4 D) of the tap traffic (C = 8, D = 8, F = 8: a quarter).
+// With that little traffic the taps no longer need staging: the footprint pixels are read straight from global
+// memory with 256-bit loads (neighbouring lanes read neighbouring 32-byte pixels: full sectors, L1 hits for the
+// overlap between lanes and planes).  No TMA box, no block-wide bounding-box negotiation, no barrier per source
+// view -- measured, the staged variant of this kernel was latency-bound on exactly that round trip (0.128 ms
+// whatever the instruction count) -- and far less L2 -> SM traffic than a 64 x 12 box per (block, view).
+// A thread whose footprint does not fit SEG_SLOTS (planes far apart: plane sweeps over the full depth range)
+// samples plane by plane with gather_cell().  Pixels outside the image contribute zero (grid_sample's padding).
+// ------------------------------------------------------------------------------------------------
+constexpr int SEG_FX = 6, SEG_FY = 5;      // footprint capacity of a thread: columns (unrolled, predicated) x rows (a loop)
+constexpr int SEG_SLOTS = SEG_FX * SEG_FY;
+#ifndef EFFI_SEG_BPS8
+#define EFFI_SEG_BPS8 6
+#endif
+#ifndef EFFI_SEG_BPS16
+#define EFFI_SEG_BPS16 5
+#endif
+#ifndef EFFI_SEG_BPS32
+#define EFFI_SEG_BPS32 4
+#endif
+template <int C> struct SegBlocksPerSM { static constexpr int value = C == 8 ? EFFI_SEG_BPS8 : (C == 16 ? EFFI_SEG_BPS16 : EFFI_SEG_BPS32); };
+
+// Sample position without upstream's normalise / un-normalise round trip and with one Newton-refined reciprocal
+// instead of two IEEE divisions: 8 instructions instead of ~36, ~2 ulp of a coordinate away from upstream's value
+// (1e-4 px at x ~ 1000).  That is the rounding noise of upstream's own chain, but on white-noise features it moves the
+// similarity by up to 2e-4 of its range -- outside the 1e-4 parity bar -- so it is opt-in (EFFIMVS_WARP_FAST_COORDS=1).
+__device__ __forceinline__ void sample_coords_fast(const Ray& r, float depth, float& ix, float& iy) {
+    const float px = fmaf(r.rx, depth, r.tx), py = fmaf(r.ry, depth, r.ty);
+    float pz = fmaf(r.rz, depth, r.tz);
+    if (pz == 0.0f) pz = 1e-8f;
+    float q;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(pz));
+    q = fmaf(q, fmaf(-pz, q, 1.0f), q);
+    ix = px * q;
+    iy = py * q;
+}
+template <bool EXACT>
+__device__ __forceinline__ void seg_coords(const Ray& r, float depth, int H, int W, float ihw, float ihh, float& ix, float& iy) {
+    if (EXACT) sample_coords(r, depth, H, W, ihw, ihh, ix, iy);
+    else sample_coords_fast(r, depth, ix, iy);
+}
+
+// eight consecutive channels of a source pixel, or zeros when the predicate is off (a pixel outside the image or outside
+// the thread's footprint): one predicated 256-bit load, no branch
+__device__ __forceinline__ O2 ldg_o2_if(const float* p, bool on) {
+    O2 o;
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\tmov.b64 %2, 0;\n\tmov.b64 %3, 0;\n\t"
+        "@q ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];\n\t}"
+        : "=l"(o.a), "=l"(o.b), "=l"(o.c), "=l"(o.d) : "l"(p), "r"((int)on));
+    return o;
+}
+
+// One source view of one thread in segment form; G = 1.  nk = number of planes of this thread.
+// consume(k, sim) receives the correlation of plane k (mean over the C channels).  strip = this thread's column of the
+// block's [SEG_SLOTS][TILE_THREADS] scratch; slot = row * SEG_FX + column (constant strides: immediate offsets).
+template <int C, int DPT, bool EXACT, class F>
+__device__ __forceinline__ void run_view_seg(float* __restrict__ strip, const float* __restrict__ src, const float* __restrict__ refp,
+                                             const Ray& ray, const float (&depth)[DPT], int nk, int H, int W, float inv_half_w,
+                                             float inv_half_h, const u64* __restrict__ ref2, F&& consume) {
+    constexpr int PB = C == 8 ? 3 : (C == 16 ? 2 : 1);      // pixels whose loads are in flight together (24 / 32 / 32 registers)
+    float ix[DPT], iy[DPT];
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) seg_coords<EXACT>(ray, depth[k], H, W, inv_half_w, inv_half_h, ix[k], iy[k]);
+
+    // ---- 1. footprint of the segment from its end planes (the position is a Moebius function of the depth: monotonic in
+    //         x and in y between two planes on the same side of the camera; a plane that falls outside it anyway -- a
+    //         hypothesis list that is not monotonic, a pole between the planes -- is sampled on its own below)
+    float jx = ix[0], jy = iy[0];
+#pragma unroll
+    for (int k = 1; k < DPT; ++k)
+        if (k == nk - 1) { jx = ix[k]; jy = iy[k]; }
+    const float lxf = floorf(fminf(ix[0], jx)), hxf = floorf(fmaxf(ix[0], jx));
+    const float lyf = floorf(fminf(iy[0], jy)), hyf = floorf(fmaxf(iy[0], jy));
+    bool on = (lxf <= (float)(W - 1)) && (hxf >= -1.0f) && (lyf <= (float)(H - 1)) && (hyf >= -1.0f) &&
+              (fabsf(lxf) < 1e9f) && (fabsf(hxf) < 1e9f) && (fabsf(lyf) < 1e9f) && (fabsf(hyf) < 1e9f);   // false for NaN/inf
+    const int lx = on ? (int)fmaxf(lxf, -1.0f) : 0, ly = on ? (int)fmaxf(lyf, -1.0f) : 0;
+    const int FX = on ? (int)fminf(hxf, (float)(W - 1)) - lx + 2 : 0, FY = on ? (int)fminf(hyf, (float)(H - 1)) - ly + 2 : 0;
+    on = on && FX <= SEG_FX && FY <= SEG_FY;
+
+    // ---- 2. g(q) = <ref, src_q> for every source pixel of the footprint -> strip[row * SEG_FX + column]
+    if (on) {
+        bool colv[SEG_FX];
+#pragma unroll
+        for (int i = 0; i < SEG_FX; ++i) colv[i] = i < FX && (unsigned)(lx + i) < (unsigned)W;
+        const float* rowp = src + (ly * W + lx) * C;          // may point outside the map: only dereferenced under a predicate
+        float* out = strip;
+        for (int j = 0; j < FY; ++j, rowp += W * C, out += SEG_FX * TILE_THREADS) {
+            const bool rowv = (unsigned)(ly + j) < (unsigned)H;
+#pragma unroll
+            for (int i0 = 0; i0 < SEG_FX; i0 += PB) {
+                O2 px[PB][C / 8];
+#pragma unroll
+                for (int i = 0; i < PB; ++i)
+#pragma unroll
+                    for (int cb = 0; cb < C / 8; ++cb) px[i][cb] = ldg_o2_if(rowp + (i0 + i) * C + cb * 8, rowv && colv[i0 + i]);
+#pragma unroll
+                for (int i = 0; i < PB; ++i) {
+                    u64 m0 = mul2(px[i][0].a, ref2[0]), m1 = mul2(px[i][0].b, ref2[1]);
+                    m0 = fma2(px[i][0].c, ref2[2], m0);
+                    m1 = fma2(px[i][0].d, ref2[3], m1);
+#pragma unroll
+                    for (int cb = 1; cb < C / 8; ++cb) {
+                        m0 = fma2(px[i][cb].a, ref2[cb * 4], m0);
+                        m1 = fma2(px[i][cb].b, ref2[cb * 4 + 1], m1);
+                        m0 = fma2(px[i][cb].c, ref2[cb * 4 + 2], m0);
+                        m1 = fma2(px[i][cb].d, ref2[cb * 4 + 3], m1);
+                    }
+                    float a0, a1, b0, b1;
+                    unpack2(m0, a0, a1);
+                    unpack2(m1, b0, b1);
+                    out[(i0 + i) * TILE_THREADS] = (a0 + a1) + (b0 + b1);
+                }
+            }
+        }
+    }
+
+    // ---- 3. the planes: four scalars and three blends each
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        float sim = 0.0f;
+        if (k < nk) {
+            const Cell c = cell_at(ix[k], iy[k], H, W);
+            if (c.live) {
+                const unsigned ox = (unsigned)(c.x0 - lx), oy = (unsigned)(c.y0 - ly);
+                if (on && ox <= (unsigned)(FX - 2) && oy <= (unsigned)(FY - 2)) {
+                    const float* g = strip + (oy * SEG_FX + ox) * TILE_THREADS;
+                    const float g00 = g[0], g01 = g[TILE_THREADS], g10 = g[SEG_FX * TILE_THREADS], g11 = g[(SEG_FX + 1) * TILE_THREADS];
+                    sim = fmaf(fmaf(g11, c.dx, g10 * c.ex), c.dy, fmaf(g01, c.dx, g00 * c.ex) * c.ey) * (1.0f / C);
+                } else {
+                    float s1[1];
+                    gather_cell<C, 1>(src, refp, c.x0, c.y0, c.ex, c.dx, c.ey, c.dy, H, W, s1);
+                    sim = s1[0];
+                }
+            }
+        }
+        consume(k, sim);
+    }
+}
+
 __device__ __forceinline__ const uint8_t* block_prologue(TileShared& sh, uint8_t* smem_raw, const float* __restrict__ proj, int n_proj) {
     const int tid = threadIdx.x;
     for (int i = tid; i < n_proj; i += TILE_THREADS) sh.P[i] = proj[i];
@@ -478,6 +630,96 @@ warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __res
                          });
 }
 
+// segment-form twins of the two kernels above (G = 1): no staging, no barriers
+template <int C, bool EXACT>
+__global__ void __launch_bounds__(TILE_THREADS, SegBlocksPerSM<C>::value)
+warp_corr_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj,
+                     const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval, const float* __restrict__ weights,
+                     int H, int W, int D, int tiles_x, int flags, float* __restrict__ sim_out, float* __restrict__ hyp_out) {
+    constexpr int DPT = 8;
+    __shared__ float sP[EFFIMVS_MAX_SRC_VIEWS * 12];
+    __shared__ float scratch[SEG_SLOTS * TILE_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.z;
+    const int HW = H * W;
+    for (int i = tid; i < n_src * 12; i += TILE_THREADS) sP[i] = proj[(size_t)b * n_src * 12 + i];
+    __syncthreads();
+    float* strip = scratch + tid;
+
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int xi = tx * TW + lane, yi = ty * TH + (tid >> 5);
+    if (xi >= W || yi >= H) return;
+    const int pix = yi * W + xi;
+    const int d0 = blockIdx.y * DPT;
+    const int nk = min(DPT, D - d0);
+    const float x = (float)xi, y = (float)yi;
+    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
+    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
+
+    const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
+    u64 ref2[C / 2];
+    load_ref2<C>(refp, ref2);
+    float depth[DPT], num[DPT];
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) {
+        const bool on = k < nk;
+        depth[k] = on ? fetch_hypothesis(hyp, hyp_mode, interval, b, d0 + k, D, pix, HW) : 1.0f;
+        if (hyp_out && on) hyp_out[((size_t)b * D + d0 + k) * HW + pix] = depth[k];
+        num[k] = 0.0f;
+    }
+    float den = 0.0f;
+    for (int v = 0; v < n_src; ++v) {
+        const Ray ray = make_ray(sP + v * 12, x, y, (flags & FLAG_RAY_UNFUSED) != 0);
+        const float w = weights ? __ldg(weights + ((size_t)b * n_src + v) * HW + pix) : 1.0f;
+        run_view_seg<C, DPT, EXACT>(strip, srcs.p[v] + (size_t)b * C * HW, refp, ray, depth, nk, H, W, inv_half_w, inv_half_h, ref2,
+                                    [&](int k, float sim) {
+                                        num[k] = weights ? __fadd_rn(num[k], __fmul_rn(sim, w)) : __fadd_rn(num[k], sim);
+                                    });
+        den = __fadd_rn(den, w);
+    }
+    const float div = weights ? __fadd_rn(den, 1e-6f) : (float)n_src;
+#pragma unroll
+    for (int k = 0; k < DPT; ++k)
+        if (k < nk) sim_out[((size_t)b * D + d0 + k) * HW + pix] = __fdiv_rn(num[k], div);
+}
+
+template <int C, bool EXACT>
+__global__ void __launch_bounds__(TILE_THREADS, SegBlocksPerSM<C>::value)
+warp_views_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj,
+                      const float* __restrict__ hyp, int hyp_mode, int H, int W, int D, int tiles_x, int flags,
+                      float* __restrict__ sims_out) {
+    constexpr int DPT = 8;
+    __shared__ float sP[12];
+    __shared__ float scratch[SEG_SLOTS * TILE_THREADS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int b = blockIdx.z, v = blockIdx.y % n_src, d0 = (blockIdx.y / n_src) * DPT;
+    const int HW = H * W;
+    if (tid < 12) sP[tid] = proj[((size_t)b * n_src + v) * 12 + tid];
+    __syncthreads();
+    float* strip = scratch + tid;
+
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int xi = tx * TW + lane, yi = ty * TH + (tid >> 5);
+    if (xi >= W || yi >= H) return;
+    const int pix = yi * W + xi;
+    const int nk = min(DPT, D - d0);
+    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
+    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
+
+    const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
+    u64 ref2[C / 2];
+    load_ref2<C>(refp, ref2);
+    const Ray ray = make_ray(sP, (float)xi, (float)yi, (flags & FLAG_RAY_UNFUSED) != 0);
+    float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
+    float depth[DPT];
+#pragma unroll
+    for (int k = 0; k < DPT; ++k) depth[k] = k < nk ? fetch_hypothesis(hyp, hyp_mode, nullptr, b, d0 + k, D, pix, HW) : 1.0f;
+    run_view_seg<C, DPT, EXACT>(strip, srcs.p[v] + (size_t)b * C * HW, refp, ray, depth, nk, H, W, inv_half_w, inv_half_h, ref2,
+                                [&](int k, float sim) {
+                                    if (k < nk) out[(size_t)(d0 + k) * HW] = sim;
+                                });
+}
+
 // softmax entropy over the D similarities of a (pixel, view) (models/Effi_MVS_plus.py:43-44); sims (N, D, HW)
 __global__ void __launch_bounds__(256)
 softmax_entropy_kernel(const float* __restrict__ sims, int D, int HW, float* __restrict__ entropy_out) {
@@ -568,14 +810,38 @@ int encode_maps(TileMaps& maps, const SrcPtrs& srcs, int n_src, int B, int H, in
     return EFFIMVS_OK;
 }
 
+// which launches take the segment form: 0 never, 1 (default) local hypotheses (the cascade's stage-2/3 volumes) and the
+// stage-1 per-view kernel, 2 every G = 1 launch
+int seg_mode() {
+    const char* e = getenv("EFFIMVS_WARP_SEG");
+    return e ? atoi(e) : 1;
+}
+bool seg_fast_coords() {
+    const char* e = getenv("EFFIMVS_WARP_FAST_COORDS");
+    return e && e[0] == '1';
+}
+
 template <int C, int G>
 int launch_tile(const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode,
                 const float* interval, const float* weights, int B, int H, int W, int D, int flags, float* sim_out, float* hyp_out,
                 cudaStream_t st) {
+    const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
+    if constexpr (G == 1) {
+        const int mode = seg_mode();
+        if (mode >= 2 || (mode == 1 && hyp_mode == EFFIMVS_HYP_LOCAL)) {
+            dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, ceil_div(D, 8), B);
+            if (seg_fast_coords())
+                warp_corr_seg_kernel<C, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
+                                                                       tiles_x, flags, sim_out, hyp_out);
+            else
+                warp_corr_seg_kernel<C, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
+                                                                      tiles_x, flags, sim_out, hyp_out);
+            return check_launch("warp_corr_seg_kernel");
+        }
+    }
     TileMaps maps;
     int rc = encode_maps<C>(maps, srcs, n_src, B, H, W);
     if (rc) return rc;
-    const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
     dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, ceil_div(D, TilePlanes<G>::value), B);
     const size_t smem = BoxBytes<C>::ALL + 1024;
     cudaFuncSetAttribute(warp_corr_tile_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -601,15 +867,23 @@ int tile_dispatch_g(int G, const float* ref, const SrcPtrs& srcs, int n_src, con
 template <int C>
 int launch_views(const float* ref, const SrcPtrs& srcs, int n_src, const float* proj, const float* hyp, int hyp_mode, int B, int H,
                  int W, int D, int flags, float* sims_out, float* entropy_out, cudaStream_t st) {
-    TileMaps maps;
-    int rc = encode_maps<C>(maps, srcs, n_src, B, H, W);
-    if (rc) return rc;
+    int rc;
     const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
     dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, n_src * ceil_div(D, 8), B);
-    const size_t smem = BoxBytes<C>::ALL + 1024;
-    cudaFuncSetAttribute(warp_views_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    warp_views_tile_kernel<C><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
-    if ((rc = check_launch("warp_views_tile_kernel"))) return rc;
+    if (seg_mode() >= 1) {
+        if (seg_fast_coords())
+            warp_views_seg_kernel<C, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
+        else
+            warp_views_seg_kernel<C, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
+        if ((rc = check_launch("warp_views_seg_kernel"))) return rc;
+    } else {
+        TileMaps maps;
+        if ((rc = encode_maps<C>(maps, srcs, n_src, B, H, W))) return rc;
+        const size_t smem = BoxBytes<C>::ALL + 1024;
+        cudaFuncSetAttribute(warp_views_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        warp_views_tile_kernel<C><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
+        if ((rc = check_launch("warp_views_tile_kernel"))) return rc;
+    }
     const dim3 egrid(ceil_div(H * W, 256), B * n_src);
     if (D <= 48) softmax_entropy_reg_kernel<48><<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);
     else if (D <= 96) softmax_entropy_reg_kernel<96><<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);

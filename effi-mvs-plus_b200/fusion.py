@@ -22,7 +22,7 @@ def get_reproj_dynamic(ref_depth, srcs_depth, ref_cam, srcs_cam, torch_inverse: 
     """Drop-in for misc/fusion.py:117 ``get_reproj_dynamic``.  Returns (reproj_xyd (n,v,3,h,w), None, None):
     the two camera-space tensors upstream also returns are never read by its own caller's
     arithmetic (vis_filter_dynamic only reshapes them, fusion.py:161-162) and are not materialised."""
-    inv = inverse_cameras(ref_cam, srcs_cam) if torch_inverse else None
+    inv = inverse_cameras(ref_cam, srcs_cam) if torch_inverse else ops.fusion_invert_cameras(ref_cam, srcs_cam)
     return ops.fusion_reproject(ref_depth, srcs_depth, ref_cam, srcs_cam, inv), None, None
 
 
@@ -40,7 +40,7 @@ def filter_view(ref_depth, ref_conf, srcs_depth, ref_cam, srcs_cam, dist_base, r
 
     ref_depth (n,1,h,w), ref_conf (n,hc,wc), srcs_depth (n,v,1,h,w), cams as upstream.
     -> dict(final (n,1,h,w) bool, depth_avg (n,1,h,w), points (n,3,h,w)[, masks (n,v,K,h,w) bool])."""
-    inv = inverse_cameras(ref_cam, srcs_cam) if torch_inverse else None
+    inv = inverse_cameras(ref_cam, srcs_cam) if torch_inverse else ops.fusion_invert_cameras(ref_cam, srcs_cam)
     final, avg, pts, masks = ops.fusion_filter(ref_depth, srcs_depth, ref_conf, ref_cam, srcs_cam, inv, float(dist_base),
                                                float(rel_diff_base), int(thres_view), float(prob_threshold), bool(relative),
                                                bool(want_masks))

@@ -513,6 +513,35 @@ def _(x, prev, weights, biases, precision, ws):
 
 
 # -------------------------------------------------------------------------------------------
+@torch.library.custom_op("effimvs::images_u8_to_f32", mutates_args=("out",))
+@_on_tensor_device
+def images_u8_to_f32(images: Tensor, out: Tensor) -> None:
+    """out[i] = images[i] / 255 (IEEE division, upstream's loader arithmetic); images uint8, out fp32, same shape, both contiguous."""
+    if not (images.is_cuda and out.is_cuda):
+        raise RuntimeError("effimvs::images_u8_to_f32 got a CPU tensor; the hot path is CUDA-only (no fallback)")
+    if images.dtype != torch.uint8 or out.dtype != torch.float32 or images.shape != out.shape or not (
+            images.is_contiguous() and out.is_contiguous()):
+        raise RuntimeError("effimvs::images_u8_to_f32: images must be uint8, out fp32, same shape, contiguous")
+    _count(1)
+    capi.check(_lib.effimvs_images_u8_to_f32(images.data_ptr(), images.numel(), out.data_ptr(), _stream()))
+
+
+@torch.library.custom_op("effimvs::fusion_invert_cameras", mutates_args=())
+@_on_tensor_device
+def fusion_invert_cameras(ref_cam: Tensor, srcs_cam: Tensor) -> Tensor:
+    ref_cam, srcs_cam = _dev(ref_cam, "fusion_invert_cameras"), _dev(srcs_cam, "fusion_invert_cameras")
+    n, v = srcs_cam.shape[0], srcs_cam.shape[1]
+    out = torch.empty(n, v + 1, 2, 4, 4, device=ref_cam.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_fusion_invert_cameras_f32(ref_cam.data_ptr(), srcs_cam.data_ptr(), n, v, out.data_ptr(), _stream()))
+    return out
+
+
+@fusion_invert_cameras.register_fake
+def _(ref_cam, srcs_cam):
+    return ref_cam.new_empty(srcs_cam.shape[0], srcs_cam.shape[1] + 1, 2, 4, 4)
+
+
 @torch.library.custom_op("effimvs::fusion_reproject", mutates_args=())
 @_on_tensor_device
 def fusion_reproject(ref_depth: Tensor, srcs_depth: Tensor, ref_cam: Tensor, srcs_cam: Tensor,

@@ -35,7 +35,10 @@ class _Slot:
 class DepthMapPipeline:
     def __init__(self, model, example: Dict, slots: int = 2, use_graph: bool = True, before_replay=None):
         """example: {"imgs" (B,V,3,H,W), "proj_matrices" {stage: (B,V,2,4,4)}, "depth_values" (B,Dv)} on the host;
-        fixes the shapes the pipeline accepts."""
+        fixes the shapes the pipeline accepts.  "imgs" may be fp32 in [0,1] (what upstream's loaders hand over) or uint8
+        (what the image files hold): 8-bit images cross PCIe as they are -- a quarter of the bytes -- and are divided by
+        255 on the device with the loaders' own arithmetic (effimvs_images_u8_to_f32), so the depth maps are the same
+        bit for bit.  `submit` accepts either, whatever the example was."""
         self.model = model
         self.device = next(model.parameters()).device
         self.compute = torch.cuda.Stream(self.device)
@@ -49,7 +52,14 @@ class DepthMapPipeline:
         with torch.no_grad():
             for _ in range(slots):
                 s = _Slot()
-                s.inputs = {"imgs": example["imgs"].to(self.device), "depth_values": example["depth_values"].to(self.device),
+                first = example["imgs"].to(self.device)
+                s.u8 = torch.empty(first.shape, dtype=torch.uint8, device=self.device)
+                if first.dtype == torch.uint8:
+                    from . import ops
+                    s.u8.copy_(first)
+                    first = torch.empty(first.shape, dtype=torch.float32, device=self.device)
+                    ops.images_u8_to_f32(s.u8, first)
+                s.inputs = {"imgs": first, "depth_values": example["depth_values"].to(self.device),
                             "proj_matrices": {k: example["proj_matrices"][k].to(self.device) for k in stages}}
                 torch.cuda.synchronize(self.device)
                 with torch.cuda.stream(self.compute):
@@ -71,10 +81,10 @@ class DepthMapPipeline:
                 s.host_conf = torch.empty(s.out[1].shape, dtype=torch.float32).pin_memory()
                 self.slots.append(s)
 
-    @property
-    def h2d_bytes(self) -> int:
-        i = self.slots[0].inputs
-        return 4 * (i["imgs"].numel() + i["depth_values"].numel() + sum(v.numel() for v in i["proj_matrices"].values()))
+    def h2d_bytes(self, sample: Dict) -> int:
+        """bytes `submit(sample)` copies host -> device"""
+        return (sample["imgs"].numel() * sample["imgs"].element_size() + 4 * sample["depth_values"].numel() +
+                4 * sum(sample["proj_matrices"][k].numel() for k in self.slots[0].inputs["proj_matrices"]))
 
     @property
     def d2h_bytes(self) -> int:
@@ -89,7 +99,8 @@ class DepthMapPipeline:
             s.done.synchronize()            # the slot's previous outputs have reached the host
         with torch.cuda.stream(self.copy):
             self.copy.wait_event(s.done)    # do not overwrite inputs a previous replay may still read
-            s.inputs["imgs"].copy_(sample["imgs"], non_blocking=True)
+            as_u8 = sample["imgs"].dtype == torch.uint8
+            (s.u8 if as_u8 else s.inputs["imgs"]).copy_(sample["imgs"], non_blocking=True)
             s.inputs["depth_values"].copy_(sample["depth_values"], non_blocking=True)
             for k, v in s.inputs["proj_matrices"].items():
                 v.copy_(sample["proj_matrices"][k], non_blocking=True)
@@ -97,6 +108,9 @@ class DepthMapPipeline:
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(s.copied)
             self.compute.wait_event(s.done)     # the slot's previous outputs have left the device (no-op the first time)
+            if as_u8:
+                from . import ops
+                ops.images_u8_to_f32(s.u8, s.inputs["imgs"])
             if self.before_replay is not None:
                 self.before_replay()
             if s.graph is not None:

@@ -188,6 +188,12 @@ int effimvs_cost_up_small_ex(const float* x, const float* prev, const float* con
                              const float* const* biases, int B, int D, int H, int W, int precision, int phases,
                              void* workspace, size_t workspace_bytes, float* out, void* stream);
 
+/* Input format next to the path: 8-bit images as they sit in the image files -> fp32 in [0,1],
+ * out[i] = (float)images[i] / 255.0f with an IEEE division -- bit for bit what upstream's loaders compute on the host
+ * (datasets/general_eval.py:83-87, np.float32 / 255.).  Lets a caller ship a quarter of the bytes over PCIe.
+ *   images (n) uint8, any layout;  out (n) fp32, same layout */
+int effimvs_images_u8_to_f32(const unsigned char* images, long long n, float* out, void* stream);
+
 /* a13: get_reproj_dynamic (misc/fusion.py:117-154).
  *   ref_depth (n,1,h,w), srcs_depth (n,v,1,h,w), ref_cam (n,2,4,4), srcs_cam (n,v,2,4,4)
  *   -> reproj_xyd (n,v,3,h,w).  Camera inverses are taken in-kernel (fp32 adjugate/LU as
@@ -196,6 +202,12 @@ int effimvs_cost_up_small_ex(const float* x, const float* prev, const float* con
 int effimvs_fusion_reproject_f32(const float* ref_depth, const float* srcs_depth, const float* ref_cam,
                                  const float* srcs_cam, const float* inv_cams, int n, int v, int h, int w,
                                  float* reproj_xyd, void* stream);
+
+/* inverse(E) and inverse(K) of the reference and the v source cameras of every batch item, fp64 Gauss-Jordan rounded once
+ * to fp32 (upstream calls torch's .inverse(), misc/fusion.py:24,32): inv_out (n,1+v,2,4,4) in the layout the inv_cams
+ * argument of the two entry points around it takes ([:,:,0] = inverse extrinsic, [:,:,1,:3,:3] = inverse intrinsic).  For
+ * callers that want no host synchronisation and no torch LU (CUDA-graph capture). */
+int effimvs_fusion_invert_cameras_f32(const float* ref_cam, const float* srcs_cam, int n, int v, float* inv_out, void* stream);
 
 /* a14 alone: vis_filter_dynamic (misc/fusion.py:157-181) on an existing reproj_xyd (n,v,3,h,w).
  *   -> masks_out (n,v,K,h,w) uint8, K = v-thres_view+1 (the last ladder step is upstream's `mask`). */

@@ -528,6 +528,34 @@ def test_pipeline_matches_direct_forward(hp):
         assert frac_within(c, want["photometric_confidence"].cpu(), 1e-3) >= 0.999
 
 
+def test_pipeline_8bit_images_equal_fp32_images(hp):
+    """8-bit host images (a quarter of the PCIe bytes) divided by 255 on the device give the depth maps of the fp32 host
+    images upstream's loaders form (np.float32 / 255., datasets/general_eval.py:83-87) bit for bit; the conversion kernel
+    itself equals the NumPy expression for all 256 values and for unaligned / ragged sizes."""
+    import numpy as np
+    from effimvs_b200 import ops, pipeline, synthetic
+    for n, off in ((256, 0), (1000003, 0), (4099, 3), (7, 1)):
+        u8 = torch.arange(n + off, dtype=torch.int64).remainder(256).to(torch.uint8)[off:]
+        dev_u8 = torch.arange(n + off, device=DEV, dtype=torch.int64).remainder(256).to(torch.uint8)[off:]
+        out = torch.empty(n, device=DEV)
+        ops.images_u8_to_f32(dev_u8.contiguous(), out)
+        assert np.array_equal(out.cpu().numpy(), u8.numpy().astype(np.float32) / np.float32(255.0))
+    model = dtu_model(hp, DEV)
+    s = synthetic.make_sample("plumbing", seed=3, width=256, height=192)
+    u8 = (s["imgs"] * 255.0).round().clamp(0, 255).to(torch.uint8)
+    f32 = torch.from_numpy(u8.numpy().astype(np.float32) / np.float32(255.0))
+    rest = {"depth_values": s["depth_values"].pin_memory(), "proj_matrices": {k: v.pin_memory() for k, v in s["proj_matrices"].items()}}
+    pipe = pipeline.DepthMapPipeline(model, dict(rest, imgs=f32.pin_memory()), slots=2)
+    a = [t.clone() for t in pipe.result(pipe.submit(dict(rest, imgs=f32.pin_memory())))]
+    b = [t.clone() for t in pipe.result(pipe.submit(dict(rest, imgs=u8.pin_memory())))]
+    c = [t.clone() for t in pipe.result(pipe.submit(dict(rest, imgs=u8.pin_memory())))]       # the other slot
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(b[0], c[0])
+    assert pipe.h2d_bytes(dict(rest, imgs=u8)) < 0.27 * pipe.h2d_bytes(dict(rest, imgs=f32))
+    pipe8 = pipeline.DepthMapPipeline(model, dict(rest, imgs=u8.pin_memory()), slots=1)       # a pipeline built from 8-bit images
+    d = pipe8.result(pipe8.submit(dict(rest, imgs=u8.pin_memory())))
+    assert torch.equal(d[0], a[0])
+
+
 # ------------------------------------------------------------------------------------------
 # remaining upstream-named call sites (SURVEY.md section 8(b)): homo_warping_new, get_depth_range_samples,
 # vis_filter_dynamic
@@ -904,3 +932,103 @@ def test_scene_runner_feature_cache_on_device(hp):
             assert frac_within(d1, d0, 1e-3 * DEPTH_RANGE) >= 0.999, mode
             n0, n1 = runs["plain"][i][0].shape[0], runs[mode][i][0].shape[0]
             assert abs(n0 - n1) <= 0.02 * H * W, mode
+
+
+# ---- segment-form warp kernels (csrc/warp_tile.cu: run_round_seg) ---------------------------------------------------
+def _with_env(**kv):
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kv}
+        os.environ.update({k: str(v) for k, v in kv.items()})
+        try:
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,D,H,W", [(8, 8, 592, 800), (16, 8, 296, 400), (8, 8, 97, 131), (16, 5, 64, 96), (32, 8, 40, 56), (8, 12, 50, 70)])
+@pytest.mark.parametrize("depth_kind,ratio", [("smooth", 1), ("noise", 1), ("steps", 2), ("smooth", 12), ("near", 1)])
+def test_local_volume_segment_form_vs_oracle(hp, ohp, C, D, H, W, depth_kind, ratio):
+    """a5 through the segment-form kernel (dot products once per source pixel of the epipolar segment's footprint) on
+    channels-last maps: against the oracle on the device, against the plane-by-plane tile kernel and against the gather
+    kernel.  smooth / noise / steps: rendered surface, white-noise depth, depth discontinuities; ratio 12: planes several
+    pixels apart (footprints that do not fit the strip: plane-by-plane path); near: depths so close that most of the
+    segments leave the source images (dead samples, clamped boxes, border cells)."""
+    from effimvs_b200 import synthetic
+    feats, cams, _, wts = synthetic.microbench_inputs(C, D, H, W, views=5, seed=C + D + H, device=DEV)
+    gen = torch.Generator().manual_seed(H)
+    if depth_kind == "smooth":
+        E, K = synthetic.camera_ring(5, W, H)
+        cur = synthetic.render_plane_scene(E[:1], K, W, H, noise=0.0)[0].reshape(1, 1, H, W).to(DEV)
+    elif depth_kind == "noise":
+        cur = (600 + 200 * torch.rand(1, 1, H, W, generator=gen)).to(DEV)
+    elif depth_kind == "near":
+        cur = (30 + 300 * torch.rand(1, 1, H, W, generator=gen)).to(DEV)
+    else:
+        cur = torch.full((1, 1, H, W), 500.0)
+        cur[..., W // 3:] = 800.0
+        cur[..., H // 2:, :] += 90.0
+        cur = cur.to(DEV)
+    iv = torch.full((1, 1, 1, 1), (1 / 425.0 - 1 / 935.0) / 384 * ratio, device=DEV)
+    cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    want, want_hyp = ohp.local_volume(cur, feats, cams, iv, wts, D, 1)
+    got, hyp = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
+    assert torch.equal(hyp, want_hyp)
+    assert rel_max(got, want) < 1e-4
+    with _with_env(EFFIMVS_WARP_FAST_COORDS=0):               # upstream's coordinate chain: only fp32 re-association is left
+        exact, _ = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
+    with _with_env(EFFIMVS_WARP_SEG=0):
+        tile, _ = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
+    assert rel_max(exact, tile) < 2e-6
+    assert rel_max(got, tile) < 1e-4
+    got_nw, _ = hp.local_volume(cur, cl, cams, iv, None, D, 1)
+    want_nw, _ = ohp.local_volume(cur, feats, cams, iv, None, D, 1)
+    assert rel_max(got_nw, want_nw) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,D,H,W,V", [(32, 48, 148, 200, 5), (32, 96, 132, 240, 7), (32, 48, 37, 53, 3), (16, 20, 64, 80, 5)])
+def test_stage1_views_segment_form_vs_oracle(ohp, C, D, H, W, V):
+    """a4 through the segment-form per-view kernel at the DTU and Tanks & Temples stage-1 shapes: per-view similarities and
+    entropies against the oracle on the device and against the plane-by-plane tile kernel."""
+    from effimvs_b200 import capi, hotpath, ops, synthetic
+    feats, cams, hyp, _ = synthetic.microbench_inputs(C, D, H, W, views=V, seed=D, device=DEV)
+    feats = [f * 0.4 for f in feats]
+    cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    planes = hyp[:, :, 0, 0].contiguous()
+    proj = hotpath.CudaHotPath().relative_projection(cams)
+    sims, ent = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
+    with _with_env(EFFIMVS_WARP_SEG=0):
+        sims_t, ent_t = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
+    with _with_env(EFFIMVS_WARP_FAST_COORDS=0):
+        sims_e, _ = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
+    assert rel_max(sims_e, sims_t) < 2e-6
+    assert rel_max(sims, sims_t) < 1e-4 and float((ent - ent_t).abs().max()) < 1e-3
+    for v in range(V - 1):
+        want = ohp.view_similarity(feats[0], feats[v + 1], cams[:, 0], cams[:, v + 1], hyp, 1)
+        assert rel_max(sims[:, v], want[:, 0]) < 1e-4
+        assert float((ent[:, v:v + 1] - ohp.similarity_entropy(want)).abs().max()) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,D,H,W", [(8, 8, 296, 400), (16, 16, 148, 200), (32, 48, 74, 100)])
+def test_plane_sweep_segment_form_forced(hp, ohp, C, D, H, W):
+    """EFFIMVS_WARP_SEG=2 sends every G = 1 launch (plane sweeps over the whole depth range, explicit per-pixel hypotheses)
+    through the segment form; most footprints do not fit the strip there and take its plane-by-plane path."""
+    from effimvs_b200 import synthetic
+    feats, cams, hyp, wts = synthetic.microbench_inputs(C, D, H, W, views=5, seed=C + D, device=DEV)
+    cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    sims = [ohp.view_similarity(feats[0], feats[v], cams[:, 0], cams[:, v], hyp, 1) for v in range(1, 5)]
+    want = ohp.weighted_aggregate(sims, [wts[:, i:i + 1] for i in range(4)])
+    with _with_env(EFFIMVS_WARP_SEG=2):
+        got = hp.warp_corr_agg(cl, cams, hyp, wts, 1)
+        got_planes = hp.warp_corr_agg(cl, cams, hyp[:, :, :1, :1].contiguous(), wts, 1)
+    assert rel_max(got, want) < 1e-4 and rel_max(got_planes, want) < 1e-4

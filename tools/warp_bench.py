@@ -63,11 +63,26 @@ def main():
             fn = lambda f: ops.warp_corr_agg(f[0], f[1:], proj, cur, capi.HYP_LOCAL, iv, wts, D, 1, True)[0]   # noqa: E731
             by = 4.0 * (V * C * H * W + H * W + (V - 1) * H * W + 2 * D * H * W)
         ms_p, out_p = timed(lambda: fn(feats), flush, reps)
-        ms_c, out_c = timed(lambda: fn(feats_cl), flush, reps)
-        diff = float((out_p - out_c).abs().max() / out_p.abs().max())
-        rows.append({"stage": i + 1, "C": C, "D": D, "H": H, "W": W, "planar_ms": ms_p, "nhwc_ms": ms_c,
-                     "planar_GBs": by / ms_p / 1e6, "nhwc_GBs": by / ms_c / 1e6, "nhwc_vs_planar_rel_diff": diff})
-        print(json.dumps(rows[-1]), flush=True)
+        row = {"stage": i + 1, "C": C, "D": D, "H": H, "W": W, "planar_ms": ms_p, "planar_GBs": by / ms_p / 1e6}
+        # channels-last maps: plane-by-plane tile kernel (SEG=0), segment form with fast / upstream-exact coordinates
+        for tag, env in (("tile", {"EFFIMVS_WARP_SEG": "0"}), ("seg", {"EFFIMVS_WARP_SEG": "1"}),
+                         ("seg_exact", {"EFFIMVS_WARP_SEG": "1", "EFFIMVS_WARP_FAST_COORDS": "1"})):
+            os.environ.pop("EFFIMVS_WARP_FAST_COORDS", None)
+            os.environ.update(env)
+            ms_c, out_c = timed(lambda: fn(feats_cl), flush, reps)
+            row.update({tag + "_ms": ms_c, tag + "_GBs": by / ms_c / 1e6,
+                        tag + "_vs_planar_rel_diff": float((out_p - out_c).abs().max() / out_p.abs().max())})
+            if i > 0:      # the same on a smooth surface (what a converged scene looks like)
+                Es, Ks = synthetic.camera_ring(V, W, H)
+                keep = cur
+                cur = synthetic.render_plane_scene(Es[:1], Ks, W, H, noise=0.0)[0].to(dev).reshape(1, 1, H, W)
+                ms_s, _ = timed(lambda: fn(feats_cl), flush, reps)
+                row.update({tag + "_smooth_ms": ms_s, tag + "_smooth_GBs": by / ms_s / 1e6})
+                cur = keep
+        os.environ.pop("EFFIMVS_WARP_FAST_COORDS", None)
+        os.environ.pop("EFFIMVS_WARP_SEG", None)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
 
 
 if __name__ == "__main__":
