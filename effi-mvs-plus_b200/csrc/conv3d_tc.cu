@@ -112,7 +112,11 @@ struct ConvProgram {
     int relu;
     int w_smem_bytes;             // packed weights of all phases (resident in shared memory, loaded once per CTA)
     int slab_bytes, n_stages;     // operand slab of one load unit; number of slab stages (1 or 2)
-    int tile_cols;                // TMEM columns of one accumulator stage (two stages are allocated)
+    int tile_cols;                // TMEM columns of one accumulator stage
+    int tmem_stages;              // accumulator stages: 2 (MMAs of tile k+1 overlap the epilogue of tile k inside one CTA), or 1 when two
+                                  // stages would take more than 256 columns and the CTA is small enough for a second one per SM --
+                                  // the neighbour CTA then provides the overlap and doubles the epilogue warps (transposed layers:
+                                  // 8 output classes make the epilogue the long pole)
     int cls_z;                    // 1: the accumulator classes are consecutive output planes (z-sweep), output z = grid z * up_z + class
     int b_lbo_rows;               // rows between the two K chunks of a packed weight block (b_rows, or 3 * b_rows when stacked)
     int out_f32_pair;             // output (8 channels, hi/lo layout geometry) stored as raw fp32: channels 0-3 in the "hi" voxel, 4-7 in the "lo" voxel
@@ -301,8 +305,8 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
             mbar_wait(&bar_w, 0);
             uint32_t u = 0, k = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-                const uint32_t acc = k & 1;
-                mbar_wait(&bar_tempty[acc], ((k >> 1) & 1) ^ 1);    // epilogue drained this accumulator stage
+                const uint32_t acc = P.tmem_stages == 2 ? (k & 1) : 0u, round = P.tmem_stages == 2 ? (k >> 1) : k;
+                mbar_wait(&bar_tempty[acc], (round & 1) ^ 1);       // epilogue drained this accumulator stage
                 tc_fence_after();
                 const uint32_t d0 = tmem + acc * (uint32_t)P.tile_cols;
                 for (int p = 0; p < P.n_phases; ++p, ++u) {
@@ -332,8 +336,8 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
             const int yp = q / P.gPx, xp = q - yp * P.gPx;
             const bool interior = yp >= 1 && yp <= P.gH && xp >= 1 && xp <= P.gW;
             const int gy = yp - 1, gx = xp - 1;
-            const uint32_t acc = k & 1;
-            mbar_wait(&bar_tfull[acc], (k >> 1) & 1);
+            const uint32_t acc = P.tmem_stages == 2 ? (k & 1) : 0u, round = P.tmem_stages == 2 ? (k >> 1) : k;
+            mbar_wait(&bar_tfull[acc], round & 1);
             tc_fence_after();
             const uint32_t lane_base = tmem + acc * (uint32_t)P.tile_cols + ((uint32_t)(warp * 32) << 16);
             for (int g = 0; g < groups; ++g) {
@@ -689,7 +693,14 @@ bool assemble(ConvProgram& P, PackTable& T, const std::vector<Term>& terms, cons
         (size_t)P.w_smem_bytes + (size_t)P.slab_bytes <= two_cta)
         P.n_stages = 1;
     P.tile_cols = P.b_rows * P.n_classes;
+    P.tmem_stages = 2;
     P.tmem_cols = pow2_cols(2 * P.tile_cols);
+    if (P.tmem_cols > 256 && pow2_cols(P.tile_cols) <= 256 && (size_t)P.w_smem_bytes + (size_t)P.slab_bytes <= two_cta &&
+        !getenv("EFFIMVS_TC_TWO_TMEM_STAGES")) {
+        P.tmem_stages = 1;
+        P.n_stages = 1;
+        P.tmem_cols = pow2_cols(P.tile_cols);
+    }
     if (P.tmem_cols > 512) return false;
     return true;
 }
@@ -819,6 +830,7 @@ bool build_conv_s1_zsweep(ConvProgram& P, PackTable& T, int Cin, int Cout, const
     if ((size_t)P.w_smem_bytes + P.slab_bytes > budget) return false;
     P.n_stages = ((size_t)P.w_smem_bytes + 2 * (size_t)P.slab_bytes <= budget) ? 2 : 1;
     P.tile_cols = R * P.b_rows;
+    P.tmem_stages = 2;
     P.tmem_cols = pow2_cols(2 * P.tile_cols);
     return P.tmem_cols <= 512 && n_blk <= MAX_BLOCKS;
 }

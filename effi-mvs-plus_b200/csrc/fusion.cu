@@ -165,8 +165,8 @@ __device__ __forceinline__ float sample_depth(const float* __restrict__ img, int
                                               float inv_half_w, float inv_half_h) {
     float gx = __fsub_rn(__fmul_rn(u, inv_half_w), 1.0f);
     float gy = __fsub_rn(__fmul_rn(v, inv_half_h), 1.0f);
-    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(w - 1));
-    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(h - 1));
+    float ix = __fmul_rn(__fadd_rn(gx, 1.0f), 0.5f * (float)(w - 1));    // = ((g + 1) / 2) * (w - 1) bit for bit (exact halving)
+    float iy = __fmul_rn(__fadd_rn(gy, 1.0f), 0.5f * (float)(h - 1));
     float fx = floorf(ix), fy = floorf(iy);
     bool x0 = (fx >= 0.0f) && (fx <= (float)(w - 1));
     bool x1 = (fx >= -1.0f) && (fx <= (float)(w - 2));

@@ -44,8 +44,10 @@ __device__ __forceinline__ void sample_coords(const Ray& r, float depth, int H, 
     div2_rn(px, py, pz, u, v);     // = px / pz, py / pz rounded to nearest, one shared reciprocal
     float gx = __fsub_rn(__fmul_rn(u, inv_half_w), 1.0f);
     float gy = __fsub_rn(__fmul_rn(v, inv_half_h), 1.0f);
-    ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
-    iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
+    // ATen: ((g + 1) / 2) * (size - 1).  The halving is exact, so one multiplication by (size - 1) / 2 (exact too)
+    // rounds the same real product: bit-identical, one instruction less per coordinate
+    ix = __fmul_rn(__fadd_rn(gx, 1.0f), 0.5f * (float)(W - 1));
+    iy = __fmul_rn(__fadd_rn(gy, 1.0f), 0.5f * (float)(H - 1));
 }
 
 // inverse-depth samples around cur_depth, exactly the op sequence of models/module.py:558-570
@@ -57,6 +59,21 @@ __device__ __forceinline__ float local_hypothesis(float cur_depth, float interva
     float step = __fmul_rn(__fsub_rn(hi, lo), __fdiv_rn(1.0f, (float)(D - 1)));   // torch (CUDA) divides by a Python scalar as a * (1/b)
     float s = fmaxf(__fadd_rn(lo, __fmul_rn((float)d, step)), 1e-5f);
     return __fdiv_rn(1.0f, s);
+}
+
+// the same split into the per-pixel part and the per-plane part (identical operations, the first five done once)
+struct LocalHyp { float lo, step; };
+__device__ __forceinline__ LocalHyp local_hypothesis_prepare(float cur_depth, float interval, int D, float inv_dm1) {
+    const float inv = __fdiv_rn(1.0f, cur_depth);
+    const float half = __fmul_rn((float)(D / 2), interval);
+    LocalHyp h;
+    h.lo = fmaxf(__fsub_rn(inv, half), 1e-4f);
+    const float hi = fminf(fmaxf(__fadd_rn(inv, half), 1e-4f), 1e4f);
+    h.step = __fmul_rn(__fsub_rn(hi, h.lo), inv_dm1);           // inv_dm1 = fl(1 / (D - 1))
+    return h;
+}
+__device__ __forceinline__ float local_hypothesis_at(const LocalHyp& h, int d) {
+    return __fdiv_rn(1.0f, fmaxf(__fadd_rn(h.lo, __fmul_rn((float)d, h.step)), 1e-5f));
 }
 
 __device__ __forceinline__ float fetch_hypothesis(const float* __restrict__ hyp, int mode, const float* __restrict__ interval,

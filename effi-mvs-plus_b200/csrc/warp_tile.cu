@@ -39,7 +39,9 @@ namespace {
 constexpr int TW = 32, TH = 4;            // reference tile of a block: one warp per tile row
 constexpr int TILE_THREADS = TW * TH;
 constexpr int FLAG_FORCE_GATHER = 1;      // debugging / tests: never stage, always gather from global
-constexpr int FLAG_RAY_UNFUSED = 2;       // ray = (r0*x + r1*y) + r2 without contraction (see warp_coords.cuh)
+constexpr int FLAG_RAY_UNFUSED = 2;
+// profiling only (EFFIMVS_WARP_DEBUG bit mask; results are wrong): no prefetch / no footprint loads / no per-plane lookups
+constexpr int FLAG_DBG_NO_PREFETCH = 16, FLAG_DBG_NO_LOADS = 32, FLAG_DBG_NO_SAMPLES = 64;       // ray = (r0*x + r1*y) + r2 without contraction (see warp_coords.cuh)
 
 // staged source box in pixels, per channel count (one sub-box holds 8 channels = 32 bytes per pixel).
 // BW * 32 is a multiple of 256 so that the swizzle bit (address bit 7) does not depend on the row.
@@ -107,6 +109,8 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* ma
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(x), "r"(y), "r"(b)
                  : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct O2 { u64 a, b, c, d; };           // eight consecutive channels
 __device__ __forceinline__ O2 ldg_o2(const float* p) {
@@ -398,78 +402,100 @@ __device__ __forceinline__ void seg_coords(const Ray& r, float depth, int H, int
     else sample_coords_fast(r, depth, ix, iy);
 }
 
-// eight consecutive channels of a source pixel, or zeros when the predicate is off (a pixel outside the image or outside
-// the thread's footprint): one predicated 256-bit load, no branch
-__device__ __forceinline__ O2 ldg_o2_if(const float* p, bool on) {
-    O2 o;
-    asm volatile(
-        "{\n\t.reg .pred q;\n\t"
-        "setp.ne.b32 q, %5, 0;\n\t"
-        "mov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\tmov.b64 %2, 0;\n\tmov.b64 %3, 0;\n\t"
-        "@q ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];\n\t}"
-        : "=l"(o.a), "=l"(o.b), "=l"(o.c), "=l"(o.d) : "l"(p), "r"((int)on));
-    return o;
-}
-
 // One source view of one thread in segment form; G = 1.  nk = number of planes of this thread.
-// consume(k, sim) receives the correlation of plane k (mean over the C channels).  strip = this thread's column of the
-// block's [SEG_SLOTS][TILE_THREADS] scratch; slot = row * SEG_FX + column (constant strides: immediate offsets).
-template <int C, int DPT, bool EXACT, class F>
+// consume(k, sim) receives the correlation of plane k (mean over the C channels: ref2 holds the reference features
+// already divided by C -- a power of two, so every product and sum scales exactly).  strip = this thread's column of the
+// block's [SEG_SLOTS][STRIDE] scratch; slot = row * SEG_FX + column (constant strides: immediate offsets).
+template <int C, int DPT, bool EXACT, int STRIDE, class F>
 __device__ __forceinline__ void run_view_seg(float* __restrict__ strip, const float* __restrict__ src, const float* __restrict__ refp,
                                              const Ray& ray, const float (&depth)[DPT], int nk, int H, int W, float inv_half_w,
-                                             float inv_half_h, const u64* __restrict__ ref2, F&& consume) {
-    constexpr int PB = C == 8 ? 3 : (C == 16 ? 2 : 1);      // pixels whose loads are in flight together (24 / 32 / 32 registers)
+                                             float inv_half_h, const u64* __restrict__ ref2, int flags, F&& consume) {
+    constexpr int PB = C == 32 ? 1 : 2;      // pixels whose loads are in flight together (16 / 32 / 32 registers)
     float ix[DPT], iy[DPT];
+    // end planes first: they fix the footprint, whose lines are then requested (prefetch: no destination registers) while
+    // the coordinates of the planes in between are computed -- otherwise every row of the footprint is a dependent
+    // L2 / DRAM round trip of its own and the kernel idles on long-scoreboard stalls
+    seg_coords<EXACT>(ray, depth[0], H, W, inv_half_w, inv_half_h, ix[0], iy[0]);
+    seg_coords<EXACT>(ray, depth[DPT - 1], H, W, inv_half_w, inv_half_h, ix[DPT - 1], iy[DPT - 1]);
+    float jx = ix[DPT - 1], jy = iy[DPT - 1];
+    if (nk < DPT) {       // a partial plane group (block-uniform): its last plane
+        jx = ix[0]; jy = iy[0];
 #pragma unroll
-    for (int k = 0; k < DPT; ++k) seg_coords<EXACT>(ray, depth[k], H, W, inv_half_w, inv_half_h, ix[k], iy[k]);
+        for (int k = 1; k < DPT - 1; ++k)
+            if (k == nk - 1) seg_coords<EXACT>(ray, depth[k], H, W, inv_half_w, inv_half_h, jx, jy);
+    }
 
     // ---- 1. footprint of the segment from its end planes (the position is a Moebius function of the depth: monotonic in
     //         x and in y between two planes on the same side of the camera; a plane that falls outside it anyway -- a
     //         hypothesis list that is not monotonic, a pole between the planes -- is sampled on its own below)
-    float jx = ix[0], jy = iy[0];
-#pragma unroll
-    for (int k = 1; k < DPT; ++k)
-        if (k == nk - 1) { jx = ix[k]; jy = iy[k]; }
     const float lxf = floorf(fminf(ix[0], jx)), hxf = floorf(fmaxf(ix[0], jx));
     const float lyf = floorf(fminf(iy[0], jy)), hyf = floorf(fmaxf(iy[0], jy));
     bool on = (lxf <= (float)(W - 1)) && (hxf >= -1.0f) && (lyf <= (float)(H - 1)) && (hyf >= -1.0f) &&
               (fabsf(lxf) < 1e9f) && (fabsf(hxf) < 1e9f) && (fabsf(lyf) < 1e9f) && (fabsf(hyf) < 1e9f);   // false for NaN/inf
+    // cells lx..hx x ly..hy, clamped to the image extended by its zero border: every cell inside is a live sample
     const int lx = on ? (int)fmaxf(lxf, -1.0f) : 0, ly = on ? (int)fmaxf(lyf, -1.0f) : 0;
     const int FX = on ? (int)fminf(hxf, (float)(W - 1)) - lx + 2 : 0, FY = on ? (int)fminf(hyf, (float)(H - 1)) - ly + 2 : 0;
     on = on && FX <= SEG_FX && FY <= SEG_FY;
-
-    // ---- 2. g(q) = <ref, src_q> for every source pixel of the footprint -> strip[row * SEG_FX + column]
-    if (on) {
-        bool colv[SEG_FX];
+    if (on && !(flags & FLAG_DBG_NO_PREFETCH)) {
+        // first and last pixel of every footprint row: with 32-byte pixels (C = 8) a row of up to 6 pixels spans at most two
+        // 128-byte lines; wider pixels get one request per pixel pair
+        const int xa = min(max(lx, 0), W - 1), xb = min(max(lx + FX - 1, 0), W - 1);
+        for (int j = 0; j < FY; ++j) {
+            const float* rowp = src + min(max(ly + j, 0), H - 1) * (W * C);
+            if (C == 8) {
+                prefetch_l1(rowp + xa * C);
+                prefetch_l1(rowp + xb * C + C - 1);
+            } else {
+                for (int x = xa; x <= xb; x += 128 / (C * 4) > 0 ? 128 / (C * 4) : 1) prefetch_l1(rowp + x * C);
+                prefetch_l1(rowp + xb * C + C - 1);
+            }
+        }
+    }
 #pragma unroll
-        for (int i = 0; i < SEG_FX; ++i) colv[i] = i < FX && (unsigned)(lx + i) < (unsigned)W;
-        const float* rowp = src + (ly * W + lx) * C;          // may point outside the map: only dereferenced under a predicate
+    for (int k = 1; k < DPT - 1; ++k) seg_coords<EXACT>(ray, depth[k], H, W, inv_half_w, inv_half_h, ix[k], iy[k]);
+
+    // ---- 2. g(q) = <ref, src_q> / C for every source pixel of the footprint -> strip[row * SEG_FX + column].  Pixels
+    //         outside the image are read at the clamped address and replaced by zero (grid_sample's zeros padding).
+    if (on) {
+        int coff[SEG_FX];
+        unsigned colv = 0;
+#pragma unroll
+        for (int i = 0; i < SEG_FX; ++i) {
+            const int x = lx + i;
+            coff[i] = min(max(x, 0), W - 1) * C;
+            colv |= ((unsigned)x < (unsigned)W) ? (1u << i) : 0u;
+        }
         float* out = strip;
-        for (int j = 0; j < FY; ++j, rowp += W * C, out += SEG_FX * TILE_THREADS) {
-            const bool rowv = (unsigned)(ly + j) < (unsigned)H;
+        for (int j = 0; j < FY; ++j, out += SEG_FX * STRIDE) {
+            const int y = ly + j;
+            const bool rowv = (unsigned)y < (unsigned)H;
+            const float* rowp = src + min(max(y, 0), H - 1) * (W * C);
 #pragma unroll
             for (int i0 = 0; i0 < SEG_FX; i0 += PB) {
-                O2 px[PB][C / 8];
+                if (i0 < FX && !(flags & FLAG_DBG_NO_LOADS)) {
+                    O2 px[PB][C / 8];
 #pragma unroll
-                for (int i = 0; i < PB; ++i)
+                    for (int i = 0; i < PB; ++i)
 #pragma unroll
-                    for (int cb = 0; cb < C / 8; ++cb) px[i][cb] = ldg_o2_if(rowp + (i0 + i) * C + cb * 8, rowv && colv[i0 + i]);
+                        for (int cb = 0; cb < C / 8; ++cb) px[i][cb] = ldg_o2(rowp + coff[i0 + i] + cb * 8);
 #pragma unroll
-                for (int i = 0; i < PB; ++i) {
-                    u64 m0 = mul2(px[i][0].a, ref2[0]), m1 = mul2(px[i][0].b, ref2[1]);
-                    m0 = fma2(px[i][0].c, ref2[2], m0);
-                    m1 = fma2(px[i][0].d, ref2[3], m1);
+                    for (int i = 0; i < PB; ++i) {
+                        u64 m0 = mul2(px[i][0].a, ref2[0]), m1 = mul2(px[i][0].b, ref2[1]);
+                        m0 = fma2(px[i][0].c, ref2[2], m0);
+                        m1 = fma2(px[i][0].d, ref2[3], m1);
 #pragma unroll
-                    for (int cb = 1; cb < C / 8; ++cb) {
-                        m0 = fma2(px[i][cb].a, ref2[cb * 4], m0);
-                        m1 = fma2(px[i][cb].b, ref2[cb * 4 + 1], m1);
-                        m0 = fma2(px[i][cb].c, ref2[cb * 4 + 2], m0);
-                        m1 = fma2(px[i][cb].d, ref2[cb * 4 + 3], m1);
+                        for (int cb = 1; cb < C / 8; ++cb) {
+                            m0 = fma2(px[i][cb].a, ref2[cb * 4], m0);
+                            m1 = fma2(px[i][cb].b, ref2[cb * 4 + 1], m1);
+                            m0 = fma2(px[i][cb].c, ref2[cb * 4 + 2], m0);
+                            m1 = fma2(px[i][cb].d, ref2[cb * 4 + 3], m1);
+                        }
+                        float a0, a1, b0, b1;
+                        unpack2(m0, a0, a1);
+                        unpack2(m1, b0, b1);
+                        const float g = (a0 + a1) + (b0 + b1);
+                        out[(i0 + i) * STRIDE] = (rowv && ((colv >> (i0 + i)) & 1u)) ? g : 0.0f;
                     }
-                    float a0, a1, b0, b1;
-                    unpack2(m0, a0, a1);
-                    unpack2(m1, b0, b1);
-                    out[(i0 + i) * TILE_THREADS] = (a0 + a1) + (b0 + b1);
                 }
             }
         }
@@ -479,22 +505,50 @@ __device__ __forceinline__ void run_view_seg(float* __restrict__ strip, const fl
 #pragma unroll
     for (int k = 0; k < DPT; ++k) {
         float sim = 0.0f;
-        if (k < nk) {
-            const Cell c = cell_at(ix[k], iy[k], H, W);
-            if (c.live) {
-                const unsigned ox = (unsigned)(c.x0 - lx), oy = (unsigned)(c.y0 - ly);
-                if (on && ox <= (unsigned)(FX - 2) && oy <= (unsigned)(FY - 2)) {
-                    const float* g = strip + (oy * SEG_FX + ox) * TILE_THREADS;
-                    const float g00 = g[0], g01 = g[TILE_THREADS], g10 = g[SEG_FX * TILE_THREADS], g11 = g[(SEG_FX + 1) * TILE_THREADS];
-                    sim = fmaf(fmaf(g11, c.dx, g10 * c.ex), c.dy, fmaf(g01, c.dx, g00 * c.ex) * c.ey) * (1.0f / C);
-                } else {
-                    float s1[1];
-                    gather_cell<C, 1>(src, refp, c.x0, c.y0, c.ex, c.dx, c.ey, c.dy, H, W, s1);
-                    sim = s1[0];
-                }
+        if (k < nk && !(flags & FLAG_DBG_NO_SAMPLES)) {
+            const float fx = floorf(ix[k]), fy = floorf(iy[k]);
+            const int x0 = (int)fx, y0 = (int)fy;
+            const float dx = __fsub_rn(ix[k], fx), dy = __fsub_rn(iy[k], fy);
+            const float ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix[k]), ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy[k]);
+            const unsigned ox = (unsigned)(x0 - lx), oy = (unsigned)(y0 - ly);
+            if (on && ox <= (unsigned)(FX - 2) && oy <= (unsigned)(FY - 2) && fabsf(fx) < 1e9f && fabsf(fy) < 1e9f) {
+                const float* g = strip + (oy * SEG_FX + ox) * STRIDE;
+                const float g00 = g[0], g01 = g[STRIDE], g10 = g[SEG_FX * STRIDE], g11 = g[(SEG_FX + 1) * STRIDE];
+                sim = fmaf(fmaf(g11, dx, g10 * ex), dy, fmaf(g01, dx, g00 * ex) * ey);
+            } else if ((fx >= -1.0f) && (fx <= (float)(W - 1)) && (fy >= -1.0f) && (fy <= (float)(H - 1))) {   // live (false for NaN/inf)
+                float s1[1];
+                gather_cell<C, 1>(src, refp, x0, y0, ex, dx, ey, dy, H, W, s1);
+                sim = s1[0];
             }
         }
         consume(k, sim);
+    }
+}
+
+// num[k] / div for all k, IEEE round-to-nearest, one shared reciprocal (see div2_rn in common.cuh)
+template <int N>
+__device__ __forceinline__ void div_all_rn(float (&num)[N], float div) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(div));
+    r = fmaf(r, fmaf(-div, r, 1.0f), r);
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        float q = __fmul_rn(num[k], r);
+        q = fmaf(fmaf(-div, q, num[k]), r, q);
+        num[k] = fmaf(fmaf(-div, q, num[k]), r, q);
+    }
+}
+
+// reference features of a pixel, divided by C (exact: C is a power of two), as packed pairs
+template <int C>
+__device__ __forceinline__ void load_ref2_scaled(const float* __restrict__ p, u64 (&ref2)[C / 2]) {
+    const ulonglong2* rp = reinterpret_cast<const ulonglong2*>(p);
+    const u64 sc = pack2(1.0f / C, 1.0f / C);
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+        const ulonglong2 v = __ldg(rp + q);
+        ref2[2 * q] = mul2(v.x, sc);
+        ref2[2 * q + 1] = mul2(v.y, sc);
     }
 }
 
@@ -630,63 +684,98 @@ warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __res
                          });
 }
 
-// segment-form twins of the two kernels above (G = 1): no staging, no barriers
-template <int C, bool EXACT>
-__global__ void __launch_bounds__(TILE_THREADS, SegBlocksPerSM<C>::value)
+// segment-form twins of the two kernels above (G = 1): no staging, no barriers.  The host passes the constants every
+// thread would otherwise derive with an fp64 / IEEE division of its own (SegConsts).
+struct SegConsts { float inv_half_w, inv_half_h, inv_dm1; };
+
+// Aggregated form: one THREAD per (reference pixel, source view).  A block is a 32 x SEGV_TY pixel tile times the n_src
+// views (threadIdx = lane / row / view), so a pixel's views run in parallel warps instead of one after the other in one
+// thread: n_src times the loads in flight, a third fewer registers per thread, ~60 % occupancy -- the version with a
+// view loop per thread was latency-bound (half of the issue slots idle on L1 / L2 loads at 24 warps per SM).  The
+// per-pixel work is split over the view-threads through shared memory: each computes the hypotheses of planes
+// view, view + n_src, ... (and writes hyp_out), and after the per-view similarities are parked in shared memory each
+// forms the weighted aggregate of those planes in upstream's view order.
+constexpr int SEGV_TY = 2, SEGV_PX = TW * SEGV_TY;
+template <int NT> struct SegvBlocksPerSM { static constexpr int value = NT <= 256 ? 4 : (NT <= 512 ? 2 : 1); };
+constexpr size_t segv_smem(int NT, int n_src) {
+    return sizeof(float) * ((size_t)SEG_SLOTS * NT + (size_t)SEGV_PX * (8 + n_src + 8 * n_src));
+}
+
+template <int C, bool EXACT, int NT>
+__global__ void __launch_bounds__(NT, SegvBlocksPerSM<NT>::value)
 warp_corr_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj,
                      const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval, const float* __restrict__ weights,
-                     int H, int W, int D, int tiles_x, int flags, float* __restrict__ sim_out, float* __restrict__ hyp_out) {
+                     int H, int W, int D, int tiles_x, int flags, const SegConsts kc, float* __restrict__ sim_out,
+                     float* __restrict__ hyp_out) {
     constexpr int DPT = 8;
-    __shared__ float sP[EFFIMVS_MAX_SRC_VIEWS * 12];
-    __shared__ float scratch[SEG_SLOTS * TILE_THREADS];
-    const int tid = threadIdx.x, lane = tid & 31;
+    extern __shared__ float seg_smem[];
+    float* const scratch = seg_smem;                                   // [SEG_SLOTS][NT]
+    float* const depth_s = scratch + SEG_SLOTS * NT;                   // [DPT][SEGV_PX]
+    float* const wts_s = depth_s + DPT * SEGV_PX;                      // [n_src][SEGV_PX]
+    float* const sims_s = wts_s + n_src * SEGV_PX;                     // [n_src][DPT][SEGV_PX]
+    const int lane = threadIdx.x, row = threadIdx.y, view = threadIdx.z;
+    const int p = row * TW + lane;                                     // pixel of the tile
+    const int tid = (view * SEGV_TY + row) * TW + lane;
     const int b = blockIdx.z;
     const int HW = H * W;
-    for (int i = tid; i < n_src * 12; i += TILE_THREADS) sP[i] = proj[(size_t)b * n_src * 12 + i];
-    __syncthreads();
-    float* strip = scratch + tid;
-
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int xi = tx * TW + lane, yi = ty * TH + (tid >> 5);
-    if (xi >= W || yi >= H) return;
-    const int pix = yi * W + xi;
+    const int xi = tx * TW + lane, yi = ty * SEGV_TY + row;
+    const bool inimg = xi < W && yi < H;
+    const int pix = inimg ? yi * W + xi : 0;
     const int d0 = blockIdx.y * DPT;
     const int nk = min(DPT, D - d0);
-    const float x = (float)xi, y = (float)yi;
-    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
-    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
 
-    const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
-    u64 ref2[C / 2];
-    load_ref2<C>(refp, ref2);
-    float depth[DPT], num[DPT];
-#pragma unroll
-    for (int k = 0; k < DPT; ++k) {
-        const bool on = k < nk;
-        depth[k] = on ? fetch_hypothesis(hyp, hyp_mode, interval, b, d0 + k, D, pix, HW) : 1.0f;
-        if (hyp_out && on) hyp_out[((size_t)b * D + d0 + k) * HW + pix] = depth[k];
-        num[k] = 0.0f;
+    // ---- A. hypotheses of planes view, view + n_src, ... -> shared memory (+ hyp_out)
+    if (inimg) {
+        LocalHyp lh;
+        if (hyp_mode == EFFIMVS_HYP_LOCAL) lh = local_hypothesis_prepare(__ldg(hyp + (size_t)b * HW + pix), __ldg(interval + b), D, kc.inv_dm1);
+        for (int k = view; k < nk; k += n_src) {
+            const float d = hyp_mode == EFFIMVS_HYP_LOCAL ? local_hypothesis_at(lh, d0 + k)
+                                                          : fetch_hypothesis(hyp, hyp_mode, interval, b, d0 + k, D, pix, HW);
+            depth_s[k * SEGV_PX + p] = d;
+            if (hyp_out) hyp_out[((size_t)b * D + d0 + k) * HW + pix] = d;
+        }
     }
-    float den = 0.0f;
-    for (int v = 0; v < n_src; ++v) {
-        const Ray ray = make_ray(sP + v * 12, x, y, (flags & FLAG_RAY_UNFUSED) != 0);
-        const float w = weights ? __ldg(weights + ((size_t)b * n_src + v) * HW + pix) : 1.0f;
-        run_view_seg<C, DPT, EXACT>(strip, srcs.p[v] + (size_t)b * C * HW, refp, ray, depth, nk, H, W, inv_half_w, inv_half_h, ref2,
-                                    [&](int k, float sim) {
-                                        num[k] = weights ? __fadd_rn(num[k], __fmul_rn(sim, w)) : __fadd_rn(num[k], sim);
-                                    });
-        den = __fadd_rn(den, w);
-    }
-    const float div = weights ? __fadd_rn(den, 1e-6f) : (float)n_src;
+    __syncthreads();
+
+    // ---- B. this thread's view: similarities of its planes -> shared memory
+    if (inimg) {
+        const float* P = proj + ((size_t)b * n_src + view) * 12;
+        float Pr[12];
 #pragma unroll
-    for (int k = 0; k < DPT; ++k)
-        if (k < nk) sim_out[((size_t)b * D + d0 + k) * HW + pix] = __fdiv_rn(num[k], div);
+        for (int i = 0; i < 12; ++i) Pr[i] = __ldg(P + i);
+        const Ray ray = make_ray(Pr, (float)xi, (float)yi, (flags & FLAG_RAY_UNFUSED) != 0);
+        const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
+        u64 ref2[C / 2];
+        load_ref2_scaled<C>(refp, ref2);
+        float depth[DPT];
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) depth[k] = k < nk ? depth_s[k * SEGV_PX + p] : 1.0f;
+        wts_s[view * SEGV_PX + p] = weights ? __ldg(weights + ((size_t)b * n_src + view) * HW + pix) : 1.0f;
+        float* mine = sims_s + view * DPT * SEGV_PX + p;
+        run_view_seg<C, DPT, EXACT, NT>(scratch + tid, srcs.p[view] + (size_t)b * C * HW, refp, ray, depth, nk, H, W, kc.inv_half_w,
+                                        kc.inv_half_h, ref2, flags, [&](int k, float sim) { mine[k * SEGV_PX] = sim; });
+    }
+    __syncthreads();
+
+    // ---- C. weighted aggregate over the views (upstream's order: view 0 first) of planes view, view + n_src, ...
+    if (inimg) {
+        for (int k = view; k < nk; k += n_src) {
+            float num = 0.0f, den = 0.0f;
+            for (int u = 0; u < n_src; ++u) {
+                const float sim = sims_s[(u * DPT + k) * SEGV_PX + p], w = wts_s[u * SEGV_PX + p];
+                num = weights ? __fadd_rn(num, __fmul_rn(sim, w)) : __fadd_rn(num, sim);
+                den = __fadd_rn(den, w);
+            }
+            sim_out[((size_t)b * D + d0 + k) * HW + pix] = __fdiv_rn(num, weights ? __fadd_rn(den, 1e-6f) : (float)n_src);
+        }
+    }
 }
 
 template <int C, bool EXACT>
 __global__ void __launch_bounds__(TILE_THREADS, SegBlocksPerSM<C>::value)
 warp_views_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj,
-                      const float* __restrict__ hyp, int hyp_mode, int H, int W, int D, int tiles_x, int flags,
+                      const float* __restrict__ hyp, int hyp_mode, int H, int W, int D, int tiles_x, int flags, const SegConsts kc,
                       float* __restrict__ sims_out) {
     constexpr int DPT = 8;
     __shared__ float sP[12];
@@ -703,21 +792,19 @@ warp_views_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__
     if (xi >= W || yi >= H) return;
     const int pix = yi * W + xi;
     const int nk = min(DPT, D - d0);
-    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
-    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
 
     const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
     u64 ref2[C / 2];
-    load_ref2<C>(refp, ref2);
+    load_ref2_scaled<C>(refp, ref2);
     const Ray ray = make_ray(sP, (float)xi, (float)yi, (flags & FLAG_RAY_UNFUSED) != 0);
-    float* out = sims_out + (((size_t)b * n_src + v) * D) * HW + pix;
+    float* out = sims_out + (((size_t)b * n_src + v) * D + d0) * HW + pix;
     float depth[DPT];
 #pragma unroll
     for (int k = 0; k < DPT; ++k) depth[k] = k < nk ? fetch_hypothesis(hyp, hyp_mode, nullptr, b, d0 + k, D, pix, HW) : 1.0f;
-    run_view_seg<C, DPT, EXACT>(strip, srcs.p[v] + (size_t)b * C * HW, refp, ray, depth, nk, H, W, inv_half_w, inv_half_h, ref2,
-                                [&](int k, float sim) {
-                                    if (k < nk) out[(size_t)(d0 + k) * HW] = sim;
-                                });
+    run_view_seg<C, DPT, EXACT, TILE_THREADS>(strip, srcs.p[v] + (size_t)b * C * HW, refp, ray, depth, nk, H, W, kc.inv_half_w,
+                                              kc.inv_half_h, ref2, flags, [&](int k, float sim) {
+                                                  if (k < nk) out[(size_t)k * HW] = sim;
+                                              });
 }
 
 // softmax entropy over the D similarities of a (pixel, view) (models/Effi_MVS_plus.py:43-44); sims (N, D, HW)
@@ -810,15 +897,26 @@ int encode_maps(TileMaps& maps, const SrcPtrs& srcs, int n_src, int B, int H, in
     return EFFIMVS_OK;
 }
 
-// which launches take the segment form: 0 never, 1 (default) local hypotheses (the cascade's stage-2/3 volumes) and the
-// stage-1 per-view kernel, 2 every G = 1 launch
+// which launches take the segment form: 0 (default) none, 1 local hypotheses (the cascade's stage-2/3 volumes), 2 every
+// G = 1 launch including the stage-1 per-view kernel.  Off by default: measured on B200 at the DTU stage-3 shape the segment
+// form executes about as many warp instructions as the staged plane-by-plane kernel (77-94 M against 87 M: the dot-first
+// saving is eaten by the footprint bookkeeping and the upstream-exact coordinate chain, which is half of either kernel)
+// and, reading its footprint through L1 in dependent batches, idles longer on long-scoreboard stalls: 0.146-0.163 ms
+// against 0.150 ms, 0.135 against 0.118 ms on a smooth surface (profiles/r2_warp_segment_form.md).
 int seg_mode() {
     const char* e = getenv("EFFIMVS_WARP_SEG");
-    return e ? atoi(e) : 1;
+    return e ? atoi(e) : 0;
 }
 bool seg_fast_coords() {
     const char* e = getenv("EFFIMVS_WARP_FAST_COORDS");
     return e && e[0] == '1';
+}
+SegConsts seg_consts(int H, int W, int D) {
+    SegConsts k;
+    k.inv_half_w = 1.0f / (float)((double)(W - 1) / 2.0);        // IEEE single division, as __fdiv_rn in the other kernels
+    k.inv_half_h = 1.0f / (float)((double)(H - 1) / 2.0);
+    k.inv_dm1 = D > 1 ? 1.0f / (float)(D - 1) : 0.0f;
+    return k;
 }
 
 template <int C, int G>
@@ -829,13 +927,22 @@ int launch_tile(const float* ref, const SrcPtrs& srcs, int n_src, const float* p
     if constexpr (G == 1) {
         const int mode = seg_mode();
         if (mode >= 2 || (mode == 1 && hyp_mode == EFFIMVS_HYP_LOCAL)) {
-            dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, ceil_div(D, 8), B);
-            if (seg_fast_coords())
-                warp_corr_seg_kernel<C, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
-                                                                       tiles_x, flags, sim_out, hyp_out);
-            else
-                warp_corr_seg_kernel<C, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
-                                                                      tiles_x, flags, sim_out, hyp_out);
+            const int tiles_y2 = ceil_div(H, SEGV_TY);
+            const dim3 block(TW, SEGV_TY, n_src), grid(tiles_x * tiles_y2, ceil_div(D, 8), B);
+            const SegConsts kc = seg_consts(H, W, D);
+            const bool fast = seg_fast_coords();
+#define EFFI_SEGV_LAUNCH(NT, EX)                                                                                                       \
+    {                                                                                                                                  \
+        const size_t smem = segv_smem(NT, n_src);                                                                                      \
+        cudaFuncSetAttribute(warp_corr_seg_kernel<C, EX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+        warp_corr_seg_kernel<C, EX, NT><<<grid, block, smem, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D, tiles_x, \
+                                                                   flags, kc, sim_out, hyp_out);                                      \
+    }
+            const int nt = TW * SEGV_TY * n_src;
+            if (nt <= 256) { if (fast) EFFI_SEGV_LAUNCH(256, false) else EFFI_SEGV_LAUNCH(256, true) }
+            else if (nt <= 512) { if (fast) EFFI_SEGV_LAUNCH(512, false) else EFFI_SEGV_LAUNCH(512, true) }
+            else { if (fast) EFFI_SEGV_LAUNCH(1024, false) else EFFI_SEGV_LAUNCH(1024, true) }
+#undef EFFI_SEGV_LAUNCH
             return check_launch("warp_corr_seg_kernel");
         }
     }
@@ -870,11 +977,16 @@ int launch_views(const float* ref, const SrcPtrs& srcs, int n_src, const float* 
     int rc;
     const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
     dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, n_src * ceil_div(D, 8), B);
-    if (seg_mode() >= 1) {
+    // Stage 1 keeps the TMA-staged plane-by-plane kernel by default: with C = 32 a source pixel is a 128-byte line of its own,
+    // and the L1 path pays per line touched (measured at the DTU stage-1 shape: 0.38 ms in segment form from global memory
+    // against 0.17 ms from the staged box).  EFFIMVS_WARP_SEG=2 forces the segment form (tests).
+    if (seg_mode() >= 2) {
         if (seg_fast_coords())
-            warp_views_seg_kernel<C, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
+            warp_views_seg_kernel<C, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
+                                                                    seg_consts(H, W, D), sims_out);
         else
-            warp_views_seg_kernel<C, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
+            warp_views_seg_kernel<C, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
+                                                                   seg_consts(H, W, D), sims_out);
         if ((rc = check_launch("warp_views_seg_kernel"))) return rc;
     } else {
         TileMaps maps;
@@ -898,6 +1010,7 @@ int warp_flags_from_env(int H, int W) {
     const char* e = getenv("EFFIMVS_WARP_FORCE_GATHER");
     if (e && e[0] == '1') flags |= FLAG_FORCE_GATHER;
     if (ray_unfused_for(H, W)) flags |= FLAG_RAY_UNFUSED;
+    if (const char* d = getenv("EFFIMVS_WARP_DEBUG")) flags |= atoi(d) & (FLAG_DBG_NO_PREFETCH | FLAG_DBG_NO_LOADS | FLAG_DBG_NO_SAMPLES);
     return flags;
 }
 

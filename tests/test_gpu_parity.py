@@ -980,16 +980,18 @@ def test_local_volume_segment_form_vs_oracle(hp, ohp, C, D, H, W, depth_kind, ra
     iv = torch.full((1, 1, 1, 1), (1 / 425.0 - 1 / 935.0) / 384 * ratio, device=DEV)
     cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
     want, want_hyp = ohp.local_volume(cur, feats, cams, iv, wts, D, 1)
-    got, hyp = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
+    with _with_env(EFFIMVS_WARP_SEG=1):                       # the segment form is opt-in (the staged tile kernel is the default)
+        got, hyp = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
     assert torch.equal(hyp, want_hyp)
     assert rel_max(got, want) < 1e-4
-    with _with_env(EFFIMVS_WARP_FAST_COORDS=0):               # upstream's coordinate chain: only fp32 re-association is left
-        exact, _ = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
-    with _with_env(EFFIMVS_WARP_SEG=0):
+    with _with_env(EFFIMVS_WARP_SEG=0):                       # same coordinates: only fp32 re-association is left
         tile, _ = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
-    assert rel_max(exact, tile) < 2e-6
-    assert rel_max(got, tile) < 1e-4
-    got_nw, _ = hp.local_volume(cur, cl, cams, iv, None, D, 1)
+    assert rel_max(got, tile) < 2e-6
+    with _with_env(EFFIMVS_WARP_SEG=1, EFFIMVS_WARP_FAST_COORDS=1):   # opt-in: no normalise / un-normalise round trip, one reciprocal
+        fast, _ = hp.local_volume(cur, cl, cams, iv, wts, D, 1)
+    assert rel_max(fast, want) < 1e-3
+    with _with_env(EFFIMVS_WARP_SEG=1):
+        got_nw, _ = hp.local_volume(cur, cl, cams, iv, None, D, 1)
     want_nw, _ = ohp.local_volume(cur, feats, cams, iv, None, D, 1)
     assert rel_max(got_nw, want_nw) < 1e-4
 
@@ -1005,12 +1007,11 @@ def test_stage1_views_segment_form_vs_oracle(ohp, C, D, H, W, V):
     cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
     planes = hyp[:, :, 0, 0].contiguous()
     proj = hotpath.CudaHotPath().relative_projection(cams)
-    sims, ent = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
+    with _with_env(EFFIMVS_WARP_SEG=2):                      # the segment form is opt-in for the per-view kernel
+        sims, ent = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
     with _with_env(EFFIMVS_WARP_SEG=0):
         sims_t, ent_t = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
-    with _with_env(EFFIMVS_WARP_FAST_COORDS=0):
-        sims_e, _ = ops.warp_corr_views(cl[0], cl[1:], proj, planes, capi.HYP_PLANES, D)
-    assert rel_max(sims_e, sims_t) < 2e-6
+    assert rel_max(sims, sims_t) < 2e-6
     assert rel_max(sims, sims_t) < 1e-4 and float((ent - ent_t).abs().max()) < 1e-3
     for v in range(V - 1):
         want = ohp.view_similarity(feats[0], feats[v + 1], cams[:, 0], cams[:, v + 1], hyp, 1)

@@ -65,8 +65,8 @@ def main():
         ms_p, out_p = timed(lambda: fn(feats), flush, reps)
         row = {"stage": i + 1, "C": C, "D": D, "H": H, "W": W, "planar_ms": ms_p, "planar_GBs": by / ms_p / 1e6}
         # channels-last maps: plane-by-plane tile kernel (SEG=0), segment form with fast / upstream-exact coordinates
-        for tag, env in (("tile", {"EFFIMVS_WARP_SEG": "0"}), ("seg", {"EFFIMVS_WARP_SEG": "1"}),
-                         ("seg_exact", {"EFFIMVS_WARP_SEG": "1", "EFFIMVS_WARP_FAST_COORDS": "1"})):
+        for tag, env in (("tile", {"EFFIMVS_WARP_SEG": "0"}), ("seg", {"EFFIMVS_WARP_SEG": "2"}),
+                         ("seg_fast", {"EFFIMVS_WARP_SEG": "2", "EFFIMVS_WARP_FAST_COORDS": "1"})):
             os.environ.pop("EFFIMVS_WARP_FAST_COORDS", None)
             os.environ.update(env)
             ms_c, out_c = timed(lambda: fn(feats_cl), flush, reps)
