@@ -405,19 +405,17 @@ def scene_leg(a, model, rank, world, dev):
     nb = lambda i, n: [j for d in range(1, n // 2 + 1) for j in ((i - d) % N, (i + d) % N)]      # noqa: E731
     pairs, fpairs = [nb(i, 4) for i in range(N)], [nb(i, min(10, (N - 1) // 2 * 2)) for i in range(N)]
     infer, fuse = scene.cuda_scene_callables(model, imgs, cams, dv, 2.0, 6.0, 2, 0.3, feature_cache=True, graphed_src_views=4)
-    with torch.no_grad():
-        mine = scene.shard_views(N, rank, world, "block")
-        if mine:
-            infer(mine[0], pairs[mine[0]])            # warm-up (graph capture happened in cuda_scene_callables)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    tm = {}
-    t0 = time.perf_counter()
-    out = scene.run_scene(infer, fuse, N, pairs, rank, world, dev, fuse_pairs=fpairs, timings=tm, sharding="block")
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    for timed_pass in (False, True):        # one untimed pass over the scene (allocator pools, NCCL channels), then the timed one
+        infer.clear_cache()                 # every pass encodes its images again
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tm = {}
+        t0 = time.perf_counter()
+        out = scene.run_scene(infer, fuse, N, pairs, rank, world, dev, fuse_pairs=fpairs, timings=tm, sharding="block")
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
     stats = torch.tensor([time.perf_counter() - t0, tm.get("all_gather_ms", 0.0), tm.get("fusion_ms", 0.0)], device=dev)
     pts = torch.tensor([float(sum(v[0].shape[0] for v in out.values()))], device=dev)
     if world > 1:
@@ -567,7 +565,6 @@ def run_ours(a, rank, world, local_rank):
     scene49 = None
     if not a.no_scene and a.shape == "dtu":
         del pipe
-        torch.cuda.empty_cache()
         try:
             scene49 = scene_leg(a, model, rank, world, dev)
         except Exception as e:  # noqa: BLE001  (an extra leg must not cost the headline line)

@@ -209,6 +209,13 @@ def cuda_scene_callables(model, imgs: torch.Tensor, cams: Dict[str, torch.Tensor
             out = model(imgs[idx].unsqueeze(0), stage_cams, depth_values.unsqueeze(0))
         return out["depth"][-1][0], out["photometric_confidence"][0]
 
+    def clear_cache():
+        """forget the encoded feature pyramids (a new scene, or a benchmark pass that must encode again)"""
+        cache.clear()
+        if runner is not None:
+            runner.cache.clear()
+    infer.clear_cache = clear_cache
+
     def fuse(i, ref_depth, conf, srcs, src_depths):
         full = cams["stage4"]
         return fusion.filter_view(ref_depth, conf, src_depths, full[i].unsqueeze(0), full[list(srcs)].unsqueeze(0),

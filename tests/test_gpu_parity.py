@@ -1033,3 +1033,21 @@ def test_plane_sweep_segment_form_forced(hp, ohp, C, D, H, W):
         got = hp.warp_corr_agg(cl, cams, hyp, wts, 1)
         got_planes = hp.warp_corr_agg(cl, cams, hyp[:, :, :1, :1].contiguous(), wts, 1)
     assert rel_max(got, want) < 1e-4 and rel_max(got_planes, want) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two CUDA devices")
+def test_ops_run_on_the_tensors_device_not_the_current_one(ohp):
+    """every effimvs:: op launches on the device (and that device's current stream) of its tensor arguments whatever torch's
+    current device is, and rejects tensors spread over two devices"""
+    from effimvs_b200 import hotpath, synthetic
+    feats, cams, hyp, wts = synthetic.microbench_inputs(8, 4, 40, 56, views=3, seed=9, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    hp1 = hotpath.CudaHotPath("f32", native_projection=True)
+    got = hp1.warp_corr_agg(feats, cams, hyp, wts, 1)
+    assert got.device == torch.device("cuda:1") and torch.cuda.current_device() == 0
+    sims = [ohp.view_similarity(feats[0], feats[v], cams[:, 0], cams[:, v], hyp, 1) for v in range(1, 3)]
+    want = ohp.weighted_aggregate(sims, [wts[:, i:i + 1] for i in range(2)])
+    assert rel_max(got, want) < 1e-4
+    with pytest.raises(RuntimeError, match="several devices"):
+        hp1.warp_corr_agg([feats[0].to("cuda:0")] + feats[1:], cams, hyp, wts, 1)
