@@ -416,18 +416,19 @@ def scene_leg(a, model, rank, world, dev):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-    stats = torch.tensor([time.perf_counter() - t0, tm.get("all_gather_ms", 0.0), tm.get("fusion_ms", 0.0)], device=dev)
+    stats = torch.tensor([time.perf_counter() - t0, tm.get("all_gather_ms", 0.0), tm.get("fusion_ms", 0.0), tm.get("depth_maps_ms", 0.0)],
+                         device=dev)
     pts = torch.tensor([float(sum(v[0].shape[0] for v in out.values()))], device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(pts)
-    secs, ag_ms, fu_ms = (float(x) for x in stats)
+    secs, ag_ms, fu_ms, dm_ms = (float(x) for x in stats)
     slots = scene.slots_per_rank(N, world)
     recv = (world - 1) * slots * H * W * 4                      # bytes every rank receives from its peers
     return {"views": N, "shape": [W, H], "n_gpus": world, "seconds": secs, "depth_maps_per_sec_incl_fusion": N / secs,
             "all_gather_ms": ag_ms if world > 1 else None, "all_gather_bytes_received_per_rank": recv if world > 1 else 0,
             "all_gather_GBs_per_rank": (recv / ag_ms / 1e6) if world > 1 and ag_ms > 0 else None,
-            "fusion_ms_max_rank": fu_ms, "fused_points": int(pts), "sharding": "block (balanced): views per rank " +
+            "depth_maps_ms_max_rank": dm_ms, "fusion_ms_max_rank": fu_ms, "fused_points": int(pts), "sharding": "block (balanced): views per rank " +
             ",".join(str(len(scene.shard_views(N, r, world, "block"))) for r in range(world)),
             "note": "4 source views for depth, 10 for fusion; feature cache + CUDA graphs; wall clock around run_scene, max over ranks; "
                     "all-gather timed with CUDA events (max over ranks)"}

@@ -144,6 +144,10 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 template <int G> struct TilePlanes { static constexpr int value = G >= 4 ? 4 : 8; };
 
+// constants every thread would otherwise derive with an fp64 / IEEE division of its own (87 + 50 warp instructions per warp
+// for the two normalisation factors alone): computed once on the host, same roundings
+struct SegConsts { float inv_half_w, inv_half_h, inv_dm1; };
+
 // Shared state of a block: projection rows, the double-buffered bounding box and the TMA barrier.
 struct TileShared {
     float P[EFFIMVS_MAX_SRC_VIEWS * 12];
@@ -583,7 +587,7 @@ __global__ void __launch_bounds__(TILE_THREADS, BlocksPerSM<C>::value)
 warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ ref_fea,
                       const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode,
                       const float* __restrict__ interval, const float* __restrict__ weights, int H, int W, int D, int tiles_x,
-                      int flags, float* __restrict__ sim_out, float* __restrict__ hyp_out) {
+                      int flags, const SegConsts kc, float* __restrict__ sim_out, float* __restrict__ hyp_out) {
     constexpr int DPT = TilePlanes<G>::value;
     extern __shared__ uint8_t smem_raw[];
     __shared__ TileShared sh;
@@ -599,8 +603,6 @@ warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __rest
     const int pix = inimg ? yi * W + xi : 0;
     const int d0 = blockIdx.y * DPT;
     const float x = (float)xi, y = (float)yi;
-    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
-    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
 
     const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
     u64 ref2[C / 2];
@@ -608,34 +610,55 @@ warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __rest
     float depth[DPT], num[DPT][G];
     unsigned valid = 0;
 #pragma unroll
-    for (int k = 0; k < DPT; ++k) {
-        const bool on = inimg && d0 + k < D;
-        valid |= on ? (1u << k) : 0u;
-        depth[k] = on ? fetch_hypothesis(hyp, hyp_mode, interval, b, d0 + k, D, pix, HW) : 1.0f;
-        if (hyp_out && on) hyp_out[((size_t)b * D + d0 + k) * HW + pix] = depth[k];
+    for (int k = 0; k < DPT; ++k) valid |= (inimg && d0 + k < D) ? (1u << k) : 0u;
+    if (hyp_mode == EFFIMVS_HYP_LOCAL) {          // the per-pixel part of the hypotheses once, not once per plane
+        const LocalHyp lh = local_hypothesis_prepare(__ldg(hyp + (size_t)b * HW + pix), __ldg(interval + b), D, kc.inv_dm1);
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) depth[k] = ((valid >> k) & 1u) ? local_hypothesis_at(lh, d0 + k) : 1.0f;
+    } else {
+#pragma unroll
+        for (int k = 0; k < DPT; ++k) depth[k] = ((valid >> k) & 1u) ? fetch_hypothesis(hyp, hyp_mode, interval, b, d0 + k, D, pix, HW) : 1.0f;
+    }
+    if (hyp_out) {
+        float* ho = hyp_out + ((size_t)b * D + d0) * HW + pix;
+#pragma unroll
+        for (int k = 0; k < DPT; ++k, ho += HW)
+            if ((valid >> k) & 1u) *ho = depth[k];
+    }
+#pragma unroll
+    for (int k = 0; k < DPT; ++k)
 #pragma unroll
         for (int g = 0; g < G; ++g) num[k][g] = 0.0f;
-    }
     float den = 0.0f;
     uint32_t phase = 0;
+    const float* wp = weights ? weights + (size_t)b * n_src * HW + pix : nullptr;
 
     for (int v = 0; v < n_src; ++v) {
         const Ray ray = make_ray(sh.P + v * 12, x, y, (flags & FLAG_RAY_UNFUSED) != 0);
-        const float w = (weights && inimg) ? __ldg(weights + ((size_t)b * n_src + v) * HW + pix) : 1.0f;
+        const float w = (wp && inimg) ? __ldg(wp + (size_t)v * HW) : 1.0f;
         run_round<C, G, DPT>(sh, tile, &maps.m[v], srcs.p[v] + (size_t)b * C * HW, refp, v, phase, flags, b, ray, depth, valid, H, W,
-                             inv_half_w, inv_half_h, ref2, [&](int k, int g, float sim) {
-                                 num[k][g] = weights ? __fadd_rn(num[k][g], __fmul_rn(sim, w)) : __fadd_rn(num[k][g], sim);
+                             kc.inv_half_w, kc.inv_half_h, ref2, [&](int k, int g, float sim) {
+                                 num[k][g] = wp ? __fadd_rn(num[k][g], __fmul_rn(sim, w)) : __fadd_rn(num[k][g], sim);
                              });
         den = __fadd_rn(den, w);
     }
     if (!inimg) return;
-    const float div = weights ? __fadd_rn(den, 1e-6f) : (float)n_src;
+    // num / div for every plane and group: IEEE round-to-nearest quotients from one shared reciprocal (div2_rn's sequence)
+    const float div = wp ? __fadd_rn(den, 1e-6f) : (float)n_src;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(div));
+    r = fmaf(r, fmaf(-div, r, 1.0f), r);
 #pragma unroll
-    for (int k = 0; k < DPT; ++k)
-        if (d0 + k < D) {
+    for (int g = 0; g < G; ++g) {
+        float* so = sim_out + (((size_t)b * G + g) * D + d0) * HW + pix;
 #pragma unroll
-            for (int g = 0; g < G; ++g) sim_out[(((size_t)b * G + g) * D + d0 + k) * HW + pix] = __fdiv_rn(num[k][g], div);
-        }
+        for (int k = 0; k < DPT; ++k, so += HW)
+            if ((valid >> k) & 1u) {
+                float q = __fmul_rn(num[k][g], r);
+                q = fmaf(fmaf(-div, q, num[k][g]), r, q);
+                *so = fmaf(fmaf(-div, q, num[k][g]), r, q);
+            }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -646,7 +669,7 @@ template <int C>
 __global__ void __launch_bounds__(TILE_THREADS, BlocksPerSM<C>::value)
 warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs,
                        int n_src, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode, int H, int W, int D,
-                       int tiles_x, int flags, float* __restrict__ sims_out) {
+                       int tiles_x, int flags, const SegConsts kc, float* __restrict__ sims_out) {
     constexpr int DPT = 8;
     extern __shared__ uint8_t smem_raw[];
     __shared__ TileShared sh;
@@ -660,8 +683,7 @@ warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __res
     const int xi = tx * TW + lane, yi = ty * TH + (tid >> 5);
     const bool inimg = xi < W && yi < H;
     const int pix = inimg ? yi * W + xi : 0;
-    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(W - 1) / 2.0));
-    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(H - 1) / 2.0));
+    const float inv_half_w = kc.inv_half_w, inv_half_h = kc.inv_half_h;
 
     const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
     u64 ref2[C / 2];
@@ -684,9 +706,7 @@ warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __res
                          });
 }
 
-// segment-form twins of the two kernels above (G = 1): no staging, no barriers.  The host passes the constants every
-// thread would otherwise derive with an fp64 / IEEE division of its own (SegConsts).
-struct SegConsts { float inv_half_w, inv_half_h, inv_dm1; };
+// segment-form twins of the two kernels above (G = 1): no staging, no barriers.
 
 // Aggregated form: one THREAD per (reference pixel, source view).  A block is a 32 x SEGV_TY pixel tile times the n_src
 // views (threadIdx = lane / row / view), so a pixel's views run in parallel warps instead of one after the other in one
@@ -953,7 +973,7 @@ int launch_tile(const float* ref, const SrcPtrs& srcs, int n_src, const float* p
     const size_t smem = BoxBytes<C>::ALL + 1024;
     cudaFuncSetAttribute(warp_corr_tile_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     warp_corr_tile_kernel<C, G><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
-                                                            tiles_x, flags, sim_out, hyp_out);
+                                                            tiles_x, flags, seg_consts(H, W, D), sim_out, hyp_out);
     return check_launch("warp_corr_tile_kernel");
 }
 
@@ -993,7 +1013,8 @@ int launch_views(const float* ref, const SrcPtrs& srcs, int n_src, const float* 
         if ((rc = encode_maps<C>(maps, srcs, n_src, B, H, W))) return rc;
         const size_t smem = BoxBytes<C>::ALL + 1024;
         cudaFuncSetAttribute(warp_views_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        warp_views_tile_kernel<C><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags, sims_out);
+        warp_views_tile_kernel<C><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
+                                                             seg_consts(H, W, D), sims_out);
         if ((rc = check_launch("warp_views_tile_kernel"))) return rc;
     }
     const dim3 egrid(ceil_div(H * W, 256), B * n_src);

@@ -88,27 +88,37 @@ def run_scene(infer: Callable, fuse: Callable, n_views: int, pairs: Sequence[Seq
     fuse_pairs = pairs if fuse_pairs is None else fuse_pairs
     mine = shard_views(n_views, rank, world, sharding)
     depths, confs = {}, {}
+    timed = timings is not None and torch.cuda.is_available() and str(device).startswith("cuda")
+    if timed:
+        ev_start = torch.cuda.Event(enable_timing=True)
+        ev_start.record()
     for i in mine:
         d, c = infer(i, list(pairs[i]))
         depths[i], confs[i] = d, c
     # a rank without a view (n_views < world) still enters the collective below with a zero block
     h, w = agree_on_size(tuple(next(iter(depths.values())).shape[-2:]) if depths else None, n_views, world, device)
     ev = None
-    if timings is not None and torch.cuda.is_available() and str(device).startswith("cuda"):
+    if timed:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ev[0].record()
     all_depths = gather_depths(depths, n_views, rank, world, h, w, device, sharding)
     if ev:
         ev[1].record()
     out = {}
+    flat = [j for i in mine for j in fuse_pairs[i]]
+    flat_dev = torch.as_tensor(flat, device=all_depths.device, dtype=torch.long) if flat else None      # ONE host -> device copy
+    at = 0
     for i in mine:
         src = list(fuse_pairs[i])
-        res = fuse(i, depths[i].reshape(1, 1, h, w), confs[i].unsqueeze(0), src, all_depths[src].reshape(1, len(src), 1, h, w))
+        sel = flat_dev[at:at + len(src)]
+        at += len(src)
+        res = fuse(i, depths[i].reshape(1, 1, h, w), confs[i].unsqueeze(0), src, all_depths.index_select(0, sel).reshape(1, len(src), 1, h, w))
         m = res["final"][0, 0]
         out[i] = (res["points"][0][:, m].t().contiguous(), depths[i])
     if ev:
         ev[2].record()
         torch.cuda.synchronize()
+        timings["depth_maps_ms"] = ev_start.elapsed_time(ev[0])
         timings["all_gather_ms"] = ev[0].elapsed_time(ev[1])
         timings["fusion_ms"] = ev[1].elapsed_time(ev[2])
     return out
@@ -126,6 +136,7 @@ class GraphedViewRunner:
         V = n_src + 1
         dev = imgs.device
         self.cache: Dict[int, list] = {}
+        self._sel: Dict[tuple, torch.Tensor] = {}
         self.stream = torch.cuda.Stream(dev)
         self.img_in = imgs[:1].reshape(1, 1, *imgs.shape[1:]).clone()
         self.ref_in = imgs[:1].clone()
@@ -151,6 +162,14 @@ class GraphedViewRunner:
                 out = model.forward_from_features(self.feat_in, self.ref_in, self.cam_in, self.dv)
             self.out = (out["depth"][-1], out["photometric_confidence"])
 
+    def _index(self, idx):
+        """device index tensor of a view list, built once: a host list -> device copy is a stream synchronisation, and one per
+        view serialises the host's enqueue work with the previous view's graph"""
+        key = tuple(idx)
+        if key not in self._sel:
+            self._sel[key] = torch.as_tensor(list(idx), device=self.imgs.device)
+        return self._sel[key]
+
     @torch.no_grad()
     def encoded(self, j: int):
         if j not in self.cache:
@@ -169,7 +188,7 @@ class GraphedViewRunner:
                 for s, e in enumerate(self.encoded(j)):
                     self.feat_in[s][v].copy_(e)
             self.ref_in.copy_(self.imgs[i:i + 1])
-            sel = torch.as_tensor(idx, device=self.imgs.device)
+            sel = self._index(idx)
             for k in self.stages:
                 self.cam_in[k].copy_(self.cams[k].index_select(0, sel).unsqueeze(0))
             self.g_fwd.replay()
@@ -216,8 +235,13 @@ def cuda_scene_callables(model, imgs: torch.Tensor, cams: Dict[str, torch.Tensor
             runner.cache.clear()
     infer.clear_cache = clear_cache
 
+    sel_cache: Dict[tuple, torch.Tensor] = {}
+
     def fuse(i, ref_depth, conf, srcs, src_depths):
         full = cams["stage4"]
-        return fusion.filter_view(ref_depth, conf, src_depths, full[i].unsqueeze(0), full[list(srcs)].unsqueeze(0),
+        key = tuple(srcs)
+        if key not in sel_cache:        # one host -> device copy (a synchronisation) per distinct source list, not per call
+            sel_cache[key] = torch.as_tensor(list(srcs), device=full.device)
+        return fusion.filter_view(ref_depth, conf, src_depths, full[i].unsqueeze(0), full.index_select(0, sel_cache[key]).unsqueeze(0),
                                   dist_base, rel_diff_base, thres_view, prob_threshold, torch_inverse=False)
     return infer, fuse
