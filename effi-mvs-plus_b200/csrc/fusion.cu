@@ -135,12 +135,18 @@ __device__ __forceinline__ void img_to_world(const Cam& c, float u, float v, flo
 
 // idx_world2cam (fusion.py:37-40)
 __device__ __forceinline__ void world_to_cam(const float4* E, int affE, const float pw[4], float pc[4]) {
+    if (affE && pw[3] == 1.0f) {   // last row (0,0,0,1) and w == 1: t[3] == 1 exactly, x / (1 + 1e-9f) == x: three rows, no division
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float4 m = E[r];
+            pc[r] = fmaf(m.w, pw[3], fmaf(m.z, pw[2], fmaf(m.y, pw[1], __fmul_rn(m.x, pw[0]))));
+        }
+        pc[3] = 1.0f;
+        return;
+    }
     float t[4];
     mat4(E, pw, t);
-    if (affE && pw[3] == 1.0f) {   // t[3] == 1 exactly
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pc[i] = t[i];
-    } else {
+    {
         float ww = __fadd_rn(t[3], 1e-9f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) pc[i] = __fdiv_rn(t[i], ww);
@@ -192,9 +198,16 @@ struct Reproj { float x, y, d; };
 // idx is estimated from e * base - tv and settled with the same comparisons upstream makes (typically one or two
 // instead of all K).  NaN passes no rung, like the comparison chain it replaces.
 __device__ __forceinline__ int ladder_count(float e, const float* __restrict__ thr, int K, float base, float tv) {
+    // thr has K + 2 entries: thr[0] = -inf, thr[1 + k] = rung k, thr[K + 1] = +inf, so the neighbours of the estimate can be
+    // read without bounds checks.  The estimate floor(e * base - tv) + 1 is the exact first rung passed up to the rounding of
+    // one product and one quotient, i.e. off by at most one: one look at each neighbour settles it with upstream's own
+    // comparisons (e < thr[k]); the two loops stay as the (never iterating) safety net for pathological bases.
     int idx = (int)fminf(fmaxf(floorf(fmaf(e, base, -tv)) + 1.0f, 0.0f), (float)K);
-    while (idx > 0 && e < thr[idx - 1]) --idx;
-    while (idx < K && !(e < thr[idx])) ++idx;
+    const float below = thr[idx], at = thr[idx + 1];      // rung idx - 1, rung idx
+    idx += (e < below) ? -1 : ((e < at) ? 0 : 1);
+    idx = max(0, min(idx, K));
+    while (idx > 0 && e < thr[idx]) --idx;
+    while (idx < K && !(e < thr[idx + 1])) ++idx;
     return K - idx;
 }
 
@@ -219,21 +232,21 @@ __global__ void __launch_bounds__(128, 6)
 fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ srcs_depth, const float* __restrict__ conf,
               const float* __restrict__ ref_cam, const float* __restrict__ srcs_cam, const float* __restrict__ inv_cams,
               int v, int h, int w, int hc, int wc, float dist_base, float rel_diff_base, int thres_view,
-              float prob_threshold, int relative, float* __restrict__ reproj_xyd, uint8_t* __restrict__ final_mask,
+              float prob_threshold, int relative, float inv_half_w, float inv_half_h, float* __restrict__ reproj_xyd, uint8_t* __restrict__ final_mask,
               float* __restrict__ depth_avg, float* __restrict__ points, uint8_t* __restrict__ masks_out) {
     __shared__ Cam cams[MAXV + 1];
-    __shared__ float thr_xy[MAXV], thr_d[MAXV];   // the ladder k / dist_base, k / rel_diff_base (fusion.py:172-176), once per block
+    __shared__ float thr_xy[MAXV + 2], thr_d[MAXV + 2];   // the ladder k / dist_base, k / rel_diff_base (fusion.py:172-176) between -inf and +inf
     const int n = blockIdx.y;
     const int K = v - thres_view + 1;
     if (threadIdx.x <= v) {
         const float* cam = threadIdx.x == 0 ? ref_cam + (size_t)n * 32 : srcs_cam + ((size_t)n * v + threadIdx.x - 1) * 32;
         const float* inv = inv_cams ? inv_cams + ((size_t)n * (v + 1) + threadIdx.x) * 32 : nullptr;
         load_cam<INVERT>(cams[threadIdx.x], cam, inv);
-    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + MAXV) {
-        const int k = threadIdx.x - 32;
+    } else if (threadIdx.x >= 32 && threadIdx.x < 32 + MAXV + 2) {
+        const int j = threadIdx.x - 32, k = j - 1;
         const float kk = (float)(thres_view + k);
-        thr_xy[k] = k < K ? __fdiv_rn(kk, dist_base) : 0.0f;
-        thr_d[k] = k < K ? __fdiv_rn(kk, rel_diff_base) : 0.0f;
+        thr_xy[j] = j == 0 ? -INFINITY : (k < K ? __fdiv_rn(kk, dist_base) : INFINITY);
+        thr_d[j] = j == 0 ? -INFINITY : (k < K ? __fdiv_rn(kk, rel_diff_base) : INFINITY);
     }
     __syncthreads();
     const int hw = h * w;
@@ -241,8 +254,6 @@ fusion_kernel(const float* __restrict__ ref_depth, const float* __restrict__ src
     if (pix >= hw) return;
     const int yi = pix / w, xi = pix - yi * w;
     const float cx = (float)xi + 0.5f, cy = (float)yi + 0.5f;
-    const float inv_half_w = __fdiv_rn(1.0f, (float)((double)(w - 1) / 2.0));
-    const float inv_half_h = __fdiv_rn(1.0f, (float)((double)(h - 1) / 2.0));
     const float dref = __ldg(ref_depth + (size_t)n * hw + pix);
     float ref_world[4];
     img_to_world(cams[0], cx, cy, dref, ref_world);
@@ -351,12 +362,13 @@ extern "C" int effimvs_fusion_reproject_f32(const float* ref_depth, const float*
     EFFI_REQUIRE(ref_depth && srcs_depth && ref_cam && srcs_cam && reproj_xyd, EFFIMVS_EINVAL, "fusion_reproject: null pointer");
     EFFI_REQUIRE(n > 0 && v >= 1 && v <= MAXV && h > 1 && w > 1, EFFIMVS_EINVAL, "fusion_reproject: bad sizes (v in [1,%d])", MAXV);
     dim3 block(128), grid(ceil_div(h * w, 128), n);
+    const float ihw = 1.0f / (float)((double)(w - 1) / 2.0), ihh = 1.0f / (float)((double)(h - 1) / 2.0);   // as __fdiv_rn on the device
     if (inv_cams)
         fusion_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, nullptr, ref_cam, srcs_cam, inv_cams, v, h, w,
-                                                                      1, 1, 1.0f, 1.0f, 1, 0.0f, 0, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
+                                                                      1, 1, 1.0f, 1.0f, 1, 0.0f, 0, ihw, ihh, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
     else
         fusion_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, nullptr, ref_cam, srcs_cam, inv_cams, v, h, w,
-                                                                     1, 1, 1.0f, 1.0f, 1, 0.0f, 0, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
+                                                                     1, 1, 1.0f, 1.0f, 1, 0.0f, 0, ihw, ihh, reproj_xyd, nullptr, nullptr, nullptr, nullptr);
     return check_launch("fusion_kernel(reproject)");
 }
 
@@ -373,13 +385,14 @@ extern "C" int effimvs_fusion_filter_f32(const float* ref_depth, const float* sr
     EFFI_REQUIRE(thres_view >= 1 && thres_view <= v, EFFIMVS_EINVAL, "fusion_filter: thres_view=%d outside [1,%d]", thres_view, v);
     EFFI_REQUIRE(dist_base > 0.0f && rel_diff_base > 0.0f, EFFIMVS_EINVAL, "fusion_filter: thresholds must be positive");
     dim3 block(128), grid(ceil_div(h * w, 128), n);
+    const float ihw = 1.0f / (float)((double)(w - 1) / 2.0), ihh = 1.0f / (float)((double)(h - 1) / 2.0);   // as __fdiv_rn on the device
     if (inv_cams)
         fusion_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, v, h, w, hc, wc,
-                                                                      dist_base, rel_diff_base, thres_view, prob_threshold, relative,
+                                                                      dist_base, rel_diff_base, thres_view, prob_threshold, relative, ihw, ihh,
                                                                       nullptr, final_mask, depth_avg, points, masks_out);
     else
         fusion_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(ref_depth, srcs_depth, conf, ref_cam, srcs_cam, inv_cams, v, h, w, hc, wc,
-                                                                     dist_base, rel_diff_base, thres_view, prob_threshold, relative,
+                                                                     dist_base, rel_diff_base, thres_view, prob_threshold, relative, ihw, ihh,
                                                                      nullptr, final_mask, depth_avg, points, masks_out);
     return check_launch("fusion_kernel(filter)");
 }

@@ -45,8 +45,14 @@ constexpr int FLAG_DBG_NO_PREFETCH = 16, FLAG_DBG_NO_LOADS = 32, FLAG_DBG_NO_SAM
 
 // staged source box in pixels, per channel count (one sub-box holds 8 channels = 32 bytes per pixel).
 // BW * 32 is a multiple of 256 so that the swizzle bit (address bit 7) does not depend on the row.
+#ifndef EFFI_BOX32_W
+#define EFFI_BOX32_W 64
+#endif
+#ifndef EFFI_BOX32_H
+#define EFFI_BOX32_H 8
+#endif
 template <int C> struct Box { static constexpr int W = 64, H = 12; };
-template <> struct Box<32> { static constexpr int W = 64, H = 8; };
+template <> struct Box<32> { static constexpr int W = EFFI_BOX32_W, H = EFFI_BOX32_H; };
 template <int C> struct BoxBytes {
     static constexpr int ROW = Box<C>::W * 32;
     static constexpr int SUB = Box<C>::W * Box<C>::H * 32;

@@ -9,70 +9,66 @@ what upstream reads and writes:
 """
 from __future__ import annotations
 
-import re
 import sys
 
 import numpy as np
 
 
+class PFMError(ValueError):
+    """A file that is not a PFM image, or an array that PFM cannot hold."""
+
+
+_PFM_KINDS = {b"PF": 3, b"Pf": 1}          # magic -> channels
+
+
 def read_pfm(filename):
-    """-> (data (H,W) or (H,W,3) float32, top row first; scale)."""
+    """-> (data (H,W) or (H,W,3) float32, top row first; scale).  PFM: three text lines (magic, "width height", scale whose
+    sign gives the byte order) followed by the rows bottom-up."""
     with open(filename, "rb") as f:
-        header = f.readline().decode("utf-8").rstrip()
-        if header == "PF":
-            color = True
-        elif header == "Pf":
-            color = False
-        else:
-            raise Exception("Not a PFM file.")
-        m = re.match(r"^(\d+)\s(\d+)\s$", f.readline().decode("utf-8"))
-        if not m:
-            raise Exception("Malformed PFM header.")
-        width, height = map(int, m.groups())
-        scale = float(f.readline().rstrip())
-        endian = "<" if scale < 0 else ">"
-        scale = abs(scale)
-        data = np.fromfile(f, endian + "f")
-    data = np.reshape(data, (height, width, 3) if color else (height, width))
-    return np.flipud(data), scale
+        magic = f.readline().strip()
+        if magic not in _PFM_KINDS:
+            raise PFMError("{}: magic {!r} is neither PF nor Pf".format(filename, magic))
+        dims = f.readline().split()
+        if len(dims) != 2 or not all(d.isdigit() for d in dims):
+            raise PFMError("{}: expected 'width height' on the second line, got {!r}".format(filename, b" ".join(dims)))
+        width, height = int(dims[0]), int(dims[1])
+        scale = float(f.readline().strip())
+        data = np.fromfile(f, dtype="<f4" if scale < 0 else ">f4")
+    channels = _PFM_KINDS[magic]
+    shape = (height, width, 3) if channels == 3 else (height, width)
+    if data.size != height * width * channels:
+        raise PFMError("{}: {} values for a {} x {} x {} image".format(filename, data.size, height, width, channels))
+    return data.reshape(shape)[::-1], abs(scale)
 
 
 def save_pfm(filename, image, scale=1):
+    """float32 (H,W), (H,W,1) or (H,W,3) -> PFM, rows written bottom-up, the scale line signed by the array's byte order."""
     image = np.asarray(image)
-    if image.dtype.name != "float32":
-        raise Exception("Image dtype must be float32.")
-    if image.ndim == 3 and image.shape[2] == 3:
-        color = True
-    elif image.ndim == 2 or (image.ndim == 3 and image.shape[2] == 1):
-        color = False
+    if image.dtype != np.float32:
+        raise PFMError("PFM stores float32, got {}".format(image.dtype))
+    if image.ndim == 2 or (image.ndim == 3 and image.shape[2] == 1):
+        magic = b"Pf"
+    elif image.ndim == 3 and image.shape[2] == 3:
+        magic = b"PF"
     else:
-        raise Exception("Image must have H x W x 3, H x W x 1 or H x W dimensions.")
-    image = np.flipud(image)
-    endian = image.dtype.byteorder
-    if endian == "<" or (endian == "=" and sys.byteorder == "little"):
-        scale = -scale
+        raise PFMError("PFM holds (H,W), (H,W,1) or (H,W,3), got shape {}".format(image.shape))
+    little = image.dtype.byteorder == "<" or (image.dtype.byteorder == "=" and sys.byteorder == "little")
     with open(filename, "wb") as f:
-        f.write(b"PF\n" if color else b"Pf\n")
-        f.write("{} {}\n".format(image.shape[1], image.shape[0]).encode("utf-8"))
-        f.write(("%f\n" % scale).encode("utf-8"))
-        image.tofile(f)
+        f.write(magic + b"\n")
+        f.write("{} {}\n".format(image.shape[1], image.shape[0]).encode("ascii"))
+        f.write(("%f\n" % (-scale if little else scale)).encode("ascii"))
+        image[::-1].tofile(f)
 
 
 def write_cam(filename, cam, depth_max, depth_min):
-    """cam (2,4,4): [0] extrinsic, [1][:3,:3] intrinsic, [1][3][:2] the two trailing numbers upstream carries there."""
+    """cam (2,4,4): [0] extrinsic, [1][:3,:3] intrinsic, [1][3][:2] the two trailing numbers upstream carries there.
+    MVSNet camera text: every matrix entry followed by one blank, a blank line between the blocks."""
+    def rows(m, n):
+        return "".join("".join(str(m[i][j]) + " " for j in range(n)) + "\n" for i in range(n))   # str(): numpy's shortest repr
+    text = "extrinsic\n" + rows(cam[0], 4) + "\nintrinsic\n" + rows(cam[1], 3)
+    text += "\n" + " ".join(str(t) for t in (cam[1][3][0], cam[1][3][1], depth_max, depth_min)) + "\n"
     with open(filename, "w") as f:
-        f.write("extrinsic\n")
-        for i in range(4):
-            for j in range(4):
-                f.write(str(cam[0][i][j]) + " ")
-            f.write("\n")
-        f.write("\n")
-        f.write("intrinsic\n")
-        for i in range(3):
-            for j in range(3):
-                f.write(str(cam[1][i][j]) + " ")
-            f.write("\n")
-        f.write("\n" + str(cam[1][3][0]) + " " + str(cam[1][3][1]) + " " + str(depth_max) + " " + str(depth_min) + "\n")
+        f.write(text)
 
 
 def read_cam_file(filename):

@@ -311,7 +311,10 @@ def test_fusion_vs_oracle_full_size():
     cx = (torch.arange(w, device=DEV) + 0.5).reshape(1, 1, 1, w)
     cy = (torch.arange(h, device=DEV) + 0.5).reshape(1, 1, h, 1)
     near = _near_threshold(want["reproj_xyd"], args[0], cx, cy, range(2, v + 1), 2, 6)
-    assert float(near.float().mean()) < 0.4, float(near.float().mean())   # the band must leave most pixels to compare
+    # the band must leave most pixels to compare: measured 0.132 of the pixels have at least one of their 10 views x 9 rungs x 2
+    # quantities inside it (1.6e-2 px / 9e-3 mm around each threshold), i.e. 1.9 % of the (pixel, view) pairs
+    print("fusion band: {:.4f} of the pixels are excluded".format(float(near.float().mean())))
+    assert float(near.float().mean()) < 0.15, float(near.float().mean())
     assert torch.equal(got["final"][~near], want["final"][~near])
     # averaged depth wherever every per-view mask of the ladder agrees (a flipped view changes the average)
     got_m = fusion.filter_view(*args, want_masks=True)["masks"]
