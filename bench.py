@@ -424,14 +424,31 @@ def scene_leg(a, model, rank, world, dev):
         dist.all_reduce(pts)
     secs, ag_ms, fu_ms, dm_ms = (float(x) for x in stats)
     slots = scene.slots_per_rank(N, world)
+    pure_ms = None
+    if world > 1:       # the same collective once more with all ranks aligned: NVLink time without the wait for the slowest rank
+        mine = torch.zeros(slots, H, W, device=dev)
+        flat = torch.empty(world * slots, H, W, device=dev)
+        dist.all_gather_into_tensor(flat, mine)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.all_gather_into_tensor(flat, mine)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pure_ms = float(t)
     recv = (world - 1) * slots * H * W * 4                      # bytes every rank receives from its peers
     return {"views": N, "shape": [W, H], "n_gpus": world, "seconds": secs, "depth_maps_per_sec_incl_fusion": N / secs,
             "all_gather_ms": ag_ms if world > 1 else None, "all_gather_bytes_received_per_rank": recv if world > 1 else 0,
             "all_gather_GBs_per_rank": (recv / ag_ms / 1e6) if world > 1 and ag_ms > 0 else None,
+            "all_gather_aligned_ms": pure_ms, "all_gather_aligned_GBs_per_rank": (recv / pure_ms / 1e6) if pure_ms else None,
             "depth_maps_ms_max_rank": dm_ms, "fusion_ms_max_rank": fu_ms, "fused_points": int(pts), "sharding": "block (balanced): views per rank " +
             ",".join(str(len(scene.shard_views(N, r, world, "block"))) for r in range(world)),
             "note": "4 source views for depth, 10 for fusion; feature cache + CUDA graphs; wall clock around run_scene, max over ranks; "
-                    "all-gather timed with CUDA events (max over ranks)"}
+                    "all_gather_ms: CUDA events around the collective inside the run, max over ranks, i.e. including the wait for the slowest rank; "
+                    "all_gather_aligned_ms: the same collective repeated after a barrier"}
 
 
 def run_ours(a, rank, world, local_rank):
