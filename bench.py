@@ -575,6 +575,31 @@ def run_ours(a, rank, world, local_rank):
             ms_e2e_f32, _ = e2e_timed(pin)                # the same with fp32 host images (4x the image bytes)
         h2d, h2d_f32 = pipe.h2d_bytes(pin_u8), pipe.h2d_bytes(pin)
 
+        # The same forward with fp32 products in every 2-D convolution (torch.backends.cudnn.allow_tf32 = False: cuDNN's fp32
+        # kernels for the FPN and the update block, whose tensor-core kernel follows the same switch) -- the setting of the
+        # parity tests.  The headline above keeps PyTorch's default, as upstream's scripts do.
+        strict = None
+        if rank == 0 and world == 1 and graph is not None:
+            saved_tf32 = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                forward()
+                g32 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g32):
+                    forward()
+
+                def step32():
+                    flush.zero_()
+                    g32.replay()
+                ms32 = timed(step32, a.steps, max(a.warmup, 3))
+                strict = {"ms_per_step": ms32 / a.steps, "value": a.steps / (ms32 / 1e3), "unit": UNIT,
+                          "what": "torch.backends.cudnn.allow_tf32 = False: fp32 products in all 2-D convolutions (FPN, update block on cuDNN)"}
+                del g32
+            except Exception as e:  # noqa: BLE001  (an extra leg must not cost the headline line)
+                strict = {"error": "{}: {}".format(type(e).__name__, e)}
+            finally:
+                torch.backends.cudnn.allow_tf32 = saved_tf32
+
         hbm_peak, tf_peak, peak_src = peaks()
         roof = roof_reg = kern = None
         if rank == 0:
@@ -611,6 +636,11 @@ def run_ours(a, rank, world, local_rank):
             "e2e_fp32_images": {"value": world * a.steps / (ms_e2e_f32 / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_f32,
                                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_f32 / a.steps},
             "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
+            "conv2d": {"cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+                       "update_block_3x3": "libeffimvs conv2d_tc (tcgen05, fp16 operands = TF32's 11 significant bits, fp32 accumulate, GRU gates as "
+                                           "epilogues) on the 1/4- and 1/2-resolution stages, cuDNN (TF32) on the 1/8 stage and for the FPN"
+                       if os.environ.get("EFFIMVS_CONV2D", "auto") != "0" else "cuDNN (TF32)"},
+            "strict_fp32": strict,
             "clocks": clk.summary(), "roofline": roof, "roofline_regularization": roof_reg, "kernels": kern}
     if scene49:
         line["scene49"] = scene49

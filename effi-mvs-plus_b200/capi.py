@@ -16,6 +16,7 @@ RANGE_SCALAR, RANGE_PIXEL = 0, 1
 FEA_NCHW, FEA_NHWC = 0, 1
 PREC_F32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 WS_PREPARE, WS_RUN = 1, 2
+CONV2D_BIAS, CONV2D_BIAS_RELU, CONV2D_ADD_RELU, CONV2D_GRU_GATES, CONV2D_GRU_UPDATE = 0, 1, 2, 3, 4
 MAX_SRC_VIEWS = 16
 
 
@@ -66,6 +67,11 @@ SIGNATURES = {
     "effimvs_encoder_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "effimvs_encoder_tail_f32": (_i, [_p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_encoder_tail_ctx_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, C.c_longlong, _i, _i, _p, _p]),
+    "effimvs_conv2d_tf32_supported": (_i, [_i, _i]),
+    "effimvs_conv2d_tf32_packed_bytes": (_sz, [_i, _i]),
+    "effimvs_conv2d_tf32_pack": (_i, [_p, _i, _i, _p, _p]),
+    "effimvs_conv2d_tf32": (_i, [_p, C.c_longlong, _i, _p, C.c_longlong, _i, _p, _p, _i, _i, _i, _i, _i,
+                                 _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _p]),
     "effimvs_gru_init_f32": (_i, [_p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_dtu_filter_f32": (_i, [_p, _p, _p, _p, C.POINTER(C.c_double), C.POINTER(C.c_float), _i, _i, _i, _f, _f, _i, _i, _i,
                                     _p, _p, _p, _p, _p, _p, _p]),

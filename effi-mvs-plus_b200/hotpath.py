@@ -286,6 +286,10 @@ class CudaHotPath:
     encoder_tail = staticmethod(ops.encoder_tail)
     encoder_tail_ctx = staticmethod(ops.encoder_tail_ctx)
     gru_init = staticmethod(ops.gru_init)
+    # the block's 3x3 convolutions on the tensor cores, gate arithmetic as epilogues (csrc/conv2d_tc.cu)
+    conv2d_tc = staticmethod(ops.conv2d_tc)
+    conv2d_tc_pack = staticmethod(ops.conv2d_tc_pack)
+    conv2d_tc_supported = staticmethod(ops.conv2d_tc_supported)
 
     # -- a11 / a12 --------------------------------------------------------------------------------
     def softmax_regress_conf(self, prob_pre, hyp):

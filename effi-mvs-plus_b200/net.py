@@ -310,7 +310,8 @@ class UpdateBlock(nn.Module):
 def _fused_update_weights(block):
     g, e = block.depth_gru, block.encoder
     ts = (g.convz.weight, g.convz.bias, g.convr.weight, g.convr.bias, e.convd.bias, e.convc.weight, e.convc.bias,
-          e.convc2.weight, e.convc2.bias, e.convd2.weight, e.convd2.bias, block.depth_head.conv2.weight)
+          e.convc2.weight, e.convc2.bias, e.convd2.weight, e.convd2.bias, block.depth_head.conv2.weight,
+          e.convd.weight, g.convq.weight, block.depth_head.conv1.weight, block.mask[0].weight)
     stamp = tuple((id(t), t._version, t.device) for t in ts)
     hit = getattr(block, "_effimvs_fused", None)
     if hit is None or hit[0] != stamp:
@@ -332,6 +333,72 @@ def _fused_update_weights(block):
             "w_d2": block.depth_head.conv2.weight.detach().contiguous()})
         object.__setattr__(block, "_effimvs_fused", hit)
     return hit[1]
+
+
+def _conv_tc_enabled(glue, h, H, W):
+    """Whether the update block's 3x3 convolutions run on the library's tensor-core kernel (csrc/conv2d_tc.cu: operands with
+    the 11 significant bits of TF32, fp32 accumulation, gate arithmetic as epilogues) instead of cuDNN.  Follows PyTorch's own
+    switch for that arithmetic class: with torch.backends.cudnn.allow_tf32 = False (fp32 products wanted) cuDNN's fp32 kernels
+    stay.  EFFIMVS_CONV2D = 0 / 1 forces it off / on; by default maps below EFFIMVS_CONV2D_MIN_PIXELS pixels (the 1/8-resolution
+    stage, where launch and prologue latency dominate and cuDNN is faster) stay on cuDNN as well."""
+    env = os.environ.get("EFFIMVS_CONV2D", "auto")
+    if env == "0" or not hasattr(glue, "conv2d_tc") or h % 16 != 0:
+        return False
+    if env != "1" and not torch.backends.cudnn.allow_tf32:
+        return False
+    sup = glue.conv2d_tc_supported
+    if not (sup(2 * h, 2 * h) and sup(2 * h, h) and sup(h, h) and sup(h, 2 * h)):
+        return False
+    return env == "1" or H * W >= int(os.environ.get("EFFIMVS_CONV2D_MIN_PIXELS", "100000"))
+
+
+def _tc_update_weights(block, glue, w):
+    """Packed weight images of the block's six 3x3 convolutions for conv2d_tc, built once per weight set (they live in the
+    dict _fused_update_weights caches, so they are rebuilt when a parameter changes)."""
+    tc = w.get("tc")
+    if tc is None:
+        g, e, hd = block.depth_gru, block.encoder, block.depth_head
+        hm = e.convd.out_channels
+        # convc (1x1, no nonlinearity in between) composed with convd: one 3x3 convolution 2h -> h
+        d_prime = torch.einsum("om,miyx->oiyx", e.convc.weight.detach()[:, :hm, 0, 0], e.convd.weight.detach())
+        tc = {"cd2": glue.conv2d_tc_pack(w["w_cd2"]), "dprime": glue.conv2d_tc_pack(d_prime.contiguous()),
+              "zr": glue.conv2d_tc_pack(w["wzr"]), "q": glue.conv2d_tc_pack(g.convq.weight.detach()),
+              "head1": glue.conv2d_tc_pack(hd.conv1.weight.detach()), "mask0": glue.conv2d_tc_pack(block.mask[0].weight.detach()),
+              "b_zr": torch.cat([g.convz.bias.detach(), g.convr.bias.detach()]).contiguous()}
+        w["tc"] = tc
+    return tc
+
+
+def _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask):
+    """The iterations of update_block_forward_fused with every 3x3 convolution on glue.conv2d_tc: encoder tail, GRU gates and
+    state update are epilogues (no encoder_tail / gru_reset / gru_update launches, cat[h, x] and cat[r * h, x] never
+    materialised).  hx (B,2h,H,W) channels-last holds [h ; x]; ctx_term (B,h,H,W) = convc's context half + bias."""
+    from . import capi
+    g, e, hd = block.depth_gru, block.encoder, block.depth_head
+    tc = _tc_update_weights(block, glue, w)
+    B, two_h, H, W = hx.shape
+    h = two_h // 2
+    ratio = int(round((block.mask[2].out_channels / 9) ** 0.5))
+    mk = lambda c: torch.empty(B, c, H, W, device=hx.device, dtype=torch.float32, memory_format=torch.channels_last)   # noqa: E731
+    cd, z, rh, t1 = mk(two_h), mk(h), mk(h), mk(h)
+    net_v, x_v = hx[:, :h], hx[:, h:]
+    inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
+    inv_seq, depth_seq = [], []
+    for it in range(iters):
+        c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
+        glue.conv2d_tc(c1d1, None, tc["cd2"], w["b_cd2"], two_h, capi.CONV2D_BIAS_RELU, cd, None, None)
+        glue.conv2d_tc(cd, None, tc["dprime"], None, h, capi.CONV2D_ADD_RELU, x_v, ctx_term, None)          # x = relu(convc(cat[convd(cd), ctx]))
+        glue.conv2d_tc(hx, None, tc["zr"], tc["b_zr"], two_h, capi.CONV2D_GRU_GATES, rh, net_v, z)          # z, r * h
+        glue.conv2d_tc(rh, x_v, tc["q"], g.convq.bias, h, capi.CONV2D_GRU_UPDATE, net_v, z, None)           # h = (1 - z) h + z tanh(q)
+        glue.conv2d_tc(net_v, None, tc["head1"], hd.conv1.bias, h, capi.CONV2D_BIAS_RELU, t1, None, None)
+        inv, depth = glue.delta_head(t1, w["w_d2"], hd.conv2.bias, inv, lo_disp, hi_disp)
+        inv_seq.append(inv)
+        depth_seq.append(depth)
+    m0 = mk(two_h)
+    glue.conv2d_tc(net_v, None, tc["mask0"], block.mask[0].bias, two_h, capi.CONV2D_BIAS_RELU, m0, None, None)
+    mask_pre = F.conv2d(m0, block.mask[2].weight, None)
+    up, depth_up = glue.convex_upsample(mask_pre, block.mask[2].bias, 0.25, inv, lo_disp, hi_disp, ratio)
+    return net_v, inv_seq, depth_seq, up, depth_up, (mask_pre if want_mask else None)
 
 
 def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map=None, want_mask=True):
@@ -362,6 +429,10 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
         hx[:, :h] = net
         ctx_src = context.contiguous(memory_format=torch.channels_last) if (tail_ctx and context.is_cuda) else context
         ctx_off, ctx_relu = 0, False
+    if _conv_tc_enabled(glue, h, hx.shape[2], hx.shape[3]) and tuple(hd.conv2.weight.shape) == (1, h, 3, 3) and h <= 128:
+        ctx_in = torch.relu(ctx_src[:, ctx_off:ctx_off + cx]) if ctx_relu else (ctx_src if ctx_src.shape[1] == cx else ctx_src[:, ctx_off:ctx_off + cx])
+        ctx_term = F.conv2d(ctx_in, w["wc_ctx"], w["bias_c"]).contiguous(memory_format=torch.channels_last)
+        return _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask)
     if not tail_ctx:
         ctx_term = F.conv2d(context, w["wc_ctx"], w["bias_c"])
     inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)

@@ -802,6 +802,80 @@ def encoder_tail_ctx(m: Tensor, w_m: Tensor, ctx: Tensor, ctx_offset: int, cx: i
                                                  w_ctx.data_ptr(), bias.data_ptr(), B * H * W, hm, h, hx.data_ptr(), _stream()))
 
 
+# -------------------------------------------------------------------------------------------
+# SURVEY section 8(f) row 3, the convolutions: 3x3 convolutions of the update block on the tensor cores (csrc/conv2d_tc.cu)
+def conv2d_tc_supported(cin: int, cout: int) -> bool:
+    return bool(_lib.effimvs_conv2d_tf32_supported(int(cin), int(cout)))
+
+
+def _cl_view(t: Tensor, name: str):
+    """(pointer, pixel stride) of a channels-last map or of a channel slice of one: dims (B,C,H,W), element strides
+    (H*W*ps, 1, W*ps, ps)."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 4:
+        raise RuntimeError("effimvs::conv2d_tc needs 4-D fp32 CUDA tensors ({})".format(name))
+    B, C, H, W = t.shape
+    ps = t.stride(3)
+    if t.stride(1) != 1 or t.stride(2) != W * ps or (B > 1 and t.stride(0) != H * W * ps) or ps < C:
+        raise RuntimeError("effimvs::conv2d_tc: {} must be a channels-last map or a channel slice of one, got strides {}".format(name, t.stride()))
+    return t.data_ptr(), ps
+
+
+@torch.library.custom_op("effimvs::conv2d_tc_pack", mutates_args=())
+@_on_tensor_device
+def conv2d_tc_pack(weight: Tensor) -> Tensor:
+    """(cout, cin, 3, 3) fp32 -> the kernel's packed fp16 weight image (once per weight tensor)."""
+    weight = _dev(weight, "conv2d_tc_pack")
+    cout, cin = weight.shape[:2]
+    if tuple(weight.shape[2:]) != (3, 3) or not conv2d_tc_supported(cin, cout):
+        raise ValueError("conv2d_tc_pack: unsupported weight shape {}".format(tuple(weight.shape)))
+    packed = torch.empty(_lib.effimvs_conv2d_tf32_packed_bytes(cin, cout) // 4, device=weight.device, dtype=torch.float32)
+    _count(1)
+    capi.check(_lib.effimvs_conv2d_tf32_pack(weight.data_ptr(), cin, cout, packed.data_ptr(), _stream()))
+    return packed
+
+
+@conv2d_tc_pack.register_fake
+def _(weight):
+    return weight.new_empty(9 * weight.shape[1] * ((weight.shape[0] + 15) // 16 * 16) // 2)
+
+
+@torch.library.custom_op("effimvs::conv2d_tc", mutates_args=("out", "aux1"))
+@_on_tensor_device
+def conv2d_tc(in0: Tensor, in1: Optional[Tensor], packed: Tensor, bias: Optional[Tensor], cout: int, mode: int, out: Tensor,
+              aux0: Optional[Tensor], aux1: Optional[Tensor]) -> None:
+    """3x3 / stride 1 / padding 1 convolution of cat[in0, in1] (channels-last maps or channel slices of such maps, read and
+    written in place) with the epilogue `mode` (capi.CONV2D_*): BIAS / BIAS_RELU -> out; ADD_RELU: out = relu(acc + aux0);
+    GRU_GATES: aux1 = z, out = r * aux0 (aux0 = h); GRU_UPDATE: out = (1 - aux0) * out + aux0 * tanh(acc + bias) (aux0 = z)."""
+    B, c0, H, W = in0.shape
+    p0, ps0 = _cl_view(in0, "in0")
+    p1, ps1, c1 = None, 0, 0
+    if in1 is not None:
+        p1, ps1 = _cl_view(in1, "in1")
+        c1 = in1.shape[1]
+        if tuple(in1.shape) != (B, c1, H, W):
+            raise ValueError("conv2d_tc: in1 {} does not match in0 {}".format(tuple(in1.shape), tuple(in0.shape)))
+    po, pso = _cl_view(out, "out")
+    h = cout // 2 if mode == capi.CONV2D_GRU_GATES else cout
+    if tuple(out.shape) != (B, h, H, W):
+        raise ValueError("conv2d_tc: out {} should be {}".format(tuple(out.shape), (B, h, H, W)))
+    pa0, psa0 = _cl_view(aux0, "aux0") if aux0 is not None else (None, 0)
+    pa1, psa1 = _cl_view(aux1, "aux1") if aux1 is not None else (None, 0)
+    for a in (aux0, aux1):
+        if a is not None and tuple(a.shape) != (B, h, H, W):
+            raise ValueError("conv2d_tc: aux map {} should be {}".format(tuple(a.shape), (B, h, H, W)))
+    if packed.numel() * 4 != _lib.effimvs_conv2d_tf32_packed_bytes(c0 + c1, cout):
+        raise ValueError("conv2d_tc: packed weights do not match cin = {} cout = {}".format(c0 + c1, cout))
+    bias = _dev(bias, "conv2d_tc") if bias is not None else None
+    _count(1)
+    capi.check(_lib.effimvs_conv2d_tf32(p0, ps0, c0, p1, ps1, c1, packed.data_ptr(), _opt(bias), cout, B, H, W, mode,
+                                        po, pso, pa0, psa0, pa1, psa1, _stream()))
+
+
+@conv2d_tc.register_fake
+def _(in0, in1, packed, bias, cout, mode, out, aux0, aux1):
+    return None
+
+
 @torch.library.custom_op("effimvs::gru_init", mutates_args=())
 @_on_tensor_device
 def gru_init(ctx_map: Tensor, h: int) -> Tensor:

@@ -294,6 +294,35 @@ int effimvs_encoder_tail_ctx_f32(const float* m, const float* w_m, const float* 
  * hx (n_pix, 2h) = cat[h, x]. */
 int effimvs_gru_init_f32(const float* ctx_map, long long n_pix, int h, int cx, float* hx, void* stream);
 
+/* ---- SURVEY section 8(f) row 3, the convolutions: 3x3 / stride 1 / zero padding 1 convolutions of the update block on the
+ * tensor cores (tcgen05 kind::tf32: operands rounded to TF32, fp32 accumulation -- the arithmetic class cuDNN uses for these
+ * layers under PyTorch's default torch.backends.cudnn.allow_tf32 = True), with the gate arithmetic as epilogues.
+ * Replaces ProjectionInput.convc2 / convd2 / convd (+ convc) (models/update.py:69-99), ConvGRU.convz / convr / convq and the
+ * gate expressions (models/update.py:33-49), DepthHead.conv1 (models/update.py:10-27), mask[0] (models/update.py:106-110).
+ * All maps are channels-last: a map is addressed as (pointer to channel 0 of pixel 0, pixel stride in floats), so channel
+ * slices of wider maps are read and written in place.  Input maps: 32-byte aligned, pixel strides and channel segments
+ * multiples of 8 floats; output / aux maps: 16-byte aligned, strides multiples of 4 floats. */
+#define EFFIMVS_CONV2D_BIAS 0       /* out = acc + bias (bias may be NULL)                                                  */
+#define EFFIMVS_CONV2D_BIAS_RELU 1  /* out = relu(acc + bias)                                                               */
+#define EFFIMVS_CONV2D_ADD_RELU 2   /* out = relu(acc + aux0[pixel]), aux0 = addend map with cout channels (bias inside)    */
+#define EFFIMVS_CONV2D_GRU_GATES 3  /* cout = 2h, weights [convz ; convr]: aux1 = z = sigmoid(acc[:h] + bias[:h]) (h channels),
+                                       out = sigmoid(acc[h:] + bias[h:]) * aux0, aux0 = previous hidden state (h channels)  */
+#define EFFIMVS_CONV2D_GRU_UPDATE 4 /* cout = h, weights convq: out = (1 - aux0) * out + aux0 * tanh(acc + bias), aux0 = z;
+                                       out is the hidden state, updated in place                                            */
+
+/* 1 if the (cin, cout) pair runs on the tensor-core kernel (cin a multiple of 16, cout a multiple of 4, the whole weight
+ * tensor resident in shared memory: 36 * cin * roundup(cout, 16) bytes + the input-row ring <= 220 KiB), else 0. */
+int effimvs_conv2d_tf32_supported(int cin, int cout);
+size_t effimvs_conv2d_tf32_packed_bytes(int cin, int cout);
+/* w (cout, cin, 3, 3) fp32 as nn.Conv2d holds it -> the kernel's shared-memory image (TF32-rounded); once per weight tensor. */
+int effimvs_conv2d_tf32_pack(const float* w, int cin, int cout, void* packed, void* stream);
+/* The input is the channel concatenation of up to two maps (c0 + c1 channels; in1 = NULL, c1 = 0 for one map) of B images
+ * of H x W pixels; packed from effimvs_conv2d_tf32_pack for cin = c0 + c1; bias (cout) or NULL; mode and aux maps as above. */
+int effimvs_conv2d_tf32(const float* in0, long long in0_pixstride, int c0, const float* in1, long long in1_pixstride, int c1,
+                        const void* packed, const float* bias, int cout, int B, int H, int W, int mode,
+                        float* out, long long out_pixstride, const float* aux0, long long aux0_pixstride,
+                        float* aux1, long long aux1_pixstride, void* stream);
+
 /* ---- the DTU pipeline's NumPy / cv2.remap geometric filter ------------------------
  * reproject_with_depth + check_geometric_consistency + the aggregation of filter_depth
  * (test_dtu_dypcd.py:164-233, 261-309, 320-337) for one reference view in one kernel.
