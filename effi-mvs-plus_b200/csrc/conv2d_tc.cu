@@ -106,14 +106,22 @@ __device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
     return done;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin)
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
         if (mbar_try(bar, parity)) return;
+        if (spin > 4) __nanosleep(32);
+    }
     __trap();
 }
-// the same for a whole warp, leaving on a vote so that the compiler sees warp-uniform control flow after the wait
+// The same for a whole warp: ONE lane polls (an mbarrier poll is a shared-memory atomic; 32 lanes polling one address
+// serialise in the shared-memory pipe and starve the stores of the working warps -- measured), and the warp leaves on a vote
+// so that the compiler sees warp-uniform control flow after the wait.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-        if (__all_sync(0xffffffffu, mbar_try(bar, parity))) return;
+    const bool poller = (threadIdx.x & 31) == 0;
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        const uint32_t done = poller ? mbar_try(bar, parity) : 0u;
+        if (__any_sync(0xffffffffu, done)) return;
+        if (spin > 4) __nanosleep(32);
+    }
     __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -212,14 +220,20 @@ __device__ __forceinline__ float4 ldg_nc4(const float* p) {
 __device__ __forceinline__ float sigmoid_t(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_t(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
+#ifdef EFFIMVS_CONV2D_TIMELINE   // profiling builds only: clock64 stamps of CTA 0's roles (tools/conv2d_check.py timeline)
 #define C2_TL(role, step, ev) do { if (P.tl && blockIdx.x == 0 && (step) < 64) P.tl[((role) * 64 + (step)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define C2_TL(role, step, ev) do { } while (0)
+#endif
 
 // Second half of the epilogue for one chunk of 4 * CPP columns of a warp's 32 pixels: lane = (pixel within a pass, 4-channel
 // group), 32 / (32 / CPP) passes, four at a time so that the shared-memory reads, the aux-map loads and the stores of
-// different pixels overlap.
-template <int CPP>
-__device__ __forceinline__ void epilogue_rows(const C2Params& P, const uint8_t* __restrict__ ebuf, const float* __restrict__ sbias, int lane,
-                                              int cb, int h, long long rowpix, int xw0, int W) {
+// different pixels overlap.  Every role of this kernel is a single-warp chain whose speed is its instruction count (measured:
+// ~6 clk per executed instruction), hence the compile-time mode, the pointer-increment addressing and the predicate-free
+// path for warps whose 32 pixels all lie inside the image.
+template <int CPP, int MODE, bool FULL>
+__device__ __forceinline__ void epilogue_rows_m(const C2Params& P, const uint8_t* __restrict__ ebuf, const float* __restrict__ sbias, int lane,
+                                                int cb, int h, long long rowpix, int xw0, int W) {
     constexpr int PPP = 32 / CPP, NPASS = 32 / PPP;
     const int sub = lane & (CPP - 1), pxl = lane / CPP;
     const int ch = cb + sub * 4;
@@ -227,52 +241,79 @@ __device__ __forceinline__ void epilogue_rows(const C2Params& P, const uint8_t* 
     const float4 b4 = *reinterpret_cast<const float4*>(sbias + ch);
     const long long pix0 = rowpix + xw0 + pxl;
     const uint8_t* src = ebuf + pxl * C2_EPI_STRIDE + sub * 16;
-    const int mode = P.mode;
-    const bool gate_r = mode == EFFIMVS_CONV2D_GRU_GATES && ch >= h;
+    const bool gate_r = MODE == EFFIMVS_CONV2D_GRU_GATES && ch >= h;
     // main output pointer and the aux map read per pixel (none for the plain modes and the z half of the gates)
-    float* o = mode == EFFIMVS_CONV2D_GRU_GATES ? (gate_r ? P.out + pix0 * P.out_ps + (ch - h) : P.aux1 + pix0 * P.aux1_ps + ch)
-                                                : P.out + pix0 * P.out_ps + ch;
-    const long long o_ps = (mode == EFFIMVS_CONV2D_GRU_GATES && !gate_r) ? P.aux1_ps : P.out_ps;
-    const bool has_aux = mode == EFFIMVS_CONV2D_ADD_RELU || mode == EFFIMVS_CONV2D_GRU_UPDATE || gate_r;
-    const float* ax = has_aux ? P.aux0 + pix0 * P.aux0_ps + (gate_r ? ch - h : ch) : nullptr;
+    float* o;
+    long long o_step;                                   // floats between the pixels of consecutive passes
+    if (MODE == EFFIMVS_CONV2D_GRU_GATES) {
+        o = gate_r ? P.out + pix0 * P.out_ps + (ch - h) : P.aux1 + pix0 * P.aux1_ps + ch;
+        o_step = (gate_r ? P.out_ps : P.aux1_ps) * PPP;
+    } else {
+        o = P.out + pix0 * P.out_ps + ch;
+        o_step = P.out_ps * PPP;
+    }
+    constexpr bool AUX = MODE == EFFIMVS_CONV2D_ADD_RELU || MODE == EFFIMVS_CONV2D_GRU_UPDATE || MODE == EFFIMVS_CONV2D_GRU_GATES;
+    const bool has_aux = MODE == EFFIMVS_CONV2D_GRU_GATES ? gate_r : AUX;
+    const float* ax = AUX ? P.aux0 + pix0 * P.aux0_ps + (gate_r ? ch - h : ch) : nullptr;
+    const long long ax_step = AUX ? P.aux0_ps * PPP : 0;
+    const int n_ok = FULL ? NPASS : (W - xw0 - pxl + PPP - 1) / PPP;      // passes whose pixel lies inside the image
 #pragma unroll
     for (int g0 = 0; g0 < NPASS; g0 += 4) {
         float4 a[4], d[4];
-        bool ok[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int ps = (g0 + j) * PPP;
-            ok[j] = xw0 + pxl + ps < W;
-            a[j] = *reinterpret_cast<const float4*>(src + ps * C2_EPI_STRIDE);
-            d[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (ok[j] && has_aux) d[j] = ldg_nc4(ax + (long long)ps * P.aux0_ps);
+            a[j] = *reinterpret_cast<const float4*>(src + (g0 + j) * PPP * C2_EPI_STRIDE);
+            if (AUX) {
+                d[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (has_aux && (FULL || g0 + j < n_ok)) d[j] = ldg_nc4(ax + (g0 + j) * ax_step);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (!ok[j]) continue;
+            if (!FULL && g0 + j >= n_ok) continue;
+            float* op = o + (g0 + j) * o_step;
             float4 w;
-            if (mode == EFFIMVS_CONV2D_BIAS || mode == EFFIMVS_CONV2D_BIAS_RELU) {
+            if (MODE == EFFIMVS_CONV2D_BIAS || MODE == EFFIMVS_CONV2D_BIAS_RELU) {
                 w.x = __fadd_rn(a[j].x, b4.x); w.y = __fadd_rn(a[j].y, b4.y); w.z = __fadd_rn(a[j].z, b4.z); w.w = __fadd_rn(a[j].w, b4.w);
-                if (mode == EFFIMVS_CONV2D_BIAS_RELU) { w.x = fmaxf(w.x, 0.0f); w.y = fmaxf(w.y, 0.0f); w.z = fmaxf(w.z, 0.0f); w.w = fmaxf(w.w, 0.0f); }
-            } else if (mode == EFFIMVS_CONV2D_ADD_RELU) {
+                if (MODE == EFFIMVS_CONV2D_BIAS_RELU) { w.x = fmaxf(w.x, 0.0f); w.y = fmaxf(w.y, 0.0f); w.z = fmaxf(w.z, 0.0f); w.w = fmaxf(w.w, 0.0f); }
+            } else if (MODE == EFFIMVS_CONV2D_ADD_RELU) {
                 w.x = fmaxf(__fadd_rn(a[j].x, d[j].x), 0.0f); w.y = fmaxf(__fadd_rn(a[j].y, d[j].y), 0.0f);
                 w.z = fmaxf(__fadd_rn(a[j].z, d[j].z), 0.0f); w.w = fmaxf(__fadd_rn(a[j].w, d[j].w), 0.0f);
-            } else if (mode == EFFIMVS_CONV2D_GRU_GATES) {
+            } else if (MODE == EFFIMVS_CONV2D_GRU_GATES) {
                 // z = sigmoid(z_pre + b_z)  |  sigmoid(r_pre + b_r) * h_prev
                 w.x = sigmoid_t(__fadd_rn(a[j].x, b4.x)); w.y = sigmoid_t(__fadd_rn(a[j].y, b4.y));
                 w.z = sigmoid_t(__fadd_rn(a[j].z, b4.z)); w.w = sigmoid_t(__fadd_rn(a[j].w, b4.w));
                 if (gate_r) { w.x = __fmul_rn(w.x, d[j].x); w.y = __fmul_rn(w.y, d[j].y); w.z = __fmul_rn(w.z, d[j].z); w.w = __fmul_rn(w.w, d[j].w); }
             } else {
-                // GRU_UPDATE: out = (1 - z) * out + z * tanh(q_pre + b_q), z = d, out = hv
-                const float4 hq = *reinterpret_cast<const float4*>(o + (long long)((g0 + j) * PPP) * o_ps);
+                // GRU_UPDATE: out = (1 - z) * out + z * tanh(q_pre + b_q), z = d
+                const float4 hq = *reinterpret_cast<const float4*>(op);
                 w.x = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].x), hq.x), __fmul_rn(d[j].x, tanh_t(__fadd_rn(a[j].x, b4.x))));
                 w.y = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].y), hq.y), __fmul_rn(d[j].y, tanh_t(__fadd_rn(a[j].y, b4.y))));
                 w.z = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].z), hq.z), __fmul_rn(d[j].z, tanh_t(__fadd_rn(a[j].z, b4.z))));
                 w.w = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].w), hq.w), __fmul_rn(d[j].w, tanh_t(__fadd_rn(a[j].w, b4.w))));
             }
-            *reinterpret_cast<float4*>(o + (long long)((g0 + j) * PPP) * o_ps) = w;
+            *reinterpret_cast<float4*>(op) = w;
         }
     }
+}
+template <int CPP>
+__device__ __forceinline__ void epilogue_rows(const C2Params& P, const uint8_t* __restrict__ ebuf, const float* __restrict__ sbias, int lane,
+                                              int cb, int h, long long rowpix, int xw0, int W) {
+    const bool full = xw0 + 32 <= W;
+#define C2_EPI_CASE(M)                                                                                          \
+    case M:                                                                                                     \
+        if (full) epilogue_rows_m<CPP, M, true>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);                   \
+        else epilogue_rows_m<CPP, M, false>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);                       \
+        break;
+    switch (P.mode) {
+        C2_EPI_CASE(EFFIMVS_CONV2D_BIAS)
+        C2_EPI_CASE(EFFIMVS_CONV2D_BIAS_RELU)
+        C2_EPI_CASE(EFFIMVS_CONV2D_ADD_RELU)
+        C2_EPI_CASE(EFFIMVS_CONV2D_GRU_GATES)
+        default:
+        C2_EPI_CASE(EFFIMVS_CONV2D_GRU_UPDATE)
+    }
+#undef C2_EPI_CASE
 }
 
 struct Unit { int b, y0, y1, x0; };
@@ -332,6 +373,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
         const int pxl = groups >= 4 ? (lane & 7) : (lane & 15), cgl0 = groups >= 4 ? (lane >> 3) : (lane >> 4);
         const int px_per_item = groups >= 4 ? 8 : 16, px_items = (C2_ROWPX + px_per_item - 1) / px_per_item;
         const int n_items = px_items * (groups >= 4 ? groups >> 2 : 1);
+        const int ps0i = (int)P.ps0, ps1i = (int)P.ps1;                  // a row of a map is < 2^31 floats
         uint32_t fill = 0;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             const Unit t = unit_of(P, u);
@@ -345,6 +387,9 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                     __syncwarp();
                     if (pw == 0 && lane == 0) C2_TL(0, fill, 0);
                     uint8_t* dst = astage + (size_t)s * P.stage_bytes;
+                    const float* r0 = P.in0 + rowpix * P.ps0;          // (pixel 0 of the row, channel 0) of the two segments
+                    const float* r1 = P.in1 + rowpix * P.ps1 - P.c0;
+                    const int ch0 = p * P.kc + cgl0 * 8, xb = t.x0 - 1 + pxl;
                     for (int it0 = pwg; it0 < n_items; it0 += 5 * P.gw) {
                         F8 v[5];
                         uint32_t off[5];
@@ -354,14 +399,12 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                             v[k].a = v[k].b = v[k].c = v[k].d = 0ull;
                             off[k] = 0xffffffffu;
                             if (it < n_items && !(P.debug & 2)) {
-                                const int cgq = it / px_items, g = it - cgq * px_items;
-                                const int px = g * px_per_item + pxl, cgl = cgq * 4 + cgl0;
-                                const int x = t.x0 - 1 + px;
-                                if (px < C2_ROWPX) off[k] = (uint32_t)(cgl * C2_CG_BYTES + px * 16);
+                                const int cgq = it >= px_items ? 1 : 0, g = it - (cgq ? px_items : 0);   // n_items <= 2 px_items
+                                const int pxo = g * px_per_item, px = pxo + pxl, x = xb + pxo;
+                                if (px < C2_ROWPX) off[k] = (uint32_t)((cgq * 4 + cgl0) * C2_CG_BYTES + px * 16);
                                 if (px < C2_TM + 2 && (unsigned)x < (unsigned)W) {
-                                    const int gc = p * P.kc + cgl * 8;
-                                    const float* src = gc < P.c0 ? P.in0 + (rowpix + x) * P.ps0 + gc : P.in1 + (rowpix + x) * P.ps1 + (gc - P.c0);
-                                    v[k] = ldg_nc8(src);
+                                    const int gc = ch0 + cgq * 32;
+                                    v[k] = ldg_nc8(gc < P.c0 ? r0 + (x * ps0i + gc) : r1 + (x * ps1i + gc));
                                 }
                             }
                         }
@@ -436,24 +479,28 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                         const uint32_t s = fill % S, n = fill / S;
                         mbar_wait_warp(&bar_afull[s], n & 1);
                         if (leader) C2_TL(1, fill, 1);
-                        tc_fence_after();
+                        if (!(P.debug & 2048)) tc_fence_after();
                         const uint64_t adesc0 = umma_desc(smem_u32(astage + (size_t)s * P.stage_bytes), C2_CG_BYTES, 128);
                         uint64_t bstep = bdesc0 + (uint64_t)((uint32_t)(p * ksteps * 3) * blk16);
-                        for (int j = 0; j < ksteps; ++j) {
+                        if (leader && mma_on) {
+                            int q0 = 0;
+                            if (p == 0 && fresh) {
+                                // first K step of a row with fresh accumulators: one MMA per output row, overwriting where fresh
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx, bstep += blk16) {
+                                for (int k = 0; k < 3; ++k)
+                                    if (k < nt)
+                                        umma_tf32(tmem + ((seq0 + k) & rm) * coutp, adesc0, bstep + (uint64_t)((kyb0 + k) * coutp), id1, ((fresh >> k) & 1u) ^ 1u);
+                                q0 = 1;
+                                bstep += blk16;
+                            }
+                            // K steps q = j * 3 + kx: channel groups 2j, 2j + 1 of the stage, x tap kx (a 16-byte shift)
+                            const uint64_t bA = bstep + (uint64_t)boffA, bB = bstep + (uint64_t)boffB;
+                            uint32_t boff = 0;
+                            for (int q = q0; q < 3 * ksteps; ++q, boff += blk16) {
+                                const int j = q / 3, kx = q - 3 * j;
                                 const uint64_t adesc = adesc0 + (uint64_t)(uint32_t)(j * 2 * (C2_CG_BYTES >> 4) + kx);
-                                if (!mma_on || !leader) continue;
-                                if (p == 0 && j == 0 && kx == 0 && fresh) {
-                                    // first K step of a row with fresh accumulators: one MMA per output row, overwrite where fresh
-#pragma unroll
-                                    for (int k = 0; k < 3; ++k)
-                                        if (k < nt)
-                                            umma_tf32(tmem + ((seq0 + k) & rm) * coutp, adesc, bstep + (uint64_t)((kyb0 + k) * coutp), id1, ((fresh >> k) & 1u) ^ 1u);
-                                } else {
-                                    umma_tf32(dA, adesc, bstep + (uint64_t)boffA, idA, 1u);
-                                    if (lenB > 0) umma_tf32(dB, adesc, bstep + (uint64_t)boffB, idB, 1u);
-                                }
+                                umma_tf32(dA, adesc, bA + boff, idA, 1u);
+                                if (lenB > 0) umma_tf32(dB, adesc, bB + boff, idB, 1u);
                             }
                         }
                         if (leader) {
@@ -496,7 +543,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                 if (lane == 0) mbar_wait(&bar_tfull[slot], (seq >> (__ffs(P.ring) - 1)) & 1u);
                 __syncwarp();
                 if (tid == 0) C2_TL(2, seq, 1);
-                tc_fence_after();
+                if (!(P.debug & 1024)) tc_fence_after();
                 const uint32_t lane_base = tmem + slot * (uint32_t)P.coutp + ((uint32_t)(warp * 32) << 16);
                 if (P.debug & 64) {
                     __syncwarp();
@@ -522,7 +569,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                         }
                     }
                     const bool last = cb + 32 >= P.coutp;
-                    if (last) tc_fence_before();
+                    if (last && !(P.debug & 1024)) tc_fence_before();
                     __syncwarp();
                     if (last && lane == 0) mbar_arrive(&bar_tempty[slot]);     // last TMEM read of this row: the slot goes back to the MMA warp
                     if (last && tid == 0) C2_TL(2, seq, 2);
@@ -612,6 +659,7 @@ extern "C" int effimvs_conv2d_tf32(const float* in0, long long in0_ps, int c0, c
                  EFFIMVS_EINVAL, "conv2d_tf32: input pixel strides must be multiples of 8 floats, the output's of 4");
     EFFI_REQUIRE((((uintptr_t)in0 | (uintptr_t)in1) & 31) == 0 && (((uintptr_t)out | (uintptr_t)aux0 | (uintptr_t)aux1 | (uintptr_t)packed) & 15) == 0,
                  EFFIMVS_EINVAL, "conv2d_tf32: input maps must be 32-byte aligned, the other pointers 16-byte aligned");
+    EFFI_REQUIRE((long long)W * in0_ps < (1ll << 31) && (long long)W * in1_ps < (1ll << 31), EFFIMVS_EUNSUPPORTED, "conv2d_tf32: a row of a map must be below 2^31 floats");
     if (mode == EFFIMVS_CONV2D_ADD_RELU) EFFI_REQUIRE(aux0 && aux0_ps % 4 == 0, EFFIMVS_EINVAL, "conv2d_tf32: ADD_RELU needs the addend map");
     if (mode == EFFIMVS_CONV2D_GRU_GATES)
         EFFI_REQUIRE(aux0 && aux1 && bias && cout % 32 == 0 && aux0_ps % 4 == 0 && aux1_ps % 4 == 0, EFFIMVS_EINVAL,

@@ -382,11 +382,16 @@ def _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, i
     mk = lambda c: torch.empty(B, c, H, W, device=hx.device, dtype=torch.float32, memory_format=torch.channels_last)   # noqa: E731
     cd, z, rh, t1 = mk(two_h), mk(h), mk(h), mk(h)
     net_v, x_v = hx[:, :h], hx[:, h:]
+    # the one layer without an epilogue to fuse (block-diagonal convc2 | convd2 + relu) can stay on cuDNN: EFFIMVS_CONV2D_CD2=cudnn
+    cd2_cudnn = os.environ.get("EFFIMVS_CONV2D_CD2", "own") == "cudnn"
     inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
     inv_seq, depth_seq = [], []
     for it in range(iters):
         c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
-        glue.conv2d_tc(c1d1, None, tc["cd2"], w["b_cd2"], two_h, capi.CONV2D_BIAS_RELU, cd, None, None)
+        if cd2_cudnn:
+            cd = conv_relu(c1d1, w["w_cd2"], w["b_cd2"], (1, 1), (1, 1))
+        else:
+            glue.conv2d_tc(c1d1, None, tc["cd2"], w["b_cd2"], two_h, capi.CONV2D_BIAS_RELU, cd, None, None)
         glue.conv2d_tc(cd, None, tc["dprime"], None, h, capi.CONV2D_ADD_RELU, x_v, ctx_term, None)          # x = relu(convc(cat[convd(cd), ctx]))
         glue.conv2d_tc(hx, None, tc["zr"], tc["b_zr"], two_h, capi.CONV2D_GRU_GATES, rh, net_v, z)          # z, r * h
         glue.conv2d_tc(rh, x_v, tc["q"], g.convq.bias, h, capi.CONV2D_GRU_UPDATE, net_v, z, None)           # h = (1 - z) h + z tanh(q)

@@ -196,7 +196,7 @@ def scale():
         out = torch.empty(1, H, W, cout, device="cuda")
         fn = lambda: run(x, None, pk, bias, cout, capi.CONV2D_BIAS_RELU, out)   # noqa: E731
         res = []
-        for dbg in ("0", "15", "271", "527", "256", "512"):
+        for dbg in ("0", "15", "14", "1"):
             os.environ["EFFIMVS_CONV2D_DEBUG"] = dbg
             os.environ["EFFIMVS_CONV2D_ROWS"] = "15"
             res.append("dbg{} {:.1f}".format(dbg, timeit(fn, flush)[1]))
@@ -234,7 +234,30 @@ def timeline():
     return 0
 
 
+def rows():
+    """One CTA, one unit of H rows x 128 pixels: time against H (slope = per-row cost of the slowest role, intercept = launch + prologue)."""
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for cin, cout, ctas in ((32, 32, "3"), (32, 32, "2"), (32, 32, "1"), (16, 16, "1")):
+        os.environ["EFFIMVS_CONV2D_CTAS"] = ctas
+        w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.1
+        bias = torch.randn(cout, device="cuda")
+        pk = pack(w)
+        for H in (8, 64):
+            x = torch.randn(1, H, 128, cin, device="cuda")
+            out = torch.empty(1, H, 128, cout, device="cuda")
+            fn = lambda: run(x, None, pk, bias, cout, capi.CONV2D_BIAS_RELU, out)   # noqa: E731
+            res = []
+            for dbg in ("0", "15", "14", "1", "2", "4"):
+                os.environ["EFFIMVS_CONV2D_DEBUG"] = dbg
+                os.environ["EFFIMVS_CONV2D_ROWS"] = str(H)
+                res.append("dbg{} {:.1f}".format(dbg, timeit(fn, flush)[1]))
+            print("rows {}->{} ctas/SM cfg {} H={}: warm us: {}".format(cin, cout, ctas, H, "  ".join(res)), flush=True)
+    return 0
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "rows":
+        return rows()
     if len(sys.argv) > 1 and sys.argv[1] == "timeline":
         return timeline()
     if len(sys.argv) > 1 and sys.argv[1] == "scale":
