@@ -540,6 +540,16 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                 const uint32_t slot = seq & (uint32_t)(P.ring - 1);
                 const long long rowpix = ((long long)t.b * H + r) * W;
                 if (tid == 0) C2_TL(2, seq, 0);
+                // the aux maps of the fused modes are read once the accumulators arrive: ask for their lines now (a lane per
+                // pixel: 32 pixels x h channels of this warp), so that the reads in epilogue_rows hit L1 instead of waiting on L2
+                if (P.mode >= EFFIMVS_CONV2D_ADD_RELU && xw0 + lane < W && !(P.debug & 4096)) {
+                    const float* a0 = P.aux0 + (rowpix + xw0 + lane) * P.aux0_ps;
+                    for (int c = 0; c < h; c += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + c));
+                    if (P.mode == EFFIMVS_CONV2D_GRU_UPDATE) {
+                        const float* o0 = P.out + (rowpix + xw0 + lane) * P.out_ps;
+                        for (int c = 0; c < h; c += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(o0 + c));
+                    }
+                }
                 if (lane == 0) mbar_wait(&bar_tfull[slot], (seq >> (__ffs(P.ring) - 1)) & 1u);
                 __syncwarp();
                 if (tid == 0) C2_TL(2, seq, 1);

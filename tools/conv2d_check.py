@@ -142,21 +142,25 @@ def timeit(fn, flush, n=10):
     return t_cold * 1e3, t_warm * 1e3
 
 
-def bench(H, W, cin, cout, flush):
+def bench(H, W, cin, cout, flush, mode="relu"):
     dev = "cuda"
     x = torch.randn(1, H, W, cin, device=dev)
     w = torch.randn(cout, cin, 3, 3, device=dev) * 0.1
     bias = torch.randn(cout, device=dev)
     pk = pack(w)
-    out = torch.empty(1, H, W, cout, device=dev)
-    t_own, w_own = timeit(lambda: run(x, None, pk, bias, cout, capi.CONV2D_BIAS_RELU, out), flush)
+    h = cout // 2 if mode == "gates" else cout
+    out = torch.empty(1, H, W, h, device=dev)
+    aux0 = torch.rand(1, H, W, h, device=dev)
+    aux1 = torch.empty(1, H, W, h, device=dev)
+    m = {"relu": capi.CONV2D_BIAS_RELU, "add": capi.CONV2D_ADD_RELU, "gates": capi.CONV2D_GRU_GATES, "update": capi.CONV2D_GRU_UPDATE}[mode]
+    t_own, w_own = timeit(lambda: run(x, None, pk, bias, cout, m, out, aux0 if mode != "relu" else None, aux1 if mode == "gates" else None), flush)
     xn = x.permute(0, 3, 1, 2)
     wn = w.contiguous(memory_format=torch.channels_last)
     torch.backends.cudnn.allow_tf32 = True
     t_cudnn, w_cudnn = timeit(lambda: torch.cudnn_convolution_relu(xn, wn, bias, (1, 1), (1, 1), (1, 1), 1), flush)
     mb = 4e-6 * H * W * (cin + cout)
-    print("time {}x{} {}->{}: own cold {:.1f} us ({:.0f} GB/s) warm {:.1f} us | cudnn-tf32 cold {:.1f} warm {:.1f} us".format(
-        H, W, cin, cout, t_own, mb / t_own * 1e3, w_own, t_cudnn, w_cudnn), flush=True)
+    print("time {}x{} {}->{} {}: own cold {:.1f} us ({:.0f} GB/s) warm {:.1f} us | cudnn-tf32 conv+relu alone cold {:.1f} warm {:.1f} us".format(
+        H, W, cin, cout, mode, t_own, mb / t_own * 1e3, w_own, t_cudnn, w_cudnn), flush=True)
 
 
 def probe():
@@ -305,6 +309,12 @@ def main():
                                 (296, 400, 64, 64), (296, 400, 64, 32), (296, 400, 32, 32), (296, 400, 32, 64),
                                 (148, 200, 96, 48), (148, 200, 48, 48), (148, 200, 48, 96)]:
             bench(H, W, cin, cout, flush)
+        for H, W, cin, cout, mode in [(592, 800, 32, 16, "add"), (592, 800, 32, 32, "gates"), (592, 800, 32, 16, "update"),
+                                      (296, 400, 64, 32, "add"), (296, 400, 64, 64, "gates"), (296, 400, 64, 32, "update")]:
+            for pf in ("0", "4096"):
+                os.environ["EFFIMVS_CONV2D_DEBUG"] = pf
+                bench(H, W, cin, cout, flush, mode)
+        os.environ["EFFIMVS_CONV2D_DEBUG"] = "0"
     print("ALL OK" if ok else "FAILURES")
     return 0 if ok else 1
 
