@@ -93,8 +93,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait parks the thread in hardware until the phase completes (or a time limit passes): a waiting role burns no issue
-// slots -- pure test_wait polling by the waiting warps of two resident CTAs measurably slowed the working ones down.
+// try_wait parks the thread in hardware for a short, system-defined time; between polls the lane sleeps.  Tried and measured:
+// a long suspend-time hint on try_wait itself makes threads wake late (32 -> 32 at 800 x 592: 41 -> 64 us with a 20 us hint);
+// backoffs of 32 / 64 / 200 ns between polls are indistinguishable; pure test_wait polling is no faster.
 // A barrier that never completes must surface as a launch failure, not as a hung GPU.
 __device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
     uint32_t done;

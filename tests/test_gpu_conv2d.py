@@ -242,3 +242,29 @@ def test_cascade_tc_vs_upstream_full_shape(monkeypatch):
           "convolutions {:.5f}, cascade with conv2d_tc {:.5f}".format(min(f_up), min(f_cud), min(f_own)))
     assert min(f_own) >= min(f_up) - 0.002
     assert min(f_own) >= min(f_cud) - 0.002
+
+
+def test_cascade_tc_graph_replay_equals_eager(monkeypatch):
+    """the cascade with the tensor-core convolutions is deterministic and CUDA-graph capturable: a replay reproduces the eager
+    forward bit for bit (all three stages forced onto conv2d_tc, 640x512x5)"""
+    from effimvs_b200 import hotpath, synthetic
+    from util import dtu_model
+    monkeypatch.setenv("EFFIMVS_CONV2D", "1")
+    s = synthetic.make_sample("plumbing", seed=5, device=DEV)
+    model = dtu_model(hotpath.CudaHotPath("bf16x3", native_projection=True), DEV, "48,8,8")
+    fwd = lambda: model(s["imgs"], s["proj_matrices"], s["depth_values"])   # noqa: E731
+    fwd()
+    eager = [d.clone() for d in fwd()["depth"]]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fwd()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = fwd()
+    for _ in range(2):
+        g.replay()
+        torch.cuda.synchronize()
+        assert all(torch.equal(a, b) for a, b in zip(out["depth"], eager))
+    assert all(bool(torch.isfinite(d).all()) for d in eager)
