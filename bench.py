@@ -377,6 +377,26 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
         vq = D * (Hs // 2) * (Ws // 2)
         fl = 2.0 * 27 * vq * (8 + 8 + 16 * 8 + 8)
         out["cost_up_small_stage{}".format(s + 1)] = {"ms": ms, "flops": fl, "tflops": fl / ms / 1e9}
+    # the update block's 3x3 convolutions on the tensor cores (csrc/conv2d_tc.cu) at the stage-3 / stage-2 shapes of this cascade:
+    # algorithmic bytes = the fp32 input and output maps once each (+ the aux maps of the fused epilogues)
+    for s, tag in ((2, "stage3"), (1, "stage2")):
+        Hs, Ws = feats[s][0].shape[2:]
+        h = model.HIDDEN[s]
+        mk = lambda c: torch.randn(B, c, Hs, Ws, device=dev).contiguous(memory_format=torch.channels_last)   # noqa: E731
+        hx, z, rh, cd = mk(2 * h), mk(h), mk(h), mk(2 * h)
+        w_full, w_half = 0.1 * torch.randn(2 * h, 2 * h, 3, 3, device=dev), 0.1 * torch.randn(h, 2 * h, 3, 3, device=dev)
+        bias2, bias1 = torch.randn(2 * h, device=dev), torch.randn(h, device=dev)
+        if not (ops.conv2d_tc_supported(2 * h, 2 * h) and ops.conv2d_tc_supported(2 * h, h)):
+            continue
+        pk_full, pk_half = ops.conv2d_tc_pack(w_full), ops.conv2d_tc_pack(w_half)
+        px = 4.0 * B * Hs * Ws
+        ms = timed(lambda: ops.conv2d_tc(hx, None, pk_full, bias2, 2 * h, capi.CONV2D_BIAS_RELU, cd, None, None))
+        out["conv2d_tc_{}_relu_{}to{}".format(tag, 2 * h, 2 * h)] = {"ms": ms, "bytes": px * 4 * h, "gbs": px * 4 * h / ms / 1e6,
+                                                                     "flops": 18.0 * B * Hs * Ws * 4 * h * h, "tflops": 18.0 * B * Hs * Ws * 4 * h * h / ms / 1e9}
+        ms = timed(lambda: ops.conv2d_tc(hx, None, pk_full, bias2, 2 * h, capi.CONV2D_GRU_GATES, rh, hx[:, :h], z))
+        out["conv2d_tc_{}_gru_gates_{}to{}".format(tag, 2 * h, 2 * h)] = {"ms": ms, "bytes": px * 5 * h, "gbs": px * 5 * h / ms / 1e6}
+        ms = timed(lambda: ops.conv2d_tc(rh, hx[:, h:], pk_half, bias1, h, capi.CONV2D_GRU_UPDATE, hx[:, :h], z, None))
+        out["conv2d_tc_{}_gru_update_{}to{}".format(tag, 2 * h, h)] = {"ms": ms, "bytes": px * 5 * h, "gbs": px * 5 * h / ms / 1e6}
     dom = out["warp_corr_agg_stage3"]
     roof = {"kernel": "warp_corr_tile_kernel<8,1> (stage 3, 800x592, D=8, 4 source views)", "bound": "hbm",
             "achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak, "traffic": ncu_traffic("stage3"),
@@ -385,6 +405,11 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
     reg_fl = out["costreg_fpn3d"]["flops"] + 2 * out["cost_up_small_stage2"]["flops"] + 2 * out["cost_up_small_stage3"]["flops"]
     roof_reg = {"kernel": "3-D regularization (costreg_fpn3d + 4x cost_up_small)", "bound": "tensor", "achieved": reg_fl / reg_ms / 1e9,
                 "peak": tf_peak, "unit": "TFLOP/s", "frac": reg_fl / reg_ms / 1e9 / tf_peak, "flops": reg_fl, "ms": reg_ms}
+    c2 = out.get("conv2d_tc_stage3_relu_32to32")
+    if c2:
+        out["roofline_update_block"] = {"kernel": "conv2d_tc_kernel (stage 3, 800x592, 32 -> 32 + bias + relu)", "bound": "hbm", "achieved": c2["gbs"],
+                                        "peak": hbm_peak, "unit": "GB/s", "frac": c2["gbs"] / hbm_peak, "algorithmic_bytes": c2["bytes"],
+                                        "ms": c2["ms"], "tflops": c2["tflops"], "peak_source": peak_src}
     return roof, roof_reg, out
 
 

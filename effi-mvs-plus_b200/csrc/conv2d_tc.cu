@@ -717,7 +717,9 @@ extern "C" int effimvs_conv2d_tf32(const float* in0, long long in0_ps, int c0, c
     // rows per unit: about one unit per CTA, at least 4 rows (each unit re-reads two halo rows)
     int chunks = std::max(1, (G + B * P.strips / 2) / (B * P.strips));
     if (const char* e = getenv("EFFIMVS_CONV2D_ROWS")) chunks = ceil_div(H, std::max(1, atoi(e)));
-    P.R = std::max(std::min(4, H), ceil_div(H, chunks));
+    int min_rows = 4;
+    if (const char* e = getenv("EFFIMVS_CONV2D_MINROWS")) min_rows = std::max(1, atoi(e));
+    P.R = std::max(std::min(min_rows, H), ceil_div(H, chunks));
     P.chunks = ceil_div(H, P.R);
     P.n_units = B * P.strips * P.chunks;
 
