@@ -155,3 +155,33 @@ def test_documents_name_only_declared_entry_points():
                 continue
             # shorthand like `effimvs_*_ex` / `effimvs_*_workspace_bytes` is written with a star and never matches; `_conv_f32` style suffixes neither
             assert name in declared or any(d.startswith(name) for d in declared), "{} names {} which the header does not declare".format(doc, name)
+
+
+def test_conv2d_entry_points_validate_on_the_host():
+    """effimvs_conv2d_tf32*: shape support, packed size and argument checks are host-side (nothing is launched)"""
+    lib = capi.lib
+    sup = lib.effimvs_conv2d_tf32_supported
+    # the layers of the three update blocks (hidden 16 / 32 / 48): 2h -> 2h, 2h -> h, h -> h, h -> 2h
+    for h in (16, 32, 48):
+        for cin, cout in ((2 * h, 2 * h), (2 * h, h), (h, h), (h, 2 * h)):
+            assert sup(cin, cout) == 1, (cin, cout)
+            assert lib.effimvs_conv2d_tf32_packed_bytes(cin, cout) == 18 * cin * ((cout + 15) // 16 * 16)
+    assert sup(12, 16) == 0 and sup(16, 6) == 0 and sup(256, 256) == 0 and sup(16, 12) == 1
+    assert lib.effimvs_conv2d_tf32_packed_bytes(0, 16) == 0
+    P = ctypes.c_void_p
+    a = P(1 << 20)                                     # 32-byte aligned dummy addresses; every call below fails before a launch
+    mode = capi.CONV2D_BIAS
+    assert lib.effimvs_conv2d_tf32(None, 32, 32, None, 0, 0, a, None, 32, 1, 8, 8, mode, a, 32, None, 0, None, 0, None) == capi.EINVAL
+    assert lib.effimvs_conv2d_tf32(a, 32, 32, None, 0, 0, a, None, 32, 1, 1, 8, mode, a, 32, None, 0, None, 0, None) == capi.EINVAL      # H < 2
+    assert lib.effimvs_conv2d_tf32(a, 32, 12, None, 0, 0, a, None, 32, 1, 8, 8, mode, a, 32, None, 0, None, 0, None) == capi.EINVAL      # segment % 8
+    assert lib.effimvs_conv2d_tf32(a, 32, 24, None, 0, 0, a, None, 32, 1, 8, 8, mode, a, 32, None, 0, None, 0, None) == capi.EUNSUPPORTED  # cin % 16
+    assert lib.effimvs_conv2d_tf32(P((1 << 20) + 16), 32, 32, None, 0, 0, a, None, 32, 1, 8, 8, mode, a, 32, None, 0, None, 0, None) == capi.EINVAL
+    assert "32-byte aligned" in capi.last_error()
+    assert lib.effimvs_conv2d_tf32(a, 32, 32, None, 0, 0, a, None, 32, 1, 8, 8, 9, a, 32, None, 0, None, 0, None) == capi.EINVAL        # mode
+    assert lib.effimvs_conv2d_tf32(a, 32, 32, None, 0, 0, a, None, 32, 1, 8, 8, capi.CONV2D_ADD_RELU, a, 32, None, 0, None, 0, None) == capi.EINVAL
+    assert "addend" in capi.last_error()
+    assert lib.effimvs_conv2d_tf32(a, 32, 32, None, 0, 0, a, None, 32, 1, 8, 8, capi.CONV2D_GRU_GATES, a, 16, a, 16, None, 0, None) == capi.EINVAL
+    assert lib.effimvs_conv2d_tf32_pack(None, 16, 16, a, None) == capi.EINVAL
+    assert lib.effimvs_conv2d_tf32_pack(a, 12, 16, a, None) == capi.EUNSUPPORTED
+    with pytest.raises(RuntimeError):
+        ops.conv2d_tc(torch.zeros(1, 16, 4, 4), None, torch.zeros(10), None, 16, mode, torch.zeros(1, 16, 4, 4), None, None)

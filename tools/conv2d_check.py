@@ -4,7 +4,11 @@ Reference for correctness: weights and activations rounded to IEEE half as the p
 them, convolved in fp64 -- products of such numbers are exact in fp32, so only the accumulation order differs and the
 bar is 5e-6 of max|ref|.  Timing: CUDA events around graph-free launches, L2 flushed, against cuDNN (TF32 allowed).
 
-    python tools/conv2d_check.py [quick]
+    python tools/conv2d_check.py [quick | case N | probe | scale | rows | timeline]
+
+probe / scale / rows time the kernel with parts switched off (EFFIMVS_CONV2D_DEBUG bits) and over CTA / row counts; timeline
+prints clock64 stamps of CTA 0's three roles and needs a library built with -DEFFIMVS_CONV2D_TIMELINE (the stamps are
+compiled out of the shipped kernel).
 """
 import os
 import sys
