@@ -107,7 +107,7 @@ __device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
     return done;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         if (mbar_try(bar, parity)) return;
         if (spin > 4) __nanosleep(32);
     }
@@ -118,7 +118,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // so that the compiler sees warp-uniform control flow after the wait.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
     const bool poller = (threadIdx.x & 31) == 0;
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
         const uint32_t done = poller ? mbar_try(bar, parity) : 0u;
         if (__any_sync(0xffffffffu, done)) return;
         if (spin > 4) __nanosleep(32);
