@@ -76,7 +76,7 @@ struct C2Params {
     int gw;                                      // producer warps per group (2 groups): 4 (416-thread CTA) or 2 (288 threads, three CTAs per SM)
     int ring;                                    // accumulator slots in use: the fewer wrap-arounds, the fewer split MMAs
     long long* tl;                               // profiling: timeline buffer [3 roles][64 steps][4 events] of clock64, written by CTA 0
-    int debug;                                   // EFFIMVS_CONV2D_DEBUG bits (profiling only, results wrong): 1 no MMAs, 2 no operand loads, 4 no epilogue body, 8 no TMEM reads,
+    int debug;                                   // EFFIMVS_CONV2D_DEBUG bits (builds with -DEFFIMVS_CONV2D_PROFILING only; results wrong): 1 no MMAs, 2 no operand loads, 4 no epilogue body, 8 no TMEM reads,
                                                  // 16 producers do not wait for free stages, 32 plain arrives instead of tcgen05.commit, 64 epilogue = wait + arrive
 };
 
@@ -297,24 +297,11 @@ __device__ __forceinline__ void epilogue_rows_m(const C2Params& P, const uint8_t
         }
     }
 }
-template <int CPP>
+template <int CPP, int MODE>
 __device__ __forceinline__ void epilogue_rows(const C2Params& P, const uint8_t* __restrict__ ebuf, const float* __restrict__ sbias, int lane,
                                               int cb, int h, long long rowpix, int xw0, int W) {
-    const bool full = xw0 + 32 <= W;
-#define C2_EPI_CASE(M)                                                                                          \
-    case M:                                                                                                     \
-        if (full) epilogue_rows_m<CPP, M, true>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);                   \
-        else epilogue_rows_m<CPP, M, false>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);                       \
-        break;
-    switch (P.mode) {
-        C2_EPI_CASE(EFFIMVS_CONV2D_BIAS)
-        C2_EPI_CASE(EFFIMVS_CONV2D_BIAS_RELU)
-        C2_EPI_CASE(EFFIMVS_CONV2D_ADD_RELU)
-        C2_EPI_CASE(EFFIMVS_CONV2D_GRU_GATES)
-        default:
-        C2_EPI_CASE(EFFIMVS_CONV2D_GRU_UPDATE)
-    }
-#undef C2_EPI_CASE
+    if (xw0 + 32 <= W) epilogue_rows_m<CPP, MODE, true>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);
+    else epilogue_rows_m<CPP, MODE, false>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);
 }
 
 struct Unit { int b, y0, y1, x0; };
@@ -330,8 +317,18 @@ __device__ __forceinline__ Unit unit_of(const C2Params& P, int u) {
     return t;
 }
 
+// One instantiation per (epilogue mode, channel groups of a K phase): every role of the kernel is a single-warp chain whose speed
+// is its instruction count, and three CTAs x three roles share the SM's instruction cache -- a run-time mode switch, a generic item
+// mapping and the profiling switches of the first version cost measurably (see DESIGN, appendix A), so they are compile-time here.
+template <int MODE, int GROUPS>
 __global__ void __launch_bounds__(C2_THREADS, 2)
 conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__ wpk) {
+#ifdef EFFIMVS_CONV2D_PROFILING
+    const int dbg = dbg;             // EFFIMVS_CONV2D_DEBUG switches (tools/conv2d_check.py probe / scale / rows) only in profiling builds
+#else
+    constexpr int dbg = 0;
+#endif
+    constexpr int KC = GROUPS * 8;       // channels per K phase
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_afull[C2_STAGES], bar_aempty[C2_STAGES], bar_tfull[C2_RING], bar_tempty[C2_RING], bar_w;
     __shared__ uint32_t tmem_base_s;
@@ -369,7 +366,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
             bulk_g2s(wsm, wpk, (uint32_t)P.w_bytes, &bar_w);
         }
         const int S = P.n_stages;
-        const int groups = P.kc >> 3;                                  // 16-byte channel groups per phase: 2, 4 or 8
+        constexpr int groups = GROUPS;                                 // 16-byte channel groups per phase: 2, 4 or 8
         // groups >= 4: an item = 8 pixels x 4 groups (a pixel's 32 channels = 128 contiguous bytes); groups == 2: 16 pixels x 2 groups
         const int pxl = groups >= 4 ? (lane & 7) : (lane & 15), cgl0 = groups >= 4 ? (lane >> 3) : (lane >> 4);
         const int px_per_item = groups >= 4 ? 8 : 16, px_items = (C2_ROWPX + px_per_item - 1) / px_per_item;
@@ -390,7 +387,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                     uint8_t* dst = astage + (size_t)s * P.stage_bytes;
                     const float* r0 = P.in0 + rowpix * P.ps0;          // (pixel 0 of the row, channel 0) of the two segments
                     const float* r1 = P.in1 + rowpix * P.ps1 - P.c0;
-                    const int ch0 = p * P.kc + cgl0 * 8, xb = t.x0 - 1 + pxl;
+                    const int ch0 = p * KC + cgl0 * 8, xb = t.x0 - 1 + pxl;
                     for (int it0 = pwg; it0 < n_items; it0 += 5 * P.gw) {
                         F8 v[5];
                         uint32_t off[5];
@@ -399,7 +396,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                             const int it = it0 + P.gw * k;
                             v[k].a = v[k].b = v[k].c = v[k].d = 0ull;
                             off[k] = 0xffffffffu;
-                            if (it < n_items && !(P.debug & 2)) {
+                            if (it < n_items && !(dbg & 2)) {
                                 const int cgq = it >= px_items ? 1 : 0, g = it - (cgq ? px_items : 0);   // n_items <= 2 px_items
                                 const int pxo = g * px_per_item, px = pxo + pxl, x = xb + pxo;
                                 if (px < C2_ROWPX) off[k] = (uint32_t)((cgq * 4 + cgl0) * C2_CG_BYTES + px * 16);
@@ -418,11 +415,11 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                             }
                         }
                     }
-                    if (P.debug & 512) {
+                    if (dbg & 512) {
                         __syncwarp();
                         if (lane == 0) { fence_async_smem(); mbar_arrive(&bar_afull[s]); }
                     } else {
-                        if (!(P.debug & 256)) fence_async_smem();           // generic-proxy stores -> visible to the tensor core's async proxy
+                        if (!(dbg & 256)) fence_async_smem();           // generic-proxy stores -> visible to the tensor core's async proxy
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_afull[s]);
                     }
@@ -442,9 +439,9 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
             const uint32_t coutp = (uint32_t)P.coutp;
             const uint32_t blk16 = (96u * coutp) >> 4;                // a packed weight block [2 K halves][3 coutp rows][16 B] in 16-byte units
             const uint64_t bdesc0 = umma_desc(smem_u32(wsm), 3u * coutp * 16u, 128);
-            const int ksteps = P.kc >> 4;
+            constexpr int ksteps = KC >> 4;
             const bool two_max = 3 * P.coutp > 256;                   // an MMA spans at most two of the three stacked row blocks
-            const bool mma_on = !(P.debug & 1);
+            const bool mma_on = !(dbg & 1);
             const uint32_t rm = (uint32_t)P.ring - 1u, rs = (uint32_t)__ffs(P.ring) - 1u;
             mbar_wait_warp(&bar_w, 0);
             __syncwarp();
@@ -480,7 +477,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                         const uint32_t s = fill % S, n = fill / S;
                         mbar_wait_warp(&bar_afull[s], n & 1);
                         if (leader) C2_TL(1, fill, 1);
-                        if (!(P.debug & 2048)) tc_fence_after();
+                        if (!(dbg & 2048)) tc_fence_after();
                         const uint64_t adesc0 = umma_desc(smem_u32(astage + (size_t)s * P.stage_bytes), C2_CG_BYTES, 128);
                         uint64_t bstep = bdesc0 + (uint64_t)((uint32_t)(p * ksteps * 3) * blk16);
                         if (leader && mma_on) {
@@ -506,14 +503,14 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                         }
                         if (leader) {
                             C2_TL(1, fill, 2);
-                            if (P.debug & 32) mbar_arrive(&bar_aempty[s]);
+                            if (dbg & 32) mbar_arrive(&bar_aempty[s]);
                             else umma_commit(&bar_aempty[s]);                 // stage reusable once these MMAs retire
                             C2_TL(1, fill, 3);
                         }
                         __syncwarp();
                     }
                     if (!leader) {
-                    } else if (P.debug & 32) {
+                    } else if (dbg & 32) {
                         if (i - 1 >= t.y0 && i - 1 < t.y1) mbar_arrive(&bar_tfull[(seq_base + (uint32_t)(i - 1 - t.y0)) & rm]);
                         if (i == H - 1 && i < t.y1) mbar_arrive(&bar_tfull[(seq_base + (uint32_t)(i - t.y0)) & rm]);
                     } else {
@@ -533,7 +530,7 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
         // every global access of the epilogue -- the stores and the aux maps of the fused modes -- then covers full 128-byte lines.
         uint8_t* ebuf = astage + (size_t)P.n_stages * P.stage_bytes + (size_t)warp * (32 * C2_EPI_STRIDE);
         uint32_t seq = 0;
-        const int h = P.mode == EFFIMVS_CONV2D_GRU_GATES ? P.cout / 2 : P.cout;
+        const int h = MODE == EFFIMVS_CONV2D_GRU_GATES ? P.cout / 2 : P.cout;
         for (int u = blockIdx.x; u < P.n_units; u += gridDim.x) {
             const Unit t = unit_of(P, u);
             const int xw0 = t.x0 + warp * 32;
@@ -543,10 +540,10 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                 if (tid == 0) C2_TL(2, seq, 0);
                 // the aux maps of the fused modes are read once the accumulators arrive: ask for their lines now (a lane per
                 // pixel: 32 pixels x h channels of this warp), so that the reads in epilogue_rows hit L1 instead of waiting on L2
-                if (P.mode >= EFFIMVS_CONV2D_ADD_RELU && xw0 + lane < W && !(P.debug & 4096)) {
+                if (MODE >= EFFIMVS_CONV2D_ADD_RELU && xw0 + lane < W && !(dbg & 4096)) {
                     const float* a0 = P.aux0 + (rowpix + xw0 + lane) * P.aux0_ps;
                     for (int c = 0; c < h; c += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + c));
-                    if (P.mode == EFFIMVS_CONV2D_GRU_UPDATE) {
+                    if (MODE == EFFIMVS_CONV2D_GRU_UPDATE) {
                         const float* o0 = P.out + (rowpix + xw0 + lane) * P.out_ps;
                         for (int c = 0; c < h; c += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(o0 + c));
                     }
@@ -554,9 +551,9 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                 if (lane == 0) mbar_wait(&bar_tfull[slot], (seq >> (__ffs(P.ring) - 1)) & 1u);
                 __syncwarp();
                 if (tid == 0) C2_TL(2, seq, 1);
-                if (!(P.debug & 1024)) tc_fence_after();
+                if (!(dbg & 1024)) tc_fence_after();
                 const uint32_t lane_base = tmem + slot * (uint32_t)P.coutp + ((uint32_t)(warp * 32) << 16);
-                if (P.debug & 64) {
+                if (dbg & 64) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_tempty[slot]);
                     continue;
@@ -567,26 +564,26 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
                         float4* mine = reinterpret_cast<float4*>(ebuf + lane * C2_EPI_STRIDE);
                         if (ncol == 32) {
                             float v[32];
-                            if (!(P.debug & 8)) tmem_ld32(lane_base + (uint32_t)cb, v);
+                            if (!(dbg & 8)) tmem_ld32(lane_base + (uint32_t)cb, v);
                             else for (int q = 0; q < 32; ++q) v[q] = 0.0f;
 #pragma unroll
                             for (int q = 0; q < 8; ++q) mine[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                         } else {
                             float v[16];
-                            if (!(P.debug & 8)) tmem_ld16(lane_base + (uint32_t)cb, v);
+                            if (!(dbg & 8)) tmem_ld16(lane_base + (uint32_t)cb, v);
                             else for (int q = 0; q < 16; ++q) v[q] = 0.0f;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) mine[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
                         }
                     }
                     const bool last = cb + 32 >= P.coutp;
-                    if (last && !(P.debug & 1024)) tc_fence_before();
+                    if (last && !(dbg & 1024)) tc_fence_before();
                     __syncwarp();
                     if (last && lane == 0) mbar_arrive(&bar_tempty[slot]);     // last TMEM read of this row: the slot goes back to the MMA warp
                     if (last && tid == 0) C2_TL(2, seq, 2);
-                    if (!(P.debug & 4)) {
-                        if (ncol == 32) epilogue_rows<8>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);
-                        else epilogue_rows<4>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);
+                    if (!(dbg & 4)) {
+                        if (ncol == 32) epilogue_rows<8, MODE>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);
+                        else epilogue_rows<4, MODE>(P, ebuf, sbias, lane, cb, h, rowpix, xw0, W);
                     }
                     __syncwarp();      // the buffer is rewritten by the next chunk / row
                 }
@@ -723,14 +720,21 @@ extern "C" int effimvs_conv2d_tf32(const float* in0, long long in0_ps, int c0, c
     P.chunks = ceil_div(H, P.R);
     P.n_units = B * P.strips * P.chunks;
 
-    static bool attr_set[64] = {};   // per device; idempotent, a race only repeats the call
+    typedef void (*KernelFn)(C2Params, const uint8_t*);
+#define C2_ROW(M) {conv2d_tc_kernel<M, 2>, conv2d_tc_kernel<M, 4>, conv2d_tc_kernel<M, 8>}
+    static const KernelFn table[5][3] = {C2_ROW(EFFIMVS_CONV2D_BIAS), C2_ROW(EFFIMVS_CONV2D_BIAS_RELU), C2_ROW(EFFIMVS_CONV2D_ADD_RELU),
+                                         C2_ROW(EFFIMVS_CONV2D_GRU_GATES), C2_ROW(EFFIMVS_CONV2D_GRU_UPDATE)};
+#undef C2_ROW
+    const int gi = P.kc == 16 ? 0 : (P.kc == 32 ? 1 : 2);
+    const KernelFn fn = table[mode][gi];
+    static bool attr_set[64][5][3] = {};   // per device and instantiation; idempotent, a race only repeats the call
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(conv2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (dev < 0 || dev >= 64 || !attr_set[dev][mode][gi]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         EFFI_REQUIRE(e == cudaSuccess, EFFIMVS_ECUDA, "conv2d_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        if (dev >= 0 && dev < 64) attr_set[dev][mode][gi] = true;
     }
-    conv2d_tc_kernel<<<std::min(G, P.n_units), (C2_PROD_WARP0 + C2_PROD_GROUPS * P.gw) * 32, smem, (cudaStream_t)stream>>>(P, (const uint8_t*)packed);
+    fn<<<std::min(G, P.n_units), (C2_PROD_WARP0 + C2_PROD_GROUPS * P.gw) * 32, smem, (cudaStream_t)stream>>>(P, (const uint8_t*)packed);
     return check_launch("conv2d_tc_kernel");
 }

@@ -7,8 +7,8 @@ bar is 5e-6 of max|ref|.  Timing: CUDA events around graph-free launches, L2 flu
     python tools/conv2d_check.py [quick | case N | probe | scale | rows | timeline]
 
 probe / scale / rows time the kernel with parts switched off (EFFIMVS_CONV2D_DEBUG bits) and over CTA / row counts; timeline
-prints clock64 stamps of CTA 0's three roles and needs a library built with -DEFFIMVS_CONV2D_TIMELINE (the stamps are
-compiled out of the shipped kernel).
+prints clock64 stamps of CTA 0's three roles.  The switches and the stamps are compiled out of the shipped kernel: build a
+profiling library with -DEFFIMVS_CONV2D_PROFILING -DEFFIMVS_CONV2D_TIMELINE and point EFFIMVS_LIB at it.
 """
 import os
 import sys
