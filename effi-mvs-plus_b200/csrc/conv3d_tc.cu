@@ -184,6 +184,19 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// two 8-column reads (the x_hi * w_hi and x_hi * w_lo halves of a hi/lo accumulator) in flight together, one wait
+__device__ __forceinline__ void tmem_ld8x2(uint32_t taddr0, uint32_t taddr1, float (&v)[8], float (&w)[8]) {
+    uint32_t r[8], q[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr0));
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+                 : "r"(taddr1));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -252,7 +265,8 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2], bar_w;
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index through a shuffle: the compiler then knows the role branches are warp-uniform (uniform-datapath operands for tcgen05.mma)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     uint8_t* wsm = smem;                              // all phases' weights, resident for the CTA's lifetime
     uint8_t* slab = smem + P.w_smem_bytes;            // n_stages slabs of slab_bytes
     const int S = P.n_stages;
@@ -367,12 +381,13 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
                     else if (P.n_classes == 4) { py = cls >> 1; px = cls & 1; }
                     const int oz = z * P.up_z + pz, oy = gy * P.up_y + py, ox = gx * P.up_x + px;
                     float v[8];
-                    tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + g * 8), v);
                     if (P.b_rows != P.N) {   // hi/lo mode: columns [N, 2N) hold x_hi * w_lo
                         float w2[8];
-                        tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + P.N + g * 8), w2);
+                        tmem_ld8x2(lane_base + (uint32_t)(cls * P.b_rows + g * 8), lane_base + (uint32_t)(cls * P.b_rows + P.N + g * 8), v, w2);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] += w2[j];
+                    } else {
+                        tmem_ld8(lane_base + (uint32_t)(cls * P.b_rows + g * 8), v);
                     }
                     if (cls == P.n_classes - 1 && g == groups - 1) {
                         // last TMEM read of this tile: hand the accumulator stage back to the MMA warp
