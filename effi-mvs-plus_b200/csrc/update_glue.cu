@@ -356,11 +356,15 @@ constexpr int EH_TX = 32, EH_R = 3, EH_PX = 2;   // a thread owns EH_PX horizont
 
 // EH_TY: rows of a block's tile.  4 by default: 64 x 8 tiles leave SMs idle on the small stages (200 x 148 is 76 such tiles)
 // and at two 256-thread blocks per SM (126 registers) the tail wave of the large one costs more than the extra halo reads.
-template <int EH_TY>
+// HT: the hidden size as a compile-time constant (16 / 32; 0 = run-time h), so that the 49 x h / 4 weight reads of the unrolled window
+// loop are shared-memory loads at immediate offsets; with h = 16 the channel loop is a single pass and the kernel needs 72 registers
+// instead of 127 (stage 3: 57 -> 47 us).  Measured no gain for 32 and a loss for 48, which stays on the run-time form.
+template <int EH_TY, int HT>
 __global__ void __launch_bounds__(EH_TX * EH_TY)
 encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restrict__ inv, const float* __restrict__ wc1,
-                    const float* __restrict__ bc1, const float* __restrict__ wd1, const float* __restrict__ bd1, int h, int H, int W,
+                    const float* __restrict__ bc1, const float* __restrict__ wd1, const float* __restrict__ bd1, int h_rt, int H, int W,
                     float* __restrict__ out) {
+    const int h = HT ? HT : h_rt;
     extern __shared__ __align__(16) float esm[];
     float* s_wd = esm;                       // [49][h]   tap-major, channels contiguous
     float* s_wc = s_wd + 49 * h;             // [CD][h]
@@ -471,10 +475,11 @@ extern "C" int effimvs_encoder_head_f32(const float* cost, const float* inv, con
     const int ty = force_ty == 8 ? 8 : 4;   // measured per DTU depth map (9 launches): 64 x 4 tiles 6.65 ms, 64 x 8 tiles 6.70 ms
     dim3 block(effimvs::EH_TX, ty), grid(tiles_x, effimvs::ceil_div(H, ty), B);
     const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX * effimvs::EH_PX + 6) * (ty + 6)) * sizeof(float);
-    if (ty == 4)
-        effimvs::encoder_head_kernel<4><<<grid, block, smem, (cudaStream_t)stream>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else
-        effimvs::encoder_head_kernel<8><<<grid, block, smem, (cudaStream_t)stream>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ty == 8) effimvs::encoder_head_kernel<8, 0><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 16) effimvs::encoder_head_kernel<4, 16><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 32) effimvs::encoder_head_kernel<4, 32><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else effimvs::encoder_head_kernel<4, 0><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
     return effimvs::check_launch("encoder_head_kernel");
 }
 
