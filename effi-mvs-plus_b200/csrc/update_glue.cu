@@ -358,9 +358,12 @@ constexpr int EH_TX = 32, EH_R = 3, EH_PX = 2;   // a thread owns EH_PX horizont
 // and at two 256-thread blocks per SM (126 registers) the tail wave of the large one costs more than the extra halo reads.
 // HT: the hidden size as a compile-time constant (16 / 32; 0 = run-time h), so that the 49 x h / 4 weight reads of the unrolled window
 // loop are shared-memory loads at immediate offsets; with h = 16 the channel loop is a single pass and the kernel needs 72 registers
-// instead of 127 (stage 3: 57 -> 47 us).  Measured no gain for 32 and a loss for 48, which stays on the run-time form.
-template <int EH_TY, int HT>
-__global__ void __launch_bounds__(EH_TX * EH_TY)
+// instead of 127 (stage 3: 57 -> 47 us).  Measured no gain for 32 (neither as a constant nor with its two chunks spread over
+// threadIdx.z: 31.7 / 34.8 us); 48 takes the z form (23.5 -> 20.4 us).
+// ZC: the 16-channel chunks of the hidden size are spread over threadIdx.z (block = 32 x EH_TY x h / 16 threads) instead of being a loop
+// of one thread: the same 72 registers for every h, h / 16 times the warps to hide the broadcast-load latency.
+template <int EH_TY, int HT, bool ZC>
+__global__ void __launch_bounds__(EH_TX * EH_TY * (ZC ? (HT ? HT / 16 : 1) : 1))
 encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restrict__ inv, const float* __restrict__ wc1,
                     const float* __restrict__ bc1, const float* __restrict__ wd1, const float* __restrict__ bd1, int h_rt, int H, int W,
                     float* __restrict__ out) {
@@ -371,7 +374,7 @@ encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restr
     float* s_b = s_wc + CD * h;              // [2h]      convc1 bias, convd1 bias
     float* s_inv = s_b + 2 * h;              // [EH_TY + 6][EH_TX * EH_PX + 6]
     constexpr int TWP = EH_TX * EH_PX, SW = TWP + 2 * EH_R, SH = EH_TY + 2 * EH_R;
-    const int tid = threadIdx.y * EH_TX + threadIdx.x, nt = EH_TX * EH_TY;
+    const int tid = (threadIdx.z * EH_TY + threadIdx.y) * EH_TX + threadIdx.x, nt = EH_TX * EH_TY * blockDim.z;
     const int b = blockIdx.z;
     for (int i = tid; i < 49 * h; i += nt) s_wd[i] = wd1[(i % h) * 49 + i / h];
     for (int i = tid; i < CD * h; i += nt) s_wc[i] = wc1[(i % h) * CD + i / h];
@@ -395,7 +398,7 @@ encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restr
     for (int p = 0; p < EH_PX; ++p)
 #pragma unroll
         for (int c = 0; c < 8; ++c) cv[p][c] = (c < CD && has[p]) ? __ldg(cost + (((size_t)b * CD + c) * H + y) * W + x + p) : 0.0f;
-    for (int ch = 0; ch < h; ch += 16) {
+    for (int ch = ZC ? threadIdx.z * 16 : 0; ch < (ZC ? threadIdx.z * 16 + 16 : h); ch += 16) {
         float acc[EH_PX][16];
 #pragma unroll
         for (int p = 0; p < EH_PX; ++p)
@@ -426,7 +429,7 @@ encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restr
     }
     // relu(convd1(inv) + b): 7x7, zero padding 3; the two pixels of a thread share a row of 8 window values
     const float* win = s_inv + threadIdx.y * SW + threadIdx.x * EH_PX;
-    for (int ch = 0; ch < h; ch += 16) {
+    for (int ch = ZC ? threadIdx.z * 16 : 0; ch < (ZC ? threadIdx.z * 16 + 16 : h); ch += 16) {
         float acc[EH_PX][16];
 #pragma unroll
         for (int p = 0; p < EH_PX; ++p)
@@ -476,10 +479,12 @@ extern "C" int effimvs_encoder_head_f32(const float* cost, const float* inv, con
     dim3 block(effimvs::EH_TX, ty), grid(tiles_x, effimvs::ceil_div(H, ty), B);
     const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX * effimvs::EH_PX + 6) * (ty + 6)) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    if (ty == 8) effimvs::encoder_head_kernel<8, 0><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else if (h == 16) effimvs::encoder_head_kernel<4, 16><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else if (h == 32) effimvs::encoder_head_kernel<4, 32><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else effimvs::encoder_head_kernel<4, 0><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    static const int zc = [] { const char* e = getenv("EFFIMVS_EH_ZCHUNKS"); return e ? atoi(e) : 1; }();   // tuning switch
+    if (ty == 8) effimvs::encoder_head_kernel<8, 0, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 16) effimvs::encoder_head_kernel<4, 16, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 48 && zc) effimvs::encoder_head_kernel<4, 48, true><<<grid, dim3(block.x, block.y, 3), smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 32) effimvs::encoder_head_kernel<4, 32, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else effimvs::encoder_head_kernel<4, 0, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
     return effimvs::check_launch("encoder_head_kernel");
 }
 
