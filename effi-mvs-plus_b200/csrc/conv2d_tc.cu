@@ -220,6 +220,24 @@ __device__ __forceinline__ float4 ldg_nc4(const float* p) {
 // longer on them than the tensor pipe spends on the row.
 __device__ __forceinline__ float sigmoid_t(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_t(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// The same two functions on channel pairs with packed fp32 arithmetic (add / mul / fma .f32x2: one issue slot for two lanes of
+// work -- the epilogue warps are instruction bound); the exponentials and reciprocals stay scalar special-function ops.
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk(float lo, float hi) { pk2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk(pk2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ pk2 add2(pk2 a, pk2 b) { pk2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 mul2(pk2 a, pk2 b) { pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 fma2(pk2 a, pk2 b, pk2 c) { pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1 / (1 + 2^(s * x)) per channel of a pair: s = -log2(e) gives sigmoid(x), s = 2 log2(e) gives (1 - tanh(x)) / 2
+__device__ __forceinline__ pk2 inv1pexp2(pk2 x, float s) {
+    float e0, e1;
+    unpk(mul2(x, pk(s, s)), e0, e1);
+    float d0, d1;
+    unpk(add2(pk(ex2f(e0), ex2f(e1)), pk(1.0f, 1.0f)), d0, d1);
+    return pk(rcpf(d0), rcpf(d1));
+}
 
 #ifdef EFFIMVS_CONV2D_TIMELINE   // profiling builds only: clock64 stamps of CTA 0's roles (tools/conv2d_check.py timeline)
 #define C2_TL(role, step, ev) do { if (P.tl && blockIdx.x == 0 && (step) < 64) P.tl[((role) * 64 + (step)) * 4 + (ev)] = clock64(); } while (0)
@@ -282,16 +300,21 @@ __device__ __forceinline__ void epilogue_rows_m(const C2Params& P, const uint8_t
                 w.z = fmaxf(__fadd_rn(a[j].z, d[j].z), 0.0f); w.w = fmaxf(__fadd_rn(a[j].w, d[j].w), 0.0f);
             } else if (MODE == EFFIMVS_CONV2D_GRU_GATES) {
                 // z = sigmoid(z_pre + b_z)  |  sigmoid(r_pre + b_r) * h_prev
-                w.x = sigmoid_t(__fadd_rn(a[j].x, b4.x)); w.y = sigmoid_t(__fadd_rn(a[j].y, b4.y));
-                w.z = sigmoid_t(__fadd_rn(a[j].z, b4.z)); w.w = sigmoid_t(__fadd_rn(a[j].w, b4.w));
-                if (gate_r) { w.x = __fmul_rn(w.x, d[j].x); w.y = __fmul_rn(w.y, d[j].y); w.z = __fmul_rn(w.z, d[j].z); w.w = __fmul_rn(w.w, d[j].w); }
+                pk2 s01 = inv1pexp2(add2(pk(a[j].x, a[j].y), pk(b4.x, b4.y)), -1.4426950408889634f);
+                pk2 s23 = inv1pexp2(add2(pk(a[j].z, a[j].w), pk(b4.z, b4.w)), -1.4426950408889634f);
+                if (gate_r) { s01 = mul2(s01, pk(d[j].x, d[j].y)); s23 = mul2(s23, pk(d[j].z, d[j].w)); }
+                unpk(s01, w.x, w.y);
+                unpk(s23, w.z, w.w);
             } else {
                 // GRU_UPDATE: out = (1 - z) * out + z * tanh(q_pre + b_q), z = d
                 const float4 hq = *reinterpret_cast<const float4*>(op);
-                w.x = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].x), hq.x), __fmul_rn(d[j].x, tanh_t(__fadd_rn(a[j].x, b4.x))));
-                w.y = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].y), hq.y), __fmul_rn(d[j].y, tanh_t(__fadd_rn(a[j].y, b4.y))));
-                w.z = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].z), hq.z), __fmul_rn(d[j].z, tanh_t(__fadd_rn(a[j].z, b4.z))));
-                w.w = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, d[j].w), hq.w), __fmul_rn(d[j].w, tanh_t(__fadd_rn(a[j].w, b4.w))));
+                // tanh(t) = 1 - 2 u with u = 1 / (1 + e^(2t));  h' = (1 - z) h + z tanh(t)
+                const pk2 one = pk(1.0f, 1.0f), m2 = pk(-2.0f, -2.0f), m1 = pk(-1.0f, -1.0f);
+                const pk2 z01 = pk(d[j].x, d[j].y), z23 = pk(d[j].z, d[j].w);
+                const pk2 q01 = fma2(inv1pexp2(add2(pk(a[j].x, a[j].y), pk(b4.x, b4.y)), 2.8853900817779268f), m2, one);
+                const pk2 q23 = fma2(inv1pexp2(add2(pk(a[j].z, a[j].w), pk(b4.z, b4.w)), 2.8853900817779268f), m2, one);
+                unpk(fma2(z01, q01, mul2(fma2(z01, m1, one), pk(hq.x, hq.y))), w.x, w.y);
+                unpk(fma2(z23, q23, mul2(fma2(z23, m1, one), pk(hq.z, hq.w))), w.z, w.w);
             }
             *reinterpret_cast<float4*>(op) = w;
         }
