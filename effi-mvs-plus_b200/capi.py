@@ -73,6 +73,7 @@ SIGNATURES = {
     "effimvs_conv2d_tf32": (_i, [_p, C.c_longlong, _i, _p, C.c_longlong, _i, _p, _p, _i, _i, _i, _i, _i,
                                  _p, C.c_longlong, _p, C.c_longlong, _p, C.c_longlong, _p]),
     "effimvs_gru_init_f32": (_i, [_p, C.c_longlong, _i, _i, _p, _p]),
+    "effimvs_gru_init_ctx_f32": (_i, [_p, C.c_longlong, _i, _i, _p, _p, _p, _p, _p]),
     "effimvs_dtu_filter_f32": (_i, [_p, _p, _p, _p, C.POINTER(C.c_double), C.POINTER(C.c_float), _i, _i, _i, _f, _f, _i, _i, _i,
                                     _p, _p, _p, _p, _p, _p, _p]),
     "effimvs_images_u8_to_f32": (_i, [_p, C.c_longlong, _p, _p]),

@@ -1,5 +1,6 @@
 // Error string, version.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -11,6 +12,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("EFFIMVS_PDL");
+        return e ? atoi(e) != 0 : false;
+    }();
+    return on;
 }
 }  // namespace effimvs
 

@@ -371,10 +371,20 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
         mbar_init(&bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < C2_MAX_COUT) sbias[tid] = (P.bias && tid < P.cout) ? __ldg(P.bias + tid) : 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // the packed weights are a constant of the model (effimvs_conv2d_tf32_pack, once per layer): their copy into shared memory
+    // starts before the programmatic-launch wait, together with the TMEM allocation and barrier set-up above -- the part of
+    // this kernel that overlaps the tail of its predecessor.  Maps and bias are only touched after the wait.
+    if (tid == C2_PROD_WARP0 * 32) {
+        mbar_expect_tx(&bar_w, (uint32_t)P.w_bytes);
+        bulk_g2s(wsm, wpk, (uint32_t)P.w_bytes, &bar_w);
+    }
+    pdl_trigger();
+    pdl_wait();
+    if (tid < C2_MAX_COUT) sbias[tid] = (P.bias && tid < P.cout) ? __ldg(P.bias + tid) : 0.0f;
+    __syncthreads();
     const uint32_t tmem = tmem_base_s;
     const int H = P.H, W = P.W;
 
@@ -384,10 +394,6 @@ conv2d_tc_kernel(const __grid_constant__ C2Params P, const uint8_t* __restrict__
         // shared store, up to 5 items = 10 loads in flight per lane.  The warps form two groups that take alternate fills, so
         // the global-memory round trips of consecutive fills overlap.
         const int pw = warp - C2_PROD_WARP0, grp = pw / P.gw, pwg = pw - grp * P.gw;
-        if (pw == 0 && lane == 0) {
-            mbar_expect_tx(&bar_w, (uint32_t)P.w_bytes);
-            bulk_g2s(wsm, wpk, (uint32_t)P.w_bytes, &bar_w);
-        }
         const int S = P.n_stages;
         constexpr int groups = GROUPS;                                 // 16-byte channel groups per phase: 2, 4 or 8
         // groups >= 4: an item = 8 pixels x 4 groups (a pixel's 32 channels = 128 contiguous bytes); groups == 2: 16 pixels x 2 groups
@@ -758,6 +764,7 @@ extern "C" int effimvs_conv2d_tf32(const float* in0, long long in0_ps, int c0, c
         EFFI_REQUIRE(e == cudaSuccess, EFFIMVS_ECUDA, "conv2d_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         if (dev >= 0 && dev < 64) attr_set[dev][mode][gi] = true;
     }
-    fn<<<std::min(G, P.n_units), (C2_PROD_WARP0 + C2_PROD_GROUPS * P.gw) * 32, smem, (cudaStream_t)stream>>>(P, (const uint8_t*)packed);
+    launch_kernel(fn, dim3(std::min(G, P.n_units)), dim3((C2_PROD_WARP0 + C2_PROD_GROUPS * P.gw) * 32), smem, (cudaStream_t)stream, P,
+                  (const uint8_t*)packed);
     return check_launch("conv2d_tc_kernel");
 }

@@ -285,6 +285,10 @@ conv_tc_kernel(const __grid_constant__ ConvProgram P, const uint4* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
+    // programmatic dependent launch: TMEM allocation and barrier set-up above overlap the predecessor's tail; the packed
+    // weights may have been written by the kernel right before this one (one-call entry points), so they wait as well
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 4) {
         // ---------------- TMA producer ----------------
@@ -519,8 +523,10 @@ __global__ void __launch_bounds__(128)
 conv_cin1_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, int D, int H, int W,
                  const ActLayout OL, int plane, uint4* __restrict__ out) {
     __shared__ __align__(16) float sw[27 * 8 + 8];
-    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];  // [tap][co]
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];  // [tap][co]  (weights: constants, before the wait)
     if (threadIdx.x < 8) sw[216 + threadIdx.x] = bias[threadIdx.x];
+    pdl_wait();
     __syncthreads();
     const int b = blockIdx.y;
     const int Ho = OL.H, Wo = OL.W;
@@ -949,7 +955,7 @@ int run_tile_kernel(const ConvProgram& P, int B, const void* in, const ActLayout
     const int grid = (int)std::min<long long>(n_tiles, (long long)kNumSMs * per_sm);
     ActLayout rl = RL ? *RL : OL;
     if (const char* dbg = getenv("EFFIMVS_TC_DEBUG")) const_cast<ConvProgram&>(P).debug = atoi(dbg);
-    conv_tc_kernel<<<grid, CTA_THREADS, smem, st>>>(P, (const uint4*)in, IL.batch_stride, (const uint8_t*)wpk, bias, OL, (uint4*)out, rl,
+    launch_kernel(conv_tc_kernel, grid, dim3(CTA_THREADS), smem, st, P, (const uint4*)in, IL.batch_stride, (const uint8_t*)wpk, bias, OL, (uint4*)out, rl,
                                                     (const uint4*)res, out_f32, (int)n_tiles, tiles_per_plane);
     return check_launch("conv_tc_kernel");
 }
@@ -958,8 +964,8 @@ int run_cin1(const float* x, const float* w, const float* bias, int B, int D, in
              void* out, cudaStream_t st) {
     size_t work = (size_t)D * OL.H * ((OL.W + CIN1_X - 1) / CIN1_X);
     dim3 grid((unsigned)((work + 127) / 128), B);
-    if (s == 2) conv_cin1_kernel<2><<<grid, 128, 0, st>>>(x, w, bias, D, H, W, OL, plane, (uint4*)out);
-    else conv_cin1_kernel<1><<<grid, 128, 0, st>>>(x, w, bias, D, H, W, OL, plane, (uint4*)out);
+    if (s == 2) launch_kernel(conv_cin1_kernel<2>, grid, dim3(128), 0, st, x, w, bias, D, H, W, OL, plane, (uint4*)out);
+    else launch_kernel(conv_cin1_kernel<1>, grid, dim3(128), 0, st, x, w, bias, D, H, W, OL, plane, (uint4*)out);
     return check_launch("conv_cin1_kernel");
 }
 
@@ -997,7 +1003,9 @@ __global__ void __launch_bounds__(128)
 conv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float* __restrict__ w, const float* __restrict__ bias, int relu,
                   float* __restrict__ out) {
     __shared__ __align__(16) float sw[27 * 8];
+    pdl_trigger();
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];   // [tap][ci]
+    pdl_wait();
     __syncthreads();
     const int b = blockIdx.y, D = IL.D, H = IL.H, W = IL.W;
     const int Wq = (W + COUT1_X - 1) / COUT1_X;
@@ -1052,7 +1060,9 @@ __global__ void __launch_bounds__(128)
 deconv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const float* __restrict__ w, const float* __restrict__ bias, int relu,
                     float* __restrict__ out) {
     __shared__ __align__(16) float sw[27 * 8];
+    pdl_trigger();
     for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) sw[(i % 27) * 8 + i / 27] = w[i];   // w[ci][0][tap] -> [tap][ci]
+    pdl_wait();
     __syncthreads();
     const int b = blockIdx.y, D = IL.D, H = IL.H, W = IL.W;
     const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1099,14 +1109,14 @@ int run_cout1(bool deconv, int B, const void* in, const ActLayout& IL, const flo
     if (deconv) {
         const size_t work = (size_t)IL.D * IL.H * IL.W;
         const dim3 grid((unsigned)((work + 127) / 128), B);
-        if (raw_f32) deconv_cout1_kernel<true><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
-        else deconv_cout1_kernel<false><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+        if (raw_f32) launch_kernel(deconv_cout1_kernel<true>, grid, dim3(128), 0, st, (const uint4*)in, IL, w, bias, relu, out);
+        else launch_kernel(deconv_cout1_kernel<false>, grid, dim3(128), 0, st, (const uint4*)in, IL, w, bias, relu, out);
         return check_launch("deconv_cout1_kernel");
     }
     const size_t work = (size_t)IL.D * IL.H * ((IL.W + COUT1_X - 1) / COUT1_X);
     const dim3 grid((unsigned)((work + 127) / 128), B);
-    if (raw_f32) conv_cout1_kernel<true><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
-    else conv_cout1_kernel<false><<<grid, 128, 0, st>>>((const uint4*)in, IL, w, bias, relu, out);
+    if (raw_f32) launch_kernel(conv_cout1_kernel<true>, grid, dim3(128), 0, st, (const uint4*)in, IL, w, bias, relu, out);
+    else launch_kernel(conv_cout1_kernel<false>, grid, dim3(128), 0, st, (const uint4*)in, IL, w, bias, relu, out);
     return check_launch("conv_cout1_kernel");
 }
 

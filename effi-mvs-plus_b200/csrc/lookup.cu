@@ -59,6 +59,7 @@ __device__ bool invert44(const double A[16], double inv[16]) {
 }
 
 __global__ void relative_projection_kernel(const float* __restrict__ cams, int B, int V, float* __restrict__ proj) {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * (V - 1)) return;
     int b = i / (V - 1), v = i % (V - 1) + 1;
@@ -107,6 +108,7 @@ __device__ __forceinline__ float lookup_1d(const float* __restrict__ vol, int D,
 __global__ void volume_lookup_kernel(const float* __restrict__ volume, const float* __restrict__ sample,
                                      const float* __restrict__ dmin, const float* __restrict__ dmax, int range_mode,
                                      int sstride, int D, int d, int H, int W, float* __restrict__ out) {
+    pdl_enter();
     const int b = blockIdx.z;
     const int HW = H * W;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,6 +142,7 @@ __device__ __forceinline__ float local_hypothesis(float cur_depth, float interva
 // caller works in (upstream passes inverse depth), `interval` (B) -> samples (B,ndepth,H,W), no reciprocal.
 __global__ void range_samples_kernel(const float* __restrict__ cur, const float* __restrict__ interval, int ndepth, int HW,
                                      float* __restrict__ out) {
+    pdl_enter();
     const int b = blockIdx.y;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
@@ -156,6 +159,7 @@ __global__ void dynamic_cost_kernel(const float* __restrict__ cur_depth, const f
                                     const float* __restrict__ reg, const float* __restrict__ interval,
                                     const float* __restrict__ dmin, const float* __restrict__ dmax, int range_mode,
                                     int ndepth, int D, int HW, float* __restrict__ out) {
+    pdl_enter();
     const int b = blockIdx.z;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
@@ -180,6 +184,7 @@ __global__ void dynamic_cost_kernel(const float* __restrict__ cur_depth, const f
 __global__ void softmax_regress_conf_kernel(const float* __restrict__ prob_pre, const float* __restrict__ hyp,
                                             int hyp_mode, int D, int HW, float* __restrict__ depth_out,
                                             float* __restrict__ conf_out) {
+    pdl_enter();
     const int b = blockIdx.y;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
@@ -209,6 +214,7 @@ __global__ void softmax_regress_conf_kernel(const float* __restrict__ prob_pre, 
 // np.array(img, dtype=np.float32) / 255.): an IEEE division, 16 pixels-channels per thread
 __global__ void __launch_bounds__(256)
 images_u8_kernel(const uint8_t* __restrict__ in, size_t n, float* __restrict__ out) {
+    pdl_enter();
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (i + 16 <= n && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
@@ -236,7 +242,7 @@ extern "C" int effimvs_relative_projection_f32(const float* cams, int B, int V, 
     EFFI_REQUIRE(cams && proj_out, EFFIMVS_EINVAL, "relative_projection: null pointer");
     EFFI_REQUIRE(B > 0 && V >= 2, EFFIMVS_EINVAL, "relative_projection: need B > 0 and V >= 2");
     int n = B * (V - 1);
-    relative_projection_kernel<<<ceil_div(n, 32), 32, 0, (cudaStream_t)stream>>>(cams, B, V, proj_out);
+    launch_kernel(relative_projection_kernel, dim3(ceil_div(n, 32)), dim3(32), 0, (cudaStream_t)stream, cams, B, V, proj_out);
     return check_launch("relative_projection_kernel");
 }
 
@@ -248,7 +254,7 @@ extern "C" int effimvs_volume_lookup_f32(const float* volume, const float* depth
     EFFI_REQUIRE(range_mode == 0 || range_mode == 1, EFFIMVS_EINVAL, "volume_lookup: range_mode=%d", range_mode);
     EFFI_REQUIRE(sample_stride == 1 || sample_stride == 2, EFFIMVS_EINVAL, "volume_lookup: sample_stride=%d", sample_stride);
     dim3 block(128), grid(ceil_div(H * W, 128), d < 8 ? d : 8, B);
-    volume_lookup_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(volume, depth_sample, depth_min, depth_max, range_mode,
+    launch_kernel(volume_lookup_kernel, grid, block, 0, (cudaStream_t)stream, volume, depth_sample, depth_min, depth_max, range_mode,
                                                                   sample_stride, D, d, H, W, out);
     return check_launch("volume_lookup_kernel");
 }
@@ -261,7 +267,7 @@ extern "C" int effimvs_dynamic_cost_f32(const float* cur_depth, const float* raw
     EFFI_REQUIRE(B > 0 && D > 1 && ndepth > 1 && H > 0 && W > 0, EFFIMVS_EINVAL, "dynamic_cost: bad sizes");
     EFFI_REQUIRE(range_mode == 0 || range_mode == 1, EFFIMVS_EINVAL, "dynamic_cost: range_mode=%d", range_mode);
     dim3 block(128), grid(ceil_div(H * W, 128), 1, B);
-    dynamic_cost_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(cur_depth, raw_volume, reg_volume, interval, depth_min,
+    launch_kernel(dynamic_cost_kernel, grid, block, 0, (cudaStream_t)stream, cur_depth, raw_volume, reg_volume, interval, depth_min,
                                                                  depth_max, range_mode, ndepth, D, H * W, out);
     return check_launch("dynamic_cost_kernel");
 }
@@ -273,7 +279,7 @@ extern "C" int effimvs_softmax_regress_conf_f32(const float* prob_pre, const flo
     EFFI_REQUIRE(hyp_mode == EFFIMVS_HYP_TENSOR || hyp_mode == EFFIMVS_HYP_PLANES, EFFIMVS_EINVAL,
                  "softmax_regress_conf: hyp_mode=%d", hyp_mode);
     dim3 block(128), grid(ceil_div(H * W, 128), B);
-    softmax_regress_conf_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(prob_pre, hyp, hyp_mode, D, H * W, depth_out, conf_out);
+    launch_kernel(softmax_regress_conf_kernel, grid, block, 0, (cudaStream_t)stream, prob_pre, hyp, hyp_mode, D, H * W, depth_out, conf_out);
     return check_launch("softmax_regress_conf_kernel");
 }
 
@@ -282,7 +288,7 @@ extern "C" int effimvs_depth_range_samples_f32(const float* cur, const float* in
     EFFI_REQUIRE(cur && interval && samples_out, EFFIMVS_EINVAL, "depth_range_samples: null pointer");
     EFFI_REQUIRE(B > 0 && ndepth > 1 && H > 0 && W > 0 && B <= 65535, EFFIMVS_EINVAL, "depth_range_samples: bad sizes");
     dim3 block(128), grid(ceil_div(H * W, 128), B);
-    range_samples_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(cur, interval, ndepth, H * W, samples_out);
+    launch_kernel(range_samples_kernel, grid, block, 0, (cudaStream_t)stream, cur, interval, ndepth, H * W, samples_out);
     return check_launch("range_samples_kernel");
 }
 
@@ -290,6 +296,6 @@ extern "C" int effimvs_images_u8_to_f32(const unsigned char* images, long long n
     EFFI_REQUIRE(images && out, EFFIMVS_EINVAL, "images_u8_to_f32: null pointer");
     EFFI_REQUIRE(n > 0, EFFIMVS_EINVAL, "images_u8_to_f32: n=%lld", n);
     const long long threads = (n + 15) / 16;
-    images_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(images, (size_t)n, out);
+    launch_kernel(images_u8_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, images, (size_t)n, out);
     return check_launch("images_u8_kernel");
 }

@@ -32,6 +32,7 @@ __device__ __forceinline__ float to_depth(float inv, float lo, float hi) {
 __global__ void __launch_bounds__(256)
 gru_reset_kernel(const float4* __restrict__ zr_pre, const float* __restrict__ bias_r, const float4* __restrict__ hx, long long n_pix, int h,
                  int cx, float4* __restrict__ rhx) {
+    pdl_enter();
     const int ct4 = (h + cx) >> 2, h4 = h >> 2;
     const long long total = n_pix * ct4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -60,6 +61,7 @@ __device__ __forceinline__ float gru_mix(float zp, float bz, float qp, float bq,
 __global__ void __launch_bounds__(256)
 gru_update_kernel(const float4* __restrict__ zr_pre, const float* __restrict__ bias_z, const float4* __restrict__ q_pre,
                   const float* __restrict__ bias_q, float4* __restrict__ hx, long long n_pix, int h, int cx, float4* __restrict__ net) {
+    pdl_enter();
     const int ct4 = (h + cx) >> 2, h4 = h >> 2;
     const long long total = n_pix * h4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -82,6 +84,7 @@ gru_update_kernel(const float4* __restrict__ zr_pre, const float* __restrict__ b
 __global__ void __launch_bounds__(256)
 gru_delta_kernel(const float* __restrict__ pre, const float* __restrict__ bias, const float* __restrict__ inv, const float* __restrict__ lo,
                  const float* __restrict__ hi, int HW, float* __restrict__ inv_out, float* __restrict__ depth_out) {
+    pdl_enter();
     const int b = blockIdx.y;
     const float l = __ldg(lo + b), hh = __ldg(hi + b);
     const float bv = pre ? __ldg(bias) : 0.0f;
@@ -106,9 +109,11 @@ convex_upsample_kernel(const float* __restrict__ mask_pre, const float* __restri
     constexpr int CH = 9 * R * R;
     __shared__ float sb[CH];
     extern __shared__ __align__(16) float s_mw[];        // CONV: [K][CH]
+    pdl_trigger();
     for (int i = threadIdx.x; i < CH; i += blockDim.x) sb[i] = mask_bias ? mask_bias[i] : 0.0f;
     if (CONV)
         for (int i = threadIdx.x; i < K * CH; i += blockDim.x) s_mw[i] = mask_w[(i % CH) * K + i / CH];
+    pdl_wait();
     __syncthreads();
     const int b = blockIdx.y;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,7 +201,7 @@ extern "C" int effimvs_gru_reset_f32(const float* zr_pre, const float* bias_r, c
     EFFI_REQUIRE(zr_pre && bias_r && hx && rhx, EFFIMVS_EINVAL, "gru_reset: null pointer");
     EFFI_REQUIRE(n_pix > 0 && h > 0 && cx >= 0 && h % 4 == 0 && cx % 4 == 0, EFFIMVS_EINVAL, "gru_reset: h=%d, cx=%d must be multiples of 4", h, cx);
     const long long work = n_pix * ((h + cx) / 4);
-    gru_reset_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)zr_pre, bias_r, (const float4*)hx, n_pix, h, cx,
+    launch_kernel(gru_reset_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)zr_pre, bias_r, (const float4*)hx, n_pix, h, cx,
                                                                            (float4*)rhx);
     return check_launch("gru_reset_kernel");
 }
@@ -206,7 +211,7 @@ extern "C" int effimvs_gru_update_f32(const float* zr_pre, const float* bias_z, 
     EFFI_REQUIRE(zr_pre && bias_z && q_pre && bias_q && hx && net_out, EFFIMVS_EINVAL, "gru_update: null pointer");
     EFFI_REQUIRE(n_pix > 0 && h > 0 && cx >= 0 && h % 4 == 0 && cx % 4 == 0, EFFIMVS_EINVAL, "gru_update: h=%d, cx=%d must be multiples of 4", h, cx);
     const long long work = n_pix * (h / 4);
-    gru_update_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)zr_pre, bias_z, (const float4*)q_pre, bias_q,
+    launch_kernel(gru_update_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)zr_pre, bias_z, (const float4*)q_pre, bias_q,
                                                                             (float4*)hx, n_pix, h, cx, (float4*)net_out);
     return check_launch("gru_update_kernel");
 }
@@ -216,7 +221,7 @@ extern "C" int effimvs_gru_delta_f32(const float* pre, const float* bias, const 
     EFFI_REQUIRE(inv && lo_disp && hi_disp && depth_out && (!pre || bias), EFFIMVS_EINVAL, "gru_delta: null pointer");
     EFFI_REQUIRE(B > 0 && B <= 65535 && HW > 0, EFFIMVS_EINVAL, "gru_delta: bad sizes");
     dim3 grid(grid_for(HW, 256), B);
-    gru_delta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pre, bias, inv, lo_disp, hi_disp, HW, inv_out, depth_out);
+    launch_kernel(gru_delta_kernel, grid, dim3(256), 0, (cudaStream_t)stream, pre, bias, inv, lo_disp, hi_disp, HW, inv_out, depth_out);
     return check_launch("gru_delta_kernel");
 }
 
@@ -242,7 +247,9 @@ delta_head_kernel(const float4* __restrict__ t, const float* __restrict__ w, con
     constexpr int h = 16 * J, h4 = 4 * J;
     __shared__ float4 s_w[9 * h4];                       // [tap][channel quad]
     float* s_wf = reinterpret_cast<float*>(s_w);
+    pdl_trigger();
     for (int i = threadIdx.x; i < 9 * h; i += blockDim.x) s_wf[i] = w[(i % h) * 9 + i / h];   // weight (1, h, 3, 3)
+    pdl_wait();
     __syncthreads();
     const int q = threadIdx.x & 3;
     const int px = blockIdx.x * DH_COLS + (threadIdx.x >> 2), y0 = blockIdx.y * DH_ROWS, b = blockIdx.z;
@@ -303,7 +310,7 @@ extern "C" int effimvs_delta_head_f32(const float* t, const float* weight, const
     cudaStream_t st = (cudaStream_t)stream;
 #define EFFI_DH_CASE(JJ)                                                                                                     \
     case 16 * JJ:                                                                                                            \
-        delta_head_kernel<JJ><<<grid, 256, 0, st>>>((const float4*)t, weight, bias, inv, lo_disp, hi_disp, H, W, inv_out, depth_out); \
+        launch_kernel(delta_head_kernel<JJ>, grid, dim3(256), 0, st, (const float4*)t, weight, bias, inv, lo_disp, hi_disp, H, W, inv_out, depth_out); \
         break;
     switch (h) {
         EFFI_DH_CASE(1) EFFI_DH_CASE(2) EFFI_DH_CASE(3) EFFI_DH_CASE(4) EFFI_DH_CASE(6) EFFI_DH_CASE(8)
@@ -322,7 +329,7 @@ extern "C" int effimvs_convex_upsample_f32(const float* mask_pre, const float* m
     EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "convex_upsample: bad sizes");
     EFFI_REQUIRE(ratio == 2, EFFIMVS_EUNSUPPORTED, "convex_upsample: ratio=%d (only 2, the value upstream uses, is built)", ratio);
     dim3 grid(ceil_div(H * W, 128), B);
-    convex_upsample_kernel<2, false><<<grid, 128, 0, (cudaStream_t)stream>>>(mask_pre, nullptr, 0, mask_bias, mask_scale, inv, lo_disp, hi_disp,
+    launch_kernel(convex_upsample_kernel<2, false>, grid, dim3(128), 0, (cudaStream_t)stream, mask_pre, nullptr, 0, mask_bias, mask_scale, inv, lo_disp, hi_disp,
                                                                             H, W, up_out, depth_out);
     return check_launch("convex_upsample_kernel");
 }
@@ -336,7 +343,7 @@ extern "C" int effimvs_convex_upsample_conv_f32(const float* t, int K, const flo
     EFFI_REQUIRE(K >= 4 && K % 4 == 0 && K <= 256, EFFIMVS_EUNSUPPORTED, "convex_upsample_conv: K=%d must be a multiple of 4 up to 256", K);
     dim3 grid(ceil_div(H * W, 128), B);
     const size_t smem = (size_t)K * 36 * sizeof(float);
-    convex_upsample_kernel<2, true><<<grid, 128, smem, (cudaStream_t)stream>>>(t, mask_w, K, mask_bias, mask_scale, inv, lo_disp, hi_disp, H, W,
+    launch_kernel(convex_upsample_kernel<2, true>, grid, dim3(128), smem, (cudaStream_t)stream, t, mask_w, K, mask_bias, mask_scale, inv, lo_disp, hi_disp, H, W,
                                                                               up_out, depth_out);
     return check_launch("convex_upsample_kernel");
 }
@@ -376,9 +383,11 @@ encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restr
     constexpr int TWP = EH_TX * EH_PX, SW = TWP + 2 * EH_R, SH = EH_TY + 2 * EH_R;
     const int tid = (threadIdx.z * EH_TY + threadIdx.y) * EH_TX + threadIdx.x, nt = EH_TX * EH_TY * blockDim.z;
     const int b = blockIdx.z;
+    pdl_trigger();       // the weight tables (constants) are staged while the predecessor drains; inv / cost after the wait
     for (int i = tid; i < 49 * h; i += nt) s_wd[i] = wd1[(i % h) * 49 + i / h];
     for (int i = tid; i < CD * h; i += nt) s_wc[i] = wc1[(i % h) * CD + i / h];
     for (int i = tid; i < 2 * h; i += nt) s_b[i] = i < h ? bc1[i] : bd1[i - h];
+    pdl_wait();
     const int x0 = blockIdx.x * TWP - EH_R, y0 = blockIdx.y * EH_TY - EH_R;
     const float* ib = inv + (size_t)b * H * W;
     for (int i = tid; i < SW * SH; i += nt) {
@@ -480,11 +489,11 @@ extern "C" int effimvs_encoder_head_f32(const float* cost, const float* inv, con
     const size_t smem = (size_t)(49 * h + CD * h + 2 * h + (effimvs::EH_TX * effimvs::EH_PX + 6) * (ty + 6)) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
     static const int zc = [] { const char* e = getenv("EFFIMVS_EH_ZCHUNKS"); return e ? atoi(e) : 1; }();   // tuning switch
-    if (ty == 8) effimvs::encoder_head_kernel<8, 0, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else if (h == 16) effimvs::encoder_head_kernel<4, 16, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else if (h == 48 && zc) effimvs::encoder_head_kernel<4, 48, true><<<grid, dim3(block.x, block.y, 3), smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else if (h == 32) effimvs::encoder_head_kernel<4, 32, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
-    else effimvs::encoder_head_kernel<4, 0, false><<<grid, block, smem, st>>>(cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    if (ty == 8) launch_kernel(effimvs::encoder_head_kernel<8, 0, false>, grid, block, smem, st, cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 16) launch_kernel(effimvs::encoder_head_kernel<4, 16, false>, grid, block, smem, st, cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 48 && zc) launch_kernel(effimvs::encoder_head_kernel<4, 48, true>, grid, dim3(block.x, block.y, 3), smem, st, cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else if (h == 32) launch_kernel(effimvs::encoder_head_kernel<4, 32, false>, grid, block, smem, st, cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
+    else launch_kernel(effimvs::encoder_head_kernel<4, 0, false>, grid, block, smem, st, cost, CD, inv, wc1, bc1, wd1, bd1, h, H, W, out);
     return effimvs::check_launch("encoder_head_kernel");
 }
 
@@ -503,7 +512,9 @@ encoder_tail_kernel(const float4* __restrict__ m, const float* __restrict__ w, c
                     int h, float4* __restrict__ hx) {
     extern __shared__ __align__(16) float tsm[];   // [hm][h]: input-major so that 4 outputs are one 128-bit broadcast load
     constexpr int HM = HM4 * 4;
+    pdl_trigger();
     for (int i = threadIdx.x; i < HM * h; i += blockDim.x) tsm[i] = w[(i % h) * HM + i / h];
+    pdl_wait();
     __syncthreads();
     const int h4 = h >> 2;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
@@ -549,9 +560,11 @@ encoder_tail_ctx_kernel(const float4* __restrict__ m, const float* __restrict__ 
     constexpr int HM = HM4 * 4;
     float* tcx = tsm + HM * h;
     float* tb = tcx + cx * h;
+    pdl_trigger();
     for (int i = threadIdx.x; i < HM * h; i += blockDim.x) tsm[i] = w_m[(i % h) * HM + i / h];
     for (int i = threadIdx.x; i < cx * h; i += blockDim.x) tcx[i] = w_ctx[(i % h) * cx + i / h];
     for (int i = threadIdx.x; i < h; i += blockDim.x) tb[i] = bias[i];
+    pdl_wait();
     __syncthreads();
     const int h4 = h >> 2;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
@@ -592,6 +605,7 @@ encoder_tail_ctx_kernel(const float4* __restrict__ m, const float* __restrict__ 
 
 __global__ void __launch_bounds__(256)
 gru_init_kernel(const float4* __restrict__ ctx_map, long long n_pix, int h4, int ct4, float4* __restrict__ hx) {
+    pdl_enter();
     const long long total = n_pix * h4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / h4;
@@ -601,8 +615,58 @@ gru_init_kernel(const float4* __restrict__ ctx_map, long long n_pix, int h4, int
     }
 }
 
+// gru_init + the context half of the encoder's 1x1 output convolution, formed ONCE per stage: ctx_term = w_ctx relu(ctx_map[:, h:]) + bias
+// -- the map the ADD_RELU epilogue of conv2d_tc adds in every GRU iteration.  One pass over the context map instead of relu
+// (a slice copy), a cuDNN 1x1 convolution and its bias add; a thread = (pixel, quad of output channels), the cx context values
+// of a pixel are shared by its h / 4 threads through L1, the weights sit in shared memory as [k][h].
+__global__ void __launch_bounds__(256)
+gru_init_ctx_kernel(const float4* __restrict__ ctx_map, long long n_pix, int h4, int cx4, const float* __restrict__ w_ctx,
+                    const float* __restrict__ bias, float4* __restrict__ hx, float4* __restrict__ ctx_term) {
+    extern __shared__ __align__(16) float gsm[];   // [cx][h] | [h]
+    const int h = h4 * 4, cx = cx4 * 4, ct4 = h4 + cx4;
+    float* tb = gsm + cx * h;
+    pdl_trigger();
+    for (int i = threadIdx.x; i < cx * h; i += blockDim.x) gsm[i] = w_ctx[(i % h) * cx + i / h];   // weight (h, cx) -> [k][o]
+    for (int i = threadIdx.x; i < h; i += blockDim.x) tb[i] = bias[i];
+    pdl_wait();
+    __syncthreads();
+    const long long total = n_pix * h4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / h4;
+        const int c4 = (int)(i - p * h4);
+        const float4 v = __ldg(ctx_map + p * ct4 + c4);
+        hx[p * (2 * h4) + c4] = make_float4(tanhf(v.x), tanhf(v.y), tanhf(v.z), tanhf(v.w));
+        float4 acc = *reinterpret_cast<const float4*>(tb + c4 * 4);
+        for (int k4 = 0; k4 < cx4; ++k4) {
+            const float4 c = __ldg(ctx_map + p * ct4 + h4 + k4);
+            const float cv[4] = {fmaxf(c.x, 0.0f), fmaxf(c.y, 0.0f), fmaxf(c.z, 0.0f), fmaxf(c.w, 0.0f)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 wv = *reinterpret_cast<const float4*>(gsm + (k4 * 4 + j) * h + c4 * 4);
+                acc.x = fmaf(cv[j], wv.x, acc.x); acc.y = fmaf(cv[j], wv.y, acc.y);
+                acc.z = fmaf(cv[j], wv.z, acc.z); acc.w = fmaf(cv[j], wv.w, acc.w);
+            }
+        }
+        ctx_term[i] = acc;
+    }
+}
+
 }  // namespace
 }  // namespace effimvs
+
+extern "C" int effimvs_gru_init_ctx_f32(const float* ctx_map, long long n_pix, int h, int cx, const float* w_ctx, const float* bias,
+                                        float* hx, float* ctx_term, void* stream) {
+    using namespace effimvs;
+    EFFI_REQUIRE(ctx_map && w_ctx && bias && hx && ctx_term, EFFIMVS_EINVAL, "gru_init_ctx: null pointer");
+    EFFI_REQUIRE(n_pix > 0 && h >= 4 && h % 4 == 0 && h <= 128 && cx >= 4 && cx % 4 == 0 && cx <= 64, EFFIMVS_EINVAL,
+                 "gru_init_ctx: h=%d (<= 128), cx=%d (4..64) must be multiples of 4", h, cx);
+    const long long blocks = (n_pix * (h / 4) + 255) / 256;
+    const int grid = (int)(blocks < (long long)kNumSMs * 16 ? blocks : (long long)kNumSMs * 16);
+    const size_t smem = (size_t)(cx * h + h) * sizeof(float);
+    launch_kernel(gru_init_ctx_kernel, grid, dim3(256), smem, (cudaStream_t)stream, (const float4*)ctx_map, n_pix, h / 4, cx / 4, w_ctx, bias,
+                  (float4*)hx, (float4*)ctx_term);
+    return check_launch("gru_init_ctx_kernel");
+}
 
 extern "C" int effimvs_gru_init_f32(const float* ctx_map, long long n_pix, int h, int cx, float* hx, void* stream) {
     using namespace effimvs;
@@ -611,7 +675,7 @@ extern "C" int effimvs_gru_init_f32(const float* ctx_map, long long n_pix, int h
                  "gru_init: h=%d, cx=%d must be multiples of 4", h, cx);
     const long long blocks = (n_pix * (h / 4) + 255) / 256;
     const int grid = (int)(blocks < (long long)kNumSMs * 16 ? blocks : (long long)kNumSMs * 16);
-    gru_init_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)ctx_map, n_pix, h / 4, (h + cx) / 4, (float4*)hx);
+    launch_kernel(gru_init_kernel, grid, dim3(256), 0, (cudaStream_t)stream, (const float4*)ctx_map, n_pix, h / 4, (h + cx) / 4, (float4*)hx);
     return check_launch("gru_init_kernel");
 }
 
@@ -630,7 +694,7 @@ extern "C" int effimvs_encoder_tail_ctx_f32(const float* m, const float* w_m, co
     cudaStream_t st = (cudaStream_t)stream;
 #define EFFI_TAILC_CASE(Q)                                                                                                        \
     case Q * 4:                                                                                                                   \
-        encoder_tail_ctx_kernel<Q><<<grid, 256, smem, st>>>((const float4*)m, w_m, ctx, ctx_stride, cx, ctx_relu, w_ctx, bias, n_pix, h, \
+        launch_kernel(encoder_tail_ctx_kernel<Q>, grid, dim3(256), smem, st, (const float4*)m, w_m, ctx, ctx_stride, cx, ctx_relu, w_ctx, bias, n_pix, h, \
                                                             (float4*)hx);                                                        \
         break;
     switch (hm) {
@@ -655,7 +719,7 @@ extern "C" int effimvs_encoder_tail_f32(const float* m, const float* w, const fl
     cudaStream_t st = (cudaStream_t)stream;
 #define EFFI_TAIL_CASE(Q)                                                                                        \
     case Q * 4:                                                                                                  \
-        encoder_tail_kernel<Q><<<grid, 256, smem, st>>>((const float4*)m, w, (const float4*)ctx_term, n_pix, h, (float4*)hx); \
+        launch_kernel(encoder_tail_kernel<Q>, grid, dim3(256), smem, st, (const float4*)m, w, (const float4*)ctx_term, n_pix, h, (float4*)hx); \
         break;
     switch (hm) {
         EFFI_TAIL_CASE(2) EFFI_TAIL_CASE(3) EFFI_TAIL_CASE(4) EFFI_TAIL_CASE(5) EFFI_TAIL_CASE(6) EFFI_TAIL_CASE(7) EFFI_TAIL_CASE(8)

@@ -147,6 +147,7 @@ warp_corr_agg_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src,
                      const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval,
                      const float* __restrict__ weights, int ray_unfused, int H, int W, int D,
                      float* __restrict__ sim_out, float* __restrict__ hyp_out) {
+    pdl_enter();
     constexpr int DPT = PlanesPerThread<G>::value;
     __shared__ float sP[EFFIMVS_MAX_SRC_VIEWS * 12];
     __shared__ const float* sSrc[EFFIMVS_MAX_SRC_VIEWS];
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(32 * DT)
 warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_src, const float* __restrict__ proj,
                        const float* __restrict__ hyp, int hyp_mode, int ray_unfused, int H, int W, int D,
                        float* __restrict__ sims_out, float* __restrict__ entropy_out) {
+    pdl_enter();
     extern __shared__ float s_sim[];  // [D][32]
     __shared__ float sP[12];
     const int b = blockIdx.z, v = blockIdx.y;
@@ -261,6 +263,7 @@ warp_corr_views_kernel(const float* __restrict__ ref_fea, SrcPtrs srcs, int n_sr
 __global__ void __launch_bounds__(128)
 homo_warp_kernel(const float* __restrict__ src_fea, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode,
                  int ray_unfused, int C, int H, int W, int D, float* __restrict__ out) {
+    pdl_enter();
     __shared__ float sP[12];
     const int b = blockIdx.z, d = blockIdx.y;
     const int HW = H * W;
@@ -289,6 +292,7 @@ homo_warp_kernel(const float* __restrict__ src_fea, const float* __restrict__ pr
 
 __global__ void weighted_agg_kernel(const float* __restrict__ sims, const float* __restrict__ weights,
                                     int n_src, int D, int HW, float* __restrict__ out) {
+    pdl_enter();
     const int b = blockIdx.z;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
@@ -317,10 +321,10 @@ int launch_agg(const float* ref, const SrcPtrs& srcs, int n_src, const float* pr
                float* hyp_out, cudaStream_t st) {
     dim3 block(AGG_THREADS), grid(ceil_div(H * W, AGG_THREADS), ceil_div(D, PlanesPerThread<G>::value), B);
     if (nhwc)
-        warp_corr_agg_kernel<C, G, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights,
+        launch_kernel(warp_corr_agg_kernel<C, G, true>, grid, block, 0, st, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights,
                                                                  ray_unfused_for(H, W), H, W, D, sim_out, hyp_out);
     else
-        warp_corr_agg_kernel<C, G, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights,
+        launch_kernel(warp_corr_agg_kernel<C, G, false>, grid, block, 0, st, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights,
                                                                   ray_unfused_for(H, W), H, W, D, sim_out, hyp_out);
     return check_launch("warp_corr_agg_kernel");
 }
@@ -416,7 +420,7 @@ extern "C" int effimvs_warp_corr_views_f32(const float* ref_fea, const float* co
 #define EFFI_VIEWS_CASE(CC, L)                                                                                                   \
     {                                                                                                                            \
         if (smem > 48 * 1024) cudaFuncSetAttribute(warp_corr_views_kernel<CC, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        warp_corr_views_kernel<CC, L><<<grid, block, smem, st>>>(ref_fea, s, n_src, proj, hyp, hyp_mode, ray_unfused_for(H, W), H, W, D, sims_out, entropy_out); \
+        launch_kernel(warp_corr_views_kernel<CC, L>, grid, block, smem, st, ref_fea, s, n_src, proj, hyp, hyp_mode, ray_unfused_for(H, W), H, W, D, sims_out, entropy_out); \
     }
     const bool nhwc = fea_layout == EFFIMVS_FEA_NHWC;
     switch (C) {
@@ -437,7 +441,7 @@ extern "C" int effimvs_weighted_agg_f32(const float* sims, const float* weights,
     EFFI_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && n_src >= 1 && n_src <= EFFIMVS_MAX_SRC_VIEWS, EFFIMVS_EINVAL,
                  "weighted_agg: bad sizes");
     dim3 block(256), grid(ceil_div(H * W, 256), D < 8 ? D : 8, B);
-    weighted_agg_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(sims, weights, n_src, D, H * W, out);
+    launch_kernel(weighted_agg_kernel, grid, block, 0, (cudaStream_t)stream, sims, weights, n_src, D, H * W, out);
     return check_launch("weighted_agg_kernel");
 }
 
@@ -447,6 +451,6 @@ extern "C" int effimvs_homo_warp_f32(const float* src_fea, const float* proj, co
     EFFI_REQUIRE(B > 0 && C > 0 && H > 1 && W > 1 && D > 0 && D <= 65535 && B <= 65535, EFFIMVS_EINVAL, "homo_warp: bad sizes");
     EFFI_REQUIRE(hyp_mode == EFFIMVS_HYP_TENSOR || hyp_mode == EFFIMVS_HYP_PLANES, EFFIMVS_EINVAL, "homo_warp: hyp_mode=%d", hyp_mode);
     dim3 block(128), grid(ceil_div(H * W, 128), D, B);
-    homo_warp_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(src_fea, proj, hyp, hyp_mode, ray_unfused_for(H, W), C, H, W, D, warped_out);
+    launch_kernel(homo_warp_kernel, grid, block, 0, (cudaStream_t)stream, src_fea, proj, hyp, hyp_mode, ray_unfused_for(H, W), C, H, W, D, warped_out);
     return check_launch("homo_warp_kernel");
 }

@@ -86,6 +86,11 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     u64 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -152,7 +157,53 @@ template <int G> struct TilePlanes { static constexpr int value = G >= 4 ? 4 : 8
 
 // constants every thread would otherwise derive with an fp64 / IEEE division of its own (87 + 50 warp instructions per warp
 // for the two normalisation factors alone): computed once on the host, same roundings
-struct SegConsts { float inv_half_w, inv_half_h, inv_dm1; };
+struct alignas(8) Pair { float lo, hi; };
+struct SegConsts {
+    Pair ihw2, ihh2, hw2, hh2;     // {inv_half_w} x 2, {inv_half_h} x 2, {(W - 1) / 2} x 2, {(H - 1) / 2} x 2: operands of the packed chain
+    Pair one2;                     // {1, 1} as a run-time value: see add2_after_mul()
+    float inv_half_w, inv_half_h, inv_dm1;
+};
+__device__ __forceinline__ u64 pair_bits(const Pair& p) { return *reinterpret_cast<const u64*>(&p); }
+// a * b (rounded) + c (rounded), as upstream's separate multiplication and addition kernels round it.  ptxas contracts
+// mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (a single rounding) even with explicit rounding modifiers and
+// -fmad=false (checked in the SASS), so the addition is issued as fma(product, 1, c) with a one the compiler cannot see
+// through: the same IEEE sum, one issue slot, no contraction.
+__device__ __forceinline__ u64 mul_then_add2(u64 a, u64 b, u64 c, u64 one_rt) { return fma2(mul2(a, b), one_rt, c); }
+
+// The coordinate chain of sample_coords() for TWO depth planes of one (pixel, view) at once on the packed fp32 pipe
+// (add / mul / fma.rn.f32x2: the same IEEE operations in the same order, so both results are bit-identical to the scalar
+// chain) -- 17 instead of 29 issue slots per sample in a kernel whose limit is instruction issue.  Every component of the
+// ray is kept duplicated in both halves of a 64-bit register.
+struct Ray2 { u64 rx, ry, rz, tx, ty, tz; };
+__device__ __forceinline__ Ray2 make_ray2(const Ray& r) {
+    Ray2 q;
+    q.rx = pack2(r.rx, r.rx); q.ry = pack2(r.ry, r.ry); q.rz = pack2(r.rz, r.rz);
+    q.tx = pack2(r.tx, r.tx); q.ty = pack2(r.ty, r.ty); q.tz = pack2(r.tz, r.tz);
+    return q;
+}
+__device__ __forceinline__ void sample_coords2(const Ray2& r, float da, float db, const SegConsts& kc, float& ixa, float& iya,
+                                               float& ixb, float& iyb) {
+    const u64 d = pack2(da, db), one_rt = pair_bits(kc.one2);
+    const u64 px = mul_then_add2(r.rx, d, r.tx, one_rt), py = mul_then_add2(r.ry, d, r.ty, one_rt);
+    float za, zb;
+    unpack2(mul_then_add2(r.rz, d, r.tz, one_rt), za, zb);
+    if (za == 0.0f) za = __fadd_rn(za, 1e-8f);
+    if (zb == 0.0f) zb = __fadd_rn(zb, 1e-8f);
+    float ra, rb;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(za));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(zb));
+    const u64 nz = pack2(-za, -zb), one = pack2(1.0f, 1.0f), mone = pack2(-1.0f, -1.0f);
+    u64 rr = pack2(ra, rb);
+    rr = fma2(rr, fma2(nz, rr, one), rr);                 // div2_rn's sequence, two lanes wide
+    u64 u = mul2(px, rr), v = mul2(py, rr);
+    u = fma2(fma2(nz, u, px), rr, u);
+    v = fma2(fma2(nz, v, py), rr, v);
+    u = fma2(fma2(nz, u, px), rr, u);
+    v = fma2(fma2(nz, v, py), rr, v);
+    const u64 gx = mul_then_add2(u, pair_bits(kc.ihw2), mone, one_rt), gy = mul_then_add2(v, pair_bits(kc.ihh2), mone, one_rt);   // x - 1 == x + (-1)
+    unpack2(mul2(add2(gx, one), pair_bits(kc.hw2)), ixa, ixb);
+    unpack2(mul2(add2(gy, one), pair_bits(kc.hh2)), iya, iyb);
+}
 
 // Shared state of a block: projection rows, the double-buffered bounding box and the TMA barrier.
 struct TileShared {
@@ -253,20 +304,20 @@ template <int C, int G, int DPT, class F>
 __device__ __forceinline__ void run_round(TileShared& sh, const uint8_t* __restrict__ tile, const CUtensorMap* map,
                                           const float* __restrict__ src, const float* __restrict__ refp, int round, uint32_t& phase,
                                           int flags, int b, const Ray& ray, const float (&depth)[DPT], unsigned valid, int H, int W,
-                                          float inv_half_w, float inv_half_h, const u64* __restrict__ ref2, F&& consume) {
+                                          const SegConsts& kc, const u64* __restrict__ ref2, F&& consume) {
     constexpr int BW = Box<C>::W, BH = Box<C>::H, ROW = BoxBytes<C>::ROW, SUB = BoxBytes<C>::SUB;
     constexpr int NACC = AccShape<C, G>::NACC, PPA = AccShape<C, G>::PPA, CG = AccShape<C, G>::CG;
     const int lane = threadIdx.x & 31;
     float ix[DPT], iy[DPT];
+    const Ray2 ray2 = make_ray2(ray);
+    float jx, jy;                          // position of the last existing plane
 
     // ---- 1. bounding box from the end planes
     {
         float dl = depth[0];
 #pragma unroll
         for (int k = 1; k < DPT; ++k) dl = ((valid >> k) & 1u) ? depth[k] : dl;
-        float jx, jy;
-        sample_coords(ray, depth[0], H, W, inv_half_w, inv_half_h, ix[0], iy[0]);
-        sample_coords(ray, dl, H, W, inv_half_w, inv_half_h, jx, jy);
+        sample_coords2(ray2, depth[0], dl, kc, ix[0], iy[0], jx, jy);
         const float lx = floorf(fminf(ix[0], jx)), hx = floorf(fmaxf(ix[0], jx));
         const float ly = floorf(fminf(iy[0], jy)), hy = floorf(fmaxf(iy[0], jy));
         // the curve touches the image extended by the -1 border (false for NaN/inf and for absent pixels)
@@ -302,12 +353,17 @@ __device__ __forceinline__ void run_round(TileShared& sh, const uint8_t* __restr
     }
 
     // ---- 3. exact positions of all planes (NaN for planes / pixels that do not exist)
+    //         planes 1 .. DPT-2 in pairs; plane DPT-1, where it exists, is the last existing plane of step 1
+    static_assert(DPT % 2 == 0, "planes are paired");
     if (!(valid & 1u)) ix[0] = __int_as_float(0x7fc00000);
 #pragma unroll
-    for (int k = 1; k < DPT; ++k) {
-        sample_coords(ray, depth[k], H, W, inv_half_w, inv_half_h, ix[k], iy[k]);
+    for (int k = 1; k + 1 < DPT; k += 2) {
+        sample_coords2(ray2, depth[k], depth[k + 1], kc, ix[k], iy[k], ix[k + 1], iy[k + 1]);
         if (!((valid >> k) & 1u)) ix[k] = __int_as_float(0x7fc00000);
+        if (!((valid >> (k + 1)) & 1u)) ix[k + 1] = __int_as_float(0x7fc00000);
     }
+    ix[DPT - 1] = ((valid >> (DPT - 1)) & 1u) ? jx : __int_as_float(0x7fc00000);
+    iy[DPT - 1] = jy;
     if (any) {
         mbar_wait(&sh.bar, phase);
         phase ^= 1u;
@@ -594,6 +650,7 @@ warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __rest
                       const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode,
                       const float* __restrict__ interval, const float* __restrict__ weights, int H, int W, int D, int tiles_x,
                       int flags, const SegConsts kc, float* __restrict__ sim_out, float* __restrict__ hyp_out) {
+    pdl_enter();
     constexpr int DPT = TilePlanes<G>::value;
     extern __shared__ uint8_t smem_raw[];
     __shared__ TileShared sh;
@@ -643,7 +700,7 @@ warp_corr_tile_kernel(const __grid_constant__ TileMaps maps, const float* __rest
         const Ray ray = make_ray(sh.P + v * 12, x, y, (flags & FLAG_RAY_UNFUSED) != 0);
         const float w = (wp && inimg) ? __ldg(wp + (size_t)v * HW) : 1.0f;
         run_round<C, G, DPT>(sh, tile, &maps.m[v], srcs.p[v] + (size_t)b * C * HW, refp, v, phase, flags, b, ray, depth, valid, H, W,
-                             kc.inv_half_w, kc.inv_half_h, ref2, [&](int k, int g, float sim) {
+                             kc, ref2, [&](int k, int g, float sim) {
                                  num[k][g] = wp ? __fadd_rn(num[k][g], __fmul_rn(sim, w)) : __fadd_rn(num[k][g], sim);
                              });
         den = __fadd_rn(den, w);
@@ -676,6 +733,7 @@ __global__ void __launch_bounds__(TILE_THREADS, BlocksPerSM<C>::value)
 warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs,
                        int n_src, const float* __restrict__ proj, const float* __restrict__ hyp, int hyp_mode, int H, int W, int D,
                        int tiles_x, int flags, const SegConsts kc, float* __restrict__ sims_out) {
+    pdl_enter();
     constexpr int DPT = 8;
     extern __shared__ uint8_t smem_raw[];
     __shared__ TileShared sh;
@@ -689,7 +747,6 @@ warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __res
     const int xi = tx * TW + lane, yi = ty * TH + (tid >> 5);
     const bool inimg = xi < W && yi < H;
     const int pix = inimg ? yi * W + xi : 0;
-    const float inv_half_w = kc.inv_half_w, inv_half_h = kc.inv_half_h;
 
     const float* refp = ref_fea + ((size_t)b * HW + pix) * C;
     u64 ref2[C / 2];
@@ -707,7 +764,7 @@ warp_views_tile_kernel(const __grid_constant__ TileMaps maps, const float* __res
         depth[k] = on ? fetch_hypothesis(hyp, hyp_mode, nullptr, b, d0 + k, D, pix, HW) : 1.0f;
     }
     run_round<C, 1, DPT>(sh, tile, &maps.m[v], srcs.p[v] + (size_t)b * C * HW, refp, 0, phase, flags, b, ray, depth, valid, H, W,
-                         inv_half_w, inv_half_h, ref2, [&](int k, int, float sim) {
+                         kc, ref2, [&](int k, int, float sim) {
                              if ((valid >> k) & 1u) out[(size_t)(d0 + k) * HW] = sim;
                          });
 }
@@ -733,6 +790,7 @@ warp_corr_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__ 
                      const float* __restrict__ hyp, int hyp_mode, const float* __restrict__ interval, const float* __restrict__ weights,
                      int H, int W, int D, int tiles_x, int flags, const SegConsts kc, float* __restrict__ sim_out,
                      float* __restrict__ hyp_out) {
+    pdl_enter();
     constexpr int DPT = 8;
     extern __shared__ float seg_smem[];
     float* const scratch = seg_smem;                                   // [SEG_SLOTS][NT]
@@ -803,6 +861,7 @@ __global__ void __launch_bounds__(TILE_THREADS, SegBlocksPerSM<C>::value)
 warp_views_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__ SrcPtrs srcs, int n_src, const float* __restrict__ proj,
                       const float* __restrict__ hyp, int hyp_mode, int H, int W, int D, int tiles_x, int flags, const SegConsts kc,
                       float* __restrict__ sims_out) {
+    pdl_enter();
     constexpr int DPT = 8;
     __shared__ float sP[12];
     __shared__ float scratch[SEG_SLOTS * TILE_THREADS];
@@ -836,6 +895,7 @@ warp_views_seg_kernel(const float* __restrict__ ref_fea, const __grid_constant__
 // softmax entropy over the D similarities of a (pixel, view) (models/Effi_MVS_plus.py:43-44); sims (N, D, HW)
 __global__ void __launch_bounds__(256)
 softmax_entropy_kernel(const float* __restrict__ sims, int D, int HW, float* __restrict__ entropy_out) {
+    pdl_enter();
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
     const float* mine = sims + (size_t)blockIdx.y * D * HW + pix;
@@ -856,6 +916,7 @@ softmax_entropy_kernel(const float* __restrict__ sims, int D, int HW, float* __r
 template <int DMAX>
 __global__ void __launch_bounds__(256)
 softmax_entropy_reg_kernel(const float* __restrict__ sims, int D, int HW, float* __restrict__ entropy_out) {
+    pdl_enter();
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= HW) return;
     const float* mine = sims + (size_t)blockIdx.y * D * HW + pix;
@@ -942,6 +1003,12 @@ SegConsts seg_consts(int H, int W, int D) {
     k.inv_half_w = 1.0f / (float)((double)(W - 1) / 2.0);        // IEEE single division, as __fdiv_rn in the other kernels
     k.inv_half_h = 1.0f / (float)((double)(H - 1) / 2.0);
     k.inv_dm1 = D > 1 ? 1.0f / (float)(D - 1) : 0.0f;
+    const float hw = 0.5f * (float)(W - 1), hh = 0.5f * (float)(H - 1);   // exact (sample_coords folds ATen's halving the same way)
+    k.ihw2 = {k.inv_half_w, k.inv_half_w};
+    k.ihh2 = {k.inv_half_h, k.inv_half_h};
+    k.hw2 = {hw, hw};
+    k.hh2 = {hh, hh};
+    k.one2 = {1.0f, 1.0f};
     return k;
 }
 
@@ -961,7 +1028,7 @@ int launch_tile(const float* ref, const SrcPtrs& srcs, int n_src, const float* p
     {                                                                                                                                  \
         const size_t smem = segv_smem(NT, n_src);                                                                                      \
         cudaFuncSetAttribute(warp_corr_seg_kernel<C, EX, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
-        warp_corr_seg_kernel<C, EX, NT><<<grid, block, smem, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D, tiles_x, \
+        launch_kernel(warp_corr_seg_kernel<C, EX, NT>, grid, block, smem, st, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D, tiles_x, \
                                                                    flags, kc, sim_out, hyp_out);                                      \
     }
             const int nt = TW * SEGV_TY * n_src;
@@ -978,7 +1045,7 @@ int launch_tile(const float* ref, const SrcPtrs& srcs, int n_src, const float* p
     dim3 block(TILE_THREADS), grid(tiles_x * tiles_y, ceil_div(D, TilePlanes<G>::value), B);
     const size_t smem = BoxBytes<C>::ALL + 1024;
     cudaFuncSetAttribute(warp_corr_tile_kernel<C, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    warp_corr_tile_kernel<C, G><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
+    launch_kernel(warp_corr_tile_kernel<C, G>, grid, block, smem, st, maps, ref, srcs, n_src, proj, hyp, hyp_mode, interval, weights, H, W, D,
                                                             tiles_x, flags, seg_consts(H, W, D), sim_out, hyp_out);
     return check_launch("warp_corr_tile_kernel");
 }
@@ -1008,10 +1075,10 @@ int launch_views(const float* ref, const SrcPtrs& srcs, int n_src, const float* 
     // against 0.17 ms from the staged box).  EFFIMVS_WARP_SEG=2 forces the segment form (tests).
     if (seg_mode() >= 2) {
         if (seg_fast_coords())
-            warp_views_seg_kernel<C, false><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
+            launch_kernel(warp_views_seg_kernel<C, false>, grid, block, 0, st, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
                                                                     seg_consts(H, W, D), sims_out);
         else
-            warp_views_seg_kernel<C, true><<<grid, block, 0, st>>>(ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
+            launch_kernel(warp_views_seg_kernel<C, true>, grid, block, 0, st, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
                                                                    seg_consts(H, W, D), sims_out);
         if ((rc = check_launch("warp_views_seg_kernel"))) return rc;
     } else {
@@ -1019,14 +1086,14 @@ int launch_views(const float* ref, const SrcPtrs& srcs, int n_src, const float* 
         if ((rc = encode_maps<C>(maps, srcs, n_src, B, H, W))) return rc;
         const size_t smem = BoxBytes<C>::ALL + 1024;
         cudaFuncSetAttribute(warp_views_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        warp_views_tile_kernel<C><<<grid, block, smem, st>>>(maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
+        launch_kernel(warp_views_tile_kernel<C>, grid, block, smem, st, maps, ref, srcs, n_src, proj, hyp, hyp_mode, H, W, D, tiles_x, flags,
                                                              seg_consts(H, W, D), sims_out);
         if ((rc = check_launch("warp_views_tile_kernel"))) return rc;
     }
     const dim3 egrid(ceil_div(H * W, 256), B * n_src);
-    if (D <= 48) softmax_entropy_reg_kernel<48><<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);
-    else if (D <= 96) softmax_entropy_reg_kernel<96><<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);
-    else softmax_entropy_kernel<<<egrid, 256, 0, st>>>(sims_out, D, H * W, entropy_out);
+    if (D <= 48) launch_kernel(softmax_entropy_reg_kernel<48>, dim3(egrid), dim3(256), 0, st, sims_out, D, H * W, entropy_out);
+    else if (D <= 96) launch_kernel(softmax_entropy_reg_kernel<96>, dim3(egrid), dim3(256), 0, st, sims_out, D, H * W, entropy_out);
+    else launch_kernel(softmax_entropy_kernel, dim3(egrid), dim3(256), 0, st, sims_out, D, H * W, entropy_out);
     return check_launch("softmax_entropy_kernel");
 }
 

@@ -286,6 +286,7 @@ class CudaHotPath:
     encoder_tail = staticmethod(ops.encoder_tail)
     encoder_tail_ctx = staticmethod(ops.encoder_tail_ctx)
     gru_init = staticmethod(ops.gru_init)
+    gru_init_ctx = staticmethod(ops.gru_init_ctx)
     # the block's 3x3 convolutions on the tensor cores, gate arithmetic as epilogues (csrc/conv2d_tc.cu)
     conv2d_tc = staticmethod(ops.conv2d_tc)
     conv2d_tc_pack = staticmethod(ops.conv2d_tc_pack)

@@ -421,7 +421,14 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
     h = g.convz.out_channels
     cx = e.convc.in_channels - e.convd.out_channels                  # context channels
     tail_ctx = hasattr(glue, "encoder_tail_ctx") and cx in (4, 8, 12) and os.environ.get("EFFIMVS_TAIL_CTX", "1") != "0"
-    if ctx_map is not None and tail_ctx and hasattr(glue, "gru_init") and ctx_map.shape[1] == h + cx and h % 4 == 0:
+    fused_start = ctx_map is not None and tail_ctx and hasattr(glue, "gru_init") and ctx_map.shape[1] == h + cx and h % 4 == 0
+    Hm, Wm = (ctx_map if ctx_map is not None else net).shape[2:]
+    tc_path = _conv_tc_enabled(glue, h, Hm, Wm) and tuple(hd.conv2.weight.shape) == (1, h, 3, 3) and h <= 128
+    if fused_start and tc_path and hasattr(glue, "gru_init_ctx") and os.environ.get("EFFIMVS_INIT_CTX", "1") != "0":
+        # start state and the iteration-invariant context term of the encoder tail in one pass over the context map
+        hx, ctx_term = glue.gru_init_ctx(ctx_map, h, w["wc_ctx"], w["bias_c"])
+        return _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask)
+    if fused_start:
         hx = glue.gru_init(ctx_map, h)                               # hx[:, :h] = tanh(hidden half)
         net = hx[:, :h]
         ctx_src, ctx_off, ctx_relu = ctx_map, h, True
@@ -434,7 +441,7 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
         hx[:, :h] = net
         ctx_src = context.contiguous(memory_format=torch.channels_last) if (tail_ctx and context.is_cuda) else context
         ctx_off, ctx_relu = 0, False
-    if _conv_tc_enabled(glue, h, hx.shape[2], hx.shape[3]) and tuple(hd.conv2.weight.shape) == (1, h, 3, 3) and h <= 128:
+    if tc_path:
         ctx_in = torch.relu(ctx_src[:, ctx_off:ctx_off + cx]) if ctx_relu else (ctx_src if ctx_src.shape[1] == cx else ctx_src[:, ctx_off:ctx_off + cx])
         ctx_term = F.conv2d(ctx_in, w["wc_ctx"], w["bias_c"]).contiguous(memory_format=torch.channels_last)
         return _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask)

@@ -897,6 +897,36 @@ def _(ctx_map, h):
     return torch.empty((B, 2 * h, H, W), device=ctx_map.device, dtype=ctx_map.dtype, memory_format=torch.channels_last)
 
 
+@torch.library.custom_op("effimvs::gru_init_ctx", mutates_args=())
+@_on_tensor_device
+def gru_init_ctx(ctx_map: Tensor, h: int, w_ctx: Tensor, bias: Tensor) -> Tuple[Tensor, Tensor]:
+    """gru_init plus the iteration-invariant context term of the encoder tail in the same pass over the context map:
+    returns (hx (B,2h,H,W) with hx[:, :h] = tanh(ctx_map[:, :h]), ctx_term (B,h,H,W) = conv1x1(relu(ctx_map[:, h:]), w_ctx) + bias),
+    both channels-last; w_ctx (h, cx[, 1, 1]) = convc.weight[:, hm:], bias (h) (models/update.py:93-95, Effi_MVS_plus.py:464-466)."""
+    ctx_map = _nhwc(ctx_map, "gru_init_ctx")
+    B, ct, H, W = ctx_map.shape
+    cx = ct - h
+    if h <= 0 or h % 4 or h > 128 or cx < 4 or cx % 4 or cx > 64:
+        raise ValueError("gru_init_ctx: hidden {} (<= 128) / context {} (4..64) channels must be multiples of 4".format(h, cx))
+    w2 = w_ctx.detach().reshape(w_ctx.shape[0], -1).contiguous().float()
+    if tuple(w2.shape) != (h, cx) or bias.numel() != h:
+        raise ValueError("gru_init_ctx: w_ctx {} / bias {} do not match h={}, cx={}".format(tuple(w_ctx.shape), tuple(bias.shape), h, cx))
+    bias = bias.detach().contiguous().float()
+    hx = torch.empty(B, 2 * h, H, W, device=ctx_map.device, dtype=torch.float32, memory_format=torch.channels_last)
+    term = torch.empty(B, h, H, W, device=ctx_map.device, dtype=torch.float32, memory_format=torch.channels_last)
+    _count(1)
+    capi.check(_lib.effimvs_gru_init_ctx_f32(ctx_map.data_ptr(), B * H * W, h, cx, w2.data_ptr(), bias.data_ptr(), hx.data_ptr(),
+                                             term.data_ptr(), _stream()))
+    return hx, term
+
+
+@gru_init_ctx.register_fake
+def _(ctx_map, h, w_ctx, bias):
+    B, _, H, W = ctx_map.shape
+    mk = lambda c: torch.empty((B, c, H, W), device=ctx_map.device, dtype=ctx_map.dtype, memory_format=torch.channels_last)   # noqa: E731
+    return mk(2 * h), mk(h)
+
+
 # -------------------------------------------------------------------------------------------
 # SURVEY section 8(f) row 2: DTU geometric filter (csrc/dtu_filter.cu)
 @torch.library.custom_op("effimvs::dtu_filter", mutates_args=())

@@ -294,6 +294,13 @@ int effimvs_encoder_tail_ctx_f32(const float* m, const float* w_m, const float* 
  * hx (n_pix, 2h) = cat[h, x]. */
 int effimvs_gru_init_f32(const float* ctx_map, long long n_pix, int h, int cx, float* hx, void* stream);
 
+/* The same start state together with the context half of ProjectionInput.convc (models/update.py:93-95 with the context of
+ * models/Effi_MVS_plus.py:466), which does not change over the GRU iterations: ctx_term (n_pix, h) channels-last =
+ * w_ctx relu(ctx_map[:, h:h+cx]) + bias, w_ctx (h, cx) = convc.weight[:, hm:], bias (h) = convc.bias + convc.weight[:, :hm] convd.bias
+ * (fp32 products).  It is the aux map of effimvs_conv2d_tf32's ADD_RELU epilogue.  h <= 128, cx in 4..64, both multiples of 4. */
+int effimvs_gru_init_ctx_f32(const float* ctx_map, long long n_pix, int h, int cx, const float* w_ctx, const float* bias,
+                             float* hx, float* ctx_term, void* stream);
+
 /* ---- SURVEY section 8(f) row 3, the convolutions: 3x3 / stride 1 / zero padding 1 convolutions of the update block on the
  * tensor cores (tcgen05 kind::tf32: operands rounded to TF32, fp32 accumulation -- the arithmetic class cuDNN uses for these
  * layers under PyTorch's default torch.backends.cudnn.allow_tf32 = True), with the gate arithmetic as epilogues.

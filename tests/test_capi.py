@@ -72,6 +72,8 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_encoder_tail_ctx_f32(one, one, one, 20, 5, 1, one, one, 10, 12, 16, one, None) == capi.EUNSUPPORTED           # cx = 5
     assert lib.effimvs_encoder_tail_ctx_f32(one, one, ctypes.c_void_p(20), 20, 4, 1, one, one, 10, 12, 16, one, None) == capi.EINVAL  # misaligned ctx
     assert lib.effimvs_gru_init_f32(one, 10, 18, 4, one, None) == capi.EINVAL
+    assert lib.effimvs_gru_init_ctx_f32(one, 10, 16, 6, one, one, one, one, None) == capi.EINVAL            # cx not a multiple of 4
+    assert lib.effimvs_gru_init_ctx_f32(one, 10, 16, 4, one, None, one, one, None) == capi.EINVAL           # no bias
     td, tf = (ctypes.c_double * 2)(1.0, 0.5), (ctypes.c_float * 2)(0.1, 0.2)
     assert lib.effimvs_dtu_filter_f32(one, one, one, one, td, tf, 2, 1, 11, 0.5, 0.75, 3, 8, 8, one, None, one, one, None, None, None) == capi.EUNSUPPORTED
     assert "non-decreasing" in capi.last_error()
@@ -98,6 +100,8 @@ def test_fake_implementations_give_shapes_without_a_device():
                                                          torch.empty(2), torch.empty(2), 2)
         assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
         assert torch.ops.effimvs.gru_init(torch.empty(2, 20, 6, 8), 16).shape == (2, 32, 6, 8)
+        hx0, term = torch.ops.effimvs.gru_init_ctx(torch.empty(2, 20, 6, 8), 16, torch.empty(16, 4, 1, 1), torch.empty(16))
+        assert hx0.shape == (2, 32, 6, 8) and term.shape == (2, 16, 6, 8)
         up, dep = torch.ops.effimvs.convex_upsample(torch.empty(2, 36, 6, 8), None, 0.25, torch.empty(2, 1, 6, 8), torch.empty(2), torch.empty(2), 2)
         assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
         ref = torch.empty(2, 16, 24, 32)

@@ -633,6 +633,32 @@ def test_gru_init_and_encoder_tail_ctx_vs_torch(h, cx, H, W):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("h,cx,H,W", [(16, 4, 37, 53), (32, 8, 24, 40), (48, 12, 19, 25), (16, 4, 592, 800)])
+def test_gru_init_ctx_vs_torch(h, cx, H, W):
+    """gru_init_ctx: the GRU start state and the iteration-invariant context term of the encoder tail (the aux map of conv2d_tc's
+    ADD_RELU epilogue) in one pass over the context map, against tanh / relu / conv1x1 + bias in torch with fp32 products
+    (models/Effi_MVS_plus.py:464-466, models/update.py:93-95); the last case is the DTU stage-3 map."""
+    import torch.nn.functional as F
+    from effimvs_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(h + W)
+    rnd = lambda *s: torch.randn(*s, device=DEV, generator=gen)      # noqa: E731
+    B = 2 if H < 100 else 1
+    ctx_map = rnd(B, h + cx, H, W).contiguous(memory_format=torch.channels_last)
+    w_ctx, bias = rnd(h, cx, 1, 1) * 0.3, rnd(h) * 0.1
+    hx, term = ops.gru_init_ctx(ctx_map, h, w_ctx.contiguous(memory_format=torch.channels_last), bias)
+    assert hx.shape == (B, 2 * h, H, W) and hx.is_contiguous(memory_format=torch.channels_last)
+    assert term.shape == (B, h, H, W) and term.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(hx[:, :h], ops.gru_init(ctx_map, h)[:, :h])
+    saved = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        want = F.conv2d(torch.relu(ctx_map[:, h:]), w_ctx, bias)
+    finally:
+        torch.backends.cudnn.allow_tf32 = saved
+    assert rel_max(term, want) < 1e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("h,B,H,W", [(16, 2, 37, 70), (32, 1, 24, 129), (48, 2, 19, 25), (16, 1, 3, 2), (64, 1, 9, 66)])
 def test_delta_head_vs_torch(h, B, H, W):
     """DepthHead.conv2 + tanh + inverse-depth step + disp_to_depth in one kernel against the torch chain

@@ -81,6 +81,11 @@ class TorchGlue:
         return hx
 
     @staticmethod
+    def gru_init_ctx(ctx_map, h, w_ctx, bias):
+        w4 = w_ctx.reshape(w_ctx.shape[0], -1, 1, 1)
+        return TorchGlue.gru_init(ctx_map, h), F.conv2d(torch.relu(ctx_map[:, h:]), w4, bias)
+
+    @staticmethod
     def encoder_head(cost, inv, wc1, bc1, wd1, bd1):
         return torch.cat([torch.relu(F.conv2d(cost, wc1, bc1)), torch.relu(F.conv2d(inv, wd1, bd1, padding=3))], dim=1)
 
