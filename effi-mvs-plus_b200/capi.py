@@ -61,10 +61,14 @@ SIGNATURES = {
     "effimvs_gru_reset_f32": (_i, [_p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_gru_update_f32": (_i, [_p, _p, _p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_gru_delta_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "effimvs_inv_init_f32": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "effimvs_delta_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_convex_upsample_f32": (_i, [_p, _p, _f, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_convex_upsample_conv_f32": (_i, [_p, _i, _p, _p, _f, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_encoder_head_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "effimvs_encoder_head_hostw_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "effimvs_encoder_head_pack_host": (_i, [_p, _p, _p, _p, _i, _i, _p]),
+    "effimvs_encoder_head_table_floats": (_i, [_i]),
     "effimvs_encoder_tail_f32": (_i, [_p, _p, _p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_encoder_tail_ctx_f32": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, C.c_longlong, _i, _i, _p, _p]),
     "effimvs_conv2d_tf32_supported": (_i, [_i, _i]),

@@ -97,6 +97,24 @@ gru_delta_kernel(const float* __restrict__ pre, const float* __restrict__ bias, 
     }
 }
 
+// Start of a stage's refinement (models/Effi_MVS_plus.py:151-164 depth_to_disp, then :138-148 disp_to_depth): the normalised
+// inverse depth of the current estimate, inv = (1 / depth - lo) / ((hi - lo) + 1e-10), and the depth it maps back to -- the same
+// IEEE operations torch issues as four kernels (reciprocal, sub, div, and the clone + disp_to_depth of the first gru_delta call).
+__global__ void __launch_bounds__(256)
+inv_init_kernel(const float* __restrict__ cur_depth, const float* __restrict__ lo, const float* __restrict__ hi, int HW,
+                float* __restrict__ inv_out, float* __restrict__ depth_out) {
+    pdl_enter();
+    const int b = blockIdx.y;
+    const float l = __ldg(lo + b), hh = __ldg(hi + b);
+    const float span = __fadd_rn(__fsub_rn(hh, l), 1e-10f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const size_t o = (size_t)b * HW + i;
+        const float v = __fdiv_rn(__fsub_rn(__frcp_rn(__ldg(cur_depth + o)), l), span);
+        inv_out[o] = v;
+        depth_out[o] = to_depth(v, l, hh);
+    }
+}
+
 // upsample_depth with ratio R (2): mask (B,H,W,9*R*R) = scale * (mask_pre + bias), channel = (k*R + ry)*R + rx;
 // softmax over the 9 neighbours k, weighted sum of the zero-padded 3x3 neighbourhood of inv.
 // CONV: mask_pre is not given; the kernel forms it from t (B,H,W,K) = relu(mask[0](net)) and mask[2].weight (CH, K) -- a
@@ -214,6 +232,15 @@ extern "C" int effimvs_gru_update_f32(const float* zr_pre, const float* bias_z, 
     launch_kernel(gru_update_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)zr_pre, bias_z, (const float4*)q_pre, bias_q,
                                                                             (float4*)hx, n_pix, h, cx, (float4*)net_out);
     return check_launch("gru_update_kernel");
+}
+
+extern "C" int effimvs_inv_init_f32(const float* cur_depth, const float* lo_disp, const float* hi_disp, int B, int HW, float* inv_out,
+                                    float* depth_out, void* stream) {
+    EFFI_REQUIRE(cur_depth && lo_disp && hi_disp && inv_out && depth_out, EFFIMVS_EINVAL, "inv_init: null pointer");
+    EFFI_REQUIRE(B > 0 && B <= 65535 && HW > 0, EFFIMVS_EINVAL, "inv_init: bad sizes");
+    dim3 grid(grid_for(HW, 256), B);
+    launch_kernel(inv_init_kernel, grid, dim3(256), 0, (cudaStream_t)stream, cur_depth, lo_disp, hi_disp, HW, inv_out, depth_out);
+    return check_launch("inv_init_kernel");
 }
 
 extern "C" int effimvs_gru_delta_f32(const float* pre, const float* bias, const float* inv, const float* lo_disp, const float* hi_disp,
@@ -473,8 +500,149 @@ encoder_head_kernel(const float* __restrict__ cost, int CD, const float* __restr
     }
 }
 
+// The same head with the weights as a KERNEL PARAMETER (constant bank): every FFMA of the unrolled 7x7 window takes its weight
+// as a c[0][imm] operand, so there is no weight staging prologue per block (ncu on the shared-memory version at 800 x 592:
+// ~30 % of the stall samples sit in the strided weight gather and the tile load before the first barrier) and no broadcast
+// LDS.128 per four FMAs (short-scoreboard / MIO-throttle stalls of the main loop).  One launch covers 16 of the h output
+// channels of each half (the table of a chunk is 3.7 KB of the 4 KB parameter space; offsets into it must be immediates, so
+// the chunk cannot be a run-time index): h / 16 launches per call.  The host needs the weights in HOST memory at launch time
+// (effimvs_encoder_head_pack_host builds the tables once per weight set); a CUDA graph keeps the copy made at capture.
+struct EHTable {
+    float wd[49][16];       // convd1.weight[ch0 + j][0][tap]   -> [tap][j]
+    float wc[8][16];        // convc1.weight[ch0 + j][c]        -> [c][j], rows >= CD zero
+    float bc[16], bd[16];   // convc1.bias, convd1.bias
+};
+static_assert(sizeof(EHTable) == 944 * sizeof(float), "EHTable layout is part of the C ABI (effimvs_encoder_head_pack_host)");
+
+template <int EH_TY>
+__global__ void __launch_bounds__(EH_TX * EH_TY)
+encoder_head_const_kernel(const __grid_constant__ EHTable T, const float* __restrict__ cost, int CD, const float* __restrict__ inv,
+                          int h, int ch0, int H, int W, float* __restrict__ out) {
+    constexpr int TWP = EH_TX * EH_PX, SW = TWP + 2 * EH_R, SH = EH_TY + 2 * EH_R;
+    static_assert(SW % 2 == 0 && EH_PX == 2, "window rows are read as float2 pairs");
+    __shared__ __align__(16) float s_inv[SH * SW];
+    pdl_enter();
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * TWP - EH_R, y0 = blockIdx.y * EH_TY - EH_R;
+    const float* ib = inv + (size_t)b * H * W;
+    for (int r = threadIdx.y; r < SH; r += EH_TY) {            // a warp per tile row: no integer division, all loads in flight
+        const int yy = y0 + r;
+        const bool rok = yy >= 0 && yy < H;
+        const float* rowp = ib + (size_t)(rok ? yy : 0) * W;
+#pragma unroll
+        for (int c0 = 0; c0 < SW; c0 += EH_TX) {
+            const int c = c0 + threadIdx.x, xx = x0 + c;
+            if (c < SW) s_inv[r * SW + c] = (rok && xx >= 0 && xx < W) ? __ldg(rowp + xx) : 0.0f;
+        }
+    }
+    const int x = blockIdx.x * TWP + threadIdx.x * EH_PX, y = blockIdx.y * EH_TY + threadIdx.y;
+    const bool inside = x < W && y < H;
+    const bool has[EH_PX] = {true, x + 1 < W};
+    // relu(convc1(cost) + b): 1x1 (loads issued before the barrier)
+    float cv[EH_PX][8];
+#pragma unroll
+    for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) cv[p][c] = (c < CD && inside && has[p]) ? __ldg(cost + (((size_t)b * CD + c) * H + y) * W + x + p) : 0.0f;
+    __syncthreads();
+    if (!inside) return;
+    float4* o[EH_PX];
+#pragma unroll
+    for (int p = 0; p < EH_PX; ++p) o[p] = reinterpret_cast<float4*>(out + (((size_t)b * H + y) * W + (has[p] ? x + p : x)) * (2 * h) + ch0);
+    {
+        float acc[EH_PX][16];
+#pragma unroll
+        for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[p][j] = T.bc[j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c < CD) {
+#pragma unroll
+                for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(cv[p][c], T.wc[c][j], acc[p][j]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < EH_PX; ++p)
+            if (has[p])
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    o[p][q] = make_float4(fmaxf(acc[p][4 * q], 0.0f), fmaxf(acc[p][4 * q + 1], 0.0f), fmaxf(acc[p][4 * q + 2], 0.0f),
+                                          fmaxf(acc[p][4 * q + 3], 0.0f));
+    }
+    // relu(convd1(inv) + b): 7x7, zero padding 3; the two pixels of a thread share a row of 8 window values (four 64-bit loads)
+    {
+        const float2* win = reinterpret_cast<const float2*>(s_inv + threadIdx.y * SW + threadIdx.x * EH_PX);
+        float acc[EH_PX][16];
+#pragma unroll
+        for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[p][j] = T.bd[j];
+#pragma unroll
+        for (int ty = 0; ty < 7; ++ty) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 t = win[ty * (SW / 2) + i];
+                v[2 * i] = t.x;
+                v[2 * i + 1] = t.y;
+            }
+#pragma unroll
+            for (int tx = 0; tx < 7; ++tx)
+#pragma unroll
+                for (int p = 0; p < EH_PX; ++p)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(v[tx + p], T.wd[ty * 7 + tx][j], acc[p][j]);
+        }
+#pragma unroll
+        for (int p = 0; p < EH_PX; ++p)
+            if (has[p])
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    o[p][(h >> 2) + q] = make_float4(fmaxf(acc[p][4 * q], 0.0f), fmaxf(acc[p][4 * q + 1], 0.0f), fmaxf(acc[p][4 * q + 2], 0.0f),
+                                                     fmaxf(acc[p][4 * q + 3], 0.0f));
+    }
+}
+
 }  // namespace
 }  // namespace effimvs
+
+extern "C" int effimvs_encoder_head_table_floats(int h) { return (h > 0 && h % 16 == 0) ? (h / 16) * 944 : 0; }
+
+extern "C" int effimvs_encoder_head_pack_host(const float* wc1, const float* bc1, const float* wd1, const float* bd1, int CD, int h,
+                                              float* tables_out) {
+    using namespace effimvs;
+    EFFI_REQUIRE(wc1 && bc1 && wd1 && bd1 && tables_out, EFFIMVS_EINVAL, "encoder_head_pack_host: null pointer");
+    EFFI_REQUIRE(CD >= 1 && CD <= 8 && h >= 16 && h % 16 == 0 && h <= 128, EFFIMVS_EUNSUPPORTED,
+                 "encoder_head_pack_host: cost channels %d must be in [1,8], hidden %d a multiple of 16 up to 128", CD, h);
+    EHTable* T = reinterpret_cast<EHTable*>(tables_out);
+    for (int k = 0; k < h / 16; ++k)
+        for (int j = 0; j < 16; ++j) {
+            const int ch = k * 16 + j;
+            for (int t = 0; t < 49; ++t) T[k].wd[t][j] = wd1[ch * 49 + t];
+            for (int c = 0; c < 8; ++c) T[k].wc[c][j] = c < CD ? wc1[ch * CD + c] : 0.0f;
+            T[k].bc[j] = bc1[ch];
+            T[k].bd[j] = bd1[ch];
+        }
+    return EFFIMVS_OK;
+}
+
+extern "C" int effimvs_encoder_head_hostw_f32(const float* cost, const float* inv, const float* host_tables, int B, int CD, int h, int H,
+                                              int W, float* out, void* stream) {
+    using namespace effimvs;
+    EFFI_REQUIRE(cost && inv && host_tables && out, EFFIMVS_EINVAL, "encoder_head_hostw: null pointer");
+    EFFI_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, EFFIMVS_EINVAL, "encoder_head_hostw: bad sizes");
+    EFFI_REQUIRE(CD >= 1 && CD <= 8 && h >= 16 && h % 16 == 0 && h <= 128, EFFIMVS_EUNSUPPORTED,
+                 "encoder_head_hostw: cost channels %d must be in [1,8], hidden %d a multiple of 16 up to 128", CD, h);
+    constexpr int TY = 4;
+    dim3 block(EH_TX, TY), grid(ceil_div(W, EH_TX * EH_PX), ceil_div(H, TY), B);
+    const EHTable* T = reinterpret_cast<const EHTable*>(host_tables);
+    for (int k = 0; k < h / 16; ++k)       // the table is copied into the launch's parameter buffer: the host array may change afterwards
+        launch_kernel(encoder_head_const_kernel<TY>, grid, block, 0, (cudaStream_t)stream, T[k], cost, CD, inv, h, k * 16, H, W, out);
+    return check_launch("encoder_head_const_kernel");
+}
 
 extern "C" int effimvs_encoder_head_f32(const float* cost, const float* inv, const float* wc1, const float* bc1, const float* wd1,
                                         const float* bd1, int B, int CD, int h, int H, int W, float* out, void* stream) {

@@ -279,6 +279,7 @@ class CudaHotPath:
     gru_reset = staticmethod(ops.gru_reset)
     gru_update = staticmethod(ops.gru_update)
     gru_delta = staticmethod(ops.gru_delta)
+    inv_init = staticmethod(ops.inv_init)
     delta_head = staticmethod(ops.delta_head)
     convex_upsample = staticmethod(ops.convex_upsample)
     convex_upsample_conv = staticmethod(ops.convex_upsample_conv)

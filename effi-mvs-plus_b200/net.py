@@ -300,8 +300,8 @@ class UpdateBlock(nn.Module):
             inv_seq.append(inv_depth)
         return net, 0.25 * self.mask[2](_conv_relu_mod(self.mask[0], net)), inv_seq
 
-    def forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map=None, want_mask=True):
-        return update_block_forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map, want_mask)
+    def forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map=None, want_mask=True, cur_depth=None):
+        return update_block_forward_fused(self, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map, want_mask, cur_depth)
 
 
 # ---- inference on CUDA: cuDNN convolutions + the glue kernels of the hot-path table ------------------
@@ -369,7 +369,18 @@ def _tc_update_weights(block, glue, w):
     return tc
 
 
-def _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask):
+def _start_inverse_depth(glue, inv_depth, cur_depth, lo_disp, hi_disp):
+    """(inv, depth) the first iteration starts from: from the stage's depth estimate in one kernel (glue.inv_init: depth_to_disp +
+    disp_to_depth, Effi_MVS_plus.py:138-164) when the caller passes it, else from the normalised inverse depth it computed."""
+    if cur_depth is not None and hasattr(glue, "inv_init") and os.environ.get("EFFIMVS_INV_INIT", "1") != "0":
+        return glue.inv_init(cur_depth, lo_disp, hi_disp)
+    if inv_depth is None:
+        lo, hi = lo_disp.reshape(-1, 1, 1, 1), hi_disp.reshape(-1, 1, 1, 1)
+        inv_depth = (cur_depth.reciprocal() - lo) / ((hi - lo) + 1e-10)
+    return glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
+
+
+def _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask, cur_depth=None):
     """The iterations of update_block_forward_fused with every 3x3 convolution on glue.conv2d_tc: encoder tail, GRU gates and
     state update are epilogues (no encoder_tail / gru_reset / gru_update launches, cat[h, x] and cat[r * h, x] never
     materialised).  hx (B,2h,H,W) channels-last holds [h ; x]; ctx_term (B,h,H,W) = convc's context half + bias."""
@@ -384,7 +395,7 @@ def _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, i
     net_v, x_v = hx[:, :h], hx[:, h:]
     # the one layer without an epilogue to fuse (block-diagonal convc2 | convd2 + relu) can stay on cuDNN: EFFIMVS_CONV2D_CD2=cudnn
     cd2_cudnn = os.environ.get("EFFIMVS_CONV2D_CD2", "own") == "cudnn"
-    inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
+    inv, depth = _start_inverse_depth(glue, inv_depth, cur_depth, lo_disp, hi_disp)
     inv_seq, depth_seq = [], []
     for it in range(iters):
         c1d1 = glue.encoder_head(cost_fn(depth, it), inv, e.convc1.weight, e.convc1.bias, e.convd1.weight, e.convd1.bias)
@@ -406,7 +417,8 @@ def _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, i
     return net_v, inv_seq, depth_seq, up, depth_up, (mask_pre if want_mask else None)
 
 
-def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map=None, want_mask=True):
+def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, iters, lo_disp, hi_disp, ctx_map=None, want_mask=True,
+                               cur_depth=None):
     """Same arithmetic as BasicUpdateBlock.forward (models/update.py:114-141) + upsample_depth + disp_to_depth
     (Effi_MVS_plus.py:138-178), with the elementwise chains between the convolutions replaced by
     glue.encoder_head / gru_reset / gru_update / gru_delta / convex_upsample.  cost_fn(depth, iteration).
@@ -427,7 +439,7 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
     if fused_start and tc_path and hasattr(glue, "gru_init_ctx") and os.environ.get("EFFIMVS_INIT_CTX", "1") != "0":
         # start state and the iteration-invariant context term of the encoder tail in one pass over the context map
         hx, ctx_term = glue.gru_init_ctx(ctx_map, h, w["wc_ctx"], w["bias_c"])
-        return _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask)
+        return _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask, cur_depth)
     if fused_start:
         hx = glue.gru_init(ctx_map, h)                               # hx[:, :h] = tanh(hidden half)
         net = hx[:, :h]
@@ -444,10 +456,10 @@ def update_block_forward_fused(block, glue, net, cost_fn, inv_depth, context, it
     if tc_path:
         ctx_in = torch.relu(ctx_src[:, ctx_off:ctx_off + cx]) if ctx_relu else (ctx_src if ctx_src.shape[1] == cx else ctx_src[:, ctx_off:ctx_off + cx])
         ctx_term = F.conv2d(ctx_in, w["wc_ctx"], w["bias_c"]).contiguous(memory_format=torch.channels_last)
-        return _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask)
+        return _update_block_forward_tc(block, glue, w, hx, ctx_term, cost_fn, inv_depth, iters, lo_disp, hi_disp, want_mask, cur_depth)
     if not tail_ctx:
         ctx_term = F.conv2d(context, w["wc_ctx"], w["bias_c"])
-    inv, depth = glue.gru_delta(None, None, inv_depth, lo_disp, hi_disp)
+    inv, depth = _start_inverse_depth(glue, inv_depth, cur_depth, lo_disp, hi_disp)
     inv_seq, depth_seq = [], []
     head_fused = (hasattr(glue, "delta_head") and h % 16 == 0 and h <= 128 and tuple(hd.conv2.weight.shape) == (1, h, 3, 3)
                   and os.environ.get("EFFIMVS_DELTA_HEAD", "1") != "0")
@@ -568,7 +580,6 @@ class EffiMVSPlus(nn.Module):
         intervals = [unit * r for r in self.RATIOS]
 
         lo_disp, hi_disp = depth_far.reciprocal(), depth_near.reciprocal()   # double reciprocal, as upstream rounds it
-        inv_span = (hi_disp - lo_disp) + 1e-10                    # depth_to_disp's denominator, Effi_MVS_plus.py:151-164
 
         def to_depth(inv):                      # disp_to_depth, Effi_MVS_plus.py:138-148
             return 1.0 / (lo_disp + (hi_disp - lo_disp) * inv).clamp(min=1e-4)
@@ -624,18 +635,18 @@ class EffiMVSPlus(nn.Module):
                     raw_vol = hp.cross_scale(self.CSP_C[s - 1], loc5, raw_prev.unsqueeze(1)).squeeze(1)
                 vol_far, vol_near = hyp[:, 0:1], hyp[:, -1:]
 
-            inv0 = (cur_depth.reciprocal() - lo_disp) / inv_span
             interval = intervals[s]
 
             def cost_fn(depth, _it=0, _raw=raw_vol, _reg=reg_vol, _iv=interval, _n=vol_near, _f=vol_far):
                 return hp.dynamic_cost(depth, _raw, _reg, _iv, _n, _f, self.cost_num)
 
-            if glue is not None:     # tanh / relu of the context map happen inside the glue kernels
+            if glue is not None:     # tanh / relu of the context map and depth_to_disp happen inside the glue kernels
                 _, _, depth_seq, _, depth_up, _ = self.update_block[s].forward_fused(
-                    glue, None, cost_fn, inv0, None, self.iters[s], lo_disp.reshape(B), hi_disp.reshape(B), ctx_pyr[s], False)
+                    glue, None, cost_fn, None, None, self.iters[s], lo_disp.reshape(B), hi_disp.reshape(B), ctx_pyr[s], False, cur_depth)
                 preds.extend(d.squeeze(1) for d in depth_seq)
                 preds.append(depth_up)
                 continue
+            inv0 = (cur_depth.reciprocal() - lo_disp) / ((hi_disp - lo_disp) + 1e-10)     # depth_to_disp, Effi_MVS_plus.py:151-164
             _, mask, inv_seq = self.update_block[s](hidden, cost_fn, inv0, context, self.iters[s], to_depth)
             for inv in inv_seq:
                 preds.append(to_depth(inv).squeeze(1))

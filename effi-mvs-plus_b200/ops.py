@@ -672,6 +672,25 @@ def _(pre, bias, inv, lo_disp, hi_disp):
     return torch.empty_like(inv), torch.empty_like(inv)
 
 
+@torch.library.custom_op("effimvs::inv_init", mutates_args=())
+@_on_tensor_device
+def inv_init(cur_depth: Tensor, lo_disp: Tensor, hi_disp: Tensor) -> Tuple[Tensor, Tensor]:
+    """cur_depth (B,1,H,W) -> (inv, depth): inv = (1 / cur_depth - lo) / ((hi - lo) + 1e-10) and depth = 1 / clamp(lo + (hi - lo) inv,
+    1e-4): depth_to_disp followed by disp_to_depth (models/Effi_MVS_plus.py:138-164), bit-identical to the torch chain."""
+    cur_depth, lo_disp, hi_disp = _dev(cur_depth, "inv_init"), _dev(lo_disp, "inv_init"), _dev(hi_disp, "inv_init")
+    B, _, H, W = cur_depth.shape
+    inv, depth = torch.empty_like(cur_depth), torch.empty_like(cur_depth)
+    _count(1)
+    capi.check(_lib.effimvs_inv_init_f32(cur_depth.data_ptr(), lo_disp.data_ptr(), hi_disp.data_ptr(), B, H * W, inv.data_ptr(),
+                                         depth.data_ptr(), _stream()))
+    return inv, depth
+
+
+@inv_init.register_fake
+def _(cur_depth, lo_disp, hi_disp):
+    return torch.empty_like(cur_depth), torch.empty_like(cur_depth)
+
+
 @torch.library.custom_op("effimvs::delta_head", mutates_args=())
 @_on_tensor_device
 def delta_head(t: Tensor, weight: Tensor, bias: Tensor, inv: Tensor, lo_disp: Tensor, hi_disp: Tensor) -> Tuple[Tensor, Tensor]:
@@ -745,6 +764,37 @@ def _(t, mask_w, mask_bias, mask_scale, inv, lo_disp, hi_disp, ratio):
     return inv.new_empty(B, ratio * H, ratio * W), inv.new_empty(B, ratio * H, ratio * W)
 
 
+# Host-side weight tables of encoder_head's constant-bank kernel (csrc/update_glue.cu: the weights travel as kernel parameters, so
+# they must be in host memory when the kernel is launched).  One entry per set of weight tensors, found by object identity: the
+# entry holds weak references and the versions / addresses it was built from, so an in-place update, a re-assigned .data or a
+# recycled id() misses and rebuilds.  Building costs one synchronous device -> host copy of ~50 h floats; it cannot happen
+# while the stream is being captured, where a miss falls back to the kernel that reads the weights from device memory.
+_EH_TABLES: dict = {}
+
+
+def _encoder_head_table(ws, CD: int, h: int):
+    import weakref
+    key = tuple(id(t) for t in ws)
+    stamp = tuple((t.data_ptr(), t._version) for t in ws)
+    hit = _EH_TABLES.get(key)
+    if hit is not None and hit[1] == stamp and all(r() is t for r, t in zip(hit[0], ws)):
+        return hit[2]
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    host = [t.detach().to("cpu", torch.float32).contiguous() for t in ws]
+    table = torch.empty(_lib.effimvs_encoder_head_table_floats(h), dtype=torch.float32)
+    capi.check(_lib.effimvs_encoder_head_pack_host(host[0].data_ptr(), host[1].data_ptr(), host[2].data_ptr(), host[3].data_ptr(), CD, h,
+                                                   table.data_ptr()))
+    if len(_EH_TABLES) >= 256:                     # temporaries (tests, one-off calls) would otherwise pile up as dead entries
+        for k in [k for k, v in _EH_TABLES.items() if any(r() is None for r in v[0])]:
+            del _EH_TABLES[k]
+    try:
+        _EH_TABLES[key] = (tuple(weakref.ref(t) for t in ws), stamp, table)
+    except TypeError:                              # not weak-referenceable (never the case for torch.Tensor): use it uncached
+        pass
+    return table
+
+
 @torch.library.custom_op("effimvs::encoder_head", mutates_args=())
 @_on_tensor_device
 def encoder_head(cost: Tensor, inv: Tensor, wc1: Tensor, bc1: Tensor, wd1: Tensor, bd1: Tensor) -> Tensor:
@@ -754,6 +804,17 @@ def encoder_head(cost: Tensor, inv: Tensor, wc1: Tensor, bc1: Tensor, wd1: Tenso
     B, CD, H, W = cost.shape
     h = wc1.shape[0]
     out = torch.empty(B, 2 * h, H, W, device=cost.device, dtype=torch.float32, memory_format=torch.channels_last)
+    # measured on B200 (tools/eh_time.py, DTU stage shapes): h = 16 at 800 x 592 40.0 us against 47.1 from device-memory weights,
+    # h = 32 at 400 x 296 31.7 / 32.8 (two launches), h = 48 at 200 x 148 33.8 / 20.4 (three launches of a grid that no longer
+    # fills the machine): by default only the single-launch case.  EFFIMVS_EH_CONST = 1 / 0 forces it on / off.
+    mode = os.environ.get("EFFIMVS_EH_CONST", "auto")
+    use_const = 1 <= CD <= 8 and h % 16 == 0 and 16 <= h <= 128 and (mode == "1" or (mode != "0" and h == 16))
+    table = _encoder_head_table((wc1, bc1, wd1, bd1), CD, h) if use_const else None
+    if table is not None:          # weights as kernel parameters: h / 16 launches, no staging prologue, no shared-memory weight reads
+        _count(h // 16)
+        capi.check(_lib.effimvs_encoder_head_hostw_f32(cost.data_ptr(), inv.data_ptr(), table.data_ptr(), B, CD, h, H, W, out.data_ptr(),
+                                                       _stream()))
+        return out
     _count(1)
     capi.check(_lib.effimvs_encoder_head_f32(cost.data_ptr(), inv.data_ptr(), wc1.data_ptr(), bc1.data_ptr(), wd1.data_ptr(), bd1.data_ptr(),
                                              B, CD, h, H, W, out.data_ptr(), _stream()))

@@ -243,6 +243,12 @@ int effimvs_gru_reset_f32(const float* zr_pre, const float* bias_r, const float*
 int effimvs_gru_update_f32(const float* zr_pre, const float* bias_z, const float* q_pre, const float* bias_q, float* hx,
                            long long n_pix, int h, int cx, float* net_out, void* stream);
 
+/* Start of a stage's refinement: inv = (1 / cur_depth - lo) / ((hi - lo) + 1e-10) (depth_to_disp, models/Effi_MVS_plus.py:151-164)
+ * and depth = 1 / clamp(lo + (hi - lo) * inv, 1e-4) (disp_to_depth, :138-148), both (B,HW); lo_disp / hi_disp (B) as below.
+ * Bit-identical to the torch chain (IEEE reciprocal, subtraction, division). */
+int effimvs_inv_init_f32(const float* cur_depth, const float* lo_disp, const float* hi_disp, int B, int HW, float* inv_out,
+                         float* depth_out, void* stream);
+
 /* DepthHead tail + BasicUpdateBlock step + disp_to_depth (models/update.py:27, 121-125;
  * models/Effi_MVS_plus.py:138-148).  pre (B,HW) = depth_head.conv2 output without bias (NULL: no step),
  * bias (1), inv (B,HW), lo_disp / hi_disp (B)  ->  inv_out = inv + tanh(pre + bias) (optional),
@@ -276,6 +282,18 @@ int effimvs_convex_upsample_conv_f32(const float* t, int K, const float* mask_w,
  *   -> out (B,H,W,2h) channels-last = cat[relu(convc1), relu(convd1)]: the input of the second encoder layer. */
 int effimvs_encoder_head_f32(const float* cost, const float* inv, const float* wc1, const float* bc1, const float* wd1,
                              const float* bd1, int B, int CD, int h, int H, int W, float* out, void* stream);
+
+/* The same head with the weights passed as KERNEL PARAMETERS (constant bank operands of the FMAs: no per-block weight staging, no
+ * shared-memory weight reads).  host_tables points to HOST memory holding h / 16 tables of 944 floats each, one per chunk of 16
+ * output channels: [49][16] convd1 taps, [8][16] convc1 rows (rows >= CD zero), [16] convc1 bias, [16] convd1 bias.  They are
+ * copied into the launch parameters during the call (the array may be reused afterwards; a CUDA graph keeps the values of the
+ * capture).  h / 16 launches.  effimvs_encoder_head_pack_host builds the tables from HOST copies of upstream's weight tensors
+ * (wc1 (h,CD,1,1), bc1 (h), wd1 (h,1,7,7), bd1 (h)); effimvs_encoder_head_table_floats(h) = (h / 16) * 944 is their size. */
+int effimvs_encoder_head_hostw_f32(const float* cost, const float* inv, const float* host_tables, int B, int CD, int h, int H, int W,
+                                   float* out, void* stream);
+int effimvs_encoder_head_pack_host(const float* wc1, const float* bc1, const float* wd1, const float* bd1, int CD, int h,
+                                   float* tables_out);
+int effimvs_encoder_head_table_floats(int h);
 
 /* ProjectionInput tail (models/update.py:93-95): x = relu(Wc[:, :hm] m + ctx_term), ctx_term (n_pix, h) = the context half of
  * convc plus both biases (constant over the GRU iterations), m (n_pix, hm) channels-last, w (h, hm) = convc.weight[:, :hm].

@@ -72,12 +72,38 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_encoder_tail_ctx_f32(one, one, one, 20, 5, 1, one, one, 10, 12, 16, one, None) == capi.EUNSUPPORTED           # cx = 5
     assert lib.effimvs_encoder_tail_ctx_f32(one, one, ctypes.c_void_p(20), 20, 4, 1, one, one, 10, 12, 16, one, None) == capi.EINVAL  # misaligned ctx
     assert lib.effimvs_gru_init_f32(one, 10, 18, 4, one, None) == capi.EINVAL
+    assert lib.effimvs_inv_init_f32(one, one, one, 1, 16, None, one, None) == capi.EINVAL
     assert lib.effimvs_gru_init_ctx_f32(one, 10, 16, 6, one, one, one, one, None) == capi.EINVAL            # cx not a multiple of 4
     assert lib.effimvs_gru_init_ctx_f32(one, 10, 16, 4, one, None, one, one, None) == capi.EINVAL           # no bias
     td, tf = (ctypes.c_double * 2)(1.0, 0.5), (ctypes.c_float * 2)(0.1, 0.2)
     assert lib.effimvs_dtu_filter_f32(one, one, one, one, td, tf, 2, 1, 11, 0.5, 0.75, 3, 8, 8, one, None, one, one, None, None, None) == capi.EUNSUPPORTED
     assert "non-decreasing" in capi.last_error()
     assert lib.effimvs_dtu_filter_f32(one, one, one, one, td, tf, 2, 1, 11, 0.5, 0.75, 40, 8, 8, one, None, one, one, None, None, None) == capi.EINVAL
+
+
+def test_encoder_head_host_tables_layout():
+    """effimvs_encoder_head_pack_host is a pure host function: the per-chunk tables (kernel parameters of the constant-bank
+    encoder head) hold convd1's taps tap-major, convc1's rows padded to 8, and the two biases."""
+    lib = capi.lib
+    h, CD = 32, 6
+    gen = torch.Generator().manual_seed(5)
+    wc1, bc1 = torch.randn(h, CD, 1, 1, generator=gen), torch.randn(h, generator=gen)
+    wd1, bd1 = torch.randn(h, 1, 7, 7, generator=gen), torch.randn(h, generator=gen)
+    n = lib.effimvs_encoder_head_table_floats(h)
+    assert n == 2 * 944 and lib.effimvs_encoder_head_table_floats(24) == 0
+    tab = torch.full((n,), float("nan"))
+    assert lib.effimvs_encoder_head_pack_host(wc1.data_ptr(), bc1.data_ptr(), wd1.data_ptr(), bd1.data_ptr(), CD, h, tab.data_ptr()) == capi.OK
+    t = tab.reshape(2, 944)
+    for k in range(2):
+        ch = slice(16 * k, 16 * k + 16)
+        assert torch.equal(t[k, :784].reshape(49, 16), wd1[ch, 0].reshape(16, 49).t())
+        assert torch.equal(t[k, 784:784 + 16 * CD].reshape(CD, 16), wc1[ch, :, 0, 0].t())
+        assert torch.count_nonzero(t[k, 784 + 16 * CD:912]) == 0
+        assert torch.equal(t[k, 912:928], bc1[ch]) and torch.equal(t[k, 928:], bd1[ch])
+    assert lib.effimvs_encoder_head_pack_host(wc1.data_ptr(), bc1.data_ptr(), wd1.data_ptr(), bd1.data_ptr(), 9, h, tab.data_ptr()) == capi.EUNSUPPORTED
+    one = ctypes.c_void_p(1)
+    assert lib.effimvs_encoder_head_hostw_f32(one, one, None, 1, 6, 16, 4, 4, one, None) == capi.EINVAL
+    assert lib.effimvs_encoder_head_hostw_f32(one, one, one, 1, 6, 20, 4, 4, one, None) == capi.EUNSUPPORTED
 
 
 def test_cpu_tensors_are_rejected_not_emulated():
@@ -100,6 +126,8 @@ def test_fake_implementations_give_shapes_without_a_device():
                                                          torch.empty(2), torch.empty(2), 2)
         assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
         assert torch.ops.effimvs.gru_init(torch.empty(2, 20, 6, 8), 16).shape == (2, 32, 6, 8)
+        iv0, dp0 = torch.ops.effimvs.inv_init(torch.empty(2, 1, 6, 8), torch.empty(2), torch.empty(2))
+        assert iv0.shape == (2, 1, 6, 8) and dp0.shape == (2, 1, 6, 8)
         hx0, term = torch.ops.effimvs.gru_init_ctx(torch.empty(2, 20, 6, 8), 16, torch.empty(16, 4, 1, 1), torch.empty(16))
         assert hx0.shape == (2, 32, 6, 8) and term.shape == (2, 16, 6, 8)
         up, dep = torch.ops.effimvs.convex_upsample(torch.empty(2, 36, 6, 8), None, 0.25, torch.empty(2, 1, 6, 8), torch.empty(2), torch.empty(2), 2)

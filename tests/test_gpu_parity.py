@@ -633,6 +633,26 @@ def test_gru_init_and_encoder_tail_ctx_vs_torch(h, cx, H, W):
 
 
 @pytest.mark.gpu
+def test_inv_init_is_bit_identical_to_the_torch_chain():
+    """inv_init = depth_to_disp + disp_to_depth of a stage's depth estimate (models/Effi_MVS_plus.py:138-164) in one kernel:
+    the same bits as torch's reciprocal / sub / div / mul / add / clamp / reciprocal chain, per-batch ranges."""
+    from effimvs_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    B, H, W = 2, 148, 201
+    cur = 425.0 + 510.0 * torch.rand(B, 1, H, W, device=DEV, generator=gen)
+    cur[0, 0, 0, :4] = torch.tensor([1e-3, 1e6, 425.0, 935.0], device=DEV)
+    dmin, dmax = torch.tensor([425.0, 300.0], device=DEV), torch.tensor([935.0, 1200.0], device=DEV)
+    far, near = dmin.reciprocal(), dmax.reciprocal()                 # the cascade's lo_disp / hi_disp: double reciprocals
+    lo, hi = far.reciprocal().reshape(B, 1, 1, 1), near.reciprocal().reshape(B, 1, 1, 1)
+    inv, depth = ops.inv_init(cur, lo.reshape(B), hi.reshape(B))
+    want_inv = (cur.reciprocal() - lo) / ((hi - lo) + 1e-10)
+    want_depth = 1.0 / (lo + (hi - lo) * want_inv).clamp(min=1e-4)
+    assert torch.equal(inv, want_inv) and torch.equal(depth, want_depth)
+    inv2, depth2 = ops.gru_delta(None, None, want_inv, lo.reshape(B), hi.reshape(B))     # the two-step form it replaces
+    assert torch.equal(inv2, inv) and torch.equal(depth2, depth)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("h,cx,H,W", [(16, 4, 37, 53), (32, 8, 24, 40), (48, 12, 19, 25), (16, 4, 592, 800)])
 def test_gru_init_ctx_vs_torch(h, cx, H, W):
     """gru_init_ctx: the GRU start state and the iteration-invariant context term of the encoder tail (the aux map of conv2d_tc's
@@ -824,8 +844,8 @@ def test_dtu_filter_vs_oracle_dtu_size():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("h,H,W", [(16, 37, 53), (32, 24, 70), (48, 19, 25)])
-def test_encoder_head_vs_torch(h, H, W):
+@pytest.mark.parametrize("h,H,W", [(16, 37, 53), (32, 24, 70), (48, 19, 25), (16, 148, 201)])
+def test_encoder_head_vs_torch(h, H, W, monkeypatch):
     """effimvs_encoder_head_f32 against relu(conv2d) of upstream's ProjectionInput head (models/update.py:88-91)"""
     import torch.nn.functional as F
     from effimvs_b200 import ops
@@ -834,10 +854,21 @@ def test_encoder_head_vs_torch(h, H, W):
     B, CD = 2, 6
     cost, inv = rnd(B, CD, H, W), torch.rand(B, 1, H, W, device=DEV, generator=gen)
     wc1, bc1, wd1, bd1 = rnd(h, CD, 1, 1) * 0.3, rnd(h), rnd(h, 1, 7, 7) * 0.2, rnd(h)
-    got = ops.encoder_head(cost, inv, wc1, bc1, wd1, bd1)
+    monkeypatch.setenv("EFFIMVS_EH_CONST", "1")                        # (by default only h = 16 takes this path)
+    before = ops.LAUNCHES
+    got = ops.encoder_head(cost, inv, wc1, bc1, wd1, bd1)              # weights as kernel parameters: one launch per 16 channels
+    assert ops.LAUNCHES - before == h // 16
     want = torch.cat([F.relu(F.conv2d(cost, wc1, bc1)), F.relu(F.conv2d(inv, wd1, bd1, padding=3))], dim=1)
     assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
     assert rel_max(got, want) < 1e-5
+    assert torch.equal(ops.encoder_head(cost, inv, wc1, bc1, wd1, bd1), got)      # second call: the cached host tables
+    wd1.mul_(2.0)                                                                  # in-place update: the tables are rebuilt
+    want2 = torch.cat([F.relu(F.conv2d(cost, wc1, bc1)), F.relu(F.conv2d(inv, wd1, bd1, padding=3))], dim=1)
+    assert rel_max(ops.encoder_head(cost, inv, wc1, bc1, wd1, bd1), want2) < 1e-5
+    monkeypatch.setenv("EFFIMVS_EH_CONST", "0")                                    # the kernel that reads the weights from device memory
+    before = ops.LAUNCHES
+    dev_w = ops.encoder_head(cost, inv, wc1, bc1, wd1.clone(), bd1)
+    assert ops.LAUNCHES - before == 1 and rel_max(dev_w, want2) < 1e-5
 
 
 @pytest.mark.gpu

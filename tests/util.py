@@ -81,6 +81,12 @@ class TorchGlue:
         return hx
 
     @staticmethod
+    def inv_init(cur_depth, lo, hi):
+        l, hh = lo.reshape(-1, 1, 1, 1), hi.reshape(-1, 1, 1, 1)
+        inv = (cur_depth.reciprocal() - l) / ((hh - l) + 1e-10)
+        return inv, TorchGlue._to_depth(inv, lo, hi)
+
+    @staticmethod
     def gru_init_ctx(ctx_map, h, w_ctx, bias):
         w4 = w_ctx.reshape(w_ctx.shape[0], -1, 1, 1)
         return TorchGlue.gru_init(ctx_map, h), F.conv2d(torch.relu(ctx_map[:, h:]), w4, bias)
