@@ -1072,15 +1072,36 @@ deconv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const floa
     const long long base = (long long)b * IL.batch_stride + IL.guard;
     const float b0 = bias ? __ldg(bias) : 0.0f;
     float acc[2][2] = {{b0, b0}, {b0, b0}};
+    // ncu: long scoreboard 13 warps per issue -- ptxas interleaves the voxel loads with the FMAs of earlier voxels to save registers
+    // (whatever the source order), so a thread waits on one L2 round trip after the other.  The lines of all three input planes are
+    // therefore requested up front with L1 prefetches (no destination registers); the x + 2 voxel of a thread is its neighbour's x + 1.
+    {
+        const bool last = (threadIdx.x & 31) == 31 || x == W - 1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const uint4* p = in + base + (long long)(z + 2 - a) * IL.zstride + (long long)(y + 1 + dy) * IL.Px + (x + 1);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+                if (RAW || lo_delta) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + lo_delta));
+                if (last) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 1));
+                    if (RAW || lo_delta) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 1 + lo_delta));
+                }
+            }
+    }
+    float v[3][2][2][8];   // plane a, input (y + dy, x + dx)
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         // out z = in z - 1 + a  ->  input plane z + 1 - a, padded index z + 2 - a
         const long long plane = base + (long long)(z + 2 - a) * IL.zstride;
-        float v[2][2][8];   // input (y + dy, x + dx)
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-            for (int dx = 0; dx < 2; ++dx) load_voxel_f32<RAW>(in, lo_delta, plane + (long long)(y + 1 + dy) * IL.Px + (x + 1 + dx), v[dy][dx]);
+            for (int dx = 0; dx < 2; ++dx) load_voxel_f32<RAW>(in, lo_delta, plane + (long long)(y + 1 + dy) * IL.Px + (x + 1 + dx), v[a][dy][dx]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
 #pragma unroll
         for (int bb = 0; bb < 3; ++bb)
 #pragma unroll
@@ -1088,7 +1109,7 @@ deconv_cout1_kernel(const uint4* __restrict__ in, const ActLayout IL, const floa
                 const int py = bb != 1, dy = bb == 0, px = c != 1, dx = c == 0;
                 const float4 w0 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8);
                 const float4 w1 = *reinterpret_cast<const float4*>(sw + (a * 9 + bb * 3 + c) * 8 + 4);
-                const float (&u)[8] = v[dy][dx];
+                const float (&u)[8] = v[a][dy][dx];
                 float t = acc[py][px];
                 t = fmaf(u[0], w0.x, t); t = fmaf(u[1], w0.y, t); t = fmaf(u[2], w0.z, t); t = fmaf(u[3], w0.w, t);
                 t = fmaf(u[4], w1.x, t); t = fmaf(u[5], w1.y, t); t = fmaf(u[6], w1.z, t); t = fmaf(u[7], w1.w, t);
