@@ -42,6 +42,7 @@ SIGNATURES = {
     "effimvs_relative_projection_f32": (_i, [_p, _i, _i, _p, _p]),
     "effimvs_homo_warp_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "effimvs_depth_range_samples_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "effimvs_depth_ranges_f32": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "effimvs_fusion_masks_f32": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _i, _i, _p, _p]),
     "effimvs_warp_corr_agg_f32": (_i, [_p, _pp, _i, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "effimvs_warp_corr_views_f32": (_i, [_p, _pp, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),

@@ -283,6 +283,48 @@ extern "C" int effimvs_softmax_regress_conf_f32(const float* prob_pre, const flo
     return check_launch("softmax_regress_conf_kernel");
 }
 
+namespace effimvs {
+namespace {
+// Everything the cascade derives from depth_values alone (models/Effi_MVS_plus.py:409-424, models/module.py:577-585), one thread per number instead of
+// ~16 single-element torch kernels per forward; the same IEEE operations: torch evaluates tensor / python-scalar on the device as
+// a * (1 / b) with the reciprocal formed in fp32, tensor * python-scalar as a * float(b), reciprocal() as 1 / x.
+// out = 8 rows of B scalars -- depth_far = 1 / min, depth_near = 1 / max, lo_disp = 1 / depth_far, hi_disp = 1 / depth_near,
+// interval_s = ((max - min) * (1 / Dv)) * ratio_s (s = 0..2), 0 -- followed by the (B, D1) plane-sweep hypotheses
+// 1 / (min + k * ((max - min) * (1 / (D1 - 1)))): every piece is contiguous for its consumer.
+__global__ void depth_ranges_kernel(const float* __restrict__ depth_values, int Dv, int D1, float r0, float r1, float r2, float inv_dv, float inv_d1m1,
+                                    float* __restrict__ out) {
+    pdl_enter();
+    const int b = blockIdx.x, t = threadIdx.x;
+    const float mn = __ldg(depth_values + (size_t)b * Dv), mx = __ldg(depth_values + (size_t)b * Dv + Dv - 1);
+    const int B = gridDim.x;
+    const float span = __fsub_rn(mx, mn);
+    if (t < 8) {
+        const float far_ = __frcp_rn(mn), near_ = __frcp_rn(mx), unit = __fmul_rn(span, inv_dv);
+        float v = 0.0f;
+        if (t == 0) v = far_;
+        else if (t == 1) v = near_;
+        else if (t == 2) v = __frcp_rn(far_);
+        else if (t == 3) v = __frcp_rn(near_);
+        else if (t == 4) v = __fmul_rn(unit, r0);
+        else if (t == 5) v = __fmul_rn(unit, r1);
+        else if (t == 6) v = __fmul_rn(unit, r2);
+        out[t * B + b] = v;
+    }
+    float* hyp = out + 8 * (size_t)B + (size_t)b * D1;
+    for (int k = t; k < D1; k += blockDim.x) hyp[k] = __frcp_rn(__fadd_rn(mn, __fmul_rn((float)k, __fmul_rn(span, inv_d1m1))));
+}
+}  // namespace
+}  // namespace effimvs
+
+extern "C" int effimvs_depth_ranges_f32(const float* depth_values, int B, int Dv, int D1, const float* ratios3, float* out, void* stream) {
+    using namespace effimvs;
+    EFFI_REQUIRE(depth_values && ratios3 && out, EFFIMVS_EINVAL, "depth_ranges: null pointer");
+    EFFI_REQUIRE(B > 0 && Dv > 1 && D1 > 1, EFFIMVS_EINVAL, "depth_ranges: B=%d, Dv=%d, D1=%d", B, Dv, D1);
+    launch_kernel(depth_ranges_kernel, dim3(B), dim3(64), 0, (cudaStream_t)stream, depth_values, Dv, D1, ratios3[0], ratios3[1], ratios3[2],
+                  1.0f / (float)Dv, 1.0f / (float)(D1 - 1), out);
+    return check_launch("depth_ranges_kernel");
+}
+
 extern "C" int effimvs_depth_range_samples_f32(const float* cur, const float* interval, int B, int ndepth, int H, int W,
                                                float* samples_out, void* stream) {
     EFFI_REQUIRE(cur && interval && samples_out, EFFIMVS_EINVAL, "depth_range_samples: null pointer");

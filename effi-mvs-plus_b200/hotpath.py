@@ -280,6 +280,7 @@ class CudaHotPath:
     gru_update = staticmethod(ops.gru_update)
     gru_delta = staticmethod(ops.gru_delta)
     inv_init = staticmethod(ops.inv_init)
+    depth_ranges = staticmethod(ops.depth_ranges)
     delta_head = staticmethod(ops.delta_head)
     convex_upsample = staticmethod(ops.convex_upsample)
     convex_upsample_conv = staticmethod(ops.convex_upsample_conv)

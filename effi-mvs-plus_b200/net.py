@@ -575,11 +575,20 @@ class EffiMVSPlus(nn.Module):
         disp_max = depth_values[:, -1].reshape(B, 1, 1, 1)
         # x.reciprocal() is what torch evaluates for 1.0 / x (followed by a multiplication by 1.0): same bits, one
         # launch instead of two.  Everything that depends on depth_values only is formed once, here.
-        depth_far, depth_near = disp_min.reciprocal(), disp_max.reciprocal()
-        unit = (disp_max - disp_min) / depth_values.size(1)
-        intervals = [unit * r for r in self.RATIOS]
-
-        lo_disp, hi_disp = depth_far.reciprocal(), depth_near.reciprocal()   # double reciprocal, as upstream rounds it
+        planes = None
+        if (hasattr(hp, "depth_ranges") and depth_values.is_cuda and not torch.is_grad_enabled()
+                and os.environ.get("EFFIMVS_DEPTH_RANGES", "1") != "0"):
+            # the same numbers from one kernel (bit-identical; ~16 single-element launches otherwise)
+            R = hp.depth_ranges(depth_values, self.ndepths[0], [float(r) for r in self.RATIOS])
+            row = lambda i: R[i * B:(i + 1) * B].reshape(B, 1, 1, 1)      # noqa: E731
+            depth_far, depth_near, lo_disp, hi_disp = row(0), row(1), row(2), row(3)
+            intervals = [row(4), row(5), row(6)]
+            planes = R[8 * B:].reshape(B, self.ndepths[0])
+        else:
+            depth_far, depth_near = disp_min.reciprocal(), disp_max.reciprocal()
+            unit = (disp_max - disp_min) / depth_values.size(1)
+            intervals = [unit * r for r in self.RATIOS]
+            lo_disp, hi_disp = depth_far.reciprocal(), depth_near.reciprocal()   # double reciprocal, as upstream rounds it
 
         def to_depth(inv):                      # disp_to_depth, Effi_MVS_plus.py:138-148
             return 1.0 / (lo_disp + (hi_disp - lo_disp) * inv).clamp(min=1e-4)
@@ -600,9 +609,11 @@ class EffiMVSPlus(nn.Module):
             H, W = f[0].shape[2:]
             if s == 0:
                 D = self.ndepths[0]
-                k = torch.arange(D, device=imgs.device, dtype=imgs.dtype).reshape(1, D)
-                inv_s = disp_min.reshape(B, 1) + k * ((disp_max - disp_min).reshape(B, 1) / (D - 1))
-                hyp = inv_s.reciprocal().reshape(B, D, 1, 1).expand(B, D, H, W)   # plane sweep: stride-0 view
+                if planes is None:
+                    k = torch.arange(D, device=imgs.device, dtype=imgs.dtype).reshape(1, D)
+                    inv_s = disp_min.reshape(B, 1) + k * ((disp_max - disp_min).reshape(B, 1) / (D - 1))
+                    planes = inv_s.reciprocal()
+                hyp = planes.reshape(B, D, 1, 1).expand(B, D, H, W)   # plane sweep: stride-0 view
                 out = hp.stage1(f, cams, hyp, self.PixelwiseNet, self.cost_regularization, self.G)
                 conf = F.interpolate(out["photometric_confidence"].unsqueeze(1), [H * 4, W * 4], mode="nearest").squeeze(1)
                 view_w = out["view_weights"]

@@ -122,6 +122,29 @@ def _(src_fea, proj, hyp, hyp_mode, D):
     return src_fea.new_empty(B, Cc, D, H, W)
 
 
+@torch.library.custom_op("effimvs::depth_ranges", mutates_args=())
+@_on_tensor_device
+def depth_ranges(depth_values: Tensor, ndepth1: int, ratios: List[float]) -> Tensor:
+    """depth_values (B,Dv) -> a flat buffer of 8 B + B ndepth1 floats: 8 rows of B scalars [depth_far, depth_near, lo_disp, hi_disp,
+    interval_1, interval_2, interval_3, 0] followed by the (B, ndepth1) plane-sweep hypotheses -- everything Effi_MVS_plus.forward
+    derives from depth_values alone (Effi_MVS_plus.py:409-424, module.py:577-585), bit-identical to the torch expressions, in one launch."""
+    import ctypes
+    depth_values = _dev(depth_values, "depth_ranges")
+    B, Dv = depth_values.shape
+    if len(ratios) != 3:
+        raise ValueError("depth_ranges: three interval ratios expected")
+    out = torch.empty(B * (8 + ndepth1), device=depth_values.device, dtype=torch.float32)
+    r3 = (ctypes.c_float * 3)(*[float(r) for r in ratios])
+    _count(1)
+    capi.check(_lib.effimvs_depth_ranges_f32(depth_values.data_ptr(), B, Dv, ndepth1, r3, out.data_ptr(), _stream()))
+    return out
+
+
+@depth_ranges.register_fake
+def _(depth_values, ndepth1, ratios):
+    return depth_values.new_empty(depth_values.shape[0] * (8 + ndepth1))
+
+
 @torch.library.custom_op("effimvs::depth_range_samples", mutates_args=())
 @_on_tensor_device
 def depth_range_samples(cur: Tensor, interval: Tensor, ndepth: int) -> Tensor:

@@ -72,6 +72,13 @@ int effimvs_relative_projection_f32(const float* cams, int B, int V, float* proj
 int effimvs_homo_warp_f32(const float* src_fea, const float* proj, const float* hyp, int hyp_mode,
                           int B, int C, int H, int W, int D, float* warped_out, void* stream);
 
+/* The scalars the cascade derives from depth_values (B,Dv) alone (models/Effi_MVS_plus.py:409-424, models/module.py:577-585), bit-identical to the
+ * torch expressions: out (8 B + B D1 floats) = 8 rows of B scalars [1/min, 1/max, 1/(1/min), 1/(1/max), interval_1..3 =
+ * ((max - min) / Dv) * ratios3[s], 0] followed by the (B, D1) plane-sweep hypotheses 1 / (min + k (max - min) / (D1 - 1));
+ * min / max = depth_values[:, 0] / [:, -1] (inverse depths).
+ * ratios3 is a HOST array of three floats (upstream's depth_interals_ratio 4, 2, 1). */
+int effimvs_depth_ranges_f32(const float* depth_values, int B, int Dv, int D1, const float* ratios3, float* out, void* stream);
+
 /* get_cur_depth_range_samples (models/module.py:554-570): ndepth samples around cur (B,H,W) in the
  * caller's space (upstream: inverse depth), half-width (ndepth/2)*interval[b], clamped like upstream.
  *   -> samples_out (B,ndepth,H,W) */

@@ -73,6 +73,7 @@ def test_argument_validation_returns_error_codes():
     assert lib.effimvs_encoder_tail_ctx_f32(one, one, ctypes.c_void_p(20), 20, 4, 1, one, one, 10, 12, 16, one, None) == capi.EINVAL  # misaligned ctx
     assert lib.effimvs_gru_init_f32(one, 10, 18, 4, one, None) == capi.EINVAL
     assert lib.effimvs_inv_init_f32(one, one, one, 1, 16, None, one, None) == capi.EINVAL
+    assert lib.effimvs_depth_ranges_f32(one, 1, 1, 48, one, one, None) == capi.EINVAL                      # a single depth value
     assert lib.effimvs_gru_init_ctx_f32(one, 10, 16, 6, one, one, one, one, None) == capi.EINVAL            # cx not a multiple of 4
     assert lib.effimvs_gru_init_ctx_f32(one, 10, 16, 4, one, None, one, one, None) == capi.EINVAL           # no bias
     td, tf = (ctypes.c_double * 2)(1.0, 0.5), (ctypes.c_float * 2)(0.1, 0.2)
@@ -126,6 +127,7 @@ def test_fake_implementations_give_shapes_without_a_device():
                                                          torch.empty(2), torch.empty(2), 2)
         assert up.shape == (2, 12, 16) and dep.shape == (2, 12, 16)
         assert torch.ops.effimvs.gru_init(torch.empty(2, 20, 6, 8), 16).shape == (2, 32, 6, 8)
+        assert torch.ops.effimvs.depth_ranges(torch.empty(2, 48), 48, [4.0, 2.0, 1.0]).shape == (2 * 56,)
         iv0, dp0 = torch.ops.effimvs.inv_init(torch.empty(2, 1, 6, 8), torch.empty(2), torch.empty(2))
         assert iv0.shape == (2, 1, 6, 8) and dp0.shape == (2, 1, 6, 8)
         hx0, term = torch.ops.effimvs.gru_init_ctx(torch.empty(2, 20, 6, 8), 16, torch.empty(16, 4, 1, 1), torch.empty(16))

@@ -633,6 +633,31 @@ def test_gru_init_and_encoder_tail_ctx_vs_torch(h, cx, H, W):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("B,Dv,D1", [(1, 48, 48), (3, 192, 48), (2, 7, 96)])
+def test_depth_ranges_is_bit_identical_to_the_torch_expressions(B, Dv, D1):
+    """depth_ranges: everything the cascade derives from depth_values alone (upstream models/Effi_MVS_plus.py:409-424 and the
+    plane sweep of get_depth_range_samples, models/module.py:577-585) from one kernel, against the torch expressions of
+    net.EffiMVSPlus.forward_from_features bit for bit."""
+    from effimvs_b200 import ops
+    gen = torch.Generator(device=DEV).manual_seed(Dv)
+    lo = 1.0 / (900.0 + 100.0 * torch.rand(B, 1, device=DEV, generator=gen))
+    hi = 1.0 / (400.0 + 50.0 * torch.rand(B, 1, device=DEV, generator=gen))
+    depth_values = lo + (hi - lo) * torch.linspace(0, 1, Dv, device=DEV).reshape(1, Dv)
+    R = ops.depth_ranges(depth_values, D1, [4.0, 2.0, 1.0])
+    row = lambda i: R[i * B:(i + 1) * B]      # noqa: E731
+    disp_min, disp_max = depth_values[:, 0], depth_values[:, -1]
+    far, near = disp_min.reciprocal(), disp_max.reciprocal()
+    unit = (disp_max - disp_min) / depth_values.size(1)
+    want = [far, near, far.reciprocal(), near.reciprocal(), unit * 4, unit * 2, unit * 1, torch.zeros_like(far)]
+    for i, w in enumerate(want):
+        assert torch.equal(row(i), w), "row {}".format(i)
+    assert torch.equal(far, 1.0 / disp_min)                         # what upstream writes (Effi_MVS_plus.py:413)
+    k = torch.arange(D1, device=DEV, dtype=torch.float32).reshape(1, D1)
+    inv_s = disp_min.reshape(B, 1) + k * ((disp_max - disp_min).reshape(B, 1) / (D1 - 1))
+    assert torch.equal(R[8 * B:].reshape(B, D1), inv_s.reciprocal())
+
+
+@pytest.mark.gpu
 def test_inv_init_is_bit_identical_to_the_torch_chain():
     """inv_init = depth_to_disp + disp_to_depth of a stage's depth estimate (models/Effi_MVS_plus.py:138-164) in one kernel:
     the same bits as torch's reciprocal / sub / div / mul / add / clamp / reciprocal chain, per-batch ranges."""
