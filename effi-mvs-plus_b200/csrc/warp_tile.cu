@@ -153,7 +153,10 @@ __device__ __forceinline__ void static_for(F&& f) {
     }
 }
 
-template <int G> struct TilePlanes { static constexpr int value = G >= 4 ? 4 : 8; };
+#ifndef EFFI_TILE_DPT1
+#define EFFI_TILE_DPT1 8      // planes per thread of the aggregated kernel with one group (tuning builds: 4)
+#endif
+template <int G> struct TilePlanes { static constexpr int value = G >= 4 ? 4 : EFFI_TILE_DPT1; };
 
 // constants every thread would otherwise derive with an fp64 / IEEE division of its own (87 + 50 warp instructions per warp
 // for the two normalisation factors alone): computed once on the host, same roundings
