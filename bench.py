@@ -274,7 +274,7 @@ def ncu_traffic(tag):
     return None
 
 
-def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
+def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=11):
     """Per-kernel device time of the hot-path launches at the bench shape, timed in isolation with
     CUDA events on the launching stream, an L2 flush (256 MiB memset) before every launch."""
     from effimvs_b200 import capi, ops
@@ -306,8 +306,14 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
         model.set_hotpath(hp)
 
     def timed(fn):
+        # the events bracket the launch on an otherwise idle stream, so the host must have the kernel enqueued before the device
+        # reaches the first event: three L2 flushes (~0.25 ms of device work) are queued ahead of it -- with one, a slow host
+        # (Python op dispatch longer than the flush) left an idle gap inside the bracket and one box reported every isolated kernel
+        # ~20 % slower than the others.  Median of `reps` launches after a dropped cold one.
         ts = []
         for _ in range(reps + 1):
+            flush.zero_()
+            flush.zero_()
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -315,7 +321,8 @@ def kernel_rooflines(hp, model, sample, hbm_peak, tf_peak, peak_src, reps=5):
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        return sum(ts[1:]) / reps   # ms, first (cold) launch dropped
+        ts = sorted(ts[1:])
+        return ts[len(ts) // 2]
 
     B, V = sample["imgs"].shape[:2]
     # stage 1: per-view similarity + entropy kernel

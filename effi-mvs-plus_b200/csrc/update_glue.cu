@@ -280,9 +280,17 @@ delta_head_kernel(const float4* __restrict__ t, const float* __restrict__ w, con
     __syncthreads();
     const int q = threadIdx.x & 3;
     const int px = blockIdx.x * DH_COLS + (threadIdx.x >> 2), y0 = blockIdx.y * DH_ROWS, b = blockIdx.z;
-    float acc[DH_ROWS];
+    // the kernel is bound by instruction issue (1.9 M threads of ~400 instructions at 800 x 592): the products run on the packed
+    // fp32 pipe (two channels per FFMA2, the two halves added at the end), and with h = 16 a thread's nine weight quads stay in
+    // registers instead of being re-read from shared memory for every (row, column, output row)
+    ulonglong2 acc2[DH_ROWS];
 #pragma unroll
-    for (int o = 0; o < DH_ROWS; ++o) acc[o] = 0.0f;
+    for (int o = 0; o < DH_ROWS; ++o) acc2[o] = make_ulonglong2(0ull, 0ull);
+    ulonglong2 wreg[J == 1 ? 9 : 1];
+    if (J == 1) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wreg[k] = *reinterpret_cast<const ulonglong2*>(&s_w[k * h4 + q]);
+    }
     if (px < W) {
 #pragma unroll
         for (int r = -1; r <= DH_ROWS; ++r) {
@@ -292,17 +300,17 @@ delta_head_kernel(const float4* __restrict__ t, const float* __restrict__ w, con
             for (int kx = 0; kx < 3; ++kx) {
                 const int xx = px + kx - 1;
                 if (xx < 0 || xx >= W) continue;
-                const float4* base = t + (((size_t)b * H + yy) * W + xx) * h4 + q;
+                const ulonglong2* base = reinterpret_cast<const ulonglong2*>(t + (((size_t)b * H + yy) * W + xx) * h4 + q);
 #pragma unroll
                 for (int j = 0; j < J; ++j) {
-                    const float4 v = __ldg(base + 4 * j);
+                    const ulonglong2 v = __ldg(base + 4 * j);
 #pragma unroll
                     for (int o = 0; o < DH_ROWS; ++o) {
                         const int ky = r - o + 1;
                         if (ky < 0 || ky > 2) continue;
-                        const float4 wv = s_w[(ky * 3 + kx) * h4 + 4 * j + q];
-                        acc[o] = fmaf(v.x, wv.x, acc[o]); acc[o] = fmaf(v.y, wv.y, acc[o]);
-                        acc[o] = fmaf(v.z, wv.z, acc[o]); acc[o] = fmaf(v.w, wv.w, acc[o]);
+                        const ulonglong2 wv = J == 1 ? wreg[ky * 3 + kx] : *reinterpret_cast<const ulonglong2*>(&s_w[(ky * 3 + kx) * h4 + 4 * j + q]);
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[o].x) : "l"(v.x), "l"(wv.x));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[o].y) : "l"(v.y), "l"(wv.y));
                     }
                 }
             }
@@ -311,7 +319,10 @@ delta_head_kernel(const float4* __restrict__ t, const float* __restrict__ w, con
     float mine = 0.0f;
 #pragma unroll
     for (int o = 0; o < DH_ROWS; ++o) {
-        float a = acc[o];
+        float a0, a1, a2, a3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc2[o].x));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a2), "=f"(a3) : "l"(acc2[o].y));
+        float a = (a0 + a1) + (a2 + a3);
         a += __shfl_xor_sync(0xffffffffu, a, 1);
         a += __shfl_xor_sync(0xffffffffu, a, 2);
         if (o == q) mine = a;
