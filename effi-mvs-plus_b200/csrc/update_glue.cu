@@ -281,16 +281,11 @@ delta_head_kernel(const float4* __restrict__ t, const float* __restrict__ w, con
     const int q = threadIdx.x & 3;
     const int px = blockIdx.x * DH_COLS + (threadIdx.x >> 2), y0 = blockIdx.y * DH_ROWS, b = blockIdx.z;
     // the kernel is bound by instruction issue (1.9 M threads of ~400 instructions at 800 x 592): the products run on the packed
-    // fp32 pipe (two channels per FFMA2, the two halves added at the end), and with h = 16 a thread's nine weight quads stay in
-    // registers instead of being re-read from shared memory for every (row, column, output row)
+    // fp32 pipe (two channels per FFMA2, the two halves added at the end).  Measured and dropped: with h = 16 the nine weight quads
+    // of a thread in registers instead of shared memory (70 registers, three 256-thread blocks per SM: 26.2 against 23.8 us).
     ulonglong2 acc2[DH_ROWS];
 #pragma unroll
     for (int o = 0; o < DH_ROWS; ++o) acc2[o] = make_ulonglong2(0ull, 0ull);
-    ulonglong2 wreg[J == 1 ? 9 : 1];
-    if (J == 1) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) wreg[k] = *reinterpret_cast<const ulonglong2*>(&s_w[k * h4 + q]);
-    }
     if (px < W) {
 #pragma unroll
         for (int r = -1; r <= DH_ROWS; ++r) {
@@ -308,7 +303,7 @@ delta_head_kernel(const float4* __restrict__ t, const float* __restrict__ w, con
                     for (int o = 0; o < DH_ROWS; ++o) {
                         const int ky = r - o + 1;
                         if (ky < 0 || ky > 2) continue;
-                        const ulonglong2 wv = J == 1 ? wreg[ky * 3 + kx] : *reinterpret_cast<const ulonglong2*>(&s_w[(ky * 3 + kx) * h4 + 4 * j + q]);
+                        const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(&s_w[(ky * 3 + kx) * h4 + 4 * j + q]);
                         asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[o].x) : "l"(v.x), "l"(wv.x));
                         asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[o].y) : "l"(v.y), "l"(wv.y));
                     }
