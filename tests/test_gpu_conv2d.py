@@ -268,3 +268,50 @@ def test_cascade_tc_graph_replay_equals_eager(monkeypatch):
         torch.cuda.synchronize()
         assert all(torch.equal(a, b) for a, b in zip(out["depth"], eager))
     assert all(bool(torch.isfinite(d).all()) for d in eager)
+
+
+_PDL_SCRIPT = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import torch
+import effimvs_b200  # noqa: F401
+from effimvs_b200 import hotpath, synthetic
+from util import dtu_model
+torch.backends.cudnn.allow_tf32 = True                 # the update block on conv2d_tc (EFFIMVS_CONV2D_MIN_PIXELS lowered by the test)
+dev = torch.device("cuda:0")
+s = synthetic.make_sample("plumbing", seed=3, device=dev, width=640, height=512)
+model = dtu_model(hotpath.CudaHotPath("bf16x3"), dev)
+with torch.no_grad():
+    out = model(s["imgs"], s["proj_matrices"], s["depth_values"])
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out2 = model(s["imgs"], s["proj_matrices"], s["depth_values"])
+    g.replay()
+torch.cuda.synchronize()
+torch.save({{"eager": [d.cpu() for d in out["depth"]], "graph": [d.cpu() for d in out2["depth"]]}}, sys.argv[1])
+"""
+
+
+@pytest.mark.gpu
+def test_programmatic_dependent_launch_switch_gives_the_same_depth_maps(tmp_path):
+    """EFFIMVS_PDL=1 (every hot-path kernel launched with the programmatic-stream-serialization attribute, griddepcontrol.wait
+    before its first dependent access; csrc/common.cuh) against the classic launches: the whole cascade at 640x512x5, eager and
+    as a CUDA graph (programmatic edges), in two fresh processes -- the switch is read once per process.  A kernel that touched a
+    predecessor's output before its wait would show up as stale data in some of the 13 depth maps."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "pdl_run.py"
+    script.write_text(_PDL_SCRIPT.format(root=root))
+    res = {}
+    for flag in ("0", "1"):
+        out = tmp_path / "pdl{}.pt".format(flag)
+        env = dict(os.environ, EFFIMVS_PDL=flag, EFFIMVS_CONV2D_MIN_PIXELS="20000")     # tensor-core update block on stages 2 and 3
+        subprocess.run([sys.executable, str(script), str(out)], check=True, env=env, timeout=600)
+        res[flag] = torch.load(out)
+    for kind in ("eager", "graph"):
+        for a, b in zip(res["0"][kind], res["1"][kind]):
+            # cuDNN picks its algorithms per process, so the two runs agree to convolution rounding, not bit for bit
+            assert float(((a - b).abs() <= 0.05).float().mean()) >= 0.999
+    for a, b in zip(res["1"]["eager"], res["1"]["graph"]):
+        assert float(((a - b).abs() <= 0.05).float().mean()) >= 0.999
