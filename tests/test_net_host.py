@@ -147,3 +147,31 @@ def test_workspace_cache_keeps_one_buffer_per_key_and_evicts_least_recently_used
     c.get(("costreg", 1), 10, "cpu")                                 # touch -> most recently used
     c.get(("cost_up", 4), 10, "cpu")                                 # evicts ("cost_up", 2)
     assert set(c._store) == {("costreg", 1), ("cost_up", 3), ("cost_up", 4)}
+
+
+def test_encoder_head_host_table_cache(monkeypatch):
+    """ops._encoder_head_table: the host-side weight tables of the constant-bank encoder head are cached by the identity and
+    version of the four weight tensors, rebuilt after an in-place update, and never built while a stream is capturing (a miss
+    there returns None = the kernel that reads the weights from device memory)."""
+    from effimvs_b200 import ops
+    capturing = [False]
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: capturing[0])
+    monkeypatch.setattr(ops, "_EH_TABLES", {})
+    h, CD = 16, 6
+    gen = torch.Generator().manual_seed(2)
+    ws = (torch.randn(h, CD, 1, 1, generator=gen), torch.randn(h, generator=gen), torch.randn(h, 1, 7, 7, generator=gen),
+          torch.randn(h, generator=gen))
+    t0 = ops._encoder_head_table(ws, CD, h)
+    assert t0.shape == (944,) and torch.equal(t0[:784].reshape(49, 16), ws[2][:, 0].reshape(16, 49).t())
+    assert ops._encoder_head_table(ws, CD, h) is t0                       # same tensors, same versions: the cached table
+    capturing[0] = True
+    assert ops._encoder_head_table(ws, CD, h) is t0                       # a hit needs no copy, so it is fine under capture
+    ws[2].mul_(2.0)                                                       # in-place update bumps the version
+    assert ops._encoder_head_table(ws, CD, h) is None                     # miss under capture: no device -> host copy there
+    capturing[0] = False
+    t1 = ops._encoder_head_table(ws, CD, h)
+    assert t1 is not t0 and torch.equal(t1[:784].reshape(49, 16), ws[2][:, 0].reshape(16, 49).t())
+    fresh = tuple(w.clone() for w in ws)                                  # other tensor objects with the same values: their own entry
+    t2 = ops._encoder_head_table(fresh, CD, h)
+    assert t2 is not t1 and torch.equal(t2, t1)
+    assert ops._encoder_head_table(ws, CD, h) is t1
